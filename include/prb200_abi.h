@@ -1,0 +1,415 @@
+/* prb200_abi.h -- the C ABI between PearRay-style C++17 host code and the B200 (sm_100a) CUDA
+ * implementation of the spectral path-tracing hot path.
+ *
+ * Everything here is POD: plain pointers, sizes and integer status codes.  No C++ / torch types.
+ * Host buffers are caller-owned; device memory is owned by the context.  One context per GPU,
+ * used from one host thread (streams live inside the context).
+ *
+ * Each entry point names the reference interface (file:line under the PearRay checkout) it replaces.
+ * All arithmetic is fp32 with FTZ/DAZ (reference src/base/Platform.h:20-34), ids are uint32.
+ */
+#ifndef PRB200_ABI_H
+#define PRB200_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRB_ABI_VERSION 1u
+#define PRB_INVALID_ID 0xFFFFFFFFu /* reference PR_INVALID_ID, src/base/config/Constants.inl */
+#define PRB_SPECTRAL_BLOB_SIZE 4	/* reference SpectralBlob, src/core/spectral/SpectralBlob.h:7-20 */
+
+typedef int32_t prb_status; /* 0 = ok, <0 = error; text via prb_last_error() */
+#define PRB_OK 0
+#define PRB_ERR_INVALID_ARG -1
+#define PRB_ERR_CUDA -2
+#define PRB_ERR_NO_SCENE -3
+#define PRB_ERR_UNSUPPORTED -4
+#define PRB_ERR_NO_DEVICE -5
+
+/* ---------------------------------------------------------------- ray / hit streams */
+/* Ray flags: reference RayFlag, src/core/ray/Ray.h:9-19 */
+#define PRB_RAY_CAMERA 0x01u
+#define PRB_RAY_LIGHT 0x02u
+#define PRB_RAY_BOUNCE 0x04u
+#define PRB_RAY_SHADOW 0x08u
+#define PRB_RAY_MONOCHROME 0x10u
+
+/* SoA ray stream as in reference RayStream (src/core/ray/RayStream.h:55-107): one array per
+ * component.  Only the geometric part is needed by the trace entry points. */
+typedef struct prb_ray_soa {
+	const float* org_x;
+	const float* org_y;
+	const float* org_z;
+	const float* dir_x;
+	const float* dir_y;
+	const float* dir_z;
+	const float* tmin; /* may be NULL -> 1e-4 (BOUNCE_RAY_MIN, src/vcm/vcm/Defaults.h:4-7) */
+	const float* tmax; /* may be NULL -> +inf */
+} prb_ray_soa;
+
+/* SoA hit stream as in reference HitStream / HitEntry (src/core/trace/HitEntry.h:7-15).  One entry
+ * per ray, misses carry entity_id == PRB_INVALID_ID (reference Scene.cpp:185-189). */
+typedef struct prb_hit_soa {
+	uint32_t* entity_id;
+	uint32_t* primitive_id;
+	float* u;
+	float* v;
+	float* t;
+} prb_hit_soa;
+
+/* ---------------------------------------------------------------- shading nodes */
+/* Flattened shading network (reference FloatSpectralNode graph, src/core/shader/INode.h). */
+enum {
+	PRB_NODE_CONST		  = 0, /* p[0]                       ConstSpectralNode, loader/shader/ConstNode.cpp:27-36 */
+	PRB_NODE_PARAM		  = 1, /* p[0..2] = a,b,c            ParametricSpectralNode :59-62 ('refl') */
+	PRB_NODE_PARAM_SCALED = 2, /* p[0..2], p[3] = power      ParametricScaledSpectralNode :85-88 ('illum') */
+	PRB_NODE_TABLE		  = 3, /* a=pool offset,b=count,p[0]=start nm,p[1]=end nm   EquidistantSpectrumView::lookup */
+	PRB_NODE_SELLMEIER	  = 4, /* a=pool offset (B[n],C[n]), b=n   SellmeierIndexNode, node/ReflectiveNode.cpp:104-140 */
+	PRB_NODE_MUL		  = 5, /* a,b = node ids             MulSpectralMath ('smul') */
+	PRB_NODE_CHECKER	  = 6  /* a,b = node ids, p[0]=su,p[1]=sv,p[2]=mode(0 none,1 iso,2 aniso)  CheckerboardNode.cpp:26-48 */
+};
+#define PRB_NODE_FLAG_SPECTRAL_VARYING 0x1u /* NodeFlag::SpectralVarying */
+#define PRB_NODE_FLAG_TEXTURE_VARYING 0x2u
+
+typedef struct prb_node {
+	uint32_t type;
+	uint32_t flags;
+	uint32_t a;
+	uint32_t b;
+	float p[4];
+} prb_node;
+
+/* ---------------------------------------------------------------- materials */
+enum {
+	PRB_MAT_DIFFUSE			= 0, /* plugins/main/materials/lambert.cpp:14-89        node[0]=albedo */
+	PRB_MAT_DIELECTRIC		= 1, /* dielectric.cpp:18-135   node[0]=specularity node[1]=transmission node[2]=ior */
+	PRB_MAT_CONDUCTOR		= 2, /* conductor.cpp:16-95     node[0]=eta node[1]=k node[2]=specularity */
+	PRB_MAT_ROUGHCONDUCTOR	= 3, /* roughconductor.cpp:16-143  nodes as CONDUCTOR, f[0]=roughness_x f[1]=roughness_y */
+	PRB_MAT_ROUGHDIELECTRIC = 4, /* roughdielectric.cpp:42-279 nodes as DIELECTRIC, f[0],f[1] roughness */
+	PRB_MAT_PRINCIPLED		= 5	 /* principled.cpp:34-631   node[0]=base node[1]=ior, f[] see PRB_PR_* */
+};
+#define PRB_MATF_TWO_SIDED 0x001u		  /* lambert two_sided (default true) */
+#define PRB_MATF_THIN 0x002u			  /* dielectric / principled 'thin' */
+#define PRB_MATF_TRANSMISSION_COLOR 0x004u /* dielectric 'transmission' given */
+#define PRB_MATF_VNDF 0x008u			  /* rough*: 'vndf' (default true) */
+#define PRB_MATF_ANISOTROPIC 0x010u		  /* rough*: roughness_x != roughness_y node */
+#define PRB_MATF_ONLY_DELTA 0x020u		  /* IMaterial::hasOnlyDeltaDistribution() */
+#define PRB_MATF_SPECTRAL_VARYING 0x040u  /* mNodeContribFlags & SpectralVarying (hero collapse when delta) */
+#define PRB_MATF_HAS_TRANSMISSION 0x080u  /* principled: diffuse_/specular_transmission present */
+
+/* principled scalar slots (principled.cpp:50-62) */
+enum {
+	PRB_PR_DIFF_TRANS = 0,
+	PRB_PR_ROUGHNESS,
+	PRB_PR_ANISOTROPIC,
+	PRB_PR_SPEC_TRANS,
+	PRB_PR_SPEC_TINT,
+	PRB_PR_FLATNESS,
+	PRB_PR_METALLIC,
+	PRB_PR_SHEEN,
+	PRB_PR_SHEEN_TINT,
+	PRB_PR_CLEARCOAT,
+	PRB_PR_CLEARCOAT_GLOSS,
+	PRB_PR__COUNT
+};
+
+typedef struct prb_material {
+	uint32_t type;
+	uint32_t flags;
+	uint32_t node[4];
+	float f[12];
+} prb_material;
+
+typedef struct prb_emission { /* plugins/main/emissions/diffuse.cpp:11-56 */
+	uint32_t radiance_node;
+	uint32_t _pad;
+} prb_emission;
+
+/* ---------------------------------------------------------------- geometry */
+enum {
+	PRB_ENTITY_MESH	  = 0, /* plugins/main/entities/mesh.cpp   (instance of a mesh BLAS) */
+	PRB_ENTITY_SPHERE = 1, /* sphere.cpp  (RTC_GEOMETRY_TYPE_SPHERE_POINT) */
+	PRB_ENTITY_PLANE  = 2  /* plane.cpp   (one world-space quad) */
+};
+#define PRB_MESH_HAS_NORMALS 0x1u
+#define PRB_MESH_HAS_UVS 0x2u
+
+/* Mesh data lives in shared pools (scene.vertices / normals / uvs / face_indices / face_slots).
+ * Faces are stored as 4 indices; triangles carry PRB_INVALID_ID in the 4th (reference mixed
+ * index layout, mesh.cpp:30-46).  Index values are relative to the mesh's vertex_offset. */
+typedef struct prb_mesh {
+	uint32_t vertex_offset; /* in vertices (x3 floats) */
+	uint32_t vertex_count;
+	uint32_t face_offset; /* in faces */
+	uint32_t face_count;
+	uint32_t features;
+	uint32_t blas_root;		 /* node index of the mesh BVH root inside scene.bvh_nodes */
+	uint32_t uv_offset;		 /* in uvs (x2 floats); one per vertex when HAS_UVS */
+	uint32_t normal_offset;	 /* in normals (x3 floats); one per vertex when HAS_NORMALS */
+} prb_mesh;
+
+/* geo[] layout
+ *  SPHERE: [0..2] world centre, [3] world radius (radius * mean column norm, sphere.cpp:91-100),
+ *          [4] local radius, [5] 1/worldSurfaceArea (mPDF_Cache, sphere.cpp:31)
+ *  PLANE : [0..2] mS, [3..5] mEx, [6..8] mEy, [9..11] mEz (unit), [12] width, [13] height
+ *          (plane.cpp:227-244), [14..25] the four world-space quad corners p, p+y, p+y+x, p+x
+ *          (plane.cpp:80-84), [26..28] normalMatrix*plane.normal (un-normalised, plane.cpp:175),
+ *          [29..31] local plane position, [32..34] local x axis, [35..37] local y axis,
+ *          [38] 1/|x|^2, [39] 1/|y|^2 (Plane::project, src/core/geometry/Plane.cpp:117-123)
+ *  MESH  : unused */
+typedef struct prb_entity {
+	uint32_t type;
+	uint32_t mesh_id;
+	uint32_t material_offset; /* into scene.entity_materials; mesh: per slot, sphere/plane: one */
+	uint32_t material_count;
+	uint32_t emission_id;
+	uint32_t light_id; /* index into scene.lights or PRB_INVALID_ID */
+	uint32_t visibility; /* EntityVisibility bits == ray flags, src/core/entity/IEntity.h:9-15 */
+	uint32_t blas_root;
+	float local_to_world[12]; /* row-major 3x4, ITransformable::transform() */
+	float world_to_local[12]; /* invTransform() */
+	float normal_matrix[9];	  /* row-major 3x3, linear().inverse().transpose() */
+	float jacobian_det;		  /* volumeScalefactor(), ITransformable.cpp:14 */
+	float world_area;		  /* IEntity::worldSurfaceArea() */
+	float pdf_area;			  /* sampleParameterPointPDF() without info */
+	float geo[45];
+} prb_entity;
+
+/* BVH8 compressed node, 80 bytes (host builder: pearray_b200/host/bvh_builder.cpp).
+ * child boxes: lo = p + q_lo * 2^e, hi = p + q_hi * 2^e per axis.
+ * meta[i]: 0xFF empty; 0x80|k internal child, node index = child_base + k;
+ *          otherwise leaf: ((count-1) << 5) | offset, prims [prim_base+offset, +count), count<=4. */
+typedef struct prb_bvh8_node {
+	float px, py, pz;
+	uint8_t ex, ey, ez, imask;
+	uint32_t child_base;
+	uint32_t prim_base;
+	uint8_t meta[8];
+	uint8_t qlo_x[8], qlo_y[8], qlo_z[8];
+	uint8_t qhi_x[8], qhi_y[8], qhi_z[8];
+} prb_bvh8_node;
+
+/* 48-byte leaf primitive: a triangle.  prim_id = face index in its mesh (0 for planes);
+ * flags bit0: second triangle of a quad (u,v -> 1-u,1-v; Embree quad convention). */
+typedef struct prb_bvh_tri {
+	float v0[3];
+	uint32_t prim_id;
+	float v1[3];
+	uint32_t flags;
+	float v2[3];
+	uint32_t _pad;
+} prb_bvh_tri;
+
+/* ---------------------------------------------------------------- lights */
+enum { PRB_LIGHT_AREA = 0, PRB_LIGHT_ENV = 1 };
+typedef struct prb_light { /* src/core/light/Light.cpp, LightSampler.cpp:11-132 */
+	uint32_t type;
+	uint32_t entity_id;	   /* AREA */
+	uint32_t emission_id;  /* AREA */
+	uint32_t radiance_node; /* ENV: radiance;  (environment.cpp) */
+	uint32_t background_node; /* ENV: background (used at depth 0 when split) */
+	uint32_t env_split;
+	float select_pdf; /* discretePdf(lightID) */
+	float scene_radius;
+	float normal_matrix[9];		/* ENV: ITransformable normalMatrix() */
+	float inv_normal_matrix[9]; /* ENV: invNormalMatrix() */
+} prb_light;
+
+/* ---------------------------------------------------------------- samplers, mapper, camera */
+enum { PRB_SAMPLER_RANDOM = 0, PRB_SAMPLER_MJITT = 1, PRB_SAMPLER_SOBOL = 2 };
+typedef struct prb_sampler { /* src/plugins/main/sampler/ */
+	uint32_t type;
+	uint32_t max_samples; /* ISampler::maxSamples() */
+	uint32_t bins_1d;	  /* mjitt m1D */
+	uint32_t m2d_x, m2d_y;
+	uint32_t seed;			/* mjitt mSeed */
+	uint32_t table_offset;	/* sobol: pool offset of max_samples 1D floats followed by max_samples (x,y) pairs */
+	uint32_t _pad;
+} prb_sampler;
+
+enum { PRB_MAPPER_RANDOM = 0, PRB_MAPPER_SPD_CMIS = 1, PRB_MAPPER_SPD_HERO = 2 };
+typedef struct prb_spectral_mapper { /* src/plugins/main/spectralmapper/spd.cpp, random.cpp */
+	uint32_t type;
+	uint32_t cdf_offset; /* pool offset of cdf_size floats (Distribution1D mCDF) */
+	uint32_t cdf_size;
+	uint32_t _pad;
+} prb_spectral_mapper;
+
+typedef struct prb_camera { /* plugins/main/cameras/perspective.cpp:45-113, no-DOF branch */
+	float origin[3];
+	float right[3]; /* mRight_Cache (already * 0.5 * width) */
+	float up[3];	/* mUp_Cache */
+	float dir[3];	/* mFocalDistance_Cache */
+	float near_t, far_t;
+} prb_camera;
+
+typedef struct prb_settings { /* RenderSettings.cpp:11-33 + DiParameters direct.cpp:34-39 */
+	uint64_t seed;
+	uint32_t film_width, film_height;
+	uint32_t view_x, view_y, view_w, view_h; /* crop window in film pixels */
+	uint32_t max_sample_count;				 /* RenderSettings::maxSampleCount() */
+	uint32_t max_ray_depth;					 /* hard, default 64 */
+	uint32_t soft_max_ray_depth;			 /* default 4 */
+	uint32_t mis_power;						 /* 0 balance, 1 power */
+	uint32_t do_nee, do_direct, emissive_scatter;
+	uint32_t spectral_mono, spectral_hero;
+	float spectral_start, spectral_end; /* camera range */
+	float light_range_start, light_range_end;
+	float time_alpha, time_beta; /* RenderTile.cpp:44-63 */
+	int32_t filter_radius;		 /* FilterCache table (2r+1)^2 at filter_offset in the pool */
+	uint32_t filter_offset;
+} prb_settings;
+
+/* ---------------------------------------------------------------- the scene */
+typedef struct prb_scene_desc {
+	uint32_t abi_version;
+	prb_settings settings;
+	prb_camera camera;
+	prb_sampler aa_sampler, lens_sampler, time_sampler;
+	prb_spectral_mapper pixel_mapper;
+
+	uint32_t n_nodes;
+	const prb_node* nodes;
+	uint32_t n_materials;
+	const prb_material* materials;
+	uint32_t n_emissions;
+	const prb_emission* emissions;
+	uint32_t n_entities;
+	const prb_entity* entities;
+	uint32_t n_entity_materials;
+	const uint32_t* entity_materials;
+	uint32_t n_meshes;
+	const prb_mesh* meshes;
+	uint32_t n_vertices;
+	const float* vertices; /* xyz */
+	const float* normals;  /* xyz per vertex (0 when mesh has none) */
+	const float* uvs;	   /* uv per vertex */
+	uint32_t n_faces;
+	const uint32_t* face_indices; /* 4 per face */
+	const uint32_t* face_slots;	  /* material slot per face */
+
+	uint32_t n_lights;
+	const prb_light* lights;
+	const float* light_cdf; /* n_lights + 1 */
+	float inf_light_selection_probability;
+
+	uint32_t tlas_root; /* node index */
+	uint32_t n_bvh_nodes;
+	const prb_bvh8_node* bvh_nodes;
+	uint32_t n_bvh_tris;
+	const prb_bvh_tri* bvh_tris;
+	uint32_t n_tlas_refs;
+	const uint32_t* tlas_refs; /* TLAS leaf prim -> entity id */
+
+	uint32_t n_pool;
+	const float* pool; /* CIE tables, illuminants, CDFs, Sobol tables, filter table */
+	uint32_t cie_offset; /* 3 x 441 floats: x, y, z (CIE 2006, 390..830 nm) */
+	uint32_t _pad;
+} prb_scene_desc;
+
+/* One render tile (reference RenderTile start/end, src/core/renderer/RenderTile.h).  Pixels are film
+ * coordinates; [sx,ex) x [sy,ey). */
+typedef struct prb_tile {
+	uint32_t sx, sy, ex, ey;
+} prb_tile;
+
+/* reference RenderStatisticEntry, src/core/renderer/RenderStatistics.h:9-24 */
+typedef struct prb_stats {
+	uint64_t camera_ray_count, light_ray_count, primary_ray_count, bounce_ray_count, shadow_ray_count,
+		monochrome_ray_count, pixel_sample_count, entity_hit_count, background_hit_count,
+		camera_depth_count, light_depth_count;
+	uint64_t kernel_launches; /* CUDA kernels launched by this context so far */
+	uint64_t wavefront_iterations;
+} prb_stats;
+
+/* material unit-call contexts: reference MaterialEvalContext / MaterialSampleContext
+ * (src/core/material/MaterialContext.h:12-110), all in shading space (N = +z) */
+typedef struct prb_material_query {
+	float V[3];
+	float L[3]; /* eval / pdf only */
+	float wavelength_nm[4];
+	float uv[2];
+	uint32_t ray_flags;
+	uint32_t material_id;
+	uint64_t rng_state; /* sample only: pcg32_fast state; updated state is returned */
+} prb_material_query;
+
+typedef struct prb_material_result {
+	float weight[4]; /* eval: Weight; sample: IntegralWeight */
+	float pdf_s[4];
+	float L[3]; /* sample only */
+	uint32_t flags; /* MaterialSampleFlag bits, src/core/material/MaterialType.h */
+	uint32_t type;	/* MaterialScatteringType */
+	uint64_t rng_state;
+} prb_material_result;
+
+typedef struct prb_ctx prb_ctx;
+
+/* -- life cycle.  Replaces RenderFactory::create / RenderContext ctor (src/core/renderer/RenderFactory.cpp:16-42). */
+prb_status prb_create(int device, prb_ctx** out);
+void prb_destroy(prb_ctx* ctx);
+const char* prb_last_error(void);
+int prb_device_count(void);
+
+/* -- scene upload.  Replaces Scene::setupScene + rtcCommitScene (src/core/scene/Scene.cpp:88-120):
+ * the BVH is built by the host (SAH BVH8) and arrives inside the descriptor. */
+prb_status prb_upload_scene(prb_ctx* ctx, const prb_scene_desc* scene);
+
+/* -- per-film-pixel RNG states.  Replaces RenderRandomMap (src/core/renderer/RenderRandomMap.cpp:11-28);
+ * n must be film_width*film_height. */
+prb_status prb_upload_rng(prb_ctx* ctx, const uint64_t* states, size_t n);
+prb_status prb_download_rng(prb_ctx* ctx, uint64_t* states, size_t n);
+
+/* -- the hot path.  Replaces IIntegratorInstance::onTile for the 'direct' integrator
+ * (src/plugins/main/integrators/direct.cpp:153-166) over a batch of tiles, for iterations
+ * [first_iteration, first_iteration + iteration_count).  Film cells of the tiles are updated
+ * (running mean over iterations as FrameOutputDevice::onEndOfIteration, FrameOutputDevice.cpp:202-221).
+ * Asynchronous; prb_sync / prb_film_download wait. */
+prb_status prb_render_tiles(prb_ctx* ctx, const prb_tile* tiles, size_t n_tiles,
+							uint32_t first_iteration, uint32_t iteration_count);
+prb_status prb_sync(prb_ctx* ctx);
+prb_status prb_film_clear(prb_ctx* ctx);
+
+/* -- film read-back.  Replaces FrameOutputDevice / FrameContainer channel access
+ * (src/loader/output/FrameOutputDevice.cpp).  xyz: W*H*3 floats (pixel filter applied),
+ * sample_count: W*H (AOV_SampleCount).  Either may be NULL. */
+prb_status prb_film_download(prb_ctx* ctx, float* xyz, uint32_t* sample_count);
+/* optional first-hit AOVs (sums over samples as commitShadingPoints, LocalFrameOutputDevice.cpp:252-302):
+ * normal (3), position (3), uv (2), depth (1), entity id (1) -> 10 floats per pixel, may be NULL */
+prb_status prb_film_download_aov(prb_ctx* ctx, float* aov10);
+/* copy the UNFILTERED film (xyz mean, 3 floats/pixel, then sample counts as float) into a caller
+ * provided DEVICE buffer of W*H*4 floats -- the buffer handed to the NCCL reduce in multi-GPU runs. */
+prb_status prb_film_export_device(prb_ctx* ctx, float* device_dst);
+/* load an (already reduced) unfiltered film back and apply the pixel filter */
+prb_status prb_film_import_device(prb_ctx* ctx, const float* device_src);
+
+/* -- stream tracing.  Replace Scene::traceRays (Scene.cpp:138-218, rtcIntersect16) and
+ * Scene::traceShadowRay (Scene.cpp:266-280, rtcOccluded1; occluded[i] = 1 if anything was hit in
+ * [tmin, tmax]).  Host-pointer variants copy in/out; *_device variants take device pointers. */
+prb_status prb_trace_closest(prb_ctx* ctx, const prb_ray_soa* rays, size_t n, prb_hit_soa* hits);
+prb_status prb_trace_any(prb_ctx* ctx, const prb_ray_soa* rays, size_t n, uint8_t* occluded);
+prb_status prb_trace_closest_device(prb_ctx* ctx, const prb_ray_soa* rays, size_t n, prb_hit_soa* hits);
+prb_status prb_trace_any_device(prb_ctx* ctx, const prb_ray_soa* rays, size_t n, uint8_t* occluded);
+/* camera rays of one iteration for the given tiles (RenderTile::constructCameraRay, RenderTile.cpp:71-132)
+ * written as a host SoA stream; does not advance the context's RNG states. n_out receives the count. */
+prb_status prb_generate_camera_rays(prb_ctx* ctx, const prb_tile* tiles, size_t n_tiles, uint32_t iteration,
+									float* org_xyz, float* dir_xyz, float* wavelengths4, uint32_t* pixel_index,
+									size_t capacity, size_t* n_out);
+
+/* -- unit-level material calls: IMaterial::eval / ::sample (src/core/material/IMaterial.h:15-55) */
+prb_status prb_material_eval(prb_ctx* ctx, const prb_material_query* q, size_t n, prb_material_result* out);
+prb_status prb_material_sample(prb_ctx* ctx, const prb_material_query* q, size_t n, prb_material_result* out);
+
+prb_status prb_get_stats(prb_ctx* ctx, prb_stats* out);
+prb_status prb_reset_stats(prb_ctx* ctx);
+/* device time (ms, CUDA events on the context stream) spent in the last prb_render_tiles / prb_trace_* call */
+prb_status prb_last_device_ms(prb_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRB200_ABI_H */

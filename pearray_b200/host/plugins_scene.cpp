@@ -1,0 +1,902 @@
+// Entity, camera, emission, infinite-light, sampler, filter, spectral-mapper and integrator plugins of the
+// hot path (SURVEY rows 13,16-20,22,23).  Names, aliases, parameter keys and defaults follow the reference.
+#include "prh.h"
+
+#include <sstream>
+
+namespace PR {
+namespace {
+// ------------------------------------------------------------------ entities
+class MeshEntity : public IEntity { // plugins/main/entities/mesh.cpp:130-256
+public:
+	MeshEntity(const std::string& name, const Transformf& t, const std::shared_ptr<MeshBase>& mesh, const std::vector<uint32>& materials, uint32 emsID)
+		: IEntity(emsID, name, t)
+		, mMaterials(materials)
+		, mMesh(mesh)
+	{
+	}
+	std::string type() const override { return "mesh"; }
+	float localSurfaceArea() const override { return mMesh->surfaceArea(Transformf::Identity()); }
+	BoundingBox worldBoundingBox() const override
+	{
+		BoundingBox b;
+		for (size_t i = 0; i < mMesh->vertexCount(); ++i)
+			b.combine(transform() * mMesh->vertex((uint32)i));
+		return b;
+	}
+	void describe(prb_entity& out, SceneCompiler& c) const override
+	{
+		out.type			= PRB_ENTITY_MESH;
+		out.mesh_id			= c.registerMesh(mMesh);
+		out.material_offset = c.registerEntityMaterials(mMaterials);
+		out.material_count	= (uint32)mMaterials.size();
+	}
+
+private:
+	std::vector<uint32> mMaterials;
+	std::shared_ptr<MeshBase> mMesh;
+};
+class MeshEntityPlugin : public IEntityPlugin {
+public:
+	std::shared_ptr<IEntity> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		const ParameterGroup& params = ctx.parameters();
+		const std::string name		 = params.getString("name", "__unnamed__");
+		const std::string mesh_name	 = params.getString("mesh", "");
+		Parameter matP				 = params.getParameter("materials");
+		if (!matP.isValid())
+			matP = params.getParameter("material");
+		const std::vector<uint32> materials = ctx.lookupMaterialIDArray(matP);
+		const uint32 emsID					= ctx.lookupEmissionID(params.getParameter("emission"));
+		if (params.getBool("ignore_normals", false))
+			PR_LOG(L_WARNING) << "mesh: ignore_normals is not supported on the device path (vertex normals are used when present)" << std::endl;
+		if (!ctx.hasMesh(mesh_name)) {
+			PR_LOG(L_ERROR) << "Could not find a mesh named " << mesh_name << std::endl;
+			return nullptr;
+		}
+		return std::make_shared<MeshEntity>(name, ctx.transform(), ctx.getMesh(mesh_name), materials, emsID);
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static std::vector<std::string> names({ "mesh" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Mesh Entity: mesh, material|materials, emission, ignore_normals"; }
+};
+
+class SphereEntity : public IEntity { // sphere.cpp:19-153
+public:
+	SphereEntity(const std::string& name, const Transformf& t, float r, uint32 matID, uint32 emsID)
+		: IEntity(emsID, name, t)
+		, mRadius(r)
+		, mMaterialID(matID)
+	{
+		mPDF_Cache = r > PR_EPSILON ? 1 / worldSurfaceArea() : 0.0f;
+	}
+	std::string type() const override { return "sphere"; }
+	float localSurfaceArea() const override { return 4 * PR_PI * mRadius * mRadius; }
+	float worldSurfaceArea() const override
+	{ // Knud Thomsen's formula, sphere.cpp:47-61
+		constexpr float P = 1.6075f;
+		const Vector3f s  = transform().scaling();
+		const float a = s.x * mRadius, b = s.y * mRadius, c = s.z * mRadius;
+		const float t = (std::pow(a * b, P) + std::pow(a * c, P) + std::pow(b * c, P)) / 3;
+		return 4 * PR_PI * std::pow(t, 1 / P);
+	}
+	float worldRadius() const
+	{
+		const Matrix3f& L = transform().linear();
+		return mRadius * ((L.col(0).norm() + L.col(1).norm() + L.col(2).norm()) / 3.0f);
+	}
+	BoundingBox worldBoundingBox() const override
+	{
+		const Vector3f c = transform() * Vector3f(0, 0, 0);
+		const float r	 = worldRadius();
+		BoundingBox b;
+		b.combine(c - Vector3f(r, r, r));
+		b.combine(c + Vector3f(r, r, r));
+		return b;
+	}
+	float sampleParameterPointPDF() const override { return mPDF_Cache; }
+	void describe(prb_entity& out, SceneCompiler& c) const override
+	{
+		out.type			= PRB_ENTITY_SPHERE;
+		out.material_offset = c.registerEntityMaterials({ mMaterialID });
+		out.material_count	= 1;
+		const Vector3f ctr	= transform() * Vector3f(0, 0, 0);
+		out.geo[0]			= ctr.x;
+		out.geo[1]			= ctr.y;
+		out.geo[2]			= ctr.z;
+		out.geo[3]			= worldRadius();
+		out.geo[4]			= mRadius;
+		out.geo[5]			= mPDF_Cache;
+	}
+
+private:
+	float mRadius;
+	uint32 mMaterialID;
+	float mPDF_Cache;
+};
+class SphereEntityPlugin : public IEntityPlugin {
+public:
+	std::shared_ptr<IEntity> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		const ParameterGroup& params = ctx.parameters();
+		return std::make_shared<SphereEntity>(params.getString("name", "__unnamed__"), ctx.transform(), params.getNumber("radius", 1.0f),
+											  ctx.lookupMaterialID(params.getParameter("material")), ctx.lookupEmissionID(params.getParameter("emission")));
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static std::vector<std::string> names({ "sphere" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Sphere Entity: radius (1), material, emission, optimize_sampling (true)"; }
+};
+
+class PlaneEntity : public IEntity { // plane.cpp:18-258
+public:
+	PlaneEntity(const std::string& name, const Transformf& t, const Vector3f& xAxis, const Vector3f& yAxis, uint32 matID, uint32 emsID, bool centering)
+		: IEntity(emsID, name, t)
+		, mPos(0, 0, 0)
+		, mX(xAxis)
+		, mY(yAxis)
+		, mMaterialID(matID)
+	{
+		if (centering)
+			mPos = -0.5f * mX - 0.5f * mY;
+	}
+	Vector3f normal() const { return mX.cross(mY).normalized(); }
+	std::string type() const override { return "plane"; }
+	float localSurfaceArea() const override { return mX.cross(mY).norm(); }
+	float worldSurfaceArea() const override { return (transform().linear() * mX).norm() * (transform().linear() * mY).norm(); }
+	BoundingBox worldBoundingBox() const override
+	{
+		BoundingBox b;
+		b.combine(transform() * mPos);
+		b.combine(transform() * (mPos + mY));
+		b.combine(transform() * (mPos + mY + mX));
+		b.combine(transform() * (mPos + mX));
+		return b;
+	}
+	float sampleParameterPointPDF() const override
+	{
+		const float garea = worldSurfaceArea();
+		return garea > PR_EPSILON ? 1.0f / garea : 0;
+	}
+	void describe(prb_entity& out, SceneCompiler& c) const override
+	{
+		out.type			= PRB_ENTITY_PLANE;
+		out.material_offset = c.registerEntityMaterials({ mMaterialID });
+		out.material_count	= 1;
+		// cache(), plane.cpp:227-244
+		const Vector3f S = transform() * mPos;
+		Vector3f Ex = transform().linear() * mX, Ey = transform().linear() * mY, Ez = normalMatrix() * normal();
+		const float w = Ex.norm(), h = Ey.norm();
+		Ex.normalize();
+		Ey.normalize();
+		Ez.normalize();
+		auto put = [&](int o, const Vector3f& v) {
+			out.geo[o]	   = v.x;
+			out.geo[o + 1] = v.y;
+			out.geo[o + 2] = v.z;
+		};
+		put(0, S);
+		put(3, Ex);
+		put(6, Ey);
+		put(9, Ez);
+		out.geo[12] = w;
+		out.geo[13] = h;
+		put(14, transform() * mPos); // constructGeometryRepresentation, plane.cpp:80-84
+		put(17, transform() * (mPos + mY));
+		put(20, transform() * (mPos + mY + mX));
+		put(23, transform() * (mPos + mX));
+		put(26, normalMatrix() * normal());
+		put(29, mPos);
+		put(32, mX);
+		put(35, mY);
+		out.geo[38] = 1 / mX.squaredNorm();
+		out.geo[39] = 1 / mY.squaredNorm();
+	}
+
+private:
+	Vector3f mPos, mX, mY;
+	uint32 mMaterialID;
+};
+class PlaneEntityPlugin : public IEntityPlugin {
+public:
+	std::shared_ptr<IEntity> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		const ParameterGroup& params = ctx.parameters();
+		Vector3f xAxis				 = params.getVector3f("x_axis", Vector3f(1, 0, 0));
+		Vector3f yAxis				 = params.getVector3f("y_axis", Vector3f(0, 1, 0));
+		const float width			 = params.getNumber("width", 1);
+		const float height			 = params.getNumber("height", 1);
+		return std::make_shared<PlaneEntity>(params.getString("name", "__unnamed__"), ctx.transform(), width * xAxis, height * yAxis,
+											 ctx.lookupMaterialID(params.getParameter("material")), ctx.lookupEmissionID(params.getParameter("emission")),
+											 params.getBool("centering", false));
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static std::vector<std::string> names({ "plane" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Plane Entity: width (1), height (1), x_axis, y_axis, material, emission, centering (false)"; }
+};
+
+// ------------------------------------------------------------------ camera
+class PerspectiveCamera : public ICamera { // plugins/main/cameras/perspective.cpp:15-137 (no-DOF branch)
+public:
+	PerspectiveCamera(const std::string& name, const Transformf& t, float w, float h, float nearT, float farT, const Vector3f& ld, const Vector3f& lr,
+					  const Vector3f& lu)
+		: ICamera(name, t)
+		, mWidth(w)
+		, mHeight(h)
+		, mNearT(nearT)
+		, mFarT(farT)
+		, mLD(ld)
+		, mLR(lr)
+		, mLU(lu)
+	{
+	}
+	std::string type() const override { return "perspective"; }
+	void describe(prb_camera& out) const override
+	{ // cache(), perspective.cpp:84-113
+		const Vector3f dir	 = transform().linear() * mLD;
+		const Vector3f right = (transform().linear() * mLR) * (0.5f * mWidth);
+		const Vector3f up	 = (transform().linear() * mLU) * (0.5f * mHeight);
+		const Vector3f o	 = transform().translation();
+		for (int i = 0; i < 3; ++i) {
+			out.origin[i] = o[i];
+			out.right[i]  = right[i];
+			out.up[i]	  = up[i];
+			out.dir[i]	  = dir[i];
+		}
+		out.near_t = mNearT;
+		out.far_t  = mFarT;
+	}
+
+private:
+	float mWidth, mHeight, mNearT, mFarT;
+	Vector3f mLD, mLR, mLU;
+};
+class PerspectiveCameraPlugin : public ICameraPlugin {
+public:
+	std::shared_ptr<ICamera> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		const ParameterGroup& params = ctx.parameters();
+		const float apr				 = params.getNumber("aperture_radius", 0.05f);
+		const float fstop			 = params.getNumber("fstop", 0);
+		if (apr > PR_EPSILON && fstop > PR_EPSILON) {
+			PR_LOG(L_ERROR) << "perspective camera: depth of field is not supported on the device path" << std::endl;
+			return nullptr;
+		}
+		// ICamera::DefaultDirection (0,1,0) /Right (1,0,0) /Up (0,0,1) (src/core/camera/ICamera.cpp:5-7) and NEAR/FAR defaults (perspective.cpp:12-13)
+		return std::make_shared<PerspectiveCamera>(params.getString("name", "__unnamed__"), ctx.transform(), params.getNumber("width", 1),
+												   params.getNumber("height", 1), params.getNumber("near", 0.000001f), params.getNumber("far", PR_INF),
+												   params.getVector3f("local_direction", Vector3f(0, 1, 0)), params.getVector3f("local_right", Vector3f(1, 0, 0)),
+												   params.getVector3f("local_up", Vector3f(0, 0, 1)));
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static std::vector<std::string> names({ "standard_camera", "standard", "default", "perspective" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Perspective Camera: width, height, near, far, local_direction, local_right, local_up"; }
+};
+
+// ------------------------------------------------------------------ emission
+class DiffuseEmission : public IEmission { // plugins/main/emissions/diffuse.cpp:11-56
+public:
+	explicit DiffuseEmission(const std::shared_ptr<FloatSpectralNode>& spec)
+		: mRadiance(spec)
+	{
+	}
+	SpectralBlob power(const SpectralBlob& wvl) const override { return NodeUtils::average(wvl, mRadiance.get()); }
+	SpectralRange spectralRange() const override { return mRadiance->spectralRange(); }
+	void describe(prb_emission& out, NodeEmitter& e) const override { out.radiance_node = mRadiance->emit(e); }
+	std::string dumpInformation() const override { return "  <DiffuseEmission>: " + mRadiance->dumpInformation() + "\n"; }
+
+private:
+	std::shared_ptr<FloatSpectralNode> mRadiance;
+};
+class DiffuseEmissionPlugin : public IEmissionPlugin {
+public:
+	std::shared_ptr<IEmission> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		return std::make_shared<DiffuseEmission>(ctx.lookupSpectralNode("radiance", 1));
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static std::vector<std::string> names({ "diffuse", "standard", "default" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Diffuse Emission: radiance (spectral, 1)"; }
+};
+
+// ------------------------------------------------------------------ environment light
+class EnvironmentLight : public IInfiniteLight { // plugins/main/infinitelights/environment.cpp (no-distribution branches)
+public:
+	EnvironmentLight(const std::string& name, const Transformf& t, const std::shared_ptr<FloatSpectralNode>& rad, const std::shared_ptr<FloatSpectralNode>& bg)
+		: IInfiniteLight(name, t)
+		, mRadiance(rad)
+		, mBackground(bg)
+	{
+	}
+	SpectralBlob power(const SpectralBlob& wvl) const override { return NodeUtils::average(wvl, mRadiance.get()); }
+	SpectralRange spectralRange() const override { return mRadiance->spectralRange(); }
+	void describe(prb_light& out, NodeEmitter& e) const override
+	{
+		out.type			= PRB_LIGHT_ENV;
+		out.radiance_node	= mRadiance->emit(e);
+		out.background_node = mBackground->emit(e);
+		out.env_split		= mRadiance != mBackground;
+		for (int i = 0; i < 9; ++i) {
+			out.normal_matrix[i]	 = normalMatrix().m[i];
+			out.inv_normal_matrix[i] = invNormalMatrix().m[i];
+		}
+	}
+
+private:
+	std::shared_ptr<FloatSpectralNode> mRadiance, mBackground;
+};
+class EnvironmentLightFactory : public IInfiniteLightPlugin {
+public:
+	std::shared_ptr<IInfiniteLight> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		const ParameterGroup& params = ctx.parameters();
+		const auto radP				 = params.getParameter("radiance");
+		const auto backgroundP		 = params.getParameter("background");
+		std::shared_ptr<FloatSpectralNode> radiance, background;
+		if (radP.isValid() && backgroundP.isValid()) {
+			radiance   = ctx.lookupSpectralNode(radP, 1);
+			background = ctx.lookupSpectralNode(backgroundP, 1);
+		} else if (radP.isValid()) {
+			radiance   = ctx.lookupSpectralNode(radP, 1);
+			background = radiance;
+		} else {
+			background = ctx.lookupSpectralNode(backgroundP, 1);
+			radiance   = background;
+		}
+		// image based radiance (queryRecommendedSize() > 1) would need the Distribution2D branch: SURVEY 8(f)-1
+		return std::make_shared<EnvironmentLight>(params.getString("name", "__unknown"), ctx.transform(), radiance, background);
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static std::vector<std::string> names({ "env", "environment", "background" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Environment Light: radiance (spectral, 1), background (spectral)"; }
+};
+
+// ------------------------------------------------------------------ samplers
+constexpr uint32 DEF_SAMPLE_COUNT = 128;
+class RandomSampler : public ISampler { // RandomSampler.cpp:11-22
+public:
+	using ISampler::ISampler;
+	float generate1D(Random& rnd, uint32) override { return rnd.getFloat(); }
+	Vector2f generate2D(Random& rnd, uint32) override { return rnd.get2D(); }
+	void describe(prb_sampler& out, std::vector<float>&) const override
+	{
+		out.type		= PRB_SAMPLER_RANDOM;
+		out.max_samples = maxSamples();
+	}
+};
+inline uint32 mj_permute(uint32 i, uint32 l, uint32 p)
+{ // Kensler, Correlated Multi-Jittered Sampling (MultiJitteredSampler.cpp:21-76)
+	uint32 w = l - 1;
+	if (w == 0)
+		return 0;
+	const bool pow2 = (l & w) == 0;
+	if (!pow2) {
+		w |= w >> 1;
+		w |= w >> 2;
+		w |= w >> 4;
+		w |= w >> 8;
+		w |= w >> 16;
+	}
+	do {
+		i ^= p;
+		i *= 0xe170893d;
+		i ^= p >> 16;
+		i ^= (i & w) >> 4;
+		i ^= p >> 8;
+		i *= 0x0929eb3f;
+		i ^= p >> 23;
+		i ^= (i & w) >> 1;
+		i *= 1 | p >> 27;
+		i *= 0x6935fa69;
+		i ^= (i & w) >> 11;
+		i *= 0x74dcb303;
+		i ^= (i & w) >> 2;
+		i *= 0x9e501cc3;
+		i ^= (i & w) >> 2;
+		i *= 0xc860a3df;
+		i &= w;
+		i ^= i >> 5;
+	} while (!pow2 && i >= l);
+	return pow2 ? ((i + p) & w) : ((i + p) % l);
+}
+class MultiJitteredSampler : public ISampler { // MultiJitteredSampler.cpp:95-157
+public:
+	MultiJitteredSampler(uint32 samples, uint32 bins, uint32 seed)
+		: ISampler(samples)
+		, m1D(bins)
+		, m2D_X(static_cast<uint32>(std::sqrt(bins)))
+		, m2D_Y((bins + m2D_X - 1) / m2D_X)
+		, mSeed(seed)
+	{
+	}
+	float generate1D(Random& rnd, uint32 index) override
+	{
+		const float j = rnd.getFloat();
+		return (index % m1D + j) / m1D;
+	}
+	Vector2f generate2D(Random& rnd, uint32 index) override
+	{
+		constexpr uint32 FH = 0x51633e2d, F1 = 0x68bc21eb, F2 = 0x02e5be93;
+		index			= mj_permute(index, std::max(1u, maxSamples()), mSeed * FH);
+		const uint32 sx = mj_permute(index % m2D_X, m2D_X, mSeed * F1);
+		const uint32 sy = mj_permute(index / m2D_X, m2D_Y, mSeed * F2);
+		const float jx	= rnd.getFloat();
+		const float jy	= rnd.getFloat();
+		return Vector2f((sx + (sy + jx) / m2D_Y) / m2D_X, (index + jy) / std::max(1u, maxSamples()));
+	}
+	void describe(prb_sampler& out, std::vector<float>&) const override
+	{
+		out.type		= PRB_SAMPLER_MJITT;
+		out.max_samples = maxSamples();
+		out.bins_1d		= m1D;
+		out.m2d_x		= m2D_X;
+		out.m2d_y		= m2D_Y;
+		out.seed		= mSeed;
+	}
+
+private:
+	uint32 m1D, m2D_X, m2D_Y, mSeed;
+};
+class SobolSampler : public ISampler { // SobolSampler.cpp:27-78
+public:
+	SobolSampler(Random& random, uint32 samples)
+		: ISampler(samples)
+	{
+		// direction numbers: dim 0 = van der Corput (2^(63-i)); dim 1 = Sobol' polynomial x+1, v_i = v_{i-1} ^ (v_{i-1} >> 1)
+		// (identical to the first two rows of SobolSamplerData.inl)
+		uint64 V0[64], V1[64];
+		for (int i = 0; i < 64; ++i)
+			V0[i] = 1ULL << (63 - i);
+		V1[0] = 1ULL << 63;
+		for (int i = 1; i < 64; ++i)
+			V1[i] = V1[i - 1] ^ (V1[i - 1] >> 1);
+		std::vector<float> s1(samples, 0.0f);
+		std::vector<Vector2f> s2(samples);
+		uint64 last[2] = { 0, 0 };
+		for (uint32 i = 1; i < samples; ++i) {
+			uint32 n	= i - 1;
+			size_t cin	= 1; // index from the right of the first zero bit
+			while (n & 1) {
+				n >>= 1;
+				++cin;
+			}
+			last[0] ^= V0[cin - 1];
+			last[1] ^= V1[cin - 1];
+			s1[i] = static_cast<float>(Random::uint64ToDouble(last[0]));
+			s2[i] = Vector2f(s1[i], static_cast<float>(Random::uint64ToDouble(last[1])));
+		}
+		// std::shuffle(m1D, rnd); std::shuffle(m2D, rnd)  (libstdc++ semantics, prh core.cpp)
+		std::vector<uint32> perm(samples);
+		for (uint32 i = 0; i < samples; ++i)
+			perm[i] = i;
+		libstdcxxShuffle(perm, random);
+		mSamples1D.resize(samples);
+		for (uint32 i = 0; i < samples; ++i)
+			mSamples1D[i] = s1[perm[i]];
+		for (uint32 i = 0; i < samples; ++i)
+			perm[i] = i;
+		libstdcxxShuffle(perm, random);
+		mSamples2D.resize(samples);
+		for (uint32 i = 0; i < samples; ++i)
+			mSamples2D[i] = s2[perm[i]];
+	}
+	float generate1D(Random& rnd, uint32 index) override { return mSamples1D.size() <= index ? rnd.getFloat() : mSamples1D[index]; }
+	Vector2f generate2D(Random& rnd, uint32 index) override { return mSamples2D.size() <= index ? rnd.get2D() : mSamples2D[index]; }
+	void describe(prb_sampler& out, std::vector<float>& pool) const override
+	{
+		out.type		 = PRB_SAMPLER_SOBOL;
+		out.max_samples	 = maxSamples();
+		out.table_offset = (uint32)pool.size();
+		pool.insert(pool.end(), mSamples1D.begin(), mSamples1D.end());
+		for (const auto& v : mSamples2D) {
+			pool.push_back(v.x);
+			pool.push_back(v.y);
+		}
+	}
+
+private:
+	std::vector<float> mSamples1D;
+	std::vector<Vector2f> mSamples2D;
+};
+enum class SamplerKind { Random, MJitt, Sobol };
+class SamplerFactory : public ISamplerFactory {
+public:
+	SamplerFactory(SamplerKind k, const ParameterGroup& params)
+		: mKind(k)
+		, mParams(params)
+	{
+	}
+	uint32 requestedSampleCount() const override { return (uint32)mParams.getUInt("sample_count", DEF_SAMPLE_COUNT); }
+	std::shared_ptr<ISampler> createInstance(uint32 sample_count, Random& rnd) const override
+	{
+		switch (mKind) {
+		case SamplerKind::MJitt: {
+			const uint32 PRIME = 14512081;
+			// note: the seed default is evaluated even when 'seed' is given (argument of getUInt) -> always one draw
+			const uint32 defSeed = PRIME ^ rnd.get32();
+			return std::make_shared<MultiJitteredSampler>(sample_count, (uint32)mParams.getUInt("bins", std::max(1u, sample_count)),
+														  (uint32)mParams.getUInt("seed", defSeed));
+		}
+		case SamplerKind::Sobol: return std::make_shared<SobolSampler>(rnd, sample_count);
+		default: return std::make_shared<RandomSampler>(sample_count);
+		}
+	}
+
+private:
+	SamplerKind mKind;
+	ParameterGroup mParams;
+};
+class SamplerPlugin : public ISamplerPlugin {
+public:
+	explicit SamplerPlugin(SamplerKind k)
+		: mKind(k)
+	{
+	}
+	std::shared_ptr<ISamplerFactory> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		if (mKind == SamplerKind::Sobol && ctx.environment()->renderSettings().progressive) {
+			PR_LOG(L_WARNING) << "Sobol sampler does not support progressive rendering. Using 'mjitt' instead" << std::endl;
+			return ctx.loadSamplerFactory("mjitt", ctx.parameters());
+		}
+		return std::make_shared<SamplerFactory>(mKind, ctx.parameters());
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> rnd({ "random" });
+		static const std::vector<std::string> sob({ "sobol" });
+		static const std::vector<std::string> mj({ "multijittered", "multi_jittered", "jittered", "multijitter", "multi_jitter", "jitter", "mjitt", "jitt" });
+		return mKind == SamplerKind::Random ? rnd : (mKind == SamplerKind::Sobol ? sob : mj);
+	}
+	std::string specification(const std::string&) const override { return "Sampler: sample_count (128) [bins, seed for mjitt]"; }
+
+private:
+	SamplerKind mKind;
+};
+
+// ------------------------------------------------------------------ filters
+class MitchellFilter : public IFilter { // plugins/main/filter/MitchellFilter.cpp
+public:
+	explicit MitchellFilter(int radius)
+		: mRadius(radius)
+	{
+		if (mRadius == 0)
+			return;
+		const int halfSize = mRadius + 1;
+		mCache.resize(halfSize * (size_t)halfSize);
+		auto mitchell = [](float x, float B, float C) {
+			x = std::abs(x);
+			if (x < 1)
+				return ((12 - 9 * B - 6 * C) * x * x * x + (-18 + 12 * B + 6 * C) * x * x + (6 - 2 * B)) / 6;
+			else if (x < 2)
+				return ((-B - 6 * C) * x * x * x + (6 * B + 30 * C) * x * x + (-12 * B - 48 * C) * x + (8 * B + 24 * C)) / 6;
+			return 0.0f;
+		};
+		float sum1 = 0, sum2 = 0, sum4 = 0;
+		for (int y = 0; y < halfSize; ++y)
+			for (int x = 0; x < halfSize; ++x) {
+				const float r			 = std::sqrt((float)(x * x + y * y));
+				const float val			 = mitchell(2 * r / mRadius, 1 / 3.0f, 1 / 3.0f);
+				mCache[y * halfSize + x] = val;
+				if (y == 0 && x == 0)
+					sum1 += val;
+				else if (y == 0 || x == 0)
+					sum2 += val;
+				else
+					sum4 += val;
+			}
+		const float norm = 1.0f / (sum1 + 2 * sum2 + 4 * sum4);
+		for (auto& v : mCache)
+			v *= norm;
+	}
+	int radius() const override { return mRadius; }
+	float evalWeight(float x, float y) const override
+	{
+		if (mRadius == 0)
+			return 1;
+		// the reference clamps to mRadius+1 and indexes a (mRadius+1)^2 table with .at(); |x|,|y| <= mRadius here
+		const int ix = std::min((int)std::round(std::abs(x)), mRadius);
+		const int iy = std::min((int)std::round(std::abs(y)), mRadius);
+		return mCache[iy * (mRadius + 1) + ix];
+	}
+
+private:
+	int mRadius;
+	std::vector<float> mCache;
+};
+class BlockFilter : public IFilter { // plugins/main/filter/BlockFilter.cpp: constant weight 1/(2r+1)^2
+public:
+	explicit BlockFilter(int radius)
+		: mRadius(radius)
+	{
+	}
+	int radius() const override { return mRadius; }
+	float evalWeight(float, float) const override { return 1.0f / ((2 * mRadius + 1) * (2 * mRadius + 1)); }
+
+private:
+	int mRadius;
+};
+class FilterFactory : public IFilterFactory {
+public:
+	FilterFactory(bool mitchell, const ParameterGroup& p)
+		: mMitchell(mitchell)
+		, mParams(p)
+	{
+	}
+	std::shared_ptr<IFilter> createInstance() const override
+	{
+		const int radius = (int)mParams.getInt("radius", 3);
+		if (mMitchell)
+			return std::make_shared<MitchellFilter>(radius);
+		return std::make_shared<BlockFilter>(radius);
+	}
+
+private:
+	bool mMitchell;
+	ParameterGroup mParams;
+};
+class FilterPlugin : public IFilterPlugin {
+public:
+	explicit FilterPlugin(bool mitchell)
+		: mMitchell(mitchell)
+	{
+	}
+	std::shared_ptr<IFilterFactory> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		return std::make_shared<FilterFactory>(mMitchell, ctx.parameters());
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> m({ "mitchell" });
+		static const std::vector<std::string> b({ "block", "blur" });
+		return mMitchell ? m : b;
+	}
+	std::string specification(const std::string&) const override { return "Pixel filter: radius"; }
+
+private:
+	bool mMitchell;
+};
+
+// ------------------------------------------------------------------ spectral mappers
+class RandomSpectralMapperFactory : public ISpectralMapperFactory { // spectralmapper/random.cpp
+public:
+	void describe(const SpectralMapperBuildInput&, prb_spectral_mapper& out, std::vector<float>&) override { out.type = PRB_MAPPER_RANDOM; }
+};
+class RandomSpectralMapperPlugin : public ISpectralMapperPlugin {
+public:
+	std::shared_ptr<ISpectralMapperFactory> create(const std::string&, const SceneLoadContext&) override { return std::make_shared<RandomSpectralMapperFactory>(); }
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> names({ "random" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Random Spectral Mapper"; }
+};
+
+struct SPDParameters { // spd.cpp:161-176
+	uint32 NumberOfBins			= (uint32)PR_CIE_WAVELENGTH_RANGE;
+	int Method					= 2; // 0 none, 1 Y, 2 XYZ, 3 sRGB
+	bool UseNormalizedLights	= true;
+	bool EnsureCompleteSampling = true;
+	uint32 SmoothIterations		= 0;
+	bool UseCMIS				= true;
+};
+class SPDSpectralMapperFactory : public ISpectralMapperFactory { // spd.cpp:192-357 (pixel distribution)
+public:
+	explicit SPDSpectralMapperFactory(const SPDParameters& p)
+		: mP(p)
+	{
+	}
+	void describe(const SpectralMapperBuildInput& in, prb_spectral_mapper& out, std::vector<float>& pool) override
+	{
+		const uint32 bins = mP.NumberOfBins;
+		std::vector<float> fullPower(bins, 0.0f), lightPower(bins, 0.0f);
+		const SpectralRange range = in.cameraRange;
+		const auto bin2wvl		  = [=](uint32 bin) { return range.Start + (bin / float(bins - 1)) * range.span(); };
+		for (const Light& light : in.lightSampler->lights()) {
+			// calcLightDistribution, spd.cpp:220-256
+			for (uint32 i = 0; i < bins; i += 4) {
+				const uint32 k = std::min<uint32>(bins - i, 4);
+				SpectralBlob wavelengths = SpectralBlob::Zero();
+				for (uint32 j = 0; j < k; ++j)
+					wavelengths(j) = bin2wvl(i + j);
+				for (uint32 j = k; j < 4; ++j)
+					wavelengths(j) = wavelengths(0);
+				const SpectralBlob output = light.averagePower(wavelengths);
+				for (uint32 j = 0; j < k; ++j)
+					lightPower[i + j] = output(j);
+			}
+			if (mP.UseNormalizedLights) {
+				const float dt = 1.0f / (bins - 1);
+				float integral = 0;
+				for (float f : lightPower)
+					integral += f * dt;
+				if (integral > PR_EPSILON) {
+					const float invnorm = 1 / integral;
+					for (float& f : lightPower)
+						f *= invnorm;
+				}
+			}
+			for (uint32 i = 0; i < bins; ++i)
+				fullPower[i] += lightPower[i];
+		}
+		// applyPostprocessing, spd.cpp:258-305
+		int method = mP.Method;
+		if (range.Start > PR_CIE_WAVELENGTH_END || range.End < PR_CIE_WAVELENGTH_START)
+			method = 0;
+		for (uint32 i = 0; i < bins; ++i) {
+			const float w = bin2wvl(i);
+			if (method == 1)
+				fullPower[i] *= CIE::eval_y(w);
+			else if (method == 2)
+				fullPower[i] *= (CIE::eval_x(w) + CIE::eval_y(w) + CIE::eval_z(w));
+			else if (method == 3) {
+				const float X = CIE::eval_x(w), Y = CIE::eval_y(w), Z = CIE::eval_z(w); // RGBConverter::fromXYZ (sRGB D65)
+				const float R = 3.240479f * X - 1.537150f * Y - 0.498535f * Z;
+				const float G = -0.969256f * X + 1.875991f * Y + 0.041556f * Z;
+				const float B = 0.055648f * X - 0.204043f * Y + 1.057311f * Z;
+				fullPower[i] *= (R + G + B);
+			}
+		}
+		for (uint32 it = 0; it < mP.SmoothIterations; ++it) {
+			const std::vector<float> tmp = fullPower;
+			for (size_t i = 0; i < tmp.size(); ++i) {
+				const float prevM = (i == 0) ? tmp.front() : tmp[i - 1];
+				const float nextM = (i == tmp.size() - 1) ? tmp.back() : tmp[i + 1];
+				fullPower[i]	  = (prevM + tmp[i] + nextM) / 3;
+			}
+		}
+		if (mP.EnsureCompleteSampling)
+			for (float& f : fullPower)
+				f = std::max(1e-2f, f);
+		Distribution1D distr(bins);
+		distr.generate([&](size_t bin) { return fullPower[bin]; });
+		out.type	   = mP.UseCMIS ? PRB_MAPPER_SPD_CMIS : PRB_MAPPER_SPD_HERO;
+		out.cdf_offset = (uint32)pool.size();
+		out.cdf_size   = (uint32)distr.cdf().size();
+		pool.insert(pool.end(), distr.cdf().begin(), distr.cdf().end());
+	}
+
+private:
+	SPDParameters mP;
+};
+class SPDSpectralMapperPlugin : public ISpectralMapperPlugin {
+public:
+	std::shared_ptr<ISpectralMapperFactory> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		SPDParameters parameters;
+		parameters.NumberOfBins = (uint32)ctx.parameters().getUInt("bins", parameters.NumberOfBins);
+		std::string weighting	= ctx.parameters().getString("weighting", "xyz");
+		std::transform(weighting.begin(), weighting.end(), weighting.begin(), ::tolower);
+		if (weighting == "none")
+			parameters.Method = 0;
+		else if (weighting == "y")
+			parameters.Method = 1;
+		else if (weighting == "rgb" || weighting == "srgb")
+			parameters.Method = 3;
+		else
+			parameters.Method = 2;
+		parameters.EnsureCompleteSampling = ctx.parameters().getBool("complete", parameters.EnsureCompleteSampling);
+		parameters.UseNormalizedLights	  = ctx.parameters().getBool("normalized", parameters.UseNormalizedLights);
+		parameters.SmoothIterations		  = (uint32)ctx.parameters().getUInt("smooth_iterations", parameters.SmoothIterations);
+		parameters.UseCMIS				  = ctx.parameters().getBool("cmis", parameters.UseCMIS);
+		return std::make_shared<SPDSpectralMapperFactory>(parameters);
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> names({ "spd", "default" });
+		return names;
+	}
+	std::string specification(const std::string&) const override
+	{
+		return "SPD Spectral Mapper: bins (440), weighting none|y|rgb|srgb|xyz (xyz), complete (true), normalized (true), smooth_iterations (0), cmis (true)";
+	}
+};
+} // namespace
+
+// ------------------------------------------------------------------ 'direct' integrator -> device
+// reference plugins/main/integrators/direct.cpp:44-569.  IntDirectInstance::onTile forwards the tile to
+// prb_render_tiles (include/prb200_abi.h) instead of walking rays on the CPU.
+class IntDirectInstance : public IIntegratorInstance {
+public:
+	void onTile(RenderTileSession& session) override;
+};
+class IntDirect : public IIntegrator {
+public:
+	IntDirect(const DiParameters& p, bool power, bool emissiveScatter)
+		: mParameters(p)
+		, mPower(power)
+		, mEmissiveScatter(emissiveScatter)
+	{
+	}
+	std::shared_ptr<IIntegratorInstance> createThreadInstance(RenderContext*, size_t) override { return std::make_shared<IntDirectInstance>(); }
+	void describe(prb_settings& s) const override
+	{
+		s.max_ray_depth		 = (uint32)mParameters.MaxCameraRayDepthHard;
+		s.soft_max_ray_depth = (uint32)mParameters.MaxCameraRayDepthSoft;
+		s.mis_power			 = mPower ? 1 : 0;
+		s.do_nee			 = mParameters.DoNEE;
+		s.do_direct			 = mParameters.DoDirect;
+		s.emissive_scatter	 = mEmissiveScatter;
+	}
+
+private:
+	DiParameters mParameters;
+	bool mPower, mEmissiveScatter;
+};
+class IntDirectFactory : public IIntegratorFactory { // direct.cpp:498-538
+public:
+	explicit IntDirectFactory(const ParameterGroup& params)
+	{
+		mParameters.MaxCameraRayDepthHard = (size_t)params.getUInt("max_ray_depth", mParameters.MaxCameraRayDepthHard);
+		mParameters.MaxCameraRayDepthSoft = std::min(mParameters.MaxCameraRayDepthHard, (size_t)params.getUInt("soft_max_ray_depth", mParameters.MaxCameraRayDepthSoft));
+		std::string mode				  = params.getString("mis", "balance");
+		std::transform(mode.begin(), mode.end(), mode.begin(), ::tolower);
+		mPower				 = mode == "power";
+		mParameters.DoNEE	 = params.getBool("nee", true);
+		mParameters.DoDirect = params.getBool("direct", true);
+		mEmissiveScatter	 = params.getBool("emissive_scatter", true);
+	}
+	std::shared_ptr<IIntegrator> createInstance() const override { return std::make_shared<IntDirect>(mParameters, mPower, mEmissiveScatter); }
+
+private:
+	DiParameters mParameters;
+	bool mPower = false, mEmissiveScatter = true;
+};
+class IntDirectFactoryFactory : public IIntegratorPlugin {
+public:
+	std::shared_ptr<IIntegratorFactory> create(const std::string&, const SceneLoadContext& ctx) override { return std::make_shared<IntDirectFactory>(ctx.parameters()); }
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> names({ "direct", "standard", "default" });
+		return names;
+	}
+	std::string specification(const std::string&) const override
+	{
+		return "PT / Unidirectional Path Tracing: max_ray_depth (64), soft_max_ray_depth (4), mis balance|power, nee (true), direct (true), emissive_scatter (true)";
+	}
+};
+
+void IntDirectInstance::onTile(RenderTileSession& session)
+{
+	const RenderTile* t = session.tile();
+	prb_tile pt{ t->sx, t->sy, t->ex, t->ey };
+	const prb_status st = prb_render_tiles(session.context()->deviceContext(), &pt, 1, session.iteration(), 1);
+	if (st != PRB_OK)
+		PR_LOG(L_ERROR) << "prb_render_tiles failed: " << prb_last_error() << std::endl;
+}
+
+void registerScenePlugins(std::vector<std::shared_ptr<IPlugin>>& out)
+{
+	out.push_back(std::make_shared<MeshEntityPlugin>());
+	out.push_back(std::make_shared<SphereEntityPlugin>());
+	out.push_back(std::make_shared<PlaneEntityPlugin>());
+	out.push_back(std::make_shared<PerspectiveCameraPlugin>());
+	out.push_back(std::make_shared<DiffuseEmissionPlugin>());
+	out.push_back(std::make_shared<EnvironmentLightFactory>());
+	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Sobol));
+	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::MJitt));
+	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Random));
+	out.push_back(std::make_shared<FilterPlugin>(true));
+	out.push_back(std::make_shared<FilterPlugin>(false));
+	out.push_back(std::make_shared<SPDSpectralMapperPlugin>());
+	out.push_back(std::make_shared<RandomSpectralMapperPlugin>());
+	out.push_back(std::make_shared<IntDirectFactoryFactory>());
+}
+} // namespace PR

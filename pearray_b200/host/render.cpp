@@ -1,0 +1,143 @@
+// Render driver: the host half of reference RenderContext::start / RenderThread::main
+// (src/core/renderer/RenderContext.cpp:65-139, RenderThread.cpp:36-70).  One RenderContext drives one GPU
+// through the C ABI; ranks of a multi-GPU job own interleaved tiles (tile_id % worldSize == rank).
+#include "prh.h"
+
+namespace PR {
+RenderContext::RenderContext(const std::shared_ptr<Environment>& env, int device, uint32 rank, uint32 worldSize)
+	: mEnv(env)
+	, mRank(rank)
+	, mWorldSize(std::max(1u, worldSize))
+{
+	SceneCompiler compiler(env.get());
+	mScene = compiler.compile();
+	if (!mScene)
+		return;
+	mIntegrator = env->renderSettings().integratorFactory->createInstance();
+	if (prb_create(device, &mCtx) != PRB_OK) {
+		PR_LOG(L_ERROR) << "prb_create failed: " << prb_last_error() << std::endl;
+		mCtx = nullptr;
+		return;
+	}
+	if (prb_upload_scene(mCtx, &mScene->desc) != PRB_OK) {
+		PR_LOG(L_ERROR) << "prb_upload_scene failed: " << prb_last_error() << std::endl;
+		prb_destroy(mCtx);
+		mCtx = nullptr;
+	}
+}
+RenderContext::~RenderContext()
+{
+	if (mCtx)
+		prb_destroy(mCtx);
+}
+
+bool RenderContext::start(uint32 rtx, uint32 rty, uint32 iterations)
+{
+	if (!mCtx)
+		return false;
+	const prb_settings& st = mScene->desc.settings;
+	if (iterations == 0)
+		iterations = st.max_sample_count;
+	// RenderRandomMap (RenderContext.cpp:84)
+	const std::vector<uint64> rng = buildRenderRandomMap(st.seed, st.film_width, st.film_height, settings().progressive ? 128 : st.max_sample_count);
+	if (prb_upload_rng(mCtx, rng.data(), rng.size()) != PRB_OK) {
+		PR_LOG(L_ERROR) << "prb_upload_rng failed: " << prb_last_error() << std::endl;
+		return false;
+	}
+	prb_film_clear(mCtx);
+	// RenderTileMap::init (RenderContext.cpp:91); interleaved ownership across ranks
+	const std::vector<RenderTile> tiles = buildTileMap(st.view_x, st.view_y, st.view_w, st.view_h, rtx, rty);
+	mOwnedTiles.clear();
+	for (size_t i = 0; i < tiles.size(); ++i)
+		if (i % mWorldSize == mRank)
+			mOwnedTiles.push_back(tiles[i]);
+	mIntegrator->onInit(this);
+	mIntegrator->onStart();
+	auto instance = mIntegrator->createThreadInstance(this, 0);
+	instance->onStart();
+	// The reference walks iteration by iteration, tile by tile (RenderThread.cpp:44-66 calling onTile).  All
+	// tiles of this rank and all iterations go to the device as ONE batch: a pixel's samples only depend on the
+	// pixel's own RNG stream, so the order across pixels is free (bit-identical results).
+	std::vector<prb_tile> pt;
+	for (const RenderTile& t : mOwnedTiles)
+		pt.push_back(prb_tile{ t.sx, t.sy, t.ex, t.ey });
+	bool ok = true;
+	if (!pt.empty() && prb_render_tiles(mCtx, pt.data(), pt.size(), 0, iterations) != PRB_OK) {
+		PR_LOG(L_ERROR) << "prb_render_tiles failed: " << prb_last_error() << std::endl;
+		ok = false;
+	}
+	instance->onEnd();
+	mIntegrator->onEnd();
+	return ok;
+}
+void RenderContext::waitForFinish()
+{
+	if (mCtx)
+		prb_sync(mCtx);
+}
+std::vector<float> RenderContext::filmXYZ()
+{
+	const prb_settings& st = mScene->desc.settings;
+	std::vector<float> xyz((size_t)st.film_width * st.film_height * 3);
+	if (mCtx && prb_film_download(mCtx, xyz.data(), nullptr) != PRB_OK)
+		PR_LOG(L_ERROR) << "prb_film_download failed: " << prb_last_error() << std::endl;
+	return xyz;
+}
+prb_stats RenderContext::statistics() const
+{
+	prb_stats s{};
+	if (mCtx)
+		prb_get_stats(mCtx, &s);
+	return s;
+}
+
+// IMaterial::eval / ::sample through the device (unit-level entry points of the C ABI)
+void IMaterial::eval(const MaterialEvalInput& in, MaterialEvalOutput& out, const RenderTileSession& session) const
+{
+	prb_material_query q{};
+	for (int i = 0; i < 3; ++i) {
+		q.V[i] = in.V[i];
+		q.L[i] = in.L[i];
+	}
+	for (int i = 0; i < 4; ++i)
+		q.wavelength_nm[i] = in.WavelengthNM[i];
+	q.uv[0]		  = in.UV.x;
+	q.uv[1]		  = in.UV.y;
+	q.ray_flags	  = in.RayFlags;
+	q.material_id = mID;
+	prb_material_result r{};
+	if (prb_material_eval(session.context()->deviceContext(), &q, 1, &r) != PRB_OK)
+		PR_LOG(L_ERROR) << "prb_material_eval failed: " << prb_last_error() << std::endl;
+	for (int i = 0; i < 4; ++i) {
+		out.Weight[i] = r.weight[i];
+		out.PDF_S[i]  = r.pdf_s[i];
+	}
+	out.Flags = r.flags;
+	out.Type  = (MaterialScatteringType)r.type;
+}
+void IMaterial::sample(const MaterialSampleInput& in, MaterialSampleOutput& out, const RenderTileSession& session) const
+{
+	prb_material_query q{};
+	for (int i = 0; i < 3; ++i)
+		q.V[i] = in.V[i];
+	for (int i = 0; i < 4; ++i)
+		q.wavelength_nm[i] = in.WavelengthNM[i];
+	q.uv[0]		  = in.UV.x;
+	q.uv[1]		  = in.UV.y;
+	q.ray_flags	  = in.RayFlags;
+	q.material_id = mID;
+	q.rng_state	  = in.RND ? in.RND->state() : 3;
+	prb_material_result r{};
+	if (prb_material_sample(session.context()->deviceContext(), &q, 1, &r) != PRB_OK)
+		PR_LOG(L_ERROR) << "prb_material_sample failed: " << prb_last_error() << std::endl;
+	for (int i = 0; i < 4; ++i) {
+		out.IntegralWeight[i] = r.weight[i];
+		out.PDF_S[i]		  = r.pdf_s[i];
+	}
+	out.L	  = Vector3f(r.L[0], r.L[1], r.L[2]);
+	out.Flags = r.flags;
+	out.Type  = (MaterialScatteringType)r.type;
+	if (in.RND)
+		in.RND->setState(r.rng_state);
+}
+} // namespace PR
