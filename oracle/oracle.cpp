@@ -1859,11 +1859,17 @@ struct Integrator {
 	}
 };
 
-void setFTZ()
-{ // setupFloatingPointEnvironment, src/base/Platform.h:20-34
-	_MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
-	_MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
-}
+struct FtzScope { // setupFloatingPointEnvironment (FTZ|DAZ), src/base/Platform.h:20-34; restored on scope exit
+	unsigned int saved;
+	FtzScope()
+		: saved(_mm_getcsr())
+	{
+		_MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
+		_MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
+	}
+	~FtzScope() { _mm_setcsr(saved); }
+};
+#define setFTZ() FtzScope ftz_scope_
 
 void initScene(Scene& sc, const prb_scene_desc* d)
 {

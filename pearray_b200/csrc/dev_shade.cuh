@@ -1,0 +1,1129 @@
+// Device shading: node evaluation, geometry points, the six materials, samplers / spectral mappers, camera
+// rays, light sampling.  Each function cites the reference file:line it implements.  Everything works on the
+// 4-wavelength SpectralBlob held in registers; no tensor cores (the path is not a dense contraction).
+#pragma once
+#include "dev_bvh.cuh"
+
+namespace prb {
+// ------------------------------------------------------------------ spectra / nodes
+PRB_DEV float tableLookup(const float* data, uint32_t count, float start, float end, float w)
+{ // EquidistantSpectrumView::lookup, src/core/spectral/EquidistantSpectrum.inl:34-41
+	const float delta = (end - start) / (count - 1);
+	const float af	  = fmaxf(0.0f, (w - start) / delta);
+	const int index	  = (int)fminf((float)(count - 2), af);
+	const float t	  = fminf((float)(count - 1), af) - index;
+	return __ldg(data + index) * (1 - t) + __ldg(data + index + 1) * t;
+}
+constexpr float CIE_START = 390, CIE_END = 830, CIE_RANGE = CIE_END - CIE_START;
+constexpr int CIE_N		   = 441;
+constexpr float CIE_Y_NORM = 113.042314572337f * (CIE_RANGE / (CIE_N - 1));
+PRB_DEV float cieEval(const DScene& S, int c, float w)
+{ // CIE::eval_x/y/z, src/core/spectral/CIE.h:41-58
+	return tableLookup(S.pool + S.cieOffset + c * CIE_N, CIE_N, CIE_START, CIE_END, w) / CIE_Y_NORM * CIE_RANGE;
+}
+
+// leaf node kinds; MUL / CHECKER reference other nodes.  The flattened graph is shallow (depth <= 3 in the
+// config scenes); an explicit small stack avoids device recursion.
+PRB_DEV Blob evalLeafNode(const DScene& S, const prb_node& n, const Blob& w)
+{
+	Blob r;
+	switch (n.type) {
+	default:
+	case PRB_NODE_CONST: return blob(n.p[0]);
+	case PRB_NODE_PARAM:
+	case PRB_NODE_PARAM_SCALED: // SpectralUpsampler::compute, SpectralUpsampler.h:45-49
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const float x = (n.p[0] * w[i] + n.p[1]) * w[i] + n.p[2];
+			r[i]		  = 0.5f * x * (1.0f / sqrtf(x * x + 1.0f)) + 0.5f;
+			if (n.type == PRB_NODE_PARAM_SCALED)
+				r[i] = r[i] * n.p[3];
+		}
+		return r;
+	case PRB_NODE_TABLE:
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			r[i] = tableLookup(S.pool + n.a, n.b, n.p[0], n.p[1], w[i]);
+		return r;
+	case PRB_NODE_SELLMEIER: { // Scattering::sellmeier2 + sqrt, Scattering.h:219-242
+		const float* B = S.pool + n.a;
+		const float* C = B + n.b;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const float qm	= w[i] / 1000;
+			const float qm2 = qm * qm;
+			float value		= 1;
+			for (uint32_t k = 0; k < n.b; ++k)
+				value += __ldg(B + k) * qm2 / (qm2 - __ldg(C + k));
+			r[i] = sqrtf(value);
+		}
+		return r;
+	}
+	}
+}
+PRB_DEV bool checkerSelectsB(const prb_node& n, float u, float v)
+{ // CheckerboardNode::check, CheckerboardNode.cpp:26-40
+	float cu = u, cv = v;
+	if (n.p[2] == 1.0f) {
+		cu = u * n.p[0];
+		cv = v * n.p[0];
+	} else if (n.p[2] == 2.0f) {
+		cu = u * n.p[0];
+		cv = v * n.p[1];
+	}
+	return ((int)floorf(cu) + (int)floorf(cv)) % 2 == 0;
+}
+__device__ __noinline__ Blob evalNode(const DScene& S, uint32_t id, const Blob& w, float u, float v)
+{
+	// product of factors: MUL nodes push both operands, CHECKER picks one; leaves multiply into the result
+	uint32_t st[8];
+	int sp	 = 0;
+	st[sp++] = id;
+	Blob acc = blob(1.0f);
+	bool first = true;
+	while (sp > 0) {
+		const prb_node n = S.nodes[st[--sp]];
+		if (n.type == PRB_NODE_MUL) {
+			if (sp + 2 <= 8) {
+				st[sp++] = n.b; // evaluated second: a * b with a first
+				st[sp++] = n.a;
+			}
+		} else if (n.type == PRB_NODE_CHECKER) {
+			if (sp < 8)
+				st[sp++] = checkerSelectsB(n, u, v) ? n.b : n.a;
+		} else {
+			const Blob leaf = evalLeafNode(S, n, w);
+			acc				= first ? leaf : acc * leaf;
+			first			= false;
+		}
+	}
+	return acc;
+}
+
+// ------------------------------------------------------------------ geometry point (GeometryPoint.h:10-25)
+struct GeomPoint {
+	V3 N, Nx, Ny;
+	float u, v;
+	uint32_t entity, prim, material, emission;
+};
+struct FaceData {
+	V3 V[4], N[4];
+	float UV[4][2];
+	bool quad;
+	uint32_t slot;
+};
+PRB_DEV void getFace(const DScene& S, const prb_mesh& m, uint32_t f, FaceData& fd, bool wantN, bool wantUV)
+{ // MeshBase::getFace, src/core/mesh/MeshBase.inl:96-134
+	const uint4 idx	 = __ldg(reinterpret_cast<const uint4*>(S.faceIndices) + (m.face_offset + f));
+	const uint32_t i[4] = { idx.x, idx.y, idx.z, idx.w };
+	fd.quad				= idx.w != PRB_INVALID_ID;
+	const int n			= fd.quad ? 4 : 3;
+	for (int j = 0; j < n; ++j) {
+		fd.V[j] = ld3(S.vertices + 3 * (size_t)(m.vertex_offset + i[j]));
+		if (wantN && (m.features & PRB_MESH_HAS_NORMALS))
+			fd.N[j] = ld3(S.normals + 3 * (size_t)(m.normal_offset + i[j]));
+		if (wantUV && (m.features & PRB_MESH_HAS_UVS)) {
+			fd.UV[j][0] = S.uvs[2 * (size_t)(m.uv_offset + i[j])];
+			fd.UV[j][1] = S.uvs[2 * (size_t)(m.uv_offset + i[j]) + 1];
+		}
+	}
+	fd.slot = S.faceSlots[m.face_offset + f];
+}
+PRB_DEV V3 triInterp(V3 v0, V3 v1, V3 v2, float u, float v) { return (v1 * u + v2 * v) + v0 * (1 - u - v); }
+PRB_DEV V3 quadInterp(V3 v0, V3 v1, V3 v2, V3 v3, float u, float v)
+{
+	return ((v0 * (1 - u) * (1 - v) + v1 * u * (1 - v)) + v2 * (1 - u) * v) + v3 * u * v;
+}
+PRB_DEV V3 faceInterpV(const FaceData& f, const V3* a, float u, float v) { return f.quad ? quadInterp(a[0], a[1], a[2], a[3], u, v) : triInterp(a[0], a[1], a[2], u, v); }
+PRB_DEV float faceArea(const FaceData& f)
+{
+	if (f.quad)
+		return 0.5f * sqrtf(norm2(cross(f.V[2] - f.V[0], f.V[3] - f.V[1])));
+	return 0.5f * sqrtf(norm2(cross(f.V[1] - f.V[0], f.V[2] - f.V[0])));
+}
+
+__device__ __noinline__ void provideGeometryPoint(const DScene& S, uint32_t entityID, uint32_t prim, float qu, float qv, V3 position, GeomPoint& pt)
+{
+	const prb_entity& en = S.entities[entityID];
+	pt.entity			 = entityID;
+	pt.emission			 = en.emission_id;
+	if (en.type == PRB_ENTITY_MESH) { // mesh.cpp:205-250
+		const prb_mesh m = S.meshes[en.mesh_id];
+		FaceData f;
+		getFace(S, m, prim, f, true, true);
+		if (m.features & PRB_MESH_HAS_NORMALS) {
+			pt.N = faceInterpV(f, f.N, qu, qv);
+			if (m.features & PRB_MESH_HAS_UVS) { // Face::tangentFromUV, Face.h:80-98
+				const V3 dp1 = f.V[1] - f.V[0], dp2 = f.V[2] - f.V[0];
+				const float du1 = f.UV[1][0] - f.UV[0][0], dv1 = f.UV[1][1] - f.UV[0][1];
+				const float du2 = f.UV[2][0] - f.UV[0][0], dv2 = f.UV[2][1] - f.UV[0][1];
+				const float det = diffProd(dv2, du1, dv1, du2);
+				if (det <= PR_EPSILON) {
+					tangent_frame(pt.N, pt.Nx, pt.Ny);
+				} else {
+					V3 nx = (dp1 * dv2 - dp2 * dv1) / det;
+					nx	  = nx - pt.N * dot(pt.N, nx);
+					nx	  = normalized(nx);
+					pt.Nx = nx;
+					pt.Ny = cross(pt.N, nx);
+				}
+			} else {
+				frame_duff(pt.N, pt.Nx, pt.Ny);
+			}
+		} else { // dPdu, dPdv of the vertex buffer (rtcInterpolate, mesh.cpp:55-80)
+			if (f.quad) {
+				pt.Nx = (1 - qv) * (f.V[1] - f.V[0]) + qv * (f.V[2] - f.V[3]);
+				pt.Ny = (1 - qu) * (f.V[3] - f.V[0]) + qu * (f.V[2] - f.V[1]);
+			} else {
+				pt.Nx = f.V[1] - f.V[0];
+				pt.Ny = f.V[2] - f.V[0];
+			}
+			pt.N = cross(pt.Nx, pt.Ny);
+		}
+		if (m.features & PRB_MESH_HAS_UVS) {
+			if (f.quad) {
+				const float a = (1 - qu) * (1 - qv), b = qu * (1 - qv), c = (1 - qu) * qv, e = qu * qv;
+				pt.u = ((f.UV[0][0] * a + f.UV[1][0] * b) + f.UV[2][0] * c) + f.UV[3][0] * e;
+				pt.v = ((f.UV[0][1] * a + f.UV[1][1] * b) + f.UV[2][1] * c) + f.UV[3][1] * e;
+			} else {
+				pt.u = (f.UV[1][0] * qu + f.UV[2][0] * qv) + f.UV[0][0] * (1 - qu - qv);
+				pt.v = (f.UV[1][1] * qu + f.UV[2][1] * qv) + f.UV[0][1] * (1 - qu - qv);
+			}
+		} else {
+			pt.u = qu;
+			pt.v = qv;
+		}
+		pt.material = f.slot < en.material_count ? S.entityMaterials[en.material_offset + f.slot] : PRB_INVALID_ID;
+		pt.N		= normalized(m3mul(en.normal_matrix, pt.N));
+		pt.Nx		= normalized(m3mul(en.normal_matrix, pt.Nx));
+		pt.Ny		= normalized(m3mul(en.normal_matrix, pt.Ny));
+		pt.prim		= prim;
+	} else if (en.type == PRB_ENTITY_SPHERE) { // sphere.cpp:128-143
+		pt.N = normalized(position - xfPoint(en.local_to_world, mk(0, 0, 0)));
+		tangent_frame(pt.N, pt.Nx, pt.Ny);
+		uv_from_normal(pt.N, pt.u, pt.v);
+		pt.prim		= 0;
+		pt.material = S.entityMaterials[en.material_offset];
+	} else { // plane.cpp:206-220
+		pt.N		= ld3(en.geo + 9);
+		pt.Nx		= ld3(en.geo + 3);
+		pt.Ny		= ld3(en.geo + 6);
+		pt.u		= qu;
+		pt.v		= qv;
+		pt.prim		= 0;
+		pt.material = S.entityMaterials[en.material_offset];
+	}
+}
+
+// ------------------------------------------------------------------ materials
+constexpr float AIR = 1.0002926f; // dielectric.cpp:17
+constexpr uint32_t MSF_Delta = 0x2, MSF_SpectralVarying = 0x4;
+struct MatEval {
+	Blob weight, pdf;
+	uint32_t flags, type;
+};
+struct MatSample {
+	V3 L;
+	Blob weight, pdf;
+	uint32_t flags, type;
+	PRB_DEV bool isDelta() const { return flags & MSF_Delta; }
+	PRB_DEV bool isHeroCollapsing() const { return (flags & MSF_Delta) && (flags & MSF_SpectralVarying); }
+};
+struct MatCtx {
+	V3 V, L;
+	Blob wvl;
+	float u, v;
+	uint32_t rayFlags;
+};
+PRB_DEV uint32_t contribFlags(const prb_material& m) { return (m.flags & PRB_MATF_SPECTRAL_VARYING) ? MSF_SpectralVarying : 0; }
+PRB_DEV void rejectSample(MatSample& s, uint32_t type, uint32_t flags)
+{
+	s.L		 = mk(0, 0, 0);
+	s.weight = blob(0);
+	s.pdf	 = blob(0);
+	s.type	 = type;
+	s.flags	 = flags;
+}
+PRB_DEV RoughDistribution roughOf(const prb_material& m)
+{
+	RoughDistribution r;
+	r.M1	= m.f[0];
+	r.M2	= m.f[1];
+	r.aniso = m.flags & PRB_MATF_ANISOTROPIC;
+	r.vndf	= m.flags & PRB_MATF_VNDF;
+	return r;
+}
+
+// --- principled closure (principled.cpp:34-447)
+struct Principled {
+	Blob Base, IOR;
+	float DiffuseTransmission, Roughness, Anisotropic, SpecularTransmission, SpecularTint, Flatness, Metallic, Sheen, SheenTint, Clearcoat, ClearcoatGloss;
+	bool vndf, thin, hasTrans;
+	static constexpr float EVAL_EPS = 1e-4f;
+	PRB_DEV static float mixf(float v0, float v1, float t) { return (1 - t) * v0 + t * v1; }
+	PRB_DEV static float schlickR0(float eta)
+	{
+		const float f = (eta - 1.0f) / (eta + 1.0f);
+		return f * f;
+	}
+	PRB_DEV float thinTransmissionRoughness() const { return fmaxf(0.0f, fminf(1.0f, (0.65f * (bsum(IOR) / 4) - 0.35f) * Roughness)); }
+	PRB_DEV RoughDistribution roughnessClosure(float r) const
+	{
+		const float aspect = sqrtf(1 - Anisotropic * 0.9f);
+		RoughDistribution d;
+		d.M1	= fmaxf(0.001f, r * r / aspect);
+		d.M2	= fmaxf(0.001f, r * r * aspect);
+		d.aniso = true;
+		d.vndf	= vndf;
+		return d;
+	}
+	PRB_DEV bool isDelta() const { return roughnessClosure(Roughness).isDelta(); }
+	PRB_DEV void lobes(V3 V, float& dr, float& dt, float& sr, float& st) const
+	{
+		dr = Roughness * Roughness * (1.0f - Metallic) * (1.0f - SpecularTransmission);
+		sr = 1;
+		if (hasTrans) {
+			const float F = fresnel_dielectric(cosTheta(V), AIR, IOR[0]);
+			dt			  = DiffuseTransmission * dr;
+			st			  = (1.0f - F) * (1.0f - Metallic) * SpecularTransmission;
+			sr *= F;
+		} else {
+			dt = 0;
+			st = 0;
+		}
+		const float norm = dr + sr + dt + st;
+		if (norm <= PR_EPSILON) {
+			dr = 1;
+			dt = sr = st = 0;
+			return;
+		}
+		dr /= norm;
+		sr /= norm;
+		dt /= norm;
+		st /= norm;
+	}
+	PRB_DEV Blob tintColor(const DScene& S, const Blob& wvl) const
+	{
+		float lum = 0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			lum = fmaxf(lum, Base[i] * cieEval(S, 1, wvl[i]));
+		return lum > PR_EPSILON ? Base / lum : blob(1);
+	}
+	PRB_DEV Blob disneyFresnelTerm(const DScene& S, float HdotV, float HdotL, const Blob& wvl) const
+	{
+		Blob res;
+		if (Metallic <= EVAL_EPS) {
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				res[i] = fresnel_dielectric(HdotV, AIR, IOR[i]);
+			return res;
+		}
+		const Blob color = tintColor(S, wvl);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const float eta = HdotV < 0 ? AIR / IOR[i] : IOR[i] / AIR;
+			const float r0	= mixf(schlickR0(eta) * mixf(1.0f, color[i], SpecularTint), Base[i], Metallic);
+			const float f1	= fresnel_dielectric(HdotV, AIR, IOR[i]);
+			const float f2	= schlick(fabsf(HdotL), r0);
+			res[i]			= mixf(f1, f2, Metallic);
+		}
+		return res;
+	}
+	PRB_DEV float retroDiffuseTerm(const MatCtx& c, float HdotL) const
+	{
+		const float alpha2 = Roughness * Roughness;
+		const float fd90   = 0.5f + 2 * HdotL * HdotL * alpha2;
+		const float lk = schlick_term(absCosTheta(c.L)), vk = schlick_term(absCosTheta(c.V));
+		return PR_INV_PI * fd90 * (lk + vk + lk * vk * (fd90 - 1.0f));
+	}
+	PRB_DEV float subsurfaceTerm(const MatCtx& c, float HdotL) const
+	{
+		const float alpha2 = Roughness * Roughness;
+		const float fss90  = HdotL * HdotL * alpha2;
+		const float lk = schlick_term(absCosTheta(c.L)), vk = schlick_term(absCosTheta(c.V));
+		const float fss = mixf(1.0f, fss90, lk) * mixf(1.0f, fss90, vk);
+		const float f	= absCosTheta(c.L) + absCosTheta(c.V);
+		if (fabsf(f) < PR_EPSILON)
+			return 0.0f;
+		return 1.25f * (fss * (1.0f / f - 0.5f) + 0.5f);
+	}
+	PRB_DEV float diffuseTerm(const MatCtx& c, float HdotL) const
+	{
+		const float lk = schlick_term(absCosTheta(c.L)), vk = schlick_term(absCosTheta(c.V));
+		float diffuse = 1;
+		if (thin)
+			diffuse = mixf(1.0f, subsurfaceTerm(c, HdotL), Flatness);
+		return PR_INV_PI * diffuse * (1 - 0.5f * lk) * (1 - 0.5f * vk);
+	}
+	PRB_DEV float clearcoatTerm(const MatCtx& c, V3 H) const
+	{
+		const float F0 = 0.04f, R = 0.25f;
+		const float D  = ndf_ggx1(H, mixf(0.1f, 0.001f, ClearcoatGloss));
+		const float hk = schlick_term(fabsf(dot(H, c.L)));
+		const float F  = mixf(F0, 1.0f, hk);
+		const float G  = g_1_smith_opt(absCosTheta(c.L), R) * g_1_smith_opt(absCosTheta(c.V), R);
+		return R * D * F * G;
+	}
+	__device__ __noinline__ Blob eval(const DScene& S, const MatCtx& c) const
+	{ // principled.cpp:274-344
+		if (absCosTheta(c.V) <= PR_EPSILON || absCosTheta(c.L) <= PR_EPSILON)
+			return blob(0);
+		const float diffuseWeight  = (1.0f - Metallic) * (1.0f - SpecularTransmission);
+		const bool isTransmission  = !sameHemisphere(c.V, c.L);
+		const bool upperHemisphere = cosTheta(c.V) >= 0.0f && !isTransmission;
+		if (!hasTrans && isTransmission)
+			return blob(0);
+		const V3 rH		  = halfway_reflection(c.V, c.L);
+		const float HdotL = dot(rH, c.L);
+		Blob value		  = blob(0);
+		if (diffuseWeight > EVAL_EPS) {
+			if (!isTransmission) {
+				const float retro = retroDiffuseTerm(c, HdotL) * diffuseWeight;
+				Blob sheen		  = blob(0);
+				if (Sheen > EVAL_EPS) {
+					const Blob tint = tintColor(S, c.wvl);
+					Blob sheenColor;
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
+						sheenColor[i] = mixf(1.0f, tint[i], SheenTint);
+					sheen = (sheenColor * Sheen) * schlick_term(fabsf(HdotL));
+				}
+				sheen = sheen * diffuseWeight;
+				value = value + (Base * retro + sheen) * absCosTheta(c.L);
+				const float diff = diffuseTerm(c, HdotL) * (thin ? 1 - DiffuseTransmission : diffuseWeight);
+				value			 = value + Base * (diff * absCosTheta(c.L));
+			}
+			if (hasTrans && thin && isTransmission) {
+				const float diff = diffuseTerm(c, HdotL) * DiffuseTransmission;
+				value			 = value + Base * (diff * absCosTheta(c.L));
+			}
+		}
+		{ // specularReflectionTerm
+			MicrofacetReflection micro{ roughnessClosure(Roughness) };
+			const float HdotV = dot(c.V, rH), HdotL2 = dot(c.L, rH);
+			const Blob F = disneyFresnelTerm(S, HdotV, HdotL2, c.wvl);
+			value		 = value + F * micro.eval(c.V, c.L);
+		}
+		if (hasTrans) {
+			const float transmissionWeight = (1.0f - Metallic) * SpecularTransmission;
+			if (transmissionWeight > EVAL_EPS) {
+				Blob weight;
+				const float scaledR = thin ? thinTransmissionRoughness() : Roughness;
+				const RoughDistribution rd = roughnessClosure(scaledR);
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					MicrofacetTransmission micro{ rd, AIR, IOR[i] };
+					const float R = micro.evalDielectric(c.V, c.L, false);
+					weight[i]	  = thin ? sqrtf(Base[i]) * R : Base[i] * R;
+				}
+				if (c.rayFlags & PRB_RAY_LIGHT) {
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						const float eta = HdotL < 0.0f ? IOR[i] / AIR : AIR / IOR[i];
+						weight[i] *= eta * eta;
+					}
+				}
+				value = value + weight * transmissionWeight;
+			}
+		}
+		if (upperHemisphere && Clearcoat > EVAL_EPS)
+			value = value + blob(clearcoatTerm(c, rH));
+		return value;
+	}
+	__device__ __noinline__ Blob pdf(const MatCtx& c) const
+	{ // principled.cpp:370-397
+		if (absCosTheta(c.V) <= PR_EPSILON || absCosTheta(c.L) <= PR_EPSILON)
+			return blob(0);
+		float dr, dt, sr, st;
+		lobes(c.V, dr, dt, sr, st);
+		const bool isTransmission = !sameHemisphere(c.V, c.L);
+		const float diffPdf		  = cos_hemi_pdf(absCosTheta(c.L));
+		Blob pdfV				  = blob(0);
+		if (!isTransmission) {
+			pdfV = pdfV + blob(dr * diffPdf);
+			if (sr > EVAL_EPS) {
+				MicrofacetReflection refl{ roughnessClosure(Roughness) };
+				pdfV = pdfV + blob(sr * refl.pdf(c.V, c.L));
+			}
+		}
+		if (hasTrans && isTransmission) {
+			pdfV = pdfV + blob(dt * diffPdf);
+			if (st > EVAL_EPS) {
+				const RoughDistribution rd = roughnessClosure(Roughness);
+				Blob p;
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					MicrofacetTransmission refr{ rd, AIR, IOR[i] };
+					p[i] = refr.pdf(c.V, c.L);
+				}
+				pdfV = pdfV + p * st;
+			}
+		}
+		return pdfV;
+	}
+	PRB_DEV V3 sampleDiffuse(Rng& rnd, V3 V) const
+	{
+		const bool flip = cosTheta(V) < 0;
+		const float u2	= rnd.getFloat();
+		const float u1	= rnd.getFloat();
+		const V3 L		= cos_hemi(u1, u2);
+		return flip ? -L : L;
+	}
+	PRB_DEV V3 sample(Rng& rnd, V3 V) const
+	{ // principled.cpp:418-435
+		if (absCosTheta(V) <= PR_EPSILON)
+			return mk(0, 0, 0);
+		float dr, dt, sr, st;
+		lobes(V, dr, dt, sr, st);
+		const float u0 = rnd.getFloat();
+		if (u0 < dr)
+			return sampleDiffuse(rnd, V);
+		if (u0 < dr + dt)
+			return -sampleDiffuse(rnd, V);
+		float x, y;
+		if (u0 < dr + dt + st) {
+			MicrofacetTransmission refr{ roughnessClosure(Roughness), AIR, IOR[0] };
+			rnd.get2D(x, y);
+			return refr.sample(x, y, V);
+		}
+		MicrofacetReflection refl{ roughnessClosure(Roughness) };
+		rnd.get2D(x, y);
+		return refl.sample(x, y, V);
+	}
+};
+PRB_DEV void makePrincipled(const DScene& S, const prb_material& m, const MatCtx& c, Principled& p)
+{
+	p.Base				   = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+	p.IOR				   = evalNode(S, m.node[1], c.wvl, c.u, c.v);
+	p.vndf				   = m.flags & PRB_MATF_VNDF;
+	p.thin				   = m.flags & PRB_MATF_THIN;
+	p.hasTrans			   = m.flags & PRB_MATF_HAS_TRANSMISSION;
+	p.DiffuseTransmission  = p.hasTrans ? m.f[PRB_PR_DIFF_TRANS] : 0.0f;
+	p.SpecularTransmission = p.hasTrans ? m.f[PRB_PR_SPEC_TRANS] : 0.0f;
+	p.Roughness			   = m.f[PRB_PR_ROUGHNESS];
+	p.Anisotropic		   = m.f[PRB_PR_ANISOTROPIC];
+	p.SpecularTint		   = m.f[PRB_PR_SPEC_TINT];
+	p.Flatness			   = m.f[PRB_PR_FLATNESS];
+	p.Metallic			   = m.f[PRB_PR_METALLIC];
+	p.Sheen				   = m.f[PRB_PR_SHEEN];
+	p.SheenTint			   = m.f[PRB_PR_SHEEN_TINT];
+	p.Clearcoat			   = m.f[PRB_PR_CLEARCOAT];
+	p.ClearcoatGloss	   = m.f[PRB_PR_CLEARCOAT_GLOSS];
+}
+
+// --- rough dielectric closure (roughdielectric.cpp:42-137)
+struct RoughDielectric {
+	RoughDistribution rd;
+	Blob Spec, Trans, IOR;
+	PRB_DEV Blob eval(V3 V, V3 L, bool isLightPath) const
+	{
+		Blob w;
+		if (sameHemisphere(V, L)) {
+			MicrofacetReflection refl{ rd };
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				w[i] = refl.evalDielectric(V, L, AIR, IOR[i]);
+			return w * Spec;
+		}
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			MicrofacetTransmission tr{ rd, AIR, IOR[i] };
+			w[i] = tr.evalDielectric(V, L, isLightPath);
+		}
+		return w * Trans;
+	}
+	PRB_DEV Blob pdf(V3 V, V3 L) const
+	{
+		Blob F, p;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			F[i] = fresnel_dielectric(cosTheta(V), AIR, IOR[i]);
+		if (sameHemisphere(V, L)) {
+			MicrofacetReflection refl{ rd };
+			const float rp = refl.pdf(L, V);
+			return F * blob(rp);
+		}
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			MicrofacetTransmission tr{ rd, AIR, IOR[i] };
+			p[i] = tr.pdf(V, L);
+		}
+		Blob omf;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			omf[i] = 1 - F[i];
+		return omf * p;
+	}
+	PRB_DEV V3 sample(Rng& rnd, V3 V) const
+	{
+		const float F = fresnel_dielectric(cosTheta(V), AIR, IOR[0]);
+		float x, y;
+		if (rnd.getFloat() <= F) {
+			MicrofacetReflection refl{ rd };
+			rnd.get2D(x, y);
+			return refl.sample(x, y, V);
+		}
+		MicrofacetTransmission tr{ rd, AIR, IOR[0] };
+		rnd.get2D(x, y);
+		return tr.sample(x, y, V);
+	}
+};
+
+__device__ __noinline__ void materialEval(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
+{
+	const prb_material m = S.materials[matID];
+	out.flags			 = 0;
+	out.type			 = 0;
+	switch (m.type) {
+	case PRB_MAT_DIFFUSE: { // lambert.cpp:33-43
+		const bool two = m.flags & PRB_MATF_TWO_SIDED;
+		const float d  = sameHemisphere(c.V, c.L) ? (two ? fabsf(c.L.z) : fmaxf(0.0f, c.L.z)) : 0;
+		out.weight	   = evalNode(S, m.node[0], c.wvl, c.u, c.v) * d * PR_INV_PI;
+		out.pdf		   = blob(cos_hemi_pdf(d));
+		break;
+	}
+	case PRB_MAT_DIELECTRIC:
+		out.pdf	   = blob(0);
+		out.weight = blob(0);
+		out.type   = 3;
+		out.flags  = MSF_Delta | contribFlags(m);
+		break;
+	case PRB_MAT_CONDUCTOR:
+		out.pdf	   = blob(0);
+		out.weight = blob(0);
+		out.type   = 1;
+		out.flags  = MSF_Delta | contribFlags(m);
+		break;
+	case PRB_MAT_ROUGHCONDUCTOR: { // roughconductor.cpp:42-66
+		out.type = 1;
+		MicrofacetReflection closure{ roughOf(m) };
+		if (closure.isDelta()) {
+			out.pdf	   = blob(0);
+			out.weight = blob(0);
+			out.flags  = MSF_Delta | contribFlags(m);
+			return;
+		}
+		const Blob eta = evalNode(S, m.node[0], c.wvl, c.u, c.v), k = evalNode(S, m.node[1], c.wvl, c.u, c.v);
+		Blob factor;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			factor[i] = closure.evalConductor(c.L, c.V, eta[i], k[i]);
+		out.weight = evalNode(S, m.node[2], c.wvl, c.u, c.v) * factor;
+		out.pdf	   = blob(closure.pdf(c.L, c.V));
+		out.flags  = contribFlags(m);
+		break;
+	}
+	case PRB_MAT_ROUGHDIELECTRIC: { // roughdielectric.cpp:177-199
+		RoughDielectric cl;
+		cl.rd = roughOf(m);
+		if (cl.rd.isDelta()) {
+			out.pdf	   = blob(0);
+			out.weight = blob(0);
+			out.flags  = MSF_Delta | contribFlags(m);
+			return;
+		}
+		cl.Spec	   = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+		cl.Trans   = (m.flags & PRB_MATF_TRANSMISSION_COLOR) ? evalNode(S, m.node[1], c.wvl, c.u, c.v) : cl.Spec;
+		cl.IOR	   = evalNode(S, m.node[2], c.wvl, c.u, c.v);
+		out.weight = cl.eval(c.V, c.L, c.rayFlags & PRB_RAY_LIGHT);
+		out.pdf	   = cl.pdf(c.V, c.L);
+		out.type   = sameHemisphere(c.V, c.L) ? 1 : 3;
+		out.flags  = contribFlags(m);
+		break;
+	}
+	case PRB_MAT_PRINCIPLED: { // principled.cpp:496-523
+		Principled cl;
+		makePrincipled(S, m, c, cl);
+		if (cl.isDelta()) {
+			out.weight = blob(0);
+			out.pdf	   = blob(0);
+			out.flags  = MSF_Delta;
+			return;
+		}
+		if (sameHemisphere(c.V, c.L))
+			out.type = cl.Roughness < 0.5f ? 1 : 0;
+		else
+			out.type = cl.Roughness < 0.5f ? 3 : 2;
+		out.weight = cl.eval(S, c);
+		out.pdf	   = cl.pdf(c);
+		break;
+	}
+	default:
+		out.weight = blob(0);
+		out.pdf	   = blob(0);
+		break;
+	}
+}
+
+__device__ __noinline__ void materialSample(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
+{
+	const prb_material m = S.materials[matID];
+	out.flags			 = 0;
+	out.type			 = 0;
+	switch (m.type) {
+	case PRB_MAT_DIFFUSE: { // lambert.cpp:53-73
+		if (!(m.flags & PRB_MATF_TWO_SIDED) && c.V.z < 0.0f) {
+			rejectSample(out, 0, 0);
+			return;
+		}
+		const float u2 = rnd.getFloat(); // cos_hemi(RND.getFloat(), RND.getFloat()): second argument drawn first
+		const float u1 = rnd.getFloat();
+		out.L		   = cos_hemi(u1, u2);
+		out.weight	   = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+		out.pdf		   = blob(cos_hemi_pdf(out.L.z));
+		out.L		   = makeSameHemisphere(c.V, out.L);
+		break;
+	}
+	case PRB_MAT_DIELECTRIC: { // dielectric.cpp:60-114
+		out.pdf		  = blob(1);
+		const Blob n2 = evalNode(S, m.node[2], c.wvl, c.u, c.v);
+		float F		  = fresnel_dielectric(cosTheta(c.V), AIR, n2[0]);
+		const bool thin = m.flags & PRB_MATF_THIN;
+		if (thin && F < 1.0f)
+			F += (1 - F) * F / (F + 1);
+		const Blob rWeight = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+		if (rnd.getFloat() <= F) {
+			out.type   = 1;
+			out.L	   = reflectZ(c.V);
+			out.weight = rWeight;
+		} else {
+			Blob tWeight = (m.flags & PRB_MATF_TRANSMISSION_COLOR) ? evalNode(S, m.node[1], c.wvl, c.u, c.v) : rWeight;
+			if (thin) {
+				out.type   = 3;
+				out.L	   = -c.V;
+				out.weight = tWeight;
+			} else {
+				if (c.rayFlags & PRB_RAY_LIGHT) {
+					const float eta = isPositiveHemisphere(c.V) ? AIR / n2[0] : n2[0] / AIR;
+					tWeight			= tWeight * (eta * eta);
+				}
+				out.L = refractZ(AIR / n2[0], c.V);
+				if (sameHemisphere(out.L, c.V)) {
+					out.type   = 1;
+					out.weight = rWeight;
+				} else {
+					out.type   = 3;
+					out.weight = tWeight;
+				}
+			}
+		}
+		out.flags = MSF_Delta | contribFlags(m);
+		break;
+	}
+	case PRB_MAT_CONDUCTOR: { // conductor.cpp:56-74
+		const Blob eta = evalNode(S, m.node[0], c.wvl, c.u, c.v), k = evalNode(S, m.node[1], c.wvl, c.u, c.v);
+		Blob fr;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			fr[i] = fresnel_conductor(absCosTheta(c.V), 1, eta[i], k[i]);
+		out.weight = fr * evalNode(S, m.node[2], c.wvl, c.u, c.v);
+		out.type   = 1;
+		out.pdf	   = blob(1);
+		out.L	   = reflectZ(c.V);
+		out.flags  = MSF_Delta | contribFlags(m);
+		break;
+	}
+	case PRB_MAT_ROUGHCONDUCTOR: { // roughconductor.cpp:82-117
+		MicrofacetReflection closure{ roughOf(m) };
+		float x, y;
+		rnd.get2D(x, y);
+		out.L	  = closure.sample(x, y, c.V);
+		out.flags = contribFlags(m);
+		if (closure.isDelta())
+			out.flags |= MSF_Delta;
+		if (!sameHemisphere(c.V, out.L)) {
+			rejectSample(out, 1, out.flags);
+			return;
+		}
+		const Blob eta = evalNode(S, m.node[0], c.wvl, c.u, c.v), k = evalNode(S, m.node[1], c.wvl, c.u, c.v);
+		Blob factor;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			factor[i] = closure.evalConductor(out.L, c.V, eta[i], k[i]);
+		out.weight = evalNode(S, m.node[2], c.wvl, c.u, c.v) * factor;
+		out.type   = 1;
+		out.pdf	   = blob(closure.pdf(out.L, c.V));
+		if (out.pdf[0] > PR_EPSILON)
+			out.weight = out.weight / out.pdf[0];
+		if (closure.isDelta())
+			out.pdf = blob(1);
+		break;
+	}
+	case PRB_MAT_ROUGHDIELECTRIC: { // roughdielectric.cpp:221-253
+		RoughDielectric cl;
+		cl.rd	  = roughOf(m);
+		cl.Spec	  = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+		cl.Trans  = (m.flags & PRB_MATF_TRANSMISSION_COLOR) ? evalNode(S, m.node[1], c.wvl, c.u, c.v) : cl.Spec;
+		cl.IOR	  = evalNode(S, m.node[2], c.wvl, c.u, c.v);
+		out.L	  = cl.sample(rnd, c.V);
+		out.flags = contribFlags(m);
+		if (cl.rd.isDelta())
+			out.flags |= MSF_Delta;
+		if (out.L.x == 0 && out.L.y == 0 && out.L.z == 0) {
+			rejectSample(out, 1, out.flags);
+			return;
+		}
+		out.weight = cl.eval(c.V, out.L, c.rayFlags & PRB_RAY_LIGHT);
+		out.pdf	   = cl.pdf(c.V, out.L);
+		if (out.pdf[0] > PR_EPSILON)
+			out.weight = out.weight / out.pdf[0];
+		if (cl.rd.isDelta())
+			out.pdf = blob(1);
+		out.type = sameHemisphere(c.V, out.L) ? 1 : 3;
+		break;
+	}
+	case PRB_MAT_PRINCIPLED: { // principled.cpp:536-590
+		Principled cl;
+		makePrincipled(S, m, c, cl);
+		out.L = cl.sample(rnd, c.V);
+		if (cl.isDelta())
+			out.flags |= MSF_Delta;
+		if (out.L.x == 0 && out.L.y == 0 && out.L.z == 0) {
+			rejectSample(out, 0, out.flags);
+			return;
+		}
+		if (sameHemisphere(c.V, out.L))
+			out.type = cl.Roughness < 0.5f ? 1 : 0;
+		else
+			out.type = cl.Roughness < 0.5f ? 3 : 2;
+		MatCtx e   = c;
+		e.L		   = out.L;
+		out.weight = cl.eval(S, e);
+		out.pdf	   = cl.pdf(e);
+		if (out.pdf[0] > PR_EPSILON)
+			out.weight = out.weight / out.pdf[0];
+		if (cl.isDelta())
+			out.pdf = blob(1);
+		break;
+	}
+	default: rejectSample(out, 0, 0); break;
+	}
+}
+
+// ------------------------------------------------------------------ samplers / mapper / camera
+PRB_DEV uint32_t mjPermute(uint32_t i, uint32_t l, uint32_t p)
+{ // Kensler CMJ permute, MultiJitteredSampler.cpp:21-76
+	uint32_t w = l - 1;
+	if (w == 0)
+		return 0;
+	const bool pow2 = (l & w) == 0;
+	if (!pow2) {
+		w |= w >> 1;
+		w |= w >> 2;
+		w |= w >> 4;
+		w |= w >> 8;
+		w |= w >> 16;
+	}
+	do {
+		i ^= p;
+		i *= 0xe170893d;
+		i ^= p >> 16;
+		i ^= (i & w) >> 4;
+		i ^= p >> 8;
+		i *= 0x0929eb3f;
+		i ^= p >> 23;
+		i ^= (i & w) >> 1;
+		i *= 1 | p >> 27;
+		i *= 0x6935fa69;
+		i ^= (i & w) >> 11;
+		i *= 0x74dcb303;
+		i ^= (i & w) >> 2;
+		i *= 0x9e501cc3;
+		i ^= (i & w) >> 2;
+		i *= 0xc860a3df;
+		i &= w;
+		i ^= i >> 5;
+	} while (!pow2 && i >= l);
+	return pow2 ? ((i + p) & w) : ((i + p) % l);
+}
+PRB_DEV void sampler2D(const DScene& S, const prb_sampler& s, Rng& rnd, uint32_t index, float& x, float& y)
+{
+	switch (s.type) {
+	case PRB_SAMPLER_SOBOL: // SobolSampler.cpp:67-73
+		if (s.max_samples <= index) {
+			rnd.get2D(x, y);
+		} else {
+			const float* t = S.pool + s.table_offset + s.max_samples;
+			x			   = __ldg(t + 2 * index);
+			y			   = __ldg(t + 2 * index + 1);
+		}
+		break;
+	case PRB_SAMPLER_MJITT: { // MultiJitteredSampler.cpp:118-150
+		constexpr uint32_t FH = 0x51633e2d, F1 = 0x68bc21eb, F2 = 0x02e5be93;
+		const uint32_t maxS = max(1u, s.max_samples);
+		index				= mjPermute(index, maxS, s.seed * FH);
+		const uint32_t sx	= mjPermute(index % s.m2d_x, s.m2d_x, s.seed * F1);
+		const uint32_t sy	= mjPermute(index / s.m2d_x, s.m2d_y, s.seed * F2);
+		const float jx		= rnd.getFloat();
+		const float jy		= rnd.getFloat();
+		x					= (sx + (sy + jx) / s.m2d_y) / s.m2d_x;
+		y					= (index + jy) / maxS;
+		break;
+	}
+	default: rnd.get2D(x, y); break;
+	}
+}
+PRB_DEV float sampler1D(const DScene& S, const prb_sampler& s, Rng& rnd, uint32_t index)
+{
+	switch (s.type) {
+	case PRB_SAMPLER_SOBOL:
+		if (s.max_samples <= index)
+			return rnd.getFloat();
+		return __ldg(S.pool + s.table_offset + index);
+	case PRB_SAMPLER_MJITT: {
+		const float j = rnd.getFloat();
+		return (index % s.bins_1d + j) / s.bins_1d;
+	}
+	default: return rnd.getFloat();
+	}
+}
+PRB_DEV int cdfSearch(const float* cdf, int size, float u)
+{ // Interval::binary_search, src/base/container/Interval.h
+	int first = 0, len = size;
+	while (len > 0) {
+		const int half = len / 2, middle = first + half;
+		if (__ldg(cdf + middle) <= u) {
+			first = middle + 1;
+			len -= half + 1;
+		} else {
+			len = half;
+		}
+	}
+	return max(0, min(first - 1, size - 2));
+}
+PRB_DEV float sampleContinuous(const float* cdf, int size, float u, float& pdf)
+{ // Distribution1D::sampleContinuous, Distribution1D.inl:76-86,119-135
+	const int off = cdfSearch(cdf, size, u);
+	const float c0 = __ldg(cdf + off), c1 = __ldg(cdf + off + 1);
+	float rem	  = u - c0;
+	const float k = c1 - c0;
+	if (k > PR_EPSILON)
+		rem /= k;
+	pdf = c1 - c0;
+	pdf *= (size - 1);
+	return (off + rem) / (size - 1);
+}
+
+struct CameraSampleOut {
+	V3 origin, dir;
+	float tmin, tmax;
+	Blob wvl, wvlPDF;
+	bool mono;
+};
+__device__ __noinline__ void constructCameraRay(const DScene& S, uint32_t px, uint32_t py, uint32_t iteration, Rng& rnd, CameraSampleOut& o)
+{ // RenderTile::constructCameraRay, RenderTile.cpp:71-132 + PerspectiveCamera::constructRay, perspective.cpp:45-82
+	const prb_settings& st = S.settings;
+	float ax, ay, lx, ly;
+	sampler2D(S, S.aa, rnd, iteration, ax, ay);
+	const float pixx = ((float)px + ax) - 0.5f, pixy = ((float)py + ay) - 0.5f;
+	sampler2D(S, S.lens, rnd, iteration, lx, ly);
+	(void)sampler1D(S, S.time, rnd, iteration); // time sample is drawn; static scenes do not use it
+	if (st.spectral_mono) {
+		o.wvl	 = blob(st.spectral_start);
+		o.wvlPDF = blob(1.0f);
+	} else {
+		const float start = st.spectral_start, end = st.spectral_end;
+		switch (S.mapper.type) {
+		case PRB_MAPPER_SPD_CMIS: // spd.cpp:40-47
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				float pdf;
+				const float x = sampleContinuous(S.pool + S.mapper.cdf_offset, (int)S.mapper.cdf_size, rnd.getFloat(), pdf);
+				o.wvl[i]	  = x * (end - start) + start;
+				o.wvlPDF[i]	  = pdf;
+			}
+			break;
+		case PRB_MAPPER_SPD_HERO: { // spd.cpp:104-112 + Standard.h:8-21
+			float pdf;
+			const float u	 = rnd.getFloat();
+			const float hero = sampleContinuous(S.pool + S.mapper.cdf_offset, (int)S.mapper.cdf_size, u, pdf) * (end - start) + start;
+			const float span = end - start, delta = span / 4, s = hero - start;
+			o.wvl[0] = hero;
+#pragma unroll
+			for (int i = 1; i < 4; ++i)
+				o.wvl[i] = start + fmodf(s + i * delta, span);
+			o.wvlPDF = blob(pdf);
+			break;
+		}
+		default: { // random.cpp:22-36
+			const float u	 = rnd.getFloat();
+			const float span = end - start, delta = span / 4, s = u * span;
+			o.wvl[0] = s + start;
+#pragma unroll
+			for (int i = 1; i < 4; ++i)
+				o.wvl[i] = start + fmodf(s + i * delta, span);
+			o.wvlPDF = blob(1.0f);
+			break;
+		}
+		}
+	}
+	const float nx = 2 * (pixx / (float)st.film_width - 0.5f);
+	const float ny = -(2 * (pixy / (float)st.film_height - 0.5f));
+	const V3 dir   = (ld3(S.camera.right) * nx + ld3(S.camera.up) * ny) + ld3(S.camera.dir);
+	o.origin	   = ld3(S.camera.origin);
+	o.dir		   = normalized(dir);
+	o.tmin		   = S.camera.near_t;
+	o.tmax		   = S.camera.far_t;
+	o.mono		   = st.spectral_mono || !st.spectral_hero;
+}
+
+// ------------------------------------------------------------------ lights
+struct SQ { // spherical rectangle, plane.cpp:100-145
+	V3 o, n;
+	float z0, x0, y0, x1, y1, b0, b1, k, S;
+};
+PRB_DEV float safe_acos(float a) { return acosf(fmaxf(-1.0f, fminf(1.0f, a))); }
+PRB_DEV void computeSQ(const prb_entity& en, V3 o, SQ& sq)
+{
+	const V3 mS = ld3(en.geo), mEx = ld3(en.geo + 3), mEy = ld3(en.geo + 6), mEz = ld3(en.geo + 9);
+	sq.o	   = o;
+	sq.n	   = mEz;
+	const V3 d = mS - sq.o;
+	sq.x0	   = dot(d, mEx);
+	sq.y0	   = dot(d, mEy);
+	sq.z0	   = dot(d, sq.n);
+	sq.x1	   = sq.x0 + en.geo[12];
+	sq.y1	   = sq.y0 + en.geo[13];
+	if (sq.z0 > 0.0f) {
+		sq.z0 = -sq.z0;
+		sq.n  = -sq.n;
+	}
+	const float a[4] = { sq.x0, sq.y1, sq.x1, sq.y0 }, b[4] = { sq.x1, sq.y0, sq.x0, sq.y1 }, c[4] = { sq.y0, sq.x1, sq.y1, sq.x0 };
+	float nz[4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const float diff = a[i] - b[i];
+		nz[i]			 = c[i] * diff;
+		nz[i] /= sqrtf(sq.z0 * sq.z0 * diff * diff + nz[i] * nz[i]);
+	}
+	const float g0 = safe_acos(-nz[0] * nz[1]), g1 = safe_acos(-nz[1] * nz[2]), g2 = safe_acos(-nz[2] * nz[3]), g3 = safe_acos(-nz[3] * nz[0]);
+	sq.b0 = nz[0];
+	sq.b1 = nz[2];
+	sq.k  = 2 * PR_PI - g2 - g3;
+	sq.S  = g0 + g1 - sq.k;
+}
+// IEntity::sampleParameterPointPDF(p, info): mesh 1/worldArea; sphere 2*pdfCache; plane spherical rectangle
+PRB_DEV float entityPositionPDF(const DScene& S, uint32_t entityID, V3 p, V3 infoOrigin)
+{
+	const prb_entity& en = S.entities[entityID];
+	if (en.type == PRB_ENTITY_SPHERE)
+		return 2 * en.geo[5];
+	if (en.type == PRB_ENTITY_PLANE) { // plane.cpp:184-195
+		SQ sq;
+		computeSQ(en, infoOrigin, sq);
+		const float pdf_s = sq.S > PR_EPSILON ? 1 / sq.S : 0.0f;
+		const V3 L		  = p - infoOrigin;
+		const float dist2 = norm2(L);
+		const float ndotv = fabsf(dot(normalized(L), ld3(en.geo + 26)));
+		return ndotv <= PR_EPSILON ? 0 : pdf_s * fabsf(ndotv) / dist2;
+	}
+	return en.pdf_area;
+}
+struct LightSample {
+	Blob radiance;
+	V3 outgoing, lightPos;
+	float posPDF, dirPDF_S, cosLight;
+	bool infinite;
+};
+// Light::sample with SamplingInfo + Point (NEE), src/core/light/Light.cpp:108-226
+__device__ __noinline__ void sampleLight(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o)
+{
+	if (l.type == PRB_LIGHT_ENV) { // environment.cpp sampleDir / samplePosDir (no distribution)
+		float dx, dy, px, py;
+		rnd.get2D(dx, dy);
+		rnd.get2D(px, py);
+		const V3 local = cos_hemi(dx, dy);
+		o.dirPDF_S	   = cos_hemi_pdf(local.z);
+		o.outgoing	   = m3mul(l.normal_matrix, local);
+		o.radiance	   = evalNode(S, l.radiance_node, wvl, dx, dy);
+		o.lightPos	   = P + l.scene_radius * o.outgoing;
+		o.posPDF	   = 1;
+		o.cosLight	   = 1;
+		o.infinite	   = true;
+		return;
+	}
+	o.infinite			 = false;
+	const prb_entity& en = S.entities[l.entity_id];
+	float rx, ry;
+	rnd.get2D(rx, ry);
+	V3 pos;
+	float su, sv, pdfA;
+	uint32_t prim = 0;
+	if (en.type == PRB_ENTITY_MESH) { // mesh.cpp:187-203
+		const prb_mesh m = S.meshes[en.mesh_id];
+		float k1, k2;
+		const float f1 = modff(rx * m.face_count, &k1); // SplitSample1D, SplitSample.h:6-26
+		const float f2 = modff(ry * m.face_count, &k2);
+		(void)k2;
+		const uint32_t faceID = min((uint32_t)k1, m.face_count - 1);
+		FaceData f;
+		getFace(S, m, faceID, f, false, false);
+		pdfA = 1.0f / (m.face_count * faceArea(f) * en.jacobian_det);
+		if (!f.quad) { // Triangle::sample, Triangle.h:46-55
+			if (f2 > f1) {
+				const float x = f1 / 2;
+				su			  = x;
+				sv			  = f2 - x;
+			} else {
+				const float y = f2 / 2;
+				su			  = f1 - y;
+				sv			  = y;
+			}
+		} else {
+			su = f1;
+			sv = f2;
+		}
+		pos	 = xfPoint(en.local_to_world, faceInterpV(f, f.V, su, sv));
+		prim = faceID;
+	} else if (en.type == PRB_ENTITY_SPHERE) { // sphere.cpp:106-116
+		V3 n			 = cartesian_from_uv(rx, ry);
+		const V3 local_o = normalized(xfPoint(en.world_to_local, P));
+		if (dot(local_o, n) < -PR_EPSILON)
+			n = -n;
+		pos = xfPoint(en.local_to_world, en.geo[4] * n);
+		uv_from_normal(n, su, sv);
+		pdfA = 2 * en.geo[5];
+	} else { // plane.cpp:147-182
+		SQ sq;
+		computeSQ(en, P, sq);
+		const V3 mEx = ld3(en.geo + 3), mEy = ld3(en.geo + 6);
+		const float au = fmaf(rx, sq.S, sq.k);
+		const float fu = fmaf(cosf(au), sq.b0, -sq.b1) / sinf(au);
+		const float cu = fminf(1.0f, fmaxf(-1.0f, copysignf(1.0f, fu) / sqrtf(sumProd(fu, fu, sq.b0, sq.b0))));
+		const float xu = fminf(sq.x1, fmaxf(sq.x0, -(cu * sq.z0) / fmaxf(1e-7f, sqrtf(fmaf(-cu, cu, 1.0f)))));
+		const float dd = sqrtf(sumProd(xu, xu, sq.z0, sq.z0));
+		const float h0 = sq.y0 / sqrtf(sumProd(dd, dd, sq.y0, sq.y0));
+		const float h1 = sq.y1 / sqrtf(sumProd(dd, dd, sq.y1, sq.y1));
+		const float hv = fmaf(ry, h1 - h0, h0);
+		const float hv2 = hv * hv;
+		const float yv	= (hv2 < 1.0f - 1e-6f) ? (hv * dd) / sqrtf(1.0f - hv2) : sq.y1;
+		pos				= ((sq.o + xu * mEx) + yv * mEy) + sq.z0 * sq.n;
+		const float pdf_s = sq.S > PR_EPSILON ? 1 / sq.S : 0.0f;
+		const V3 L		  = pos - P;
+		const float dist2 = norm2(L);
+		const float ndotv = fabsf(dot(normalized(L), ld3(en.geo + 26)));
+		pdfA			  = ndotv <= PR_EPSILON ? 0 : pdf_s * ndotv / dist2;
+		const V3 lp		  = xfPoint(en.world_to_local, pos) - ld3(en.geo + 29); // Plane::project
+		su				  = dot(ld3(en.geo + 32), lp) * en.geo[38];
+		sv				  = dot(ld3(en.geo + 35), lp) * en.geo[39];
+	}
+	GeomPoint gp;
+	provideGeometryPoint(S, l.entity_id, prim, su, sv, pos, gp);
+	o.outgoing = normalized(pos - P);
+	o.dirPDF_S = 1;
+	o.cosLight = fminf(1.0f, fmaxf(-1.0f, -dot(o.outgoing, gp.N)));
+	o.radiance = evalNode(S, S.emissions[l.emission_id].radiance_node, wvl, gp.u, gp.v);
+	o.posPDF   = pdfA;
+	o.lightPos = pos;
+}
+PRB_DEV void envEval(const DScene& S, const prb_light& l, V3 dir, uint32_t depth, const Blob& wvl, Blob& rad, float& pdfS)
+{ // EnvironmentLight::eval (no distribution), environment.cpp
+	const V3 ld = m3mul(l.inv_normal_matrix, dir);
+	float u, v;
+	uv_from_normal(ld, u, v);
+	const uint32_t node = (l.env_split && depth == 0) ? l.background_node : l.radiance_node;
+	rad					= evalNode(S, node, wvl, u, v);
+	pdfS				= cos_hemi_pdf(fabsf(ld.z));
+}
+} // namespace prb

@@ -1,0 +1,650 @@
+// Wavefront kernels of the 'direct' path tracer (reference src/plugins/main/integrators/direct.cpp:44-473,
+// src/vcm/vcm/Walker.h:24-55) restructured for the GPU:
+//
+//   slot == one film pixel owned by this context.  A pixel's samples are generated strictly one after the other
+//   because all decisions of a pixel draw from the pixel's own pcg32_fast stream (RenderRandomMap), carried
+//   across iterations.  Slots are independent, so the wave always holds (#owned pixels) paths in flight:
+//   a slot whose path ended is refilled with its next sample ("regeneration").
+//
+//   per wavefront iteration:  generate (regen queue -> camera rays) -> extend (closest hit) -> shade (emission,
+//   NEE, scattering; appends to the next extend queue / the regen queue / the shadow queue) -> shadow (any hit,
+//   adds the NEE contribution).  Queues are uint32 slot lists in HBM appended with warp-aggregated atomics
+//   (ballot + popc + shuffle).  All kernels are persistent-style: fixed grid, grid-stride over the queue whose
+//   length is read from device memory, so the whole loop is launched without host round trips.
+#pragma once
+#include "dev_shade.cuh"
+
+namespace prb {
+enum { CNT_EXTEND0 = 0, CNT_EXTEND1 = 1, CNT_REGEN = 2, CNT_SHADOW = 3, CNT_RETIRED = 4, CNT__COUNT = 8 };
+enum { ST_CAMERA_RAY = 0, ST_LIGHT_RAY, ST_PRIMARY, ST_BOUNCE, ST_SHADOW, ST_MONO, ST_PIXEL_SAMPLE, ST_ENTITY_HIT, ST_BG_HIT, ST_CAMERA_DEPTH, ST_LIGHT_DEPTH, ST__COUNT };
+
+constexpr uint32_t FD_DEPTH_MASK   = 0xFFFFu;
+constexpr uint32_t FD_FLAGS_SHIFT  = 16; // ray flags (8 bit)
+constexpr uint32_t FD_LAST_DELTA   = 1u << 30;
+constexpr uint32_t FD_LAST_EMISSIVE = 1u << 31;
+
+struct WFState {
+	// per slot
+	uint32_t* pixel;
+	uint32_t* iter; // next iteration to generate
+	float4* rayO;	// xyz, tmin
+	float4* rayD;	// xyz, tmax
+	float4* wvl;
+	uint32_t* flagsDepth;
+	float4* thr;
+	float4* pathPDF;
+	float4* prevPDF;
+	float4* wvlPDF;
+	float4* lastPos;
+	uint4* hit; // entity, prim, u bits, v bits
+	float* hitT;
+	float4* shO;   // shadow origin xyz, tmin
+	float4* shD;   // shadow dir xyz, tmax
+	float4* shXYZ; // contribution if visible
+	float4* iterXYZ;
+	// queues + counters
+	uint32_t* qExtend[2];
+	uint32_t* qRegen;
+	uint32_t* qShadow;
+	uint32_t* counters;
+	// film (indexed by film pixel)
+	uint64_t* rng;
+	float* filmMean; // 3 per pixel, running mean, unfiltered
+	uint32_t* sampleCount;
+	float* aov; // 10 per pixel or null
+	unsigned long long* stats;
+	uint32_t nSlots, firstIter, endIter;
+};
+
+// warp-aggregated append; must be called by all 32 lanes of the warp (convergent point)
+PRB_DEV void queuePush(uint32_t* counter, uint32_t* queue, bool pred, uint32_t value)
+{
+	const unsigned mask = __ballot_sync(0xFFFFFFFFu, pred);
+	if (mask == 0)
+		return;
+	const int lane	 = threadIdx.x & 31;
+	const int leader = __ffs(mask) - 1;
+	uint32_t base	 = 0;
+	if (lane == leader)
+		base = atomicAdd(counter, (uint32_t)__popc(mask));
+	base = __shfl_sync(0xFFFFFFFFu, base, leader);
+	if (pred)
+		queue[base + __popc(mask & ((1u << lane) - 1))] = value;
+}
+PRB_DEV void statAdd(unsigned long long* stats, int which, uint32_t v)
+{ // one atomic per warp per counter (all lanes call)
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+	if ((threadIdx.x & 31) == 0 && v)
+		atomicAdd(stats + which, (unsigned long long)v);
+}
+
+__global__ void k_init_slots(WFState W)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.nSlots; i += gridDim.x * blockDim.x) {
+		W.iter[i]	 = W.firstIter;
+		W.iterXYZ[i] = make_float4(0, 0, 0, 0);
+		W.qRegen[i]	 = i;
+	}
+}
+
+// ------------------------------------------------------------------ generate
+__global__ void __launch_bounds__(256) k_generate(DScene S, WFState W, int extendSel)
+{
+	const uint32_t n = W.counters[CNT_REGEN];
+	uint32_t nSamples = 0;
+	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+		const uint32_t idx = base + threadIdx.x;
+		bool push		   = false;
+		bool retired	   = false;
+		uint32_t slot	   = 0;
+		if (idx < n) {
+			slot			   = W.qRegen[idx];
+			const uint32_t pix = W.pixel[slot];
+			uint32_t it		   = W.iter[slot];
+			if (it > W.firstIter) { // a sample just finished: FrameOutputDevice::onEndOfIteration (running mean)
+				const float4 acc   = W.iterXYZ[slot];
+				const float fin	   = (float)(it - 1); // 0-based index of the finished iteration
+				const float iterf  = (float)it;
+				float* m		   = W.filmMean + 3 * (size_t)pix;
+				m[0]			   = (m[0] * fin + acc.x) / iterf;
+				m[1]			   = (m[1] * fin + acc.y) / iterf;
+				m[2]			   = (m[2] * fin + acc.z) / iterf;
+				W.iterXYZ[slot]	   = make_float4(0, 0, 0, 0);
+			}
+			if (it >= W.endIter) {
+				retired = true;
+			} else {
+				Rng rnd{ W.rng[pix] };
+				CameraSampleOut cs;
+				const uint32_t fw = S.settings.film_width;
+				constructCameraRay(S, pix % fw, pix / fw, it, rnd, cs);
+				W.rng[pix]		   = rnd.s;
+				W.iter[slot]	   = it + 1;
+				W.rayO[slot]	   = make_float4(cs.origin.x, cs.origin.y, cs.origin.z, cs.tmin);
+				W.rayD[slot]	   = make_float4(cs.dir.x, cs.dir.y, cs.dir.z, cs.tmax);
+				W.wvl[slot]		   = tof4(cs.wvl);
+				W.wvlPDF[slot]	   = tof4(cs.wvlPDF);
+				W.thr[slot]		   = make_float4(1, 1, 1, 1);
+				W.pathPDF[slot]	   = make_float4(1, 1, 1, 1);
+				W.prevPDF[slot]	   = make_float4(1, 1, 1, 1);
+				W.lastPos[slot]	   = make_float4(0, 0, 0, 0);
+				const uint32_t rf  = PRB_RAY_CAMERA | (cs.mono ? PRB_RAY_MONOCHROME : 0);
+				W.flagsDepth[slot] = (rf << FD_FLAGS_SHIFT) | FD_LAST_DELTA; // depth 0, LastWasDelta = true
+				push			   = true;
+				++nSamples;
+			}
+		}
+		queuePush(W.counters + extendSel, W.qExtend[extendSel], push, slot);
+		const unsigned rmask = __ballot_sync(0xFFFFFFFFu, retired);
+		if ((threadIdx.x & 31) == 0 && rmask)
+			atomicAdd(W.counters + CNT_RETIRED, (uint32_t)__popc(rmask));
+	}
+	statAdd(W.stats, ST_PIXEL_SAMPLE, nSamples);
+	statAdd(W.stats, ST_CAMERA_RAY, nSamples);
+	statAdd(W.stats, ST_PRIMARY, nSamples);
+}
+
+// ------------------------------------------------------------------ extend
+__global__ void __launch_bounds__(256) k_extend(DScene S, WFState W, int extendSel)
+{
+	const uint32_t n  = W.counters[extendSel];
+	const uint32_t* q = W.qExtend[extendSel];
+	for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+		const uint32_t slot = q[idx];
+		const float4 o = W.rayO[slot], d = W.rayD[slot];
+		HitRec h;
+		traverseScene<false>(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
+		W.hit[slot]	 = make_uint4(h.entity, h.prim, __float_as_uint(h.u), __float_as_uint(h.v));
+		W.hitT[slot] = h.t;
+	}
+}
+
+// ------------------------------------------------------------------ shade
+PRB_DEV float misTerm(bool power, float a) { return power ? a * a : a; } // vcm/MIS.h:7-30
+PRB_DEV Blob misTermB(bool power, Blob a) { return power ? a * a : a; }
+
+// LocalFrameOutputDevice::commitSpectrals2 (LocalFrameOutputDevice.cpp:88-164) for one fragment; the pixel filter
+// is applied as a linear post pass.  Returns false when the fragment is rejected (NaN / Inf / negative).
+PRB_DEV bool fragmentXYZ(const DScene& S, const Blob& mis, const Blob& importance, const Blob& radiance, uint32_t rayFlags, bool groupMono, const Blob& grpWvl,
+						 float xyz[3])
+{
+	const bool isMono		  = rayFlags & PRB_RAY_MONOCHROME;
+	const Blob heroFactor	  = isMono ? heroOnly() : blob(1);
+	const Blob grpImportance  = groupMono ? heroOnly() : blob(1); // CameraRay Importance (* HeroOnly when monochrome), RenderTile.cpp:124-128
+	const Blob imp			  = grpImportance * importance;
+	const Blob contrib		  = heroFactor * ((mis * imp) * radiance);
+	bool invalid			  = false;
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+		if (isinf(contrib[i]) || isnan(contrib[i]) || contrib[i] < -PR_EPSILON)
+			invalid = true;
+	if (invalid)
+		return false;
+	xyz[0] = xyz[1] = xyz[2] = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+#pragma unroll
+		for (int c = 0; c < 3; ++c)
+			xyz[c] += contrib[k] * cieEval(S, c, grpWvl[k]);
+	}
+	// BlendWeight == 1 for all supported spectral mappers
+	return true;
+}
+
+PRB_DEV float rrProbability(const DScene& S, uint32_t pathLength, bool delta)
+{ // RussianRoulette::probability, vcm/RussianRoulette.h:22-34 (table computed by the host in double like std::pow)
+	if (pathLength == 0 || delta)
+		return 1.0f;
+	return __ldg(S.rrProb + min(pathLength, S.rrCount - 1));
+}
+
+__global__ void __launch_bounds__(128) k_shade(DScene S, WFState W, int extendSel)
+{
+	const uint32_t n	   = W.counters[extendSel];
+	const uint32_t* q	   = W.qExtend[extendSel];
+	const int nextSel	   = 1 - extendSel;
+	const prb_settings& st = S.settings;
+	const bool power	   = st.mis_power;
+	uint32_t sEntity = 0, sBg = 0, sDepth = 0, sShadow = 0, sBounce = 0, sMono = 0;
+	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+		const uint32_t idx = base + threadIdx.x;
+		bool pushExtend = false, pushRegen = false, pushShadow = false;
+		uint32_t slot = 0;
+		if (idx < n) {
+			slot				= q[idx];
+			const uint32_t pix	= W.pixel[slot];
+			const uint4 hraw	= W.hit[slot];
+			const float4 ro = W.rayO[slot], rd = W.rayD[slot];
+			const uint32_t fd	= W.flagsDepth[slot];
+			const uint32_t depth = fd & FD_DEPTH_MASK;
+			const uint32_t rayFlags = (fd >> FD_FLAGS_SHIFT) & 0xFFu;
+			const Blob wvl		= blob4(W.wvl[slot]);
+			const bool groupMono = st.spectral_mono || !st.spectral_hero;
+			const V3 O			= mk(ro.x, ro.y, ro.z);
+			V3 D				= mk(rd.x, rd.y, rd.z);
+			if (depth == 0)
+				D = normalized(D); // RayStream::getRay re-normalises on read, RayStream.cpp:167
+			float4 accv = W.iterXYZ[slot];
+			float acc[3] = { accv.x, accv.y, accv.z };
+			Blob Throughput = blob4(W.thr[slot]), PathPDF = blob4(W.pathPDF[slot]), PrevPathPDF = blob4(W.prevPDF[slot]);
+			const Blob WavelengthPDF = blob4(W.wvlPDF[slot]);
+			bool LastWasDelta = fd & FD_LAST_DELTA, LastWasEmissive = fd & FD_LAST_EMISSIVE;
+			bool alive = false;
+			float xyz[3];
+
+			if (hraw.x == PRB_INVALID_ID) {
+				// ---------------- miss
+				++sBg;
+				if (depth == 0) { // IntegratorUtils::handleBackgroundGroup, IntegratorUtils.h:16-53
+					++sDepth;
+					bool illuminated = false;
+					for (uint32_t i = 0; i < S.nLights; ++i) {
+						const prb_light& l = S.lights[i];
+						if (l.type != PRB_LIGHT_ENV)
+							continue;
+						illuminated = true;
+						Blob rad;
+						float pdfS;
+						envEval(S, l, D, depth, wvl, rad, pdfS);
+						if (fragmentXYZ(S, blob(1), blob(1), rad, rayFlags, groupMono, wvl, xyz)) {
+							acc[0] += xyz[0];
+							acc[1] += xyz[1];
+							acc[2] += xyz[2];
+						}
+					}
+					(void)illuminated; // a zero fragment adds nothing
+				} else { // handleInfLights / handleZero, direct.cpp:415-464
+					const bool mono		  = rayFlags & PRB_RAY_MONOCHROME;
+					const Blob heroFactor = mono ? heroOnly() : blob(1);
+					if (S.hasEnvLight && st.do_direct) {
+						float denom_mis = 0;
+						Blob radiance	= blob(0);
+						for (uint32_t i = 0; i < S.nLights; ++i) {
+							const prb_light& l = S.lights[i];
+							if (l.type != PRB_LIGHT_ENV)
+								continue;
+							Blob rad;
+							float pdfS;
+							envEval(S, l, D, depth, wvl, rad, pdfS);
+							const float pdf_S = pdfS * l.select_pdf;
+							radiance		  = radiance + rad;
+							denom_mis += bsum(misTermB(power, PrevPathPDF * pdf_S));
+						}
+						Blob mis;
+						if (!st.do_nee || LastWasDelta) {
+							mis = heroFactor / (WavelengthPDF * bsum(heroFactor));
+						} else {
+							const float denom = bsum(misTermB(power, PathPDF)) + denom_mis;
+							mis				  = (heroFactor * misTerm(power, PathPDF[0])) / (misTermB(power, WavelengthPDF) * denom);
+						}
+						if (fragmentXYZ(S, mis, Throughput, radiance, rayFlags, groupMono, wvl, xyz)) {
+							acc[0] += xyz[0];
+							acc[1] += xyz[1];
+							acc[2] += xyz[2];
+						}
+					}
+				}
+			} else {
+				// ---------------- hit: makeIP (RenderTileSession::traceSingleRay :80-101, IntersectionPoint::setForSurface :61-75)
+				const float t = W.hitT[slot];
+				const V3 P	  = O + t * D;
+				GeomPoint g;
+				provideGeometryPoint(S, hraw.x, hraw.y, __uint_as_float(hraw.z), __uint_as_float(hraw.w), P, g);
+				const float depth2 = norm2(O - P);
+				const float NdotV  = dot(D, g.N);
+				// ---------------- handleCameraVertex, direct.cpp:73-105
+				++sEntity;
+				++sDepth;
+				if (depth == 0) { // pushSPFragment -> commitShadingPoints, LocalFrameOutputDevice.cpp:252-302
+					W.sampleCount[pix] += 1;
+					if (W.aov) {
+						float* a = W.aov + 10 * (size_t)pix;
+						a[0] += g.N.x;
+						a[1] += g.N.y;
+						a[2] += g.N.z;
+						a[3] += P.x;
+						a[4] += P.y;
+						a[5] += P.z;
+						a[6] += g.u;
+						a[7] += g.v;
+						a[8] += sqrtf(depth2);
+						a[9] += (float)g.entity;
+					}
+				}
+				const bool hasEmission = g.emission != PRB_INVALID_ID;
+				bool cont			   = true;
+				if (st.do_direct && hasEmission) {
+					// ------------ handleDirectHit, direct.cpp:355-412
+					if (g.emission < S.nEmissions) {
+						const float cosC = -NdotV;
+						if (!(fabsf(cosC) <= PR_EPSILON)) {
+							const bool hitFromBehind = cosC < 0.0f;
+							const Blob radiance		 = hitFromBehind ? blob(0) : evalNode(S, S.emissions[g.emission].radiance_node, wvl, g.u, g.v);
+							const bool mono			 = rayFlags & PRB_RAY_MONOCHROME;
+							const Blob heroFactor	 = mono ? heroOnly() : blob(1);
+							Blob mis;
+							if (!st.do_nee || hitFromBehind || LastWasDelta) {
+								mis = heroFactor / (WavelengthPDF * bsum(heroFactor));
+							} else {
+								const prb_entity& en = S.entities[g.entity];
+								const float selProb	 = en.light_id != PRB_INVALID_ID ? S.lights[en.light_id].select_pdf : 0.0f;
+								float posPDF		 = 0;
+								if (en.light_id != PRB_INVALID_ID) {
+									const float4 lp = W.lastPos[slot];
+									posPDF			= entityPositionPDF(S, g.entity, P, mk(lp.x, lp.y, lp.z));
+									posPDF			= posPDF * depth2 / fabsf(cosC); // IS::toSolidAngle
+								}
+								const float posPDF_S = posPDF * selProb;
+								const float denom	 = bsum(misTermB(power, PrevPathPDF * posPDF_S)) + bsum(misTermB(power, PathPDF));
+								mis					 = (heroFactor * misTerm(power, PathPDF[0])) / (misTermB(power, WavelengthPDF) * denom);
+							}
+							if (fragmentXYZ(S, mis, Throughput, radiance, rayFlags, groupMono, wvl, xyz)) {
+								acc[0] += xyz[0];
+								acc[1] += xyz[1];
+								acc[2] += xyz[2];
+							}
+						}
+					}
+					if (!st.emissive_scatter)
+						cont = false;
+				}
+				const uint32_t matID = g.material;
+				if (matID >= S.nMaterials)
+					cont = false;
+				if (cont) {
+					Rng rnd{ W.rng[pix] };
+					const bool onlyDelta = S.materials[matID].flags & PRB_MATF_ONLY_DELTA;
+					MatCtx mc;
+					mc.V		= toTangentSpace(g.N, g.Nx, g.Ny, -D);
+					mc.wvl		= wvl;
+					mc.u		= g.u;
+					mc.v		= g.v;
+					mc.rayFlags = rayFlags;
+					if (st.do_nee && !onlyDelta && !hasEmission && S.nLights > 0) {
+						// -------- handleNEE, direct.cpp:233-352
+						const float usel  = rnd.getFloat();
+						const int lightID = cdfSearch(S.lightCDF, (int)S.nLights + 1, usel);
+						const float selPdf = S.lightCDF[lightID + 1] - S.lightCDF[lightID];
+						const prb_light& light = S.lights[lightID];
+						LightSample ls;
+						sampleLight(S, light, P, wvl, rnd, ls);
+						const float sqrD = norm2(ls.lightPos - P);
+						const V3 L		 = ls.outgoing;
+						const float cosC = fabsf(dot(L, g.N));
+						const float cosL = fabsf(ls.cosLight);
+						if (cosC * cosL > 1e-5f && sqrD > 1e-5f) { // GEOMETRY_EPS / DISTANCE_EPS
+							mc.L = toTangentSpace(g.N, g.Nx, g.Ny, L);
+							MatEval mout;
+							materialEval(S, matID, mc, mout);
+							if (!(mout.flags & MSF_Delta)) {
+								const bool rayMono		 = rayFlags & PRB_RAY_MONOCHROME;
+								const bool bsdfMono		 = rayMono; // a non-delta eval result is never hero collapsing
+								const Blob rayHeroFactor = rayMono ? heroOnly() : blob(1);
+								const Blob heroFactor	 = bsdfMono ? heroOnly() : blob(1);
+								const Blob bsdfWvlPdfS	 = mout.pdf * heroFactor;
+								if (!allLE(bsdfWvlPdfS, 1e-6f)) { // PDF_EPS
+									const Blob connectionW = ls.radiance * mout.weight;
+									const bool worthACheck = !blobIsZero(connectionW, PR_EPSILON);
+									float lightPdfS		   = ls.infinite ? ls.dirPDF_S : ls.posPDF * sqrD / cosL;
+									lightPdfS *= selPdf;
+									const bool normalPdf = !(isnan(lightPdfS) || isinf(lightPdfS) || lightPdfS == 0.0f || fabsf(lightPdfS) < 1.17549435e-38f);
+									if (normalPdf && !(lightPdfS <= 1e-6f)) {
+										const Blob lightPdfS2 = rayHeroFactor * lightPdfS;
+										if (!allLE(lightPdfS2, 1e-6f)) {
+											Blob mis;
+											if (st.do_direct && !LastWasEmissive) {
+												const float cameraRoulette = rrProbability(S, depth + 1, false);
+												const Blob bsdfPdfS		   = bsdfWvlPdfS * cameraRoulette;
+												const float denom = bsum(misTermB(power, PathPDF * lightPdfS2)) + bsum(misTermB(power, PathPDF * bsdfPdfS));
+												mis = blob(misTerm(power, PathPDF[0] * lightPdfS2[0])) / ((heroFactor * denom) * misTermB(power, WavelengthPDF));
+											} else {
+												mis = heroFactor / (WavelengthPDF * bsum(heroFactor));
+											}
+											const float distance = ls.infinite ? PRB_INF : sqrtf(sqrD);
+											// shadow ray: cameraIP.nextRay(L, Shadow, SHADOW_RAY_MIN, distance), IntersectionPoint.h:116-124
+											const V3 oN		= dot(L, g.N) < 0 ? -g.N : g.N;
+											const V3 sO		= safePosition(P, L, oN);
+											const uint32_t shadowFlags = rayFlags | PRB_RAY_SHADOW;
+											if (ls.infinite)
+												++sBg;
+											else
+												++sEntity;
+											if (worthACheck) {
+												++sShadow;
+												const Blob contrib = connectionW / lightPdfS2[0];
+												if (fragmentXYZ(S, mis, Throughput, contrib, shadowFlags, groupMono, wvl, xyz)) {
+													// Scene::traceShadowRay: tnear = MinT (1e-4), tfar = distance - 0.001, Scene.cpp:266-280
+													W.shO[slot]	  = make_float4(sO.x, sO.y, sO.z, 0.0001f);
+													W.shD[slot]	  = make_float4(L.x, L.y, L.z, distance - 0.001f);
+													W.shXYZ[slot] = make_float4(xyz[0], xyz[1], xyz[2], 0);
+													pushShadow	  = true;
+												}
+											}
+										}
+									}
+								}
+							}
+						}
+					}
+					LastWasEmissive = hasEmission;
+					// -------- handleScattering, direct.cpp:170-230
+					const float scatProb = rrProbability(S, depth + 1, onlyDelta);
+					bool scatter		 = scatProb > PR_EPSILON;
+					if (scatter && scatProb < 1.0f) {
+						if (rnd.getFloat() > scatProb)
+							scatter = false;
+					}
+					if (scatter) {
+						MatSample sout;
+						mc.L = mk(0, 0, 0);
+						materialSample(S, matID, mc, rnd, sout);
+						const V3 L	 = normalized(fromTangentSpace(g.N, g.Nx, g.Ny, sout.L)); // MaterialSampleOutput::globalL
+						LastWasDelta = sout.isDelta();
+						PrevPathPDF	 = PathPDF;
+						PathPDF		 = PathPDF * (sout.pdf * scatProb);
+						if (!allLE(PathPDF, 1e-6f)) {
+							Throughput = Throughput * sout.weight;
+							if (sout.isHeroCollapsing()) {
+								Throughput = Throughput * heroOnly();
+								PathPDF	   = PathPDF * heroOnly();
+							}
+							if (!blobIsZero(Throughput, PR_EPSILON)) {
+								uint32_t nf = rayFlags | PRB_RAY_BOUNCE;
+								if (sout.isHeroCollapsing())
+									nf |= PRB_RAY_MONOCHROME;
+								const uint32_t nd = depth + 1;
+								if (nd < st.max_ray_depth) { // Walker::traverse loop bound, vcm/Walker.h:26
+									const V3 oN		 = dot(L, g.N) < 0 ? -g.N : g.N;
+									const V3 nO		 = safePosition(P, L, oN);
+									W.rayO[slot]	 = make_float4(nO.x, nO.y, nO.z, 0.0001f); // BOUNCE_RAY_MIN
+									W.rayD[slot]	 = make_float4(L.x, L.y, L.z, PRB_INF);
+									W.thr[slot]		 = tof4(Throughput);
+									W.pathPDF[slot]	 = tof4(PathPDF);
+									W.prevPDF[slot]	 = tof4(PrevPathPDF);
+									W.lastPos[slot]	 = make_float4(P.x, P.y, P.z, 0);
+									W.flagsDepth[slot] = nd | (nf << FD_FLAGS_SHIFT) | (LastWasDelta ? FD_LAST_DELTA : 0) | (LastWasEmissive ? FD_LAST_EMISSIVE : 0);
+									alive = true;
+									++sBounce;
+									if (nf & PRB_RAY_MONOCHROME)
+										++sMono;
+								}
+							}
+						}
+					}
+					W.rng[pix] = rnd.s;
+				}
+			}
+			W.iterXYZ[slot] = make_float4(acc[0], acc[1], acc[2], 0);
+			pushExtend		= alive;
+			pushRegen		= !alive;
+		}
+		queuePush(W.counters + nextSel, W.qExtend[nextSel], pushExtend, slot);
+		queuePush(W.counters + CNT_SHADOW, W.qShadow, pushShadow, slot);
+		// a path that ended while its last NEE shadow ray is still pending is regenerated only after the shadow
+		// kernel ran (the generate kernel of the NEXT wavefront iteration consumes the regen queue) -> ordering holds
+		queuePush(W.counters + CNT_REGEN, W.qRegen, pushRegen, slot);
+	}
+	statAdd(W.stats, ST_ENTITY_HIT, sEntity);
+	statAdd(W.stats, ST_BG_HIT, sBg);
+	statAdd(W.stats, ST_CAMERA_DEPTH, sDepth);
+	statAdd(W.stats, ST_SHADOW, sShadow);
+	statAdd(W.stats, ST_BOUNCE, sBounce);
+	statAdd(W.stats, ST_CAMERA_RAY, sBounce);
+	statAdd(W.stats, ST_MONO, sMono);
+}
+
+// ------------------------------------------------------------------ shadow
+__global__ void __launch_bounds__(256) k_shadow(DScene S, WFState W)
+{
+	const uint32_t n = W.counters[CNT_SHADOW];
+	for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+		const uint32_t slot = W.qShadow[idx];
+		const float4 o = W.shO[slot], d = W.shD[slot];
+		HitRec h;
+		const bool occluded = traverseScene<true>(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
+		if (!occluded) {
+			const float4 c = W.shXYZ[slot];
+			float4 acc	   = W.iterXYZ[slot];
+			acc.x += c.x;
+			acc.y += c.y;
+			acc.z += c.z;
+			W.iterXYZ[slot] = acc;
+		}
+	}
+}
+
+// ------------------------------------------------------------------ stream tracing (prb_trace_closest / _any)
+__global__ void __launch_bounds__(256) k_trace_closest(DScene S, const float* ox, const float* oy, const float* oz, const float* dx, const float* dy,
+														const float* dz, const float* tmin, const float* tmax, uint32_t n, uint32_t* ent, uint32_t* prim,
+														float* u, float* v, float* t)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		HitRec h;
+		const float t0 = tmin ? tmin[i] : 0.0001f, t1 = tmax ? tmax[i] : PRB_INF;
+		const bool ok = traverseScene<false>(S, mk(ox[i], oy[i], oz[i]), mk(dx[i], dy[i], dz[i]), t0, t1, h);
+		ent[i]		  = ok ? h.entity : PRB_INVALID_ID;
+		prim[i]		  = ok ? h.prim : PRB_INVALID_ID;
+		u[i]		  = ok ? h.u : 0.0f;
+		v[i]		  = ok ? h.v : 0.0f;
+		t[i]		  = ok ? h.t : t1;
+	}
+}
+__global__ void __launch_bounds__(256) k_trace_any(DScene S, const float* ox, const float* oy, const float* oz, const float* dx, const float* dy,
+													const float* dz, const float* tmin, const float* tmax, uint32_t n, uint8_t* occluded)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		HitRec h;
+		const float t0 = tmin ? tmin[i] : 0.0001f, t1 = tmax ? tmax[i] : PRB_INF;
+		occluded[i]	   = traverseScene<true>(S, mk(ox[i], oy[i], oz[i]), mk(dx[i], dy[i], dz[i]), t0, t1, h) ? 1 : 0;
+	}
+}
+
+// camera rays only (prb_generate_camera_rays): does not touch the RNG map
+__global__ void k_camera_rays(DScene S, const uint64_t* rng, const uint32_t* pixels, uint32_t n, uint32_t iteration, float* org, float* dir, float* wvl)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t pix = pixels[i];
+		Rng rnd{ rng[pix] };
+		CameraSampleOut cs;
+		const uint32_t fw = S.settings.film_width;
+		constructCameraRay(S, pix % fw, pix / fw, iteration, rnd, cs);
+		org[3 * i] = cs.origin.x, org[3 * i + 1] = cs.origin.y, org[3 * i + 2] = cs.origin.z;
+		dir[3 * i] = cs.dir.x, dir[3 * i + 1] = cs.dir.y, dir[3 * i + 2] = cs.dir.z;
+		for (int k = 0; k < 4; ++k)
+			wvl[4 * i + k] = cs.wvl[k];
+	}
+}
+
+// unit-level material calls (IMaterial::eval / ::sample)
+__global__ void k_material_eval(DScene S, const prb_material_query* q, uint32_t n, prb_material_result* out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		MatCtx c;
+		c.V = ld3(q[i].V);
+		c.L = ld3(q[i].L);
+		for (int k = 0; k < 4; ++k)
+			c.wvl[k] = q[i].wavelength_nm[k];
+		c.u		   = q[i].uv[0];
+		c.v		   = q[i].uv[1];
+		c.rayFlags = q[i].ray_flags;
+		MatEval e;
+		materialEval(S, q[i].material_id, c, e);
+		for (int k = 0; k < 4; ++k) {
+			out[i].weight[k] = e.weight[k];
+			out[i].pdf_s[k]	 = e.pdf[k];
+		}
+		out[i].L[0] = out[i].L[1] = out[i].L[2] = 0;
+		out[i].flags							= e.flags;
+		out[i].type								= e.type;
+		out[i].rng_state						= q[i].rng_state;
+	}
+}
+__global__ void k_material_sample(DScene S, const prb_material_query* q, uint32_t n, prb_material_result* out)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		MatCtx c;
+		c.V = ld3(q[i].V);
+		c.L = mk(0, 0, 0);
+		for (int k = 0; k < 4; ++k)
+			c.wvl[k] = q[i].wavelength_nm[k];
+		c.u		   = q[i].uv[0];
+		c.v		   = q[i].uv[1];
+		c.rayFlags = q[i].ray_flags;
+		Rng rnd{ q[i].rng_state };
+		MatSample e;
+		materialSample(S, q[i].material_id, c, rnd, e);
+		for (int k = 0; k < 4; ++k) {
+			out[i].weight[k] = e.weight[k];
+			out[i].pdf_s[k]	 = e.pdf[k];
+		}
+		out[i].L[0] = e.L.x, out[i].L[1] = e.L.y, out[i].L[2] = e.L.z;
+		out[i].flags	 = e.flags;
+		out[i].type		 = e.type;
+		out[i].rng_state = rnd.s;
+	}
+}
+
+// pixel filter post pass (FilterCache table, zero padded) and film export / import
+__global__ void k_filter(const float* in, float* out, int W, int H, int r, const float* tab)
+{
+	const int n = W * H;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const int x = i % W, y = i / W;
+		float s[3] = { 0, 0, 0 };
+		const int dia = 2 * r + 1;
+		// gather form of the reference's splat: out[p] = sum_q w(p - q) * in[q]; the table is symmetric
+		for (int dy = -r; dy <= r; ++dy)
+			for (int dx = -r; dx <= r; ++dx) {
+				const int sx = x - dx, sy = y - dy;
+				if (sx < 0 || sy < 0 || sx >= W || sy >= H)
+					continue;
+				const float w = tab[(dy + r) * dia + (dx + r)];
+				if (!(w > PR_EPSILON))
+					continue;
+				for (int c = 0; c < 3; ++c)
+					s[c] += w * in[3 * (sy * W + sx) + c];
+			}
+		out[3 * i] = s[0], out[3 * i + 1] = s[1], out[3 * i + 2] = s[2];
+	}
+}
+__global__ void k_film_export(const float* mean, const uint32_t* count, float* dst, uint32_t n)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		dst[4 * i]	   = mean[3 * i];
+		dst[4 * i + 1] = mean[3 * i + 1];
+		dst[4 * i + 2] = mean[3 * i + 2];
+		dst[4 * i + 3] = (float)count[i];
+	}
+}
+__global__ void k_film_import(const float* src, float* mean, uint32_t* count, uint32_t n)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		mean[3 * i]		= src[4 * i];
+		mean[3 * i + 1] = src[4 * i + 1];
+		mean[3 * i + 2] = src[4 * i + 2];
+		count[i]		= (uint32_t)src[4 * i + 3];
+	}
+}
+} // namespace prb

@@ -1,0 +1,768 @@
+// C-ABI implementation (include/prb200_abi.h) over the CUDA kernels.  sm_100a only; no CPU fallback: every
+// entry point fails with PRB_ERR_NO_DEVICE / PRB_ERR_CUDA when no B200-class device is usable.
+#include "dev_wavefront.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace prb;
+
+namespace {
+thread_local std::string g_err;
+prb_status fail(prb_status code, const std::string& msg)
+{
+	g_err = msg;
+	return code;
+}
+#define CU(x)                                                                                                     \
+	do {                                                                                                          \
+		cudaError_t e_ = (x);                                                                                     \
+		if (e_ != cudaSuccess)                                                                                    \
+			return fail(PRB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));                           \
+	} while (0)
+
+template <typename T>
+struct DBuf {
+	T* p	 = nullptr;
+	size_t n = 0;
+	cudaError_t alloc(size_t count)
+	{
+		if (count <= n && p)
+			return cudaSuccess;
+		release();
+		n = count;
+		if (count == 0)
+			return cudaSuccess;
+		return cudaMalloc(&p, count * sizeof(T));
+	}
+	cudaError_t upload(const T* h, size_t count, cudaStream_t s)
+	{
+		cudaError_t e = alloc(std::max<size_t>(count, 1));
+		if (e != cudaSuccess || count == 0)
+			return e;
+		return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		n = 0;
+	}
+};
+} // namespace
+
+struct prb_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evA = nullptr, evB = nullptr;
+	int smCount = 148;
+	bool haveScene = false;
+	DScene S{};
+	// scene storage
+	DBuf<prb_node> nodes;
+	DBuf<prb_material> materials;
+	DBuf<prb_emission> emissions;
+	DBuf<prb_entity> entities;
+	DBuf<uint32_t> entityMaterials, faceIndices, faceSlots, tlasRefs;
+	DBuf<prb_mesh> meshes;
+	DBuf<float> vertices, normals, uvs, lightCDF, pool, rrProb;
+	DBuf<prb_light> lights;
+	DBuf<uint4> bvhNodes;
+	DBuf<float4> bvhTris;
+	// film
+	DBuf<uint64_t> rng;
+	DBuf<float> filmMean, filmTmp, aov;
+	DBuf<uint32_t> sampleCount;
+	DBuf<unsigned long long> stats;
+	// wavefront
+	DBuf<uint32_t> pixel, iter, flagsDepth, qExtend0, qExtend1, qRegen, qShadow, counters;
+	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ;
+	DBuf<uint4> hit;
+	DBuf<float> hitT;
+	std::vector<prb_tile> cachedTiles;
+	uint32_t nSlots = 0;
+	uint32_t* hostCounters = nullptr; // pinned
+	// generic scratch for the host-pointer entry points
+	DBuf<float> scratchF;
+	DBuf<uint32_t> scratchU;
+	DBuf<uint8_t> scratchB;
+	DBuf<prb_material_query> scratchQ;
+	DBuf<prb_material_result> scratchR;
+	// bookkeeping
+	uint64_t kernelLaunches = 0, wavefrontIterations = 0;
+	float lastMs = 0;
+	cudaGraphExec_t graphExec = nullptr;
+	uint32_t graphSlots = 0;
+	bool wantAOV = true;
+};
+
+extern "C" {
+const char* prb_last_error(void) { return g_err.c_str(); }
+
+int prb_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess)
+		return 0;
+	return n;
+}
+
+prb_status prb_create(int device, prb_ctx** out)
+{
+	if (!out)
+		return fail(PRB_ERR_INVALID_ARG, "out == NULL");
+	*out  = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+		return fail(PRB_ERR_NO_DEVICE, "no CUDA device available (the path has no CPU fallback)");
+	if (device < 0 || device >= n)
+		return fail(PRB_ERR_INVALID_ARG, "invalid device index");
+	CU(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		return fail(PRB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only");
+	auto* c		= new prb_ctx();
+	c->device	= device;
+	c->smCount	= prop.multiProcessorCount;
+	cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&c->evA);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&c->evB);
+	if (e == cudaSuccess)
+		e = cudaMallocHost(&c->hostCounters, CNT__COUNT * sizeof(uint32_t));
+	if (e == cudaSuccess)
+		e = c->stats.alloc(ST__COUNT);
+	if (e == cudaSuccess)
+		e = cudaMemsetAsync(c->stats.p, 0, ST__COUNT * sizeof(unsigned long long), c->stream);
+	if (e != cudaSuccess) {
+		delete c;
+		return fail(PRB_ERR_CUDA, std::string("context set-up failed: ") + cudaGetErrorString(e));
+	}
+	*out = c;
+	return PRB_OK;
+}
+
+void prb_destroy(prb_ctx* c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	if (c->graphExec)
+		cudaGraphExecDestroy(c->graphExec);
+	DBuf<uint32_t>* ub[] = { &c->entityMaterials, &c->faceIndices, &c->faceSlots, &c->tlasRefs, &c->sampleCount, &c->pixel, &c->iter, &c->flagsDepth,
+							 &c->qExtend0, &c->qExtend1, &c->qRegen, &c->qShadow, &c->counters, &c->scratchU };
+	for (auto* b : ub)
+		b->release();
+	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->hitT, &c->scratchF };
+	for (auto* b : fb)
+		b->release();
+	DBuf<float4>* f4[] = { &c->bvhTris, &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ };
+	for (auto* b : f4)
+		b->release();
+	c->nodes.release();
+	c->materials.release();
+	c->emissions.release();
+	c->entities.release();
+	c->meshes.release();
+	c->lights.release();
+	c->bvhNodes.release();
+	c->rng.release();
+	c->stats.release();
+	c->hit.release();
+	c->scratchB.release();
+	c->scratchQ.release();
+	c->scratchR.release();
+	if (c->hostCounters)
+		cudaFreeHost(c->hostCounters);
+	cudaEventDestroy(c->evA);
+	cudaEventDestroy(c->evB);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
+{
+	if (!c || !d)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (d->abi_version != PRB_ABI_VERSION)
+		return fail(PRB_ERR_INVALID_ARG, "scene descriptor ABI version mismatch");
+	static_assert(sizeof(prb_bvh8_node) == 80, "node must be 80 bytes");
+	static_assert(sizeof(prb_bvh_tri) == 48, "triangle must be 48 bytes");
+	CU(cudaSetDevice(c->device));
+	cudaStream_t s = c->stream;
+	CU(c->nodes.upload(d->nodes, d->n_nodes, s));
+	CU(c->materials.upload(d->materials, d->n_materials, s));
+	CU(c->emissions.upload(d->emissions, d->n_emissions, s));
+	CU(c->entities.upload(d->entities, d->n_entities, s));
+	CU(c->entityMaterials.upload(d->entity_materials, d->n_entity_materials, s));
+	CU(c->meshes.upload(d->meshes, d->n_meshes, s));
+	CU(c->vertices.upload(d->vertices, (size_t)d->n_vertices * 3, s));
+	CU(c->normals.upload(d->normals, (size_t)d->n_vertices * 3, s));
+	CU(c->uvs.upload(d->uvs, (size_t)d->n_vertices * 2, s));
+	CU(c->faceIndices.upload(d->face_indices, (size_t)d->n_faces * 4, s));
+	CU(c->faceSlots.upload(d->face_slots, d->n_faces, s));
+	CU(c->lights.upload(d->lights, d->n_lights, s));
+	CU(c->lightCDF.upload(d->light_cdf, (size_t)d->n_lights + 1, s));
+	CU(c->bvhNodes.upload(reinterpret_cast<const uint4*>(d->bvh_nodes), (size_t)d->n_bvh_nodes * 5, s));
+	CU(c->bvhTris.upload(reinterpret_cast<const float4*>(d->bvh_tris), (size_t)d->n_bvh_tris * 3, s));
+	CU(c->tlasRefs.upload(d->tlas_refs, d->n_tlas_refs, s));
+	CU(c->pool.upload(d->pool, d->n_pool, s));
+	// RussianRoulette::probability table (vcm/RussianRoulette.h:22-34): min(1, pow(0.9f, len - soft)) evaluated in
+	// double and rounded to float exactly like std::pow(float, size_t) does on the host
+	const uint32_t soft = d->settings.soft_max_ray_depth;
+	const uint32_t nrr	= std::max(d->settings.max_ray_depth, soft) + 5;
+	std::vector<float> rr(nrr, 1.0f);
+	for (uint32_t len = 0; len < nrr; ++len)
+		if (len >= soft) {
+			const float p = std::min<float>(1.0f, (float)std::pow((double)0.9f, (double)(len - soft)));
+			rr[len]		  = p <= 1e-4f ? 0.0f : p;
+		}
+	CU(c->rrProb.upload(rr.data(), rr.size(), s));
+	const size_t npix = (size_t)d->settings.film_width * d->settings.film_height;
+	CU(c->rng.alloc(npix));
+	CU(c->filmMean.alloc(npix * 3));
+	CU(c->filmTmp.alloc(npix * 4));
+	CU(c->sampleCount.alloc(npix));
+	CU(c->aov.alloc(npix * 10));
+	CU(cudaMemsetAsync(c->filmMean.p, 0, npix * 3 * sizeof(float), s));
+	CU(cudaMemsetAsync(c->sampleCount.p, 0, npix * sizeof(uint32_t), s));
+	CU(cudaMemsetAsync(c->aov.p, 0, npix * 10 * sizeof(float), s));
+	CU(cudaMemsetAsync(c->rng.p, 0, npix * sizeof(uint64_t), s));
+	DScene& S		  = c->S;
+	S.settings		  = d->settings;
+	S.camera		  = d->camera;
+	S.aa			  = d->aa_sampler;
+	S.lens			  = d->lens_sampler;
+	S.time			  = d->time_sampler;
+	S.mapper		  = d->pixel_mapper;
+	S.nodes			  = c->nodes.p;
+	S.materials		  = c->materials.p;
+	S.emissions		  = c->emissions.p;
+	S.entities		  = c->entities.p;
+	S.entityMaterials = c->entityMaterials.p;
+	S.meshes		  = c->meshes.p;
+	S.vertices		  = c->vertices.p;
+	S.normals		  = c->normals.p;
+	S.uvs			  = c->uvs.p;
+	S.faceIndices	  = c->faceIndices.p;
+	S.faceSlots		  = c->faceSlots.p;
+	S.lights		  = c->lights.p;
+	S.lightCDF		  = c->lightCDF.p;
+	S.bvhNodes		  = c->bvhNodes.p;
+	S.bvhTris		  = c->bvhTris.p;
+	S.tlasRefs		  = c->tlasRefs.p;
+	S.pool			  = c->pool.p;
+	S.rrProb		  = c->rrProb.p;
+	S.rrCount		  = nrr;
+	S.nMaterials	  = d->n_materials;
+	S.nEmissions	  = d->n_emissions;
+	S.nEntities		  = d->n_entities;
+	S.nLights		  = d->n_lights;
+	S.nMeshes		  = d->n_meshes;
+	S.tlasRoot		  = d->tlas_root;
+	S.cieOffset		  = d->cie_offset;
+	S.hasEnvLight	  = 0;
+	for (uint32_t i = 0; i < d->n_lights; ++i)
+		if (d->lights[i].type == PRB_LIGHT_ENV)
+			S.hasEnvLight = 1;
+	CU(cudaStreamSynchronize(s));
+	c->haveScene = true;
+	c->cachedTiles.clear();
+	c->nSlots = 0;
+	return PRB_OK;
+}
+
+prb_status prb_upload_rng(prb_ctx* c, const uint64_t* states, size_t n)
+{
+	if (!c || !states)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (n != (size_t)c->S.settings.film_width * c->S.settings.film_height)
+		return fail(PRB_ERR_INVALID_ARG, "rng state count must be film_width*film_height");
+	CU(cudaSetDevice(c->device));
+	CU(cudaMemcpyAsync(c->rng.p, states, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_download_rng(prb_ctx* c, uint64_t* states, size_t n)
+{
+	if (!c || !states)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (n != (size_t)c->S.settings.film_width * c->S.settings.film_height)
+		return fail(PRB_ERR_INVALID_ARG, "rng state count must be film_width*film_height");
+	CU(cudaSetDevice(c->device));
+	CU(cudaMemcpyAsync(states, c->rng.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+
+prb_status prb_film_clear(prb_ctx* c)
+{
+	if (!c || !c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	CU(cudaSetDevice(c->device));
+	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
+	CU(cudaMemsetAsync(c->filmMean.p, 0, npix * 3 * sizeof(float), c->stream));
+	CU(cudaMemsetAsync(c->sampleCount.p, 0, npix * sizeof(uint32_t), c->stream));
+	CU(cudaMemsetAsync(c->aov.p, 0, npix * 10 * sizeof(float), c->stream));
+	return PRB_OK;
+}
+
+static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
+{
+	const bool same = c->cachedTiles.size() == n_tiles && (n_tiles == 0 || std::memcmp(c->cachedTiles.data(), tiles, n_tiles * sizeof(prb_tile)) == 0);
+	if (same && c->nSlots > 0)
+		return PRB_OK;
+	const uint32_t W = c->S.settings.film_width, H = c->S.settings.film_height;
+	std::vector<uint32_t> pix;
+	for (size_t t = 0; t < n_tiles; ++t) {
+		if (tiles[t].ex > W || tiles[t].ey > H || tiles[t].sx >= tiles[t].ex || tiles[t].sy >= tiles[t].ey)
+			return fail(PRB_ERR_INVALID_ARG, "tile outside the film");
+		for (uint32_t y = tiles[t].sy; y < tiles[t].ey; ++y)
+			for (uint32_t x = tiles[t].sx; x < tiles[t].ex; ++x)
+				pix.push_back(y * W + x);
+	}
+	const size_t n = pix.size();
+	CU(c->pixel.upload(pix.data(), n, c->stream));
+	CU(c->iter.alloc(n));
+	CU(c->flagsDepth.alloc(n));
+	CU(c->qExtend0.alloc(n));
+	CU(c->qExtend1.alloc(n));
+	CU(c->qRegen.alloc(n));
+	CU(c->qShadow.alloc(n));
+	CU(c->counters.alloc(CNT__COUNT));
+	DBuf<float4>* f4[] = { &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ };
+	for (auto* b : f4)
+		CU(b->alloc(n));
+	CU(c->hit.alloc(n));
+	CU(c->hitT.alloc(n));
+	CU(cudaStreamSynchronize(c->stream));
+	c->cachedTiles.assign(tiles, tiles + n_tiles);
+	c->nSlots = (uint32_t)n;
+	return PRB_OK;
+}
+
+static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
+{
+	WFState W{};
+	W.pixel		  = c->pixel.p;
+	W.iter		  = c->iter.p;
+	W.rayO		  = c->rayO.p;
+	W.rayD		  = c->rayD.p;
+	W.wvl		  = c->wvl.p;
+	W.flagsDepth  = c->flagsDepth.p;
+	W.thr		  = c->thr.p;
+	W.pathPDF	  = c->pathPDF.p;
+	W.prevPDF	  = c->prevPDF.p;
+	W.wvlPDF	  = c->wvlPDF.p;
+	W.lastPos	  = c->lastPos.p;
+	W.hit		  = c->hit.p;
+	W.hitT		  = c->hitT.p;
+	W.shO		  = c->shO.p;
+	W.shD		  = c->shD.p;
+	W.shXYZ		  = c->shXYZ.p;
+	W.iterXYZ	  = c->iterXYZ.p;
+	W.qExtend[0]  = c->qExtend0.p;
+	W.qExtend[1]  = c->qExtend1.p;
+	W.qRegen	  = c->qRegen.p;
+	W.qShadow	  = c->qShadow.p;
+	W.counters	  = c->counters.p;
+	W.rng		  = c->rng.p;
+	W.filmMean	  = c->filmMean.p;
+	W.sampleCount = c->sampleCount.p;
+	W.aov		  = c->wantAOV ? c->aov.p : nullptr;
+	W.stats		  = c->stats.p;
+	W.nSlots	  = c->nSlots;
+	W.firstIter	  = first;
+	W.endIter	  = first + count;
+	return W;
+}
+
+prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count)
+{
+	if (!c || !tiles)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (n_tiles == 0 || iteration_count == 0)
+		return PRB_OK;
+	CU(cudaSetDevice(c->device));
+	prb_status st = setupSlots(c, tiles, n_tiles);
+	if (st != PRB_OK)
+		return st;
+	cudaStream_t s = c->stream;
+	const WFState W = makeWF(c, first_iteration, iteration_count);
+	const int grid	= c->smCount * 4;
+	CU(cudaEventRecord(c->evA, s));
+	CU(cudaMemsetAsync(c->counters.p, 0, CNT__COUNT * sizeof(uint32_t), s));
+	k_init_slots<<<grid, 256, 0, s>>>(W);
+	CU(cudaMemcpyAsync(c->counters.p + CNT_REGEN, &c->nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+	c->kernelLaunches += 1;
+	// one wavefront iteration = generate -> extend -> shade -> shadow; 2 iterations (both queue parities) form one
+	// CUDA graph that is replayed; the retired-slot counter is polled every few replays.
+	auto enqueueIteration = [&](int sel) -> cudaError_t {
+		cudaError_t e = cudaMemsetAsync(c->counters.p + (1 - sel), 0, sizeof(uint32_t), s);
+		if (e != cudaSuccess)
+			return e;
+		k_generate<<<grid, 256, 0, s>>>(c->S, W, sel);
+		e = cudaMemsetAsync(c->counters.p + CNT_REGEN, 0, sizeof(uint32_t), s);
+		if (e != cudaSuccess)
+			return e;
+		k_extend<<<grid, 256, 0, s>>>(c->S, W, sel);
+		e = cudaMemsetAsync(c->counters.p + CNT_SHADOW, 0, sizeof(uint32_t), s);
+		if (e != cudaSuccess)
+			return e;
+		k_shade<<<c->smCount * 8, 128, 0, s>>>(c->S, W, sel);
+		k_shadow<<<grid, 256, 0, s>>>(c->S, W);
+		return cudaGetLastError();
+	};
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t exec = nullptr;
+	CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+	cudaError_t ce = enqueueIteration(0);
+	if (ce == cudaSuccess)
+		ce = enqueueIteration(1);
+	cudaError_t ee = cudaStreamEndCapture(s, &graph);
+	if (ce != cudaSuccess || ee != cudaSuccess) {
+		if (graph)
+			cudaGraphDestroy(graph);
+		return fail(PRB_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+	}
+	CU(cudaGraphInstantiate(&exec, graph, 0));
+	cudaGraphDestroy(graph);
+	// upper bound on wavefront iterations: every sample needs at most max_ray_depth+1 iterations
+	const uint64_t maxIters = (uint64_t)iteration_count * (c->S.settings.max_ray_depth + 2) + 8;
+	uint64_t done = 0;
+	const int replaysPerPoll = 16;
+	bool finished = false;
+	while (!finished && done < maxIters + 2 * replaysPerPoll) {
+		for (int r = 0; r < replaysPerPoll; ++r) {
+			cudaError_t e = cudaGraphLaunch(exec, s);
+			if (e != cudaSuccess) {
+				cudaGraphExecDestroy(exec);
+				return fail(PRB_ERR_CUDA, std::string("graph launch failed: ") + cudaGetErrorString(e));
+			}
+		}
+		done += 2 * replaysPerPoll;
+		c->kernelLaunches += 8 * replaysPerPoll;
+		cudaError_t e = cudaMemcpyAsync(c->hostCounters, c->counters.p, CNT__COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(s);
+		if (e != cudaSuccess) {
+			cudaGraphExecDestroy(exec);
+			return fail(PRB_ERR_CUDA, std::string("wavefront loop failed: ") + cudaGetErrorString(e));
+		}
+		finished = c->hostCounters[CNT_RETIRED] >= c->nSlots;
+	}
+	cudaGraphExecDestroy(exec);
+	c->wavefrontIterations += done;
+	CU(cudaEventRecord(c->evB, s));
+	CU(cudaEventSynchronize(c->evB));
+	CU(cudaEventElapsedTime(&c->lastMs, c->evA, c->evB));
+	if (!finished)
+		return fail(PRB_ERR_CUDA, "wavefront loop did not terminate within the iteration bound");
+	return PRB_OK;
+}
+
+prb_status prb_sync(prb_ctx* c)
+{
+	if (!c)
+		return fail(PRB_ERR_INVALID_ARG, "null context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+
+static prb_status filteredFilm(prb_ctx* c, float** out)
+{
+	const prb_settings& st = c->S.settings;
+	const int r			   = st.filter_radius;
+	bool identity		   = true; // centre weight 1, everything else <= eps (e.g. mitchell radius 1)
+	if (r > 0)
+		identity = false;
+	if (identity) {
+		*out = c->filmMean.p;
+		return PRB_OK;
+	}
+	k_filter<<<c->smCount * 4, 256, 0, c->stream>>>(c->filmMean.p, c->filmTmp.p, (int)st.film_width, (int)st.film_height, r, c->pool.p + st.filter_offset);
+	c->kernelLaunches++;
+	CU(cudaGetLastError());
+	*out = c->filmTmp.p;
+	return PRB_OK;
+}
+
+prb_status prb_film_download(prb_ctx* c, float* xyz, uint32_t* sample_count)
+{
+	if (!c || !c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	CU(cudaSetDevice(c->device));
+	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
+	if (xyz) {
+		float* src = nullptr;
+		prb_status st = filteredFilm(c, &src);
+		if (st != PRB_OK)
+			return st;
+		CU(cudaMemcpyAsync(xyz, src, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	}
+	if (sample_count)
+		CU(cudaMemcpyAsync(sample_count, c->sampleCount.p, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_film_download_aov(prb_ctx* c, float* aov10)
+{
+	if (!c || !c->haveScene || !aov10)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded / null buffer");
+	CU(cudaSetDevice(c->device));
+	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
+	CU(cudaMemcpyAsync(aov10, c->aov.p, npix * 10 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_film_export_device(prb_ctx* c, float* device_dst)
+{
+	if (!c || !c->haveScene || !device_dst)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded / null buffer");
+	CU(cudaSetDevice(c->device));
+	const uint32_t npix = c->S.settings.film_width * c->S.settings.film_height;
+	k_film_export<<<c->smCount * 4, 256, 0, c->stream>>>(c->filmMean.p, c->sampleCount.p, device_dst, npix);
+	c->kernelLaunches++;
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_film_import_device(prb_ctx* c, const float* device_src)
+{
+	if (!c || !c->haveScene || !device_src)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded / null buffer");
+	CU(cudaSetDevice(c->device));
+	const uint32_t npix = c->S.settings.film_width * c->S.settings.film_height;
+	k_film_import<<<c->smCount * 4, 256, 0, c->stream>>>(device_src, c->filmMean.p, c->sampleCount.p, npix);
+	c->kernelLaunches++;
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+
+// ------------------------------------------------------------------ stream tracing
+static prb_status traceDevice(prb_ctx* c, const prb_ray_soa* r, size_t n, prb_hit_soa* hits, uint8_t* occluded)
+{
+	const int grid = c->smCount * 4;
+	CU(cudaEventRecord(c->evA, c->stream));
+	if (hits)
+		k_trace_closest<<<grid, 256, 0, c->stream>>>(c->S, r->org_x, r->org_y, r->org_z, r->dir_x, r->dir_y, r->dir_z, r->tmin, r->tmax, (uint32_t)n,
+													  hits->entity_id, hits->primitive_id, hits->u, hits->v, hits->t);
+	else
+		k_trace_any<<<grid, 256, 0, c->stream>>>(c->S, r->org_x, r->org_y, r->org_z, r->dir_x, r->dir_y, r->dir_z, r->tmin, r->tmax, (uint32_t)n, occluded);
+	c->kernelLaunches++;
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->evB, c->stream));
+	CU(cudaEventSynchronize(c->evB));
+	CU(cudaEventElapsedTime(&c->lastMs, c->evA, c->evB));
+	return PRB_OK;
+}
+prb_status prb_trace_closest_device(prb_ctx* c, const prb_ray_soa* rays, size_t n, prb_hit_soa* hits)
+{
+	if (!c || !rays || !hits)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (n == 0)
+		return PRB_OK;
+	CU(cudaSetDevice(c->device));
+	return traceDevice(c, rays, n, hits, nullptr);
+}
+prb_status prb_trace_any_device(prb_ctx* c, const prb_ray_soa* rays, size_t n, uint8_t* occluded)
+{
+	if (!c || !rays || !occluded)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (n == 0)
+		return PRB_OK;
+	CU(cudaSetDevice(c->device));
+	return traceDevice(c, rays, n, nullptr, occluded);
+}
+static prb_status stageRays(prb_ctx* c, const prb_ray_soa* rays, size_t n, prb_ray_soa& dev)
+{
+	CU(c->scratchF.alloc(n * 8));
+	const float* src[8] = { rays->org_x, rays->org_y, rays->org_z, rays->dir_x, rays->dir_y, rays->dir_z, rays->tmin, rays->tmax };
+	const float* dst[8];
+	for (int k = 0; k < 8; ++k) {
+		if (!src[k]) {
+			if (k < 6)
+				return fail(PRB_ERR_INVALID_ARG, "ray origin/direction arrays must not be NULL");
+			dst[k] = nullptr;
+			continue;
+		}
+		CU(cudaMemcpyAsync(c->scratchF.p + k * n, src[k], n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+		dst[k] = c->scratchF.p + k * n;
+	}
+	dev = prb_ray_soa{ dst[0], dst[1], dst[2], dst[3], dst[4], dst[5], dst[6], dst[7] };
+	return PRB_OK;
+}
+prb_status prb_trace_closest(prb_ctx* c, const prb_ray_soa* rays, size_t n, prb_hit_soa* hits)
+{
+	if (!c || !rays || !hits)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (n == 0)
+		return PRB_OK;
+	CU(cudaSetDevice(c->device));
+	prb_ray_soa dr;
+	prb_status st = stageRays(c, rays, n, dr);
+	if (st != PRB_OK)
+		return st;
+	CU(c->scratchU.alloc(n * 5));
+	prb_hit_soa dh{ c->scratchU.p, c->scratchU.p + n, reinterpret_cast<float*>(c->scratchU.p + 2 * n), reinterpret_cast<float*>(c->scratchU.p + 3 * n),
+					reinterpret_cast<float*>(c->scratchU.p + 4 * n) };
+	st = traceDevice(c, &dr, n, &dh, nullptr);
+	if (st != PRB_OK)
+		return st;
+	CU(cudaMemcpyAsync(hits->entity_id, dh.entity_id, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hits->primitive_id, dh.primitive_id, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hits->u, dh.u, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hits->v, dh.v, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(hits->t, dh.t, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_trace_any(prb_ctx* c, const prb_ray_soa* rays, size_t n, uint8_t* occluded)
+{
+	if (!c || !rays || !occluded)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (n == 0)
+		return PRB_OK;
+	CU(cudaSetDevice(c->device));
+	prb_ray_soa dr;
+	prb_status st = stageRays(c, rays, n, dr);
+	if (st != PRB_OK)
+		return st;
+	CU(c->scratchB.alloc(n));
+	st = traceDevice(c, &dr, n, nullptr, c->scratchB.p);
+	if (st != PRB_OK)
+		return st;
+	CU(cudaMemcpyAsync(occluded, c->scratchB.p, n, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+
+prb_status prb_generate_camera_rays(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, uint32_t iteration, float* org_xyz, float* dir_xyz,
+									float* wavelengths4, uint32_t* pixel_index, size_t capacity, size_t* n_out)
+{
+	if (!c || !tiles || !org_xyz || !dir_xyz || !wavelengths4 || !pixel_index || !n_out)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	CU(cudaSetDevice(c->device));
+	const uint32_t W = c->S.settings.film_width, H = c->S.settings.film_height;
+	std::vector<uint32_t> pix;
+	for (size_t t = 0; t < n_tiles; ++t) {
+		if (tiles[t].ex > W || tiles[t].ey > H)
+			return fail(PRB_ERR_INVALID_ARG, "tile outside the film");
+		for (uint32_t y = tiles[t].sy; y < tiles[t].ey; ++y)
+			for (uint32_t x = tiles[t].sx; x < tiles[t].ex; ++x)
+				if (pix.size() < capacity)
+					pix.push_back(y * W + x);
+	}
+	const size_t n = pix.size();
+	*n_out		   = n;
+	if (n == 0)
+		return PRB_OK;
+	CU(c->scratchU.upload(pix.data(), n, c->stream));
+	CU(c->scratchF.alloc(n * 10));
+	float *dorg = c->scratchF.p, *ddir = c->scratchF.p + 3 * n, *dwvl = c->scratchF.p + 6 * n;
+	k_camera_rays<<<c->smCount * 4, 256, 0, c->stream>>>(c->S, c->rng.p, c->scratchU.p, (uint32_t)n, iteration, dorg, ddir, dwvl);
+	c->kernelLaunches++;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(org_xyz, dorg, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(dir_xyz, ddir, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(wavelengths4, dwvl, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	std::memcpy(pixel_index, pix.data(), n * sizeof(uint32_t));
+	return PRB_OK;
+}
+
+static prb_status materialCall(prb_ctx* c, const prb_material_query* q, size_t n, prb_material_result* out, bool sample)
+{
+	if (!c || !q || !out)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	for (size_t i = 0; i < n; ++i)
+		if (q[i].material_id >= c->S.nMaterials)
+			return fail(PRB_ERR_INVALID_ARG, "material id out of range");
+	if (n == 0)
+		return PRB_OK;
+	CU(cudaSetDevice(c->device));
+	CU(c->scratchQ.upload(q, n, c->stream));
+	CU(c->scratchR.alloc(n));
+	const int grid = (int)std::min<size_t>((n + 127) / 128, (size_t)c->smCount * 4);
+	if (sample)
+		k_material_sample<<<grid, 128, 0, c->stream>>>(c->S, c->scratchQ.p, (uint32_t)n, c->scratchR.p);
+	else
+		k_material_eval<<<grid, 128, 0, c->stream>>>(c->S, c->scratchQ.p, (uint32_t)n, c->scratchR.p);
+	c->kernelLaunches++;
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, c->scratchR.p, n * sizeof(prb_material_result), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_material_eval(prb_ctx* c, const prb_material_query* q, size_t n, prb_material_result* out) { return materialCall(c, q, n, out, false); }
+prb_status prb_material_sample(prb_ctx* c, const prb_material_query* q, size_t n, prb_material_result* out) { return materialCall(c, q, n, out, true); }
+
+prb_status prb_get_stats(prb_ctx* c, prb_stats* out)
+{
+	if (!c || !out)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	CU(cudaSetDevice(c->device));
+	unsigned long long h[ST__COUNT];
+	CU(cudaMemcpyAsync(h, c->stats.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	out->camera_ray_count	  = h[ST_CAMERA_RAY];
+	out->light_ray_count	  = h[ST_LIGHT_RAY];
+	out->primary_ray_count	  = h[ST_PRIMARY];
+	out->bounce_ray_count	  = h[ST_BOUNCE];
+	out->shadow_ray_count	  = h[ST_SHADOW];
+	out->monochrome_ray_count = h[ST_MONO];
+	out->pixel_sample_count	  = h[ST_PIXEL_SAMPLE];
+	out->entity_hit_count	  = h[ST_ENTITY_HIT];
+	out->background_hit_count = h[ST_BG_HIT];
+	out->camera_depth_count	  = h[ST_CAMERA_DEPTH];
+	out->light_depth_count	  = h[ST_LIGHT_DEPTH];
+	out->kernel_launches	  = c->kernelLaunches;
+	out->wavefront_iterations = c->wavefrontIterations;
+	return PRB_OK;
+}
+prb_status prb_reset_stats(prb_ctx* c)
+{
+	if (!c)
+		return fail(PRB_ERR_INVALID_ARG, "null context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaMemsetAsync(c->stats.p, 0, ST__COUNT * sizeof(unsigned long long), c->stream));
+	c->kernelLaunches	   = 0;
+	c->wavefrontIterations = 0;
+	return PRB_OK;
+}
+prb_status prb_last_device_ms(prb_ctx* c, float* ms)
+{
+	if (!c || !ms)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	*ms = c->lastMs;
+	return PRB_OK;
+}
+}

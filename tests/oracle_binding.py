@@ -1,0 +1,151 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY (the checker, never the product)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import pearray_b200 as prb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        l = C.CDLL(path)
+        l.orc_scene_create.restype = C.c_void_p
+        l.orc_scene_create.argtypes = [C.POINTER(prb.SceneDesc)]
+        l.orc_scene_destroy.argtypes = [C.c_void_p]
+        l.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(prb.Tile), C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int]
+        l.orc_apply_filter.argtypes = [C.POINTER(prb.SceneDesc), C.c_void_p, C.c_void_p]
+        l.orc_trace_closest.argtypes = [C.c_void_p, C.POINTER(prb.RaySoA), C.c_size_t, C.POINTER(prb.HitSoA), C.c_int]
+        l.orc_trace_any.argtypes = [C.c_void_p, C.POINTER(prb.RaySoA), C.c_size_t, C.c_void_p, C.c_int]
+        l.orc_generate_camera_rays.restype = C.c_size_t
+        l.orc_generate_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(prb.Tile), C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_size_t]
+        l.orc_material_eval.argtypes = [C.c_void_p, C.POINTER(prb.MaterialQuery), C.c_size_t, C.POINTER(prb.MaterialResult)]
+        l.orc_material_sample.argtypes = [C.c_void_p, C.POINTER(prb.MaterialQuery), C.c_size_t, C.POINTER(prb.MaterialResult)]
+        for n in ("orc_fresnel_dielectric", "orc_fresnel_schlick"):
+            getattr(l, n).restype = C.c_float
+            getattr(l, n).argtypes = [C.c_float] * 3
+        l.orc_fresnel_conductor.restype = C.c_float
+        l.orc_fresnel_conductor.argtypes = [C.c_float] * 4
+        for n in ("orc_ndf_ggx_iso", "orc_pdf_ggx_iso"):
+            getattr(l, n).restype = C.c_float
+            getattr(l, n).argtypes = [C.c_void_p, C.c_float]
+        for n in ("orc_ndf_ggx_aniso", "orc_pdf_ggx_aniso"):
+            getattr(l, n).restype = C.c_float
+            getattr(l, n).argtypes = [C.c_void_p, C.c_float, C.c_float]
+        l.orc_microfacet_reflection_eval_conductor.restype = C.c_float
+        l.orc_microfacet_reflection_eval_conductor.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float]
+        l.orc_reflect.argtypes = [C.c_void_p] * 3
+        l.orc_refract.argtypes = [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        l.orc_halfway_reflection.argtypes = [C.c_void_p] * 3
+        l.orc_cos_hemi.argtypes = [C.c_float, C.c_float, C.c_void_p]
+        l.orc_tangent_frame.argtypes = [C.c_void_p] * 3
+        l.orc_random_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        l.orc_eval_node.restype = C.c_float
+        l.orc_eval_node.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float]
+        _lib = l
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def f3(v):
+    return np.ascontiguousarray(v, dtype=np.float32)
+
+
+class OracleScene:
+    def __init__(self, scene):
+        self.scene = scene
+        self._h = lib().orc_scene_create(scene.desc)
+
+    def render(self, tiles, first_iteration, iteration_count, rng=None, threads=None, film=None, count=None, aov=True):
+        """returns dict(film (unfiltered mean), filtered, count, aov, stats, rng)"""
+        w, h = self.scene.width, self.scene.height
+        rng = self.scene.rng_map() if rng is None else np.array(rng, dtype=np.uint64, copy=True)
+        film = np.zeros((h, w, 3), np.float32) if film is None else film
+        count = np.zeros((h, w), np.uint32) if count is None else count
+        aovb = np.zeros((h, w, 10), np.float32) if aov else None
+        stats = np.zeros(11, np.uint64)
+        threads = threads or os.cpu_count() or 1
+        arr = prb.make_tiles(tiles)
+        lib().orc_render(self._h, _p(rng), arr, len(tiles), first_iteration, iteration_count, _p(film), _p(count),
+                         _p(aovb) if aov else None, _p(stats), threads)
+        filtered = np.empty_like(film)
+        lib().orc_apply_filter(self.scene.desc, _p(film), _p(filtered))
+        names = ["camera_ray_count", "light_ray_count", "primary_ray_count", "bounce_ray_count", "shadow_ray_count", "monochrome_ray_count",
+                 "pixel_sample_count", "entity_hit_count", "background_hit_count", "camera_depth_count", "light_depth_count"]
+        return dict(film=film, filtered=filtered, count=count, aov=aovb, stats=dict(zip(names, (int(x) for x in stats))), rng=rng)
+
+    @staticmethod
+    def _soa(o, d, tmin, tmax, keep):
+        cols = [np.ascontiguousarray(o[:, i], dtype=np.float32) for i in range(3)] + [np.ascontiguousarray(d[:, i], dtype=np.float32) for i in range(3)]
+        cols.append(None if tmin is None else np.ascontiguousarray(tmin, dtype=np.float32))
+        cols.append(None if tmax is None else np.ascontiguousarray(tmax, dtype=np.float32))
+        keep.extend(cols)
+        return prb.RaySoA(*[None if c is None else c.ctypes.data for c in cols])
+
+    def trace_closest(self, origins, dirs, tmin=None, tmax=None, threads=None):
+        n = len(origins)
+        keep = []
+        rays = self._soa(np.asarray(origins), np.asarray(dirs), tmin, tmax, keep)
+        ent = np.empty(n, np.uint32); prim = np.empty(n, np.uint32)
+        u = np.empty(n, np.float32); v = np.empty(n, np.float32); t = np.empty(n, np.float32)
+        hits = prb.HitSoA(ent.ctypes.data, prim.ctypes.data, u.ctypes.data, v.ctypes.data, t.ctypes.data)
+        lib().orc_trace_closest(self._h, C.byref(rays), n, C.byref(hits), threads or os.cpu_count() or 1)
+        return ent, prim, u, v, t
+
+    def trace_any(self, origins, dirs, tmin=None, tmax=None, threads=None):
+        n = len(origins)
+        keep = []
+        rays = self._soa(np.asarray(origins), np.asarray(dirs), tmin, tmax, keep)
+        occ = np.empty(n, np.uint8)
+        lib().orc_trace_any(self._h, C.byref(rays), n, _p(occ), threads or os.cpu_count() or 1)
+        return occ
+
+    def generate_camera_rays(self, tiles, iteration, rng=None):
+        rng = self.scene.rng_map() if rng is None else rng
+        arr = prb.make_tiles(tiles)
+        cap = sum((t[2] - t[0]) * (t[3] - t[1]) for t in tiles)
+        org = np.empty((cap, 3), np.float32); dr = np.empty((cap, 3), np.float32)
+        wvl = np.empty((cap, 4), np.float32); pix = np.empty(cap, np.uint32)
+        n = lib().orc_generate_camera_rays(self._h, _p(rng), arr, len(tiles), iteration, _p(org), _p(dr), _p(wvl), _p(pix), cap)
+        return org[:n], dr[:n], wvl[:n], pix[:n]
+
+    def material_eval(self, queries):
+        out = (prb.MaterialResult * len(queries))()
+        lib().orc_material_eval(self._h, queries, len(queries), out)
+        return out
+
+    def material_sample(self, queries):
+        out = (prb.MaterialResult * len(queries))()
+        lib().orc_material_sample(self._h, queries, len(queries), out)
+        return out
+
+    def eval_node(self, node, wavelength, u=0.0, v=0.0):
+        return float(lib().orc_eval_node(self._h, node, wavelength, u, v))
+
+    def close(self):
+        if self._h:
+            lib().orc_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
