@@ -432,10 +432,13 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, WFState W, int extendSe
 					// -------- handleScattering, direct.cpp:170-230
 					const float scatProb = rrProbability(S, depth + 1, onlyDelta);
 					bool scatter		 = scatProb > PR_EPSILON;
-					if (scatter && scatProb < 1.0f) {
-						if (rnd.getFloat() > scatProb)
-							scatter = false;
-					}
+					// RussianRoulette::check: one draw only when 0 < p < 1.  Written branch-free on purpose: the nested form
+					// `if (p < 1) { if (draw > p) scatter = false; }` is folded to "always kill" by nvcc 12.9's NVVM here
+					// (seen in the PTX; caught by the oracle parity test), this form is compiled faithfully.
+					float rrDraw = 0.0f;
+					if (scatter && scatProb < 1.0f)
+						rrDraw = rnd.getFloat();
+					scatter = scatter && !(rrDraw > scatProb);
 					if (scatter) {
 						MatSample sout;
 						mc.L = mk(0, 0, 0);
