@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""bench.py -- spectral path samples/s of the 'direct' (unidirectional PT) hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene c2] [--partition samples|tiles]
+
+Workload (BASELINE.json configs[1]): cornellbox.prc, 500x500, 'direct' integrator depth 6, mjitt sampler,
+1024 spp, diffuse materials + one area light.  One "step" = one complete render of that configuration
+(500*500*1024 = 262 144 000 spectral path samples, 4 wavelengths each) through prb_render_tiles.
+
+Our arm prints one JSON line:
+  value   samples/s with the scene, RNG map and film resident in HBM (CUDA events via the C ABI, max over ranks)
+  e2e     samples/s through the C ABI with HOST buffers: per step the RNG map is uploaded, the tiles rendered and the
+          film (xyz + sample counts) downloaded inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches as the contract asks (see DESIGN.md section "Measurement").
+Multi-GPU (torchrun, one rank per GPU): scene replicated, work partitioned by sample ranges (default; every rank
+renders the full film for its own 1024-iteration range with a decorrelated RNG map -> weak scaling) or by interleaved
+tiles (--partition tiles; bit-identical to 1 GPU, strong scaling); films combined by one NCCL reduce to rank 0
+inside the timed region.
+
+--impl reference: the reference's own CPU implementation cannot be built here (Eigen/Embree/TBB/OIIO absent, SURVEY
+F4), so the arm times oracle/ (the CPU restatement, std::thread x all host cores) on a bounded sample of the same
+workload.  This file and tests/ are the only places that execute oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SCENES = {
+    "c1": ("c1_sphere.prc", "sphere.prc 1000x1000 direct sobol 64spp"),
+    "c2": ("c2_cornellbox.prc", "cornellbox.prc 500x500 direct(depth 6) mjitt 1024spp"),
+    "c3": ("c3_cornellbox_glassy.prc", "cornellbox_glassy.prc 256x256 direct(depth 16, power MIS) mjitt 128spp"),
+    "c4": ("c4_boltsandgears.prc", "boltsandgears.prc 1000x1000 direct mjitt 256spp"),
+}
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self._stop.is_set():
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def bvh_depth_bytes(n_tris):
+    """minimal-path bytes of one closest-hit / any-hit ray, SURVEY 8(d): 32 + (24|4) + 80*ceil(log8(N/4)) + 4*48"""
+    import math
+    levels = max(1, math.ceil(math.log(max(n_tris / 4.0, 1.0001), 8)))
+    return 32 + 24 + 80 * levels + 4 * 48, 32 + 4 + 80 * levels + 4 * 48
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import numpy as np
+    import pearray_b200 as prb
+    from oracle_binding import OracleScene
+    fname, label = SCENES[args.scene]
+    scene = prb.Scene.from_file(os.path.join(ROOT, "scenes", fname))
+    ora = OracleScene(scene)
+    cores = os.cpu_count() or 1
+    tiles = scene.tiles(8, 8)
+    npix = scene.width * scene.height
+    rng = scene.rng_map()
+    # calibrate: 1 spp, then size a step to ~4 s of CPU work
+    t0 = time.perf_counter()
+    r = ora.render(tiles, 0, 1, rng=rng, threads=cores, aov=False)
+    t1 = time.perf_counter() - t0
+    spp = max(1, min(int(scene.settings.max_sample_count), int(round(4.0 / max(t1, 1e-3)))))
+    film = np.zeros((scene.height, scene.width, 3), np.float32)
+    cnt = np.zeros((scene.height, scene.width), np.uint32)
+    for _ in range(args.warmup):
+        ora.render(tiles, 0, 1, rng=rng, threads=cores, film=film, count=cnt, aov=False)
+    t0 = time.perf_counter()
+    rays = 0
+    for k in range(args.steps):
+        r = ora.render(tiles, k * spp, spp, rng=rng, threads=cores, film=film, count=cnt, aov=False)
+        rays += r["stats"]["primary_ray_count"] + r["stats"]["bounce_ray_count"] + r["stats"]["shadow_ray_count"]
+    dt = time.perf_counter() - t0
+    value = npix * spp * args.steps / dt
+    sample = "%d spp per step over the full %dx%d film (of %d spp), %d threads" % (spp, scene.width, scene.height, scene.settings.max_sample_count, cores)
+    line = {"impl": "reference", "metric": "spectral path samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
+            "config": {"workload": label, "scene": fname, "note": "reference not buildable here (Eigen/Embree/TBB/OIIO absent): CPU oracle port, bounded sample"},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import pearray_b200 as prb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    fname, label = SCENES[args.scene]
+    scene = prb.Scene.from_file(os.path.join(ROOT, "scenes", fname))
+    W, H = scene.width, scene.height
+    spp = int(scene.settings.max_sample_count) if args.spp is None else args.spp
+    all_tiles = scene.tiles(8, 8)
+    if args.partition == "tiles" and world > 1:
+        tiles = [t for i, t in enumerate(all_tiles) if i % world == rank]  # interleaved tiles, bit-identical for any G
+        first_iter = 0
+        scaling = "strong"
+        seed_rank = 0
+    else:
+        tiles = all_tiles
+        first_iter = 0  # sample-range partition: every rank renders its own spp iterations of the full film, decorrelated RNG map
+        scaling = "weak"
+        seed_rank = rank
+    npix_rank = sum((t[2] - t[0]) * (t[3] - t[1]) for t in tiles)
+    samples_rank = npix_rank * spp
+    scene.settings.seed = int(scene.settings.seed) + 7919 * seed_rank  # decorrelated per-rank RNG map in sample-range mode
+    ctx = prb.Context(local_rank)
+    ctx.upload_scene(scene)
+    rng_host = scene.rng_map()
+    # pinned host buffers for the e2e leg
+    rng_pinned = torch.empty(W * H, dtype=torch.int64).pin_memory()
+    rng_pinned.numpy().view(np.uint64)[:] = rng_host
+    film_pinned = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    cnt_pinned = torch.empty((H, W), dtype=torch.int32).pin_memory()
+    film_dev = torch.zeros((H * W * 4,), dtype=torch.float32, device=dev)  # export buffer handed to the NCCL reduce
+
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+
+    def reduce_films():
+        """film export (own kernel) + one NCCL reduce to rank 0; returns device ms (CUDA events on torch's stream)"""
+        if world == 1:
+            return 0.0
+        ev0.record()
+        ctx.film_export_device(film_dev.data_ptr())
+        if scaling == "weak":
+            film_dev.div_(world)  # average of the per-rank sample ranges
+        dist.reduce(film_dev, dst=0, op=dist.ReduceOp.SUM)
+        ev1.record()
+        ev1.synchronize()
+        return ev0.elapsed_time(ev1)
+
+    def step_resident():
+        ctx.render_tiles(tiles, first_iter, spp)  # returns when the wavefront retired every sample
+        return ctx.last_device_ms() + reduce_films()
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        ctx.upload_rng(rng_pinned.numpy().view(np.uint64))
+        ctx.render_tiles(tiles, first_iter, spp)
+        reduce_films()
+        if world > 1 and rank == 0:
+            ctx.film_import_device(film_dev.data_ptr())
+        if rank == 0 or world == 1:
+            ctx.film(out=film_pinned.numpy(), count_out=cnt_pinned.numpy().view(np.uint32))
+        return 1e3 * (time.perf_counter() - t0)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx.upload_rng(rng_host)
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.reset_stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed: K steps, device time (CUDA events on the context stream inside prb_render_tiles), max over ranks
+    barrier()
+    wall0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        dev_ms += step_resident()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    dev_ms = max_over_ranks(dev_ms)
+    st = ctx.stats()
+    launches = int(st.kernel_launches)
+    rays_rank = st.ray_count
+    # ---- e2e leg: host buffers through the C ABI
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    barrier()
+    e2e_ms = 0.0
+    for _ in range(args.steps):
+        e2e_ms += step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks(e2e_ms)
+    if rank == 0:
+        sampler.stop()
+    # ---- per-stage profile pass (rank 0): event pair around every kernel launch of one more identical step
+    roofline = None
+    stage = None
+    if rank == 0:
+        ctx.set_profiling(True)
+        ctx.reset_stats()
+        prof_spp = min(spp, 64)
+        ctx.render_tiles(tiles, first_iter, prof_spp)
+        stage = ctx.stage_times()
+        pst = ctx.stats()
+        ctx.set_profiling(False)
+        total = sum(v[0] for v in stage.values()) or 1.0
+        dom = max(stage, key=lambda k: stage[k][0])
+        n_tris = int(scene.desc.contents.n_bvh_tris)
+        b_closest, b_any = bvh_depth_bytes(n_tris)
+        # algorithmic bytes per unit (DESIGN.md "Measurement"): extend = B_ray per closest-hit ray; shadow = B_any per any-hit ray;
+        # shade = wavefront state r+w per vertex; generate = camera sample state per sample
+        units = {"generate": int(pst.pixel_sample_count), "extend": int(pst.primary_ray_count + pst.bounce_ray_count),
+                 "shade": int(pst.primary_ray_count + pst.bounce_ray_count), "shadow": int(pst.shadow_ray_count)}
+        per_unit = {"generate": 16 + 16 + 7 * 16 + 8, "extend": b_closest, "shade": 2 * 59 + 24 + 2 * 92 + 16 + 16, "shadow": b_any}
+        ms_dom, n_dom = stage[dom]
+        peak, peak_src = measured_peak_gbs()
+        achieved = units[dom] * per_unit[dom] / (ms_dom * 1e-3) / 1e9 if ms_dom > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "avg_launch_us": 1e3 * ms_dom / max(n_dom, 1), "launches": n_dom,
+                    "bytes_per_unit": per_unit[dom], "units_per_launch": units[dom] / max(n_dom, 1),
+                    "stage_share": {k: v[0] / total for k, v in stage.items()},
+                    "note": "scene is L2-resident (%d triangles): HBM is not the binding resource, see DESIGN.md" % n_tris}
+    # ---- cpu baseline (rank 0, N=1 only): the oracle port on all host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle_binding import OracleScene
+        ora = OracleScene(scene)
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        ora.render(all_tiles, 0, 1, rng=rng_host, threads=cores, aov=False)
+        t1 = time.perf_counter() - t0
+        n = max(1, min(spp, int(round(12.0 / max(t1, 1e-3)))))
+        t0 = time.perf_counter()
+        ora.render(all_tiles, 0, n, rng=rng_host, threads=cores, aov=False)
+        dt = time.perf_counter() - t0
+        cpu = {"value": W * H * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "%d of %d spp over the full %dx%d film, oracle (C++17 restatement, std::thread x %d)" % (n, spp, W, H, cores)}
+    if rank == 0:
+        total_samples = samples_rank * world * args.steps if scaling == "weak" else W * H * spp * args.steps
+        value = total_samples / (dev_ms * 1e-3)
+        e2e = total_samples / (e2e_ms * 1e-3)
+        h2d = W * H * 8 + len(tiles) * 16
+        d2h = W * H * 3 * 4 + W * H * 4
+        line = {"metric": "spectral path samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "mrays_per_s": rays_rank * world / (dev_ms * 1e-3) / 1e6 if scaling == "weak" else None,
+                "wall_ms_per_step": wall_ms / args.steps,
+                "config": {"workload": label, "scene": fname, "spp_per_step": spp, "film": [W, H], "partition": args.partition if world > 1 else "single",
+                           "l2": "wavefront state (%d paths x ~250 B) and film are re-written every wavefront iteration; scene is L2-resident by nature" % npix_rank},
+                "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
+                "stage_ms": {k: v[0] for k, v in stage.items()} if stage else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="c2", choices=sorted(SCENES))
+    ap.add_argument("--spp", type=int, default=None, help="iterations per step (default: the scene's sample count)")
+    ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import __graft_entry__ as g
+    if rank == 0 and not os.path.exists(os.path.join(ROOT, "pearray_b200", "libprb200.so")):
+        g.build()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

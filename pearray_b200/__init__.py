@@ -141,7 +141,8 @@ ABI_SYMBOLS = ["prb_create", "prb_destroy", "prb_last_error", "prb_device_count"
                "prb_download_rng", "prb_render_tiles", "prb_sync", "prb_film_clear", "prb_film_download",
                "prb_film_download_aov", "prb_film_export_device", "prb_film_import_device", "prb_trace_closest",
                "prb_trace_any", "prb_trace_closest_device", "prb_trace_any_device", "prb_generate_camera_rays",
-               "prb_material_eval", "prb_material_sample", "prb_get_stats", "prb_reset_stats", "prb_last_device_ms"]
+               "prb_material_eval", "prb_material_sample", "prb_get_stats", "prb_reset_stats", "prb_last_device_ms",
+               "prb_set_profiling", "prb_get_stage_times"]
 
 
 def device_lib():
@@ -177,6 +178,8 @@ def device_lib():
         lib.prb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.prb_reset_stats.argtypes = [C.c_void_p]
         lib.prb_last_device_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        lib.prb_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        lib.prb_get_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
         _dev = lib
     return _dev
 
@@ -442,6 +445,16 @@ class Context:
         ms = C.c_float()
         self._chk(self._lib.prb_last_device_ms(self._h, C.byref(ms)), "prb_last_device_ms")
         return float(ms.value)
+
+    def set_profiling(self, enabled):
+        self._chk(self._lib.prb_set_profiling(self._h, 1 if enabled else 0), "prb_set_profiling")
+
+    def stage_times(self):
+        """{stage: (ms, launches)} accumulated since set_profiling(True)"""
+        ms = (C.c_float * 4)()
+        ln = (C.c_uint64 * 4)()
+        self._chk(self._lib.prb_get_stage_times(self._h, ms, ln), "prb_get_stage_times")
+        return {n: (float(ms[i]), int(ln[i])) for i, n in enumerate(("generate", "extend", "shade", "shadow"))}
 
     def close(self):
         if self._h:

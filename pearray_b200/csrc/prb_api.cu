@@ -99,6 +99,11 @@ struct prb_ctx {
 	cudaGraphExec_t graphExec = nullptr;
 	uint32_t graphSlots = 0;
 	bool wantAOV = true;
+	// per-stage profiling (prb_set_profiling)
+	bool profiling = false;
+	std::vector<cudaEvent_t> profEvents; // pairs
+	float stageMs[PRB_STAGE__COUNT] = { 0, 0, 0, 0 };
+	uint64_t stageLaunches[PRB_STAGE__COUNT] = { 0, 0, 0, 0 };
 };
 
 extern "C" {
@@ -182,6 +187,8 @@ void prb_destroy(prb_ctx* c)
 	c->scratchR.release();
 	if (c->hostCounters)
 		cudaFreeHost(c->hostCounters);
+	for (cudaEvent_t ev : c->profEvents)
+		cudaEventDestroy(ev);
 	cudaEventDestroy(c->evA);
 	cudaEventDestroy(c->evB);
 	cudaStreamDestroy(c->stream);
@@ -427,6 +434,61 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 		k_shadow<<<grid, 256, 0, s>>>(c->S, W);
 		return cudaGetLastError();
 	};
+	// upper bound on wavefront iterations: every sample needs at most max_ray_depth+1 iterations
+	const uint64_t maxIters = (uint64_t)iteration_count * (c->S.settings.max_ray_depth + 2) + 8;
+	const int replaysPerPoll = 16;
+	if (c->profiling) {
+		// same launch sequence without graph replay, every kernel bracketed by an event pair on the context stream
+		const size_t needEvents = (size_t)replaysPerPoll * 2 * PRB_STAGE__COUNT * 2;
+		while (c->profEvents.size() < needEvents) {
+			cudaEvent_t ev;
+			CU(cudaEventCreate(&ev));
+			c->profEvents.push_back(ev);
+		}
+		uint64_t done = 0;
+		bool finished = false;
+		while (!finished && done < maxIters + 2 * replaysPerPoll) {
+			size_t ne = 0;
+			for (int r = 0; r < 2 * replaysPerPoll; ++r) {
+				const int sel = r & 1;
+				CU(cudaMemsetAsync(c->counters.p + (1 - sel), 0, sizeof(uint32_t), s));
+				CU(cudaEventRecord(c->profEvents[ne++], s));
+				k_generate<<<grid, 256, 0, s>>>(c->S, W, sel);
+				CU(cudaEventRecord(c->profEvents[ne++], s));
+				CU(cudaMemsetAsync(c->counters.p + CNT_REGEN, 0, sizeof(uint32_t), s));
+				CU(cudaEventRecord(c->profEvents[ne++], s));
+				k_extend<<<grid, 256, 0, s>>>(c->S, W, sel);
+				CU(cudaEventRecord(c->profEvents[ne++], s));
+				CU(cudaMemsetAsync(c->counters.p + CNT_SHADOW, 0, sizeof(uint32_t), s));
+				CU(cudaEventRecord(c->profEvents[ne++], s));
+				k_shade<<<c->smCount * 8, 128, 0, s>>>(c->S, W, sel);
+				CU(cudaEventRecord(c->profEvents[ne++], s));
+				CU(cudaEventRecord(c->profEvents[ne++], s));
+				k_shadow<<<grid, 256, 0, s>>>(c->S, W);
+				CU(cudaEventRecord(c->profEvents[ne++], s));
+				CU(cudaGetLastError());
+			}
+			done += 2 * replaysPerPoll;
+			c->kernelLaunches += 8 * replaysPerPoll;
+			CU(cudaMemcpyAsync(c->hostCounters, c->counters.p, CNT__COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+			CU(cudaStreamSynchronize(s));
+			for (size_t i = 0; i + 1 < ne; i += 2) {
+				float ms = 0;
+				CU(cudaEventElapsedTime(&ms, c->profEvents[i], c->profEvents[i + 1]));
+				const int stage = (int)((i / 2) % PRB_STAGE__COUNT);
+				c->stageMs[stage] += ms;
+				c->stageLaunches[stage] += 1;
+			}
+			finished = c->hostCounters[CNT_RETIRED] >= c->nSlots;
+		}
+		c->wavefrontIterations += done;
+		CU(cudaEventRecord(c->evB, s));
+		CU(cudaEventSynchronize(c->evB));
+		CU(cudaEventElapsedTime(&c->lastMs, c->evA, c->evB));
+		if (!finished)
+			return fail(PRB_ERR_CUDA, "wavefront loop did not terminate within the iteration bound");
+		return PRB_OK;
+	}
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t exec = nullptr;
 	CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -441,10 +503,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 	}
 	CU(cudaGraphInstantiate(&exec, graph, 0));
 	cudaGraphDestroy(graph);
-	// upper bound on wavefront iterations: every sample needs at most max_ray_depth+1 iterations
-	const uint64_t maxIters = (uint64_t)iteration_count * (c->S.settings.max_ray_depth + 2) + 8;
 	uint64_t done = 0;
-	const int replaysPerPoll = 16;
 	bool finished = false;
 	while (!finished && done < maxIters + 2 * replaysPerPoll) {
 		for (int r = 0; r < replaysPerPoll; ++r) {
@@ -756,6 +815,27 @@ prb_status prb_reset_stats(prb_ctx* c)
 	CU(cudaMemsetAsync(c->stats.p, 0, ST__COUNT * sizeof(unsigned long long), c->stream));
 	c->kernelLaunches	   = 0;
 	c->wavefrontIterations = 0;
+	return PRB_OK;
+}
+prb_status prb_set_profiling(prb_ctx* c, int enabled)
+{
+	if (!c)
+		return fail(PRB_ERR_INVALID_ARG, "null context");
+	c->profiling = enabled != 0;
+	for (int i = 0; i < PRB_STAGE__COUNT; ++i) {
+		c->stageMs[i]		= 0;
+		c->stageLaunches[i] = 0;
+	}
+	return PRB_OK;
+}
+prb_status prb_get_stage_times(prb_ctx* c, float* ms4, uint64_t* launches4)
+{
+	if (!c || !ms4 || !launches4)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	for (int i = 0; i < PRB_STAGE__COUNT; ++i) {
+		ms4[i]		 = c->stageMs[i];
+		launches4[i] = c->stageLaunches[i];
+	}
 	return PRB_OK;
 }
 prb_status prb_last_device_ms(prb_ctx* c, float* ms)
