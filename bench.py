@@ -164,8 +164,9 @@ def run_ours(args, rank, world, local_rank):
     W, H = scene.width, scene.height
     spp = int(scene.settings.max_sample_count) if args.spp is None else args.spp
     all_tiles = scene.tiles(8, 8)
+    from pearray_b200 import multigpu
     if args.partition == "tiles" and world > 1:
-        tiles = [t for i, t in enumerate(all_tiles) if i % world == rank]  # interleaved tiles, bit-identical for any G
+        tiles = multigpu.partition_tiles(all_tiles, rank, world)  # interleaved tiles, bit-identical for any G
         first_iter = 0
         scaling = "strong"
         seed_rank = 0
@@ -176,7 +177,7 @@ def run_ours(args, rank, world, local_rank):
         seed_rank = rank
     npix_rank = sum((t[2] - t[0]) * (t[3] - t[1]) for t in tiles)
     samples_rank = npix_rank * spp
-    scene.settings.seed = int(scene.settings.seed) + 7919 * seed_rank  # decorrelated per-rank RNG map in sample-range mode
+    scene.settings.seed = multigpu.rank_seed(scene.settings.seed, seed_rank)  # decorrelated per-rank RNG map in sample-range mode
     ctx = prb.Context(local_rank)
     ctx.upload_scene(scene)
     rng_host = scene.rng_map()
@@ -196,9 +197,7 @@ def run_ours(args, rank, world, local_rank):
             return 0.0
         ev0.record()
         ctx.film_export_device(film_dev.data_ptr())
-        if scaling == "weak":
-            film_dev.div_(world)  # average of the per-rank sample ranges
-        dist.reduce(film_dev, dst=0, op=dist.ReduceOp.SUM)
+        multigpu.reduce_film(film_dev.view(-1, 4), "samples" if scaling == "weak" else "tiles", world)
         ev1.record()
         ev1.synchronize()
         return ev0.elapsed_time(ev1)

@@ -2160,4 +2160,23 @@ void orc_random_stream(uint64_t seed, uint32_t n, uint32_t* out32, float* outf)
 	}
 }
 float orc_eval_node(orc_scene* s, uint32_t node, float wavelength, float u, float v) { return evalNode(s->sc, node, blob(wavelength), u, v)[0]; }
+// MicrofacetReflection<...>::eval / ::pdf (src/base/math/MicrofacetReflection.h), src/tests/microfacets.cpp reciprocity cases
+float orc_microfacet_reflection_eval(const float* wIn, const float* wOut, float m1, float m2, int aniso, int vndf)
+{
+	MicrofacetReflection r{ RoughDistribution{ m1, m2, aniso != 0, vndf != 0 } };
+	return r.eval(mk(wIn[0], wIn[1], wIn[2]), mk(wOut[0], wOut[1], wOut[2]));
+}
+float orc_microfacet_reflection_pdf(const float* wIn, const float* wOut, float m1, float m2, int aniso, int vndf)
+{
+	MicrofacetReflection r{ RoughDistribution{ m1, m2, aniso != 0, vndf != 0 } };
+	return r.pdf(mk(wIn[0], wIn[1], wIn[2]), mk(wOut[0], wOut[1], wOut[2]));
+}
+void orc_halfway_refractive(float n_in, const float* a, float n_out, const float* b, float* out)
+{
+	const V3 r = halfway_refractive(n_in, mk(a[0], a[1], a[2]), n_out, mk(b[0], b[1], b[2]));
+	out[0] = r.x, out[1] = r.y, out[2] = r.z;
+}
+// Distribution1D over a caller-built CDF (size entries, cdf[0] = 0, cdf[size-1] = 1): src/tests/distribution.cpp
+float orc_sample_continuous(const float* cdf, int size, float u, float* pdf) { return sampleContinuous(cdf, size, u, *pdf); }
+int orc_sample_discrete(const float* cdf, int size, float u, float* pdf) { return sampleDiscrete(cdf, size, u, *pdf); }
 }

@@ -56,6 +56,14 @@ def lib():
         l.orc_random_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         l.orc_eval_node.restype = C.c_float
         l.orc_eval_node.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float]
+        for n in ("orc_microfacet_reflection_eval", "orc_microfacet_reflection_pdf"):
+            getattr(l, n).restype = C.c_float
+            getattr(l, n).argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int]
+        l.orc_halfway_refractive.argtypes = [C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        l.orc_sample_continuous.restype = C.c_float
+        l.orc_sample_continuous.argtypes = [C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_float)]
+        l.orc_sample_discrete.restype = C.c_int
+        l.orc_sample_discrete.argtypes = [C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_float)]
         _lib = l
     return _lib
 

@@ -1,0 +1,49 @@
+"""Small inline .prc scenes for unit-level tests (the analogue of the reference's src/tests/testscene.inl)."""
+
+# every material plugin on the scoped path; rough variants with roughness 0.164 as in reference src/tests/materials.cpp:37-47
+MATERIAL_ZOO = """
+(scene :name 'zoo' :render_width 32 :render_height 32 :camera 'Camera'
+ (integrator :type 'direct' :max_ray_depth 8)
+ (sampler :slot 'aa' :type 'mjitt' :sample_count 16)
+ (camera :name 'Camera' :type 'standard' :width 1 :height 1 :local_direction [0,0,-1] :local_up [0,1,0] :local_right [1,0,0]
+   :near 0.1 :far 100 :transform [1,0,0,0, 0,1,0,0, 0,0,1,4, 0,0,0,1])
+ (emission :name 'em' :type 'standard' :radiance (illuminant "D65"))
+ (material :name 'm_diffuse' :type 'diffuse' :albedo (refl 0.8 0.2 0.3))
+ (material :name 'm_glass' :type 'glass' :index 1.55)
+ (material :name 'm_glass_bk7' :type 'glass' :index (lookup_index "bk7"))
+ (material :name 'm_conductor' :type 'conductor' :eta 0.051585 :k 3.9046)
+ (material :name 'm_roughconductor' :type 'roughconductor' :eta 0.051585 :k 3.9046 :roughness 0.164)
+ (material :name 'm_roughconductor_aniso' :type 'roughconductor' :eta 0.2 :k 3.0 :roughness_x 0.1 :roughness_y 0.3)
+ (material :name 'm_roughglass' :type 'roughglass' :index 1.55 :roughness 0.164)
+ (material :name 'm_roughglass_bk7' :type 'glass' :index (lookup_index "bk7") :roughness 0.05)
+ (material :name 'm_principled' :type 'principled' :base (refl 0.6 0.5 0.3) :roughness 0.164 :metallic 0.3 :sheen 0.2 :clearcoat 0.4)
+ (material :name 'm_principled_trans' :type 'principled' :base (refl 0.9 0.9 0.9) :roughness 0.3 :specular_transmission 0.8 :diffuse_transmission 0.2)
+ (entity :name 'floor' :type 'plane' :centering true :width 4 :height 4 :material 'm_diffuse' :position [0,0,-1])
+ (entity :name 's0' :type 'sphere' :radius 0.4 :material 'm_glass' :position [-1.2,0.8,0])
+ (entity :name 's1' :type 'sphere' :radius 0.4 :material 'm_glass_bk7' :position [-0.4,0.8,0])
+ (entity :name 's2' :type 'sphere' :radius 0.4 :material 'm_conductor' :position [0.4,0.8,0])
+ (entity :name 's3' :type 'sphere' :radius 0.4 :material 'm_roughconductor' :position [1.2,0.8,0])
+ (entity :name 's4' :type 'sphere' :radius 0.4 :material 'm_roughconductor_aniso' :position [-1.2,-0.2,0])
+ (entity :name 's5' :type 'sphere' :radius 0.4 :material 'm_roughglass' :position [-0.4,-0.2,0])
+ (entity :name 's6' :type 'sphere' :radius 0.4 :material 'm_roughglass_bk7' :position [0.4,-0.2,0])
+ (entity :name 's7' :type 'sphere' :radius 0.4 :material 'm_principled' :position [1.2,-0.2,0])
+ (entity :name 's8' :type 'sphere' :radius 0.4 :material 'm_principled_trans' :position [0,-1.2,0])
+ (entity :name 'lamp' :type 'plane' :centering true :width 1 :height 1 :material 'm_diffuse' :emission 'em' :transform [1,0,0,0, 0,-1,0,0, 0,0,-1,3, 0,0,0,1])
+ (light :type 'env' :radiance (illuminant "D65"))
+)
+"""
+
+# white furnace (reference src/tests/python/whitefurnance.py:142-195): unit sphere, albedo 1, constant env radiance 1
+FURNACE = """
+(scene :name 'furnace' :render_width 48 :render_height 48 :camera 'Camera' :spectral_hero %(hero)s
+ (integrator :type 'direct' :max_ray_depth 4)
+ (sampler :slot 'aa' :type 'random' :sample_count 8)
+ (filter :slot 'pixel' :type 'block' :radius 0)
+ (spectral_mapper :type 'random')
+ (camera :name 'Camera' :type 'standard' :width 1 :height 1 :local_direction [0,0,-1] :local_up [0,1,0] :local_right [1,0,0]
+   :near 0.01 :far 100 :transform [1,0,0,0, 0,1,0,0, 0,0,1,3, 0,0,0,1])
+ (material :name 'white' :type 'diffuse' :albedo 1)
+ (entity :name 'ball' :type 'sphere' :radius 1 :material 'white')
+ (light :type 'env' :radiance 1)
+)
+"""

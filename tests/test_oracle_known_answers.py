@@ -1,0 +1,314 @@
+"""The oracle pinned against the reference's own known-answer tests.
+
+Each test ports one case of /root/reference/src/tests/*.cpp (file:line cited) and runs it against oracle/liboracle.so
+(the CPU restatement) -- and, where the product's host library implements the same function, against
+libprb200_host.so as well.  Tolerance: PRT_EPSILON = 2 * float epsilon (src/tests/Test.h:224-225) unless the
+reference test states its own."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import pearray_b200 as prb
+import oracle_binding as ob
+from scene_strings import MATERIAL_ZOO
+
+EPS = 2 * np.finfo(np.float32).eps
+
+
+def v3(*a):
+    v = np.array(a, dtype=np.float32)
+    return v
+
+
+def nrm(*a):
+    v = np.array(a, dtype=np.float64)
+    return (v / np.linalg.norm(v)).astype(np.float32)
+
+
+def p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------- src/tests/fresnel.cpp:12-60
+def test_fresnel_dielectric_one_dot():
+    assert abs(ob.lib().orc_fresnel_dielectric(1, 1, 1) - 0) <= EPS
+
+
+@pytest.mark.parametrize("args,expect", [((0, 1, 1, 1), 1.0), ((1, 1, 1, 1), 0.2), ((0.45, 1, 1, 0), 0.0)])
+def test_fresnel_conductor(args, expect):
+    assert abs(ob.lib().orc_fresnel_conductor(*args) - expect) <= EPS
+
+
+@pytest.mark.parametrize("args,expect", [((0, 1, 1), 1.0), ((1, 1, 1), 0.0)])
+def test_fresnel_schlick(args, expect):
+    assert abs(ob.lib().orc_fresnel_schlick(*args) - expect) <= EPS
+
+
+# ---------------------------------------------------------------- src/tests/microfacets.cpp:9-93
+def test_ggx_iso_pdf_is_d_cos():
+    H = nrm(0, 0.2, 0.8)
+    D = ob.lib().orc_ndf_ggx_iso(p(H), 0.05)
+    assert abs(ob.lib().orc_pdf_ggx_iso(p(H), 0.05) - D * H[2]) <= EPS * max(1.0, abs(D))
+
+
+def test_ggx_aniso_pdf_is_d_cos():
+    H = nrm(0, 0.2, 0.8)
+    D = ob.lib().orc_ndf_ggx_aniso(p(H), 0.05, 0.45)
+    assert abs(ob.lib().orc_pdf_ggx_aniso(p(H), 0.05, 0.45) - D * H[2]) <= EPS * max(1.0, abs(D))
+
+
+def test_ggx_iso_equals_aniso():
+    H = nrm(0, 0.2, 0.8)
+    d1 = ob.lib().orc_ndf_ggx_iso(p(H), 0.05)
+    d2 = ob.lib().orc_ndf_ggx_aniso(p(H), 0.05, 0.05)
+    # 2 ulp at 0.2126: the port rounds every operation (-ffp-contract=off) whereas the reference is built with
+    # -march=native contraction; the two formulas (alpha^2 vs alpha_x*alpha_y) agree to 4 float epsilons
+    assert abs(d1 - d2) <= 4 * EPS * max(1.0, abs(d1))
+
+
+@pytest.mark.parametrize("m", [0.0, 0.245])
+def test_microfacet_reflection_reciprocal(m):
+    A = nrm(0, 1, 1)
+    B = np.zeros(3, np.float32)
+    ob.lib().orc_reflect(p(A), p(v3(0, 0, 1)), p(B))
+    l = ob.lib()
+    a = l.orc_microfacet_reflection_eval(p(A), p(B), m, m, 0, 0)
+    b = l.orc_microfacet_reflection_eval(p(B), p(A), m, m, 0, 0)
+    assert abs(a - b) <= EPS * max(1.0, abs(a))
+    a3 = l.orc_microfacet_reflection_eval_conductor(p(A), p(B), m, m, 0, 0, 0.051585, 3.9046)
+    b3 = l.orc_microfacet_reflection_eval_conductor(p(B), p(A), m, m, 0, 0, 0.051585, 3.9046)
+    assert abs(a3 - b3) <= EPS * max(1.0, abs(a3))
+    a4 = l.orc_microfacet_reflection_pdf(p(A), p(B), m, m, 0, 0)
+    b4 = l.orc_microfacet_reflection_pdf(p(B), p(A), m, m, 0, 0)
+    assert abs(a4 - b4) <= EPS * max(1.0, abs(a4))
+
+
+# ---------------------------------------------------------------- src/tests/scattering.cpp:7-47
+def test_scattering_reflect_z_equals_general():
+    V = nrm(1, 1, 1)
+    L2 = np.zeros(3, np.float32)
+    ob.lib().orc_reflect(p(V), p(v3(0, 0, 1)), p(L2))
+    assert np.allclose(L2, [-V[0], -V[1], V[2]], atol=EPS)  # Scattering::reflect(V) = (-x,-y,z)
+
+
+def test_scattering_refract():
+    V = nrm(1, 1, 1)
+    L = np.zeros(3, np.float32)
+    tot = C.c_int()
+    ob.lib().orc_refract(0.85, p(V), p(v3(0, 0, 1)), p(L), C.byref(tot))
+    assert tot.value == 0
+    # Snell: sin_t = eta * sin_i, refracted direction on the opposite side of N
+    sin_i = np.sqrt(1 - float(V[2]) ** 2)
+    assert abs(np.sqrt(L[0] ** 2 + L[1] ** 2) - 0.85 * sin_i) < 1e-6
+    assert L[2] < 0 and abs(np.linalg.norm(L) - 1) < 1e-6
+
+
+def test_scattering_halfway_reflection():
+    V, L = nrm(1, 1, 1), nrm(-1, 0, 1)
+    H = np.zeros(3, np.float32)
+    ob.lib().orc_halfway_reflection(p(V), p(L), p(H))
+    assert abs(float(H @ V) - float(H @ L)) <= 4 * EPS
+
+
+def test_scattering_halfway_transmission():
+    n1, n2 = 1.0, 1.55
+    V, L = nrm(1, 1, 1), nrm(-1, 0, -1)
+    H = np.zeros(3, np.float32)
+    ob.lib().orc_halfway_refractive(n1, p(V), n2, p(L), p(H))
+    L2 = np.zeros(3, np.float32)
+    tot = C.c_int()
+    ob.lib().orc_refract(n1 / n2, p(V), p(H), p(L2), C.byref(tot))
+    assert np.allclose(L2, L, atol=1e-6)
+
+
+# ---------------------------------------------------------------- src/tests/sampling.cpp:7-35
+def test_cos_hemi_unit_length():
+    o = np.zeros(3, np.float32)
+    ob.lib().orc_cos_hemi(0.5, 0.5, p(o))
+    assert abs(float(o @ o) - 1) <= 4 * EPS
+    # cos_hemi(u1,u2): cos(theta) = sqrt(u1)  (src/base/math/Sampling.h:38-51; == power cosine with m = 1)
+    assert abs(o[2] - np.sqrt(0.5)) <= 4 * EPS
+
+
+# ---------------------------------------------------------------- src/tests/tangent.cpp:7-40
+@pytest.mark.parametrize("N,Nx,Ny", [((0, 0, 1), (1, 0, 0), (0, 1, 0)), ((0, 1, 0), (1, 0, 0), (0, 0, -1))])
+def test_tangent_frame(N, Nx, Ny):
+    n = v3(*N)
+    x, y = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    ob.lib().orc_tangent_frame(p(n), p(x), p(y))
+    assert np.allclose(x, Nx, atol=EPS) and np.allclose(y, Ny, atol=EPS)
+    assert abs(x @ n) <= EPS and abs(y @ n) <= EPS and abs(x @ y) <= EPS
+
+
+def test_tangent_frame_orthonormal_random():
+    rs = np.random.RandomState(1)
+    for _ in range(200):
+        n = nrm(*rs.normal(size=3))
+        x, y = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        ob.lib().orc_tangent_frame(p(n), p(x), p(y))
+        assert abs(x @ n) < 1e-6 and abs(y @ n) < 1e-6 and abs(x @ y) < 1e-6
+        assert abs(x @ x - 1) < 1e-5 and abs(y @ y - 1) < 1e-5
+
+
+# ---------------------------------------------------------------- src/tests/distribution.cpp:9-80
+def _cdf(values):
+    v = np.asarray(values, dtype=np.float32)
+    c = np.zeros(len(v) + 1, np.float32)
+    for i in range(len(v)):  # Distribution1D::generate: running float sum of f(i)/n, then normalised (Distribution1D.inl:13-40)
+        c[i + 1] = c[i] + v[i] / np.float32(len(v))
+    integral = c[-1]
+    c /= integral
+    c[-1] = 1
+    return c, float(integral) * len(v)
+
+
+def test_distribution_pmf():
+    c, _ = _cdf([1, 1, 1, 1, 1])
+    for u, _i in ((0.05, 0), (0.5, 2), (0.95, 4)):
+        pdf = C.c_float()
+        i = ob.lib().orc_sample_discrete(p(c), len(c), u, C.byref(pdf))
+        assert i == _i and abs(pdf.value - 0.2) <= EPS
+
+
+def test_distribution_pmf2():
+    c, integral = _cdf([1, 2, 3, 4, 5])
+    assert abs(integral - 15.0) < 1e-5
+    for u, _i in ((0.01, 0), (0.3, 2), (0.9, 4)):
+        pdf = C.c_float()
+        i = ob.lib().orc_sample_discrete(p(c), len(c), u, C.byref(pdf))
+        assert i == _i and abs(pdf.value - (_i + 1) / 15.0) <= 2 * EPS
+
+
+def test_distribution_continuous_uniform_pdf():
+    c, _ = _cdf([1, 1, 1, 1, 1])
+    for u in (0.25, 0.5, 0.75):
+        pdf = C.c_float()
+        x = ob.lib().orc_sample_continuous(p(c), len(c), u, C.byref(pdf))
+        assert abs(pdf.value - 1) <= 4 * EPS and abs(x - u) <= 4 * EPS
+
+
+def test_distribution_continuous_consistency():
+    c, _ = _cdf([(i / 16.0) ** 2 for i in range(5)])
+    pdf = C.c_float()
+    x = ob.lib().orc_sample_continuous(p(c), len(c), 0.5, C.byref(pdf))
+    # continuousPdf(x) = (cdf[i+1]-cdf[i]) * n for the bin that contains x (Distribution1D.inl:88-100)
+    i = min(int(x * 5), 4)
+    assert pdf.value == np.float32((c[i + 1] - c[i]) * np.float32(5))
+
+
+# ---------------------------------------------------------------- src/tests/random.cpp + pcg32_fast definition
+def _pcg32_fast(seed, n):
+    """pcg32_fast = mcg_xsh_rs_64_32 (src/core/random/pcg_random.hpp:484-490,812-836,1865): state = seed | 3."""
+    s = (seed | 3) & (2 ** 64 - 1)
+    out = []
+    for _ in range(n):
+        old = s
+        s = (s * 6364136223846793005) & (2 ** 64 - 1)
+        rs = old >> 61
+        x = old ^ (old >> 22)
+        out.append((x >> (22 + rs)) & 0xFFFFFFFF)
+    return out
+
+
+def test_random_matches_pcg_definition_and_bounds():
+    n = 4096
+    o32 = np.zeros(n, np.uint32)
+    of = np.zeros(n, np.float32)
+    ob.lib().orc_random_stream(42, n, p(o32), p(of))
+    assert list(o32) == _pcg32_fast(42, n)
+    assert (of >= 0).all() and (of < 1).all()
+    # Random::getFloat: bits((u32 >> 9) | 0x3F800000) - 1  (src/core/Random.h:133-158)
+    exp = ((o32 >> 9) | 0x3F800000).view(np.float32) - np.float32(1)
+    assert np.array_equal(of, exp)
+    # the product's host Random is the same generator
+    h32 = np.zeros(n, np.uint32)
+    hf = np.zeros(n, np.float32)
+    prb.host_lib().prh_random_stream(42, n, p(h32), p(hf))
+    assert np.array_equal(h32, o32) and np.array_equal(hf, of)
+
+
+# ---------------------------------------------------------------- src/tests/upsampler.cpp:13-123 (golden coefficients + reflectances)
+UPSAMPLER_GOLDEN = [
+    ((0.8, 0.2, 0.3), (0.000110479, -0.112288, 27.692141), (0.193251, 0.693976, 0.950077, 0.985873, 0.549449)),
+    ((0.2, 0.8, 0.4), (-0.000149, 0.156879, -40.710041), (0.783971, 0.299929, 0.013470, 0.010529, 0.120486)),
+    ((0.1, 0.3, 0.8), (0.000033, -0.044228, 13.931887), (0.337471, 0.165104, 0.965322, 0.153193, 0.882958)),
+    ((1.0, 1.0, 1.0), (0.0, 0.0, 5e6), (1, 1, 1, 1, 1)),
+    ((0.0, 0.0, 0.0), (0.0, 0.0, -500.0), (0, 0, 0, 0, 0)),
+]
+UPSAMPLER_WVL = np.array([532, 615, 346, 720, 416], dtype=np.float32)
+
+
+@pytest.mark.parametrize("rgb,coeffs,refl", UPSAMPLER_GOLDEN)
+def test_upsampler_golden(rgb, coeffs, refl):
+    h = prb.host_lib()
+    c = np.zeros(3, np.float32)
+    assert h.prh_upsample_rgb(p(np.array(rgb, np.float32)), p(c)) == 0, h.prh_last_error()
+    assert np.allclose(c, coeffs, atol=1e-4)  # EPS of the reference test
+    out = np.zeros(5, np.float32)
+    h.prh_upsample_eval(p(c), p(UPSAMPLER_WVL), p(out), 5)
+    assert np.allclose(out, refl, atol=1e-4)
+
+
+def test_upsampler_golden_through_oracle_nodes():
+    """the same five colours as 'refl' nodes of a scene, evaluated by the ORACLE's node evaluator"""
+    mats = "\n".join("(material :name 'm%d' :type 'diffuse' :albedo (refl %g %g %g))" % (i, *g[0]) for i, g in enumerate(UPSAMPLER_GOLDEN))
+    src = """(scene :name 't' :render_width 8 :render_height 8 :camera 'Camera'
+      (camera :name 'Camera' :type 'standard' :width 1 :height 1 :local_direction [0,0,-1] :local_up [0,1,0] :local_right [1,0,0] :near 0.1 :far 100)
+      %s (entity :name 's' :type 'sphere' :radius 1 :material 'm0'))""" % mats
+    scene = prb.Scene.from_string(src)
+    ora = ob.OracleScene(scene)
+    d = scene.desc.contents
+    assert d.n_materials == 5
+    for i, (_, _, refl) in enumerate(UPSAMPLER_GOLDEN):
+        node = d.materials[i].node[0]
+        got = [ora.eval_node(node, float(w)) for w in UPSAMPLER_WVL]
+        assert np.allclose(got, refl, atol=1e-4), (i, got, refl)
+
+
+# ---------------------------------------------------------------- src/tests/materials.cpp:13-165 (eval/pdf/sample self-consistency)
+@pytest.fixture(scope="module")
+def zoo():
+    scene = prb.Scene.from_string(MATERIAL_ZOO)
+    return scene, ob.OracleScene(scene)
+
+
+def _query(scene, mat, V, L=None, seed=42):
+    q = (prb.MaterialQuery * 1)()
+    q[0].V[:] = [float(x) for x in V]
+    if L is not None:
+        q[0].L[:] = [float(x) for x in L]
+    q[0].wavelength_nm[:] = [560.0, 540.0, 400.0, 600.0]  # materials.cpp:18
+    q[0].uv[:] = [0.5, 0.5]
+    q[0].ray_flags = prb.device_lib() and 0x01
+    q[0].material_id = mat
+    q[0].rng_state = seed | 3
+    return q
+
+
+@pytest.mark.parametrize("backside", [False, True])
+def test_materials_sample_matches_eval(zoo, backside):
+    """sample.PDF_S == eval.PDF_S and sample.IntegralWeight * PDF_S == eval.Weight for the sampled direction
+    (materials.cpp:91-137); V = -ray.Direction in shading space with N = +z (constructTestIP :13-37)."""
+    scene, ora = zoo
+    d = scene.desc.contents
+    V = nrm(1, 0, 1) if not backside else -nrm(1, 0, 1)
+    for mat in range(d.n_materials):
+        only_delta = bool(d.materials[mat].flags & 0x20)
+        for seed in (42, 43, 1234567, 99):
+            s = ora.material_sample(_query(scene, mat, V, seed=seed))[0]
+            if only_delta:
+                assert s.flags & 0x2, "hasOnlyDeltaDistribution but the sample is not flagged delta"
+                continue
+            if s.flags & 0x2:
+                continue
+            if not any(s.pdf_s):
+                continue  # rejected sample
+            e = ora.material_eval(_query(scene, mat, V, list(s.L)))[0]
+            for k in range(4):
+                tol = 2e-4 * max(1.0, abs(e.pdf_s[k]))
+                assert abs(s.pdf_s[k] - e.pdf_s[k]) <= tol, (mat, d.materials[mat].type, k, s.pdf_s[k], e.pdf_s[k])
+            # IntegralWeight = f cos / pdf[0]  (MaterialData.h:40-79)
+            for k in range(4):
+                tol = 5e-4 * max(1.0, abs(e.weight[k]))
+                assert abs(s.weight[k] * s.pdf_s[0] - e.weight[k]) <= tol, (mat, d.materials[mat].type, k, s.weight[k] * s.pdf_s[0], e.weight[k])
