@@ -275,14 +275,17 @@ def run_ours(args, rank, world, local_rank):
         dom = max(stage, key=lambda k: stage[k][0])
         n_tris = int(scene.desc.contents.n_bvh_tris)
         b_closest, b_any = bvh_depth_bytes(n_tris)
-        # algorithmic bytes per unit (DESIGN.md "Measurement"): extend = B_ray per closest-hit ray; shadow = B_any per any-hit ray;
-        # shade = wavefront state r+w per vertex; generate = camera sample state per sample
-        units = {"generate": int(pst.pixel_sample_count), "extend": int(pst.primary_ray_count + pst.bounce_ray_count),
-                 "shade": int(pst.primary_ray_count + pst.bounce_ray_count), "shadow": int(pst.shadow_ray_count)}
-        per_unit = {"generate": 16 + 16 + 7 * 16 + 8, "extend": b_closest, "shade": 2 * 59 + 24 + 2 * 92 + 16 + 16, "shadow": b_any}
+        # algorithmic bytes per launch (DESIGN.md "Measurement"): trace = B_ray per closest-hit ray + B_any per any-hit ray
+        # (SURVEY 8(d)); shade = wavefront state read + written per path vertex (ray 2x32, hit 20, path state 5x16 r+w,
+        # RNG 16, film/accumulator 32, shadow ray out 48)
+        n_closest = int(pst.primary_ray_count + pst.bounce_ray_count)
+        n_any = int(pst.shadow_ray_count)
+        units = {"trace": n_closest + n_any, "shade": n_closest}
+        bytes_total = {"trace": n_closest * b_closest + n_any * b_any, "shade": n_closest * (64 + 20 + 160 + 16 + 32 + 48)}
+        per_unit = {k: bytes_total[k] / max(units[k], 1) for k in units}
         ms_dom, n_dom = stage[dom]
         peak, peak_src = measured_peak_gbs()
-        achieved = units[dom] * per_unit[dom] / (ms_dom * 1e-3) / 1e9 if ms_dom > 0 else 0.0
+        achieved = bytes_total[dom] / (ms_dom * 1e-3) / 1e9 if ms_dom > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "avg_launch_us": 1e3 * ms_dom / max(n_dom, 1), "launches": n_dom,
                     "bytes_per_unit": per_unit[dom], "units_per_launch": units[dom] / max(n_dom, 1),

@@ -412,11 +412,12 @@ prb_status prb_last_device_ms(prb_ctx* ctx, float* ms);
 
 /* -- per-stage device times of the wavefront kernels (the analogue of the reference's PR_PROFILE scope timers,
  * src/base/Profiler.h:53-106).  While enabled, prb_render_tiles launches the stage kernels directly (no CUDA-graph
- * replay) with a CUDA-event pair around every launch on the context stream and accumulates
- * ms[]/launches[] per stage; stage order: PRB_STAGE_GENERATE, _EXTEND, _SHADE, _SHADOW. */
-enum { PRB_STAGE_GENERATE = 0, PRB_STAGE_EXTEND = 1, PRB_STAGE_SHADE = 2, PRB_STAGE_SHADOW = 3, PRB_STAGE__COUNT = 4 };
+ * replay) with a CUDA-event pair around every launch on the context stream and accumulates ms[] / launches[] per stage:
+ * PRB_STAGE_TRACE (k_trace: shadow any-hit + closest hit), PRB_STAGE_SHADE (k_shade: shading, NEE, scattering, film,
+ * camera-sample regeneration).  Arrays hold PRB_STAGE__COUNT entries. */
+enum { PRB_STAGE_TRACE = 0, PRB_STAGE_SHADE = 1, PRB_STAGE__COUNT = 2 };
 prb_status prb_set_profiling(prb_ctx* ctx, int enabled);
-prb_status prb_get_stage_times(prb_ctx* ctx, float* ms4, uint64_t* launches4);
+prb_status prb_get_stage_times(prb_ctx* ctx, float* ms, uint64_t* launches);
 
 #ifdef __cplusplus
 }

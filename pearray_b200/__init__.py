@@ -451,10 +451,10 @@ class Context:
 
     def stage_times(self):
         """{stage: (ms, launches)} accumulated since set_profiling(True)"""
-        ms = (C.c_float * 4)()
-        ln = (C.c_uint64 * 4)()
+        ms = (C.c_float * 2)()
+        ln = (C.c_uint64 * 2)()
         self._chk(self._lib.prb_get_stage_times(self._h, ms, ln), "prb_get_stage_times")
-        return {n: (float(ms[i]), int(ln[i])) for i, n in enumerate(("generate", "extend", "shade", "shadow"))}
+        return {n: (float(ms[i]), int(ln[i])) for i, n in enumerate(("trace", "shade"))}
 
     def close(self):
         if self._h:

@@ -142,10 +142,23 @@ PRB_DEV float safeInv(float d)
 }
 
 constexpr int BVH_STACK = 96;
-constexpr uint32_t STACK_INSTANCE_EXIT = 0xFFFFFFFEu;
+// stack entry .x encodings (.y = entry distance bits, used to cull popped subtrees behind the closest hit)
+//   00nn nnnn ...   internal node index
+//   1ccf ffff ...   leaf: (count-1) in bits 29..30, first primitive in bits 0..28 (triangle range in a BLAS, entity ref in the TLAS)
+//   0xFFFFFFFF      leave the current BLAS (restore the world-space ray)
+constexpr uint32_t STK_LEAF	 = 0x80000000u;
+constexpr uint32_t STK_EXIT	 = 0xFFFFFFFFu;
+constexpr uint32_t STK_NONE	 = 0xFFFFFFFEu;
 
-// Traverses TLAS + BLAS.  ANY: returns at the first accepted primitive.  `nodeVisits`/`triTests` are optional
-// work counters (profiling builds).
+// float(q) for a byte q without an int->float conversion: 0x4B000000 | q is 2^23 + q
+PRB_DEV float byteToFloat(uint32_t word, uint32_t sel) { return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f; }
+
+// Traverses TLAS + BLAS.  ANY: returns at the first accepted primitive.
+//
+// One loop iteration = at most one internal-node step followed by at most one leaf step, so the lanes of a warp
+// re-converge at both phases ("if-if" traversal).  A node step tests the 8 quantised child boxes branch-free, keeps
+// the nearest hit child in registers as the next entry and pushes the others; a leaf step runs the watertight test on
+// <= 4 triangles (BLAS) or enters an entity (TLAS: analytic sphere, or ray transformed into the mesh's local space).
 template <bool ANY>
 PRB_DEV bool traverseScene(const DScene& S, V3 wO, V3 wD, float tmin, float tmax, HitRec& best)
 {
@@ -156,146 +169,127 @@ PRB_DEV bool traverseScene(const DScene& S, V3 wO, V3 wD, float tmin, float tmax
 	uint2 stack[BVH_STACK];
 	int sp = 0;
 	V3 O = wO, D = wD;
-	V3 inv			 = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
-	uint32_t curEnt	 = PRB_INVALID_ID; // entity whose BLAS is being traversed
-	bool found		 = false;
-	uint32_t node	 = S.tlasRoot;
+	V3 inv			= mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
+	uint32_t curEnt = PRB_INVALID_ID; // entity whose BLAS is being traversed (TLAS level when invalid)
+	uint32_t cur	= S.tlasRoot;
 	for (;;) {
-		// ---- visit internal node `node`
-		const uint4* np = S.bvhNodes + 5 * (size_t)node;
-		const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-		const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
-		const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
-					sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
-		const uint32_t childBase = n1.x, primBase = n1.y;
-		const uint32_t metaLo = n1.z, metaHi = n1.w;
-		const float tcur = found ? best.t : tmax;
-		// near-first ordering: collect internal hits, leaves are intersected immediately
-		uint32_t hitNode[8];
-		float hitDist[8];
-		int nh = 0;
+		// ---------------------------------------------------------------- internal node step
+		if (!(cur & STK_LEAF)) {
+			const uint4* np = S.bvhNodes + 5 * (size_t)cur;
+			const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+			const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+			const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
+						sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+			const uint32_t childBase = n1.x, primBase = n1.y;
+			const float tcur = best.t; // == tmax until something was hit
+			uint32_t nearEntry = STK_NONE;
+			float nearDist	   = PRB_INF;
 #pragma unroll
-		for (int i = 0; i < 8; ++i) {
-			const uint32_t meta = ((i < 4 ? metaLo : metaHi) >> (8 * (i & 3))) & 0xFFu;
-			if (meta == 0xFFu)
-				continue;
-			const uint32_t sh = 8 * (i & 3);
-			const uint32_t qlx = ((i < 4 ? n2.x : n2.y) >> sh) & 0xFFu, qly = ((i < 4 ? n2.z : n2.w) >> sh) & 0xFFu;
-			const uint32_t qlz = ((i < 4 ? n3.x : n3.y) >> sh) & 0xFFu, qhx = ((i < 4 ? n3.z : n3.w) >> sh) & 0xFFu;
-			const uint32_t qhy = ((i < 4 ? n4.x : n4.y) >> sh) & 0xFFu, qhz = ((i < 4 ? n4.z : n4.w) >> sh) & 0xFFu;
-			const float lox = px + (float)qlx * sx, loy = py + (float)qly * sy, loz = pz + (float)qlz * sz;
-			const float hix = px + (float)qhx * sx, hiy = py + (float)qhy * sy, hiz = pz + (float)qhz * sz;
-			const float ax = (lox - O.x) * inv.x, bx = (hix - O.x) * inv.x;
-			const float ay = (loy - O.y) * inv.y, by = (hiy - O.y) * inv.y;
-			const float az = (loz - O.z) * inv.z, bz = (hiz - O.z) * inv.z;
-			float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-			float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-			tn		 = tn - fabsf(tn) * 4e-7f; // conservative: never cull what the triangle test could accept
-			tf		 = tf + fabsf(tf) * 4e-7f;
-			if (!(fmaxf(tn, tmin) <= fminf(tf, tcur)))
-				continue;
-			if (meta & 0x80u) {
-				hitNode[nh] = childBase + (meta & 0x7Fu);
-				hitDist[nh] = tn;
-				++nh;
+			for (int i = 0; i < 8; ++i) {
+				const uint32_t meta = ((i < 4 ? n1.z : n1.w) >> (8 * (i & 3))) & 0xFFu;
+				const uint32_t sel	= 0x7440u + (uint32_t)(i & 3); // byte (i&3) of the first operand into the low mantissa byte
+				// child box: lo = p + q_lo * 2^e (the product is exact, so the fused form rounds like the builder's decodeCoord)
+				const float lox = fmaf(byteToFloat(i < 4 ? n2.x : n2.y, sel), sx, px), loy = fmaf(byteToFloat(i < 4 ? n2.z : n2.w, sel), sy, py);
+				const float loz = fmaf(byteToFloat(i < 4 ? n3.x : n3.y, sel), sz, pz), hix = fmaf(byteToFloat(i < 4 ? n3.z : n3.w, sel), sx, px);
+				const float hiy = fmaf(byteToFloat(i < 4 ? n4.x : n4.y, sel), sy, py), hiz = fmaf(byteToFloat(i < 4 ? n4.z : n4.w, sel), sz, pz);
+				const float ax = (lox - O.x) * inv.x, bx = (hix - O.x) * inv.x;
+				const float ay = (loy - O.y) * inv.y, by = (hiy - O.y) * inv.y;
+				const float az = (loz - O.z) * inv.z, bz = (hiz - O.z) * inv.z;
+				float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+				float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+				tn		 = tn - fabsf(tn) * 4e-7f; // conservative: never cull what the triangle test could accept
+				tf		 = tf + fabsf(tf) * 4e-7f;
+				const bool hit = (meta != 0xFFu) && (fmaxf(tn, tmin) <= fminf(tf, tcur));
+				if (hit) {
+					const uint32_t entry = (meta & 0x80u) ? (childBase + (meta & 0x7Fu)) : (STK_LEAF | (((meta >> 5) & 3u) << 29) | (primBase + (meta & 0x1Fu)));
+					// keep the nearest child in registers, push the other one
+					const bool nearer	 = tn < nearDist;
+					const uint32_t pe	 = nearer ? nearEntry : entry;
+					const float pd		 = nearer ? nearDist : tn;
+					nearEntry			 = nearer ? entry : nearEntry;
+					nearDist			 = nearer ? tn : nearDist;
+					if (pe != STK_NONE && sp < BVH_STACK)
+						stack[sp++] = make_uint2(pe, __float_as_uint(pd));
+				}
+			}
+			cur = nearEntry;
+		}
+		// ---------------------------------------------------------------- leaf step
+		if (cur != STK_NONE && (cur & STK_LEAF)) {
+			const uint32_t first = cur & 0x1FFFFFFFu, count = ((cur >> 29) & 3u) + 1;
+			if (curEnt == PRB_INVALID_ID) {
+				// TLAS leaf = one entity (the TLAS is built with one reference per leaf)
+				const uint32_t e	 = __ldg(S.tlasRefs + first);
+				const prb_entity& en = S.entities[e];
+				const uint32_t type	 = en.type;
+				if (type == PRB_ENTITY_SPHERE) {
+					float t;
+					if (sphereTest(O, D, tmin, best.t, ld3(en.geo), en.geo[3], t) && betterHit(t, e, 0, best)) {
+						best.entity = e;
+						best.prim	= 0;
+						best.t		= t;
+						best.u = best.v = 0;
+						if (ANY)
+							return true;
+					}
+					cur = STK_NONE;
+				} else {
+					// enter the entity's BLAS; the matching exit marker restores the world-space ray
+					if (sp < BVH_STACK)
+						stack[sp++] = make_uint2(STK_EXIT, 0);
+					curEnt = e;
+					if (type == PRB_ENTITY_MESH) { // planes are stored in world space: no transform (plane.cpp:71-94)
+						O	= xfPoint(en.world_to_local, wO);
+						D	= xfVec(en.world_to_local, wD);
+						inv = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
+					}
+					cur = en.blas_root;
+					continue;
+				}
 			} else {
-				const uint32_t first = primBase + (meta & 0x1Fu), count = ((meta >> 5) & 3u) + 1;
 				for (uint32_t k = first; k < first + count; ++k) {
-					if (curEnt == PRB_INVALID_ID) {
-						// ---- TLAS leaf: an entity
-						const uint32_t e	 = __ldg(S.tlasRefs + k);
-						const prb_entity& en = S.entities[e];
-						if (en.type == PRB_ENTITY_SPHERE) {
-							float t;
-							if (sphereTest(O, D, tmin, found ? best.t : tmax, ld3(en.geo), en.geo[3], t)) {
-								if (betterHit(t, e, 0, best)) {
-									best.entity = e;
-									best.prim	= 0;
-									best.t		= t;
-									best.u = best.v = 0;
-								}
-								found = true;
-								if (ANY)
-									return true;
-							}
-						} else if (sp + 2 <= BVH_STACK) {
-							// defer: push the instance (entered when popped); distance = this leaf box entry
-							stack[sp++] = make_uint2(0x80000000u | e, __float_as_uint(tn));
-						}
-					} else {
-						const float4* tp = S.bvhTris + 3 * (size_t)k;
-						const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-						float t, u, v;
-						if (triTest(O, D, tmin, found ? best.t : tmax, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v)) {
-							const uint32_t prim = __float_as_uint(a.w);
+					const float4* tp = S.bvhTris + 3 * (size_t)k;
+					const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+					float t, u, v;
+					if (triTest(O, D, tmin, best.t, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v)) {
+						const uint32_t prim = __float_as_uint(a.w);
+						if (betterHit(t, curEnt, prim, best)) {
 							if (__float_as_uint(b.w) & 1u) {
 								u = 1 - u;
 								v = 1 - v;
 							}
-							if (betterHit(t, curEnt, prim, best)) {
-								best.entity = curEnt;
-								best.prim	= prim;
-								best.t		= t;
-								best.u		= u;
-								best.v		= v;
-							}
-							found = true;
+							best.entity = curEnt;
+							best.prim	= prim;
+							best.t		= t;
+							best.u		= u;
+							best.v		= v;
 							if (ANY)
 								return true;
 						}
 					}
 				}
+				cur = STK_NONE;
 			}
 		}
-		// push internal hits far-to-near (selection by insertion sort on <= 8 entries)
-		for (int i = 1; i < nh; ++i) {
-			const float d	 = hitDist[i];
-			const uint32_t n = hitNode[i];
-			int j			 = i - 1;
-			while (j >= 0 && hitDist[j] < d) {
-				hitDist[j + 1] = hitDist[j];
-				hitNode[j + 1] = hitNode[j];
-				--j;
-			}
-			hitDist[j + 1] = d;
-			hitNode[j + 1] = n;
-		}
-		for (int i = 0; i < nh && sp < BVH_STACK; ++i)
-			stack[sp++] = make_uint2(hitNode[i], __float_as_uint(hitDist[i]));
-		// ---- pop
-		bool haveNode = false;
-		while (sp > 0) {
-			const uint2 e = stack[--sp];
-			if (e.x == STACK_INSTANCE_EXIT) { // leave the BLAS: restore the world-space ray
-				O	   = wO;
-				D	   = wD;
-				inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
-				curEnt = PRB_INVALID_ID;
-				continue;
-			}
-			if (found && __uint_as_float(e.y) > best.t)
-				continue; // subtree entirely behind the current closest hit
-			if (e.x & 0x80000000u) { // enter instance
-				const uint32_t ent	 = e.x & 0x7FFFFFFFu;
-				const prb_entity& en = S.entities[ent];
-				stack[sp++]			 = make_uint2(STACK_INSTANCE_EXIT, 0);
-				curEnt				 = ent;
-				if (en.type == PRB_ENTITY_MESH) {
-					O = xfPoint(en.world_to_local, wO);
-					D = xfVec(en.world_to_local, wD);
-				} // planes are stored in world space: no transform (plane.cpp:71-94)
-				inv		 = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
-				node	 = en.blas_root;
-				haveNode = true;
+		// ---------------------------------------------------------------- pop
+		if (cur == STK_NONE) {
+			for (;;) {
+				if (sp == 0)
+					return best.entity != PRB_INVALID_ID;
+				const uint2 e = stack[--sp];
+				if (e.x == STK_EXIT) { // leave the BLAS: restore the world-space ray
+					O	   = wO;
+					D	   = wD;
+					inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
+					curEnt = PRB_INVALID_ID;
+					continue;
+				}
+				if (__uint_as_float(e.y) > best.t)
+					continue; // subtree entirely behind the current closest hit
+				cur = e.x;
 				break;
 			}
-			node	 = e.x;
-			haveNode = true;
-			break;
 		}
-		if (!haveNode)
-			break;
 	}
-	return found;
 }
 } // namespace prb

@@ -4,18 +4,22 @@
 //   slot == one film pixel owned by this context.  A pixel's samples are generated strictly one after the other
 //   because all decisions of a pixel draw from the pixel's own pcg32_fast stream (RenderRandomMap), carried
 //   across iterations.  Slots are independent, so the wave always holds (#owned pixels) paths in flight:
-//   a slot whose path ended is refilled with its next sample ("regeneration").
+//   a slot whose path ended is refilled IN PLACE with its next sample ("path regeneration"), which keeps every
+//   lane busy until the pixel ran out of samples and makes slot == thread: all state accesses are coalesced SoA
+//   float4 loads/stores, no queue indirection.
 //
-//   per wavefront iteration:  generate (regen queue -> camera rays) -> extend (closest hit) -> shade (emission,
-//   NEE, scattering; appends to the next extend queue / the regen queue / the shadow queue) -> shadow (any hit,
-//   adds the NEE contribution).  Queues are uint32 slot lists in HBM appended with warp-aggregated atomics
-//   (ballot + popc + shuffle).  All kernels are persistent-style: fixed grid, grid-stride over the queue whose
-//   length is read from device memory, so the whole loop is launched without host round trips.
+//   one wavefront iteration = 2 kernels
+//     k_trace  per slot: the pending NEE shadow ray (any hit; adds its contribution, and finishes the previous sample
+//              when that sample ended with the shadow ray still in flight), then the path's next ray (closest hit)
+//     k_shade  per slot: emission / environment on the hit or miss, NEE (light sample + material eval + MIS -> shadow
+//              ray), Russian roulette + material sample -> next ray; when the path ends: fold the sample into the film
+//              (running mean) and start the pixel's next camera sample
+//   Slots retire when their pixel has no samples left; a device counter tells the host when all have retired.
 #pragma once
 #include "dev_shade.cuh"
 
 namespace prb {
-enum { CNT_EXTEND0 = 0, CNT_EXTEND1 = 1, CNT_REGEN = 2, CNT_SHADOW = 3, CNT_RETIRED = 4, CNT__COUNT = 8 };
+enum { CNT_RETIRED = 0, CNT__COUNT = 4 };
 enum { ST_CAMERA_RAY = 0, ST_LIGHT_RAY, ST_PRIMARY, ST_BOUNCE, ST_SHADOW, ST_MONO, ST_PIXEL_SAMPLE, ST_ENTITY_HIT, ST_BG_HIT, ST_CAMERA_DEPTH, ST_LIGHT_DEPTH, ST__COUNT };
 
 constexpr uint32_t FD_DEPTH_MASK   = 0xFFFFu;
@@ -23,12 +27,18 @@ constexpr uint32_t FD_FLAGS_SHIFT  = 16; // ray flags (8 bit)
 constexpr uint32_t FD_LAST_DELTA   = 1u << 30;
 constexpr uint32_t FD_LAST_EMISSIVE = 1u << 31;
 
+// slot state bits
+constexpr uint32_t SF_ACTIVE   = 1u; // rayO/rayD hold a ray to extend
+constexpr uint32_t SF_SHADOW   = 2u; // shO/shD/shXYZ hold a pending NEE shadow ray
+constexpr uint32_t SF_FINALIZE = 4u; // the sample that spawned the shadow ray already ended: fold prevAcc (+ contribution) into the film
+
 struct WFState {
 	// per slot
 	uint32_t* pixel;
-	uint32_t* iter; // next iteration to generate
-	float4* rayO;	// xyz, tmin
-	float4* rayD;	// xyz, tmax
+	uint32_t* iter;	 // number of samples started so far (== index of the next iteration to generate)
+	uint32_t* state; // SF_* bits
+	float4* rayO;	 // xyz, tmin
+	float4* rayD;	 // xyz, tmax
 	float4* wvl;
 	uint32_t* flagsDepth;
 	float4* thr;
@@ -38,14 +48,11 @@ struct WFState {
 	float4* lastPos;
 	uint4* hit; // entity, prim, u bits, v bits
 	float* hitT;
-	float4* shO;   // shadow origin xyz, tmin
-	float4* shD;   // shadow dir xyz, tmax
-	float4* shXYZ; // contribution if visible
-	float4* iterXYZ;
-	// queues + counters
-	uint32_t* qExtend[2];
-	uint32_t* qRegen;
-	uint32_t* qShadow;
+	float4* shO;	 // shadow origin xyz, tmin
+	float4* shD;	 // shadow dir xyz, tmax
+	float4* shXYZ;	 // contribution if visible
+	float4* iterXYZ; // XYZ accumulated by the running sample
+	float4* prevAcc; // XYZ of the sample waiting for its last shadow ray, w = its 1-based iteration count
 	uint32_t* counters;
 	// film (indexed by film pixel)
 	uint64_t* rng;
@@ -56,21 +63,6 @@ struct WFState {
 	uint32_t nSlots, firstIter, endIter;
 };
 
-// warp-aggregated append; must be called by all 32 lanes of the warp (convergent point)
-PRB_DEV void queuePush(uint32_t* counter, uint32_t* queue, bool pred, uint32_t value)
-{
-	const unsigned mask = __ballot_sync(0xFFFFFFFFu, pred);
-	if (mask == 0)
-		return;
-	const int lane	 = threadIdx.x & 31;
-	const int leader = __ffs(mask) - 1;
-	uint32_t base	 = 0;
-	if (lane == leader)
-		base = atomicAdd(counter, (uint32_t)__popc(mask));
-	base = __shfl_sync(0xFFFFFFFFu, base, leader);
-	if (pred)
-		queue[base + __popc(mask & ((1u << lane) - 1))] = value;
-}
 PRB_DEV void statAdd(unsigned long long* stats, int which, uint32_t v)
 { // one atomic per warp per counter (all lanes call)
 #pragma unroll
@@ -80,79 +72,88 @@ PRB_DEV void statAdd(unsigned long long* stats, int which, uint32_t v)
 		atomicAdd(stats + which, (unsigned long long)v);
 }
 
-__global__ void k_init_slots(WFState W)
+// FrameOutputDevice::onEndOfIteration (FrameOutputDevice.cpp:202-221): film = (film * (i - 1) + sample) / i
+PRB_DEV void foldSampleIntoFilm(const WFState& W, uint32_t pix, float x, float y, float z, uint32_t iterCount)
 {
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.nSlots; i += gridDim.x * blockDim.x) {
-		W.iter[i]	 = W.firstIter;
-		W.iterXYZ[i] = make_float4(0, 0, 0, 0);
-		W.qRegen[i]	 = i;
-	}
+	const float fin	  = (float)(iterCount - 1);
+	const float iterf = (float)iterCount;
+	float* m		  = W.filmMean + 3 * (size_t)pix;
+	m[0]			  = (m[0] * fin + x) / iterf;
+	m[1]			  = (m[1] * fin + y) / iterf;
+	m[2]			  = (m[2] * fin + z) / iterf;
 }
 
-// ------------------------------------------------------------------ generate
-__global__ void __launch_bounds__(256) k_generate(DScene S, WFState W, int extendSel)
+// starts the pixel's next camera sample in `slot` (RenderTile::constructCameraRay); returns false when the pixel has
+// no samples left (the slot retires)
+PRB_DEV bool startNextSample(const DScene& S, const WFState& W, uint32_t slot, uint32_t pix)
 {
-	const uint32_t n = W.counters[CNT_REGEN];
-	uint32_t nSamples = 0;
-	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-		const uint32_t idx = base + threadIdx.x;
-		bool push		   = false;
-		bool retired	   = false;
-		uint32_t slot	   = 0;
-		if (idx < n) {
-			slot			   = W.qRegen[idx];
-			const uint32_t pix = W.pixel[slot];
-			uint32_t it		   = W.iter[slot];
-			if (it > W.firstIter) { // a sample just finished: FrameOutputDevice::onEndOfIteration (running mean)
-				const float4 acc   = W.iterXYZ[slot];
-				const float fin	   = (float)(it - 1); // 0-based index of the finished iteration
-				const float iterf  = (float)it;
-				float* m		   = W.filmMean + 3 * (size_t)pix;
-				m[0]			   = (m[0] * fin + acc.x) / iterf;
-				m[1]			   = (m[1] * fin + acc.y) / iterf;
-				m[2]			   = (m[2] * fin + acc.z) / iterf;
-				W.iterXYZ[slot]	   = make_float4(0, 0, 0, 0);
-			}
-			if (it >= W.endIter) {
-				retired = true;
-			} else {
-				Rng rnd{ W.rng[pix] };
-				CameraSampleOut cs;
-				const uint32_t fw = S.settings.film_width;
-				constructCameraRay(S, pix % fw, pix / fw, it, rnd, cs);
-				W.rng[pix]		   = rnd.s;
-				W.iter[slot]	   = it + 1;
-				W.rayO[slot]	   = make_float4(cs.origin.x, cs.origin.y, cs.origin.z, cs.tmin);
-				W.rayD[slot]	   = make_float4(cs.dir.x, cs.dir.y, cs.dir.z, cs.tmax);
-				W.wvl[slot]		   = tof4(cs.wvl);
-				W.wvlPDF[slot]	   = tof4(cs.wvlPDF);
-				W.thr[slot]		   = make_float4(1, 1, 1, 1);
-				W.pathPDF[slot]	   = make_float4(1, 1, 1, 1);
-				W.prevPDF[slot]	   = make_float4(1, 1, 1, 1);
-				W.lastPos[slot]	   = make_float4(0, 0, 0, 0);
-				const uint32_t rf  = PRB_RAY_CAMERA | (cs.mono ? PRB_RAY_MONOCHROME : 0);
-				W.flagsDepth[slot] = (rf << FD_FLAGS_SHIFT) | FD_LAST_DELTA; // depth 0, LastWasDelta = true
-				push			   = true;
-				++nSamples;
-			}
+	const uint32_t it = W.iter[slot];
+	if (it >= W.endIter)
+		return false;
+	Rng rnd{ W.rng[pix] };
+	CameraSampleOut cs;
+	const uint32_t fw = S.settings.film_width;
+	constructCameraRay(S, pix % fw, pix / fw, it, rnd, cs);
+	W.rng[pix]		   = rnd.s;
+	W.iter[slot]	   = it + 1;
+	W.rayO[slot]	   = make_float4(cs.origin.x, cs.origin.y, cs.origin.z, cs.tmin);
+	W.rayD[slot]	   = make_float4(cs.dir.x, cs.dir.y, cs.dir.z, cs.tmax);
+	W.wvl[slot]		   = tof4(cs.wvl);
+	W.wvlPDF[slot]	   = tof4(cs.wvlPDF);
+	W.thr[slot]		   = make_float4(1, 1, 1, 1);
+	W.pathPDF[slot]	   = make_float4(1, 1, 1, 1);
+	W.prevPDF[slot]	   = make_float4(1, 1, 1, 1);
+	W.lastPos[slot]	   = make_float4(0, 0, 0, 0);
+	const uint32_t rf  = PRB_RAY_CAMERA | (cs.mono ? PRB_RAY_MONOCHROME : 0);
+	W.flagsDepth[slot] = (rf << FD_FLAGS_SHIFT) | FD_LAST_DELTA; // depth 0, LastWasDelta = true
+	return true;
+}
+
+__global__ void __launch_bounds__(128) k_init_slots(DScene S, WFState W)
+{
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t started	= 0;
+	if (slot < W.nSlots) {
+		W.iter[slot]	= W.firstIter;
+		W.iterXYZ[slot] = make_float4(0, 0, 0, 0);
+		const bool ok	= startNextSample(S, W, slot, W.pixel[slot]);
+		W.state[slot]	= ok ? SF_ACTIVE : 0u;
+		started			= ok ? 1u : 0u;
+		if (!ok)
+			atomicAdd(W.counters + CNT_RETIRED, 1u);
+	}
+	statAdd(W.stats, ST_PIXEL_SAMPLE, started);
+	statAdd(W.stats, ST_CAMERA_RAY, started);
+	statAdd(W.stats, ST_PRIMARY, started);
+}
+
+// ------------------------------------------------------------------ trace: pending shadow ray, then the path's next ray
+__global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
+{
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= W.nSlots)
+		return;
+	const uint32_t st = W.state[slot];
+	if (st == 0)
+		return;
+	if (st & SF_SHADOW) {
+		const float4 o = W.shO[slot], d = W.shD[slot];
+		HitRec h;
+		const bool occluded = traverseScene<true>(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
+		const float4 c		= occluded ? make_float4(0, 0, 0, 0) : W.shXYZ[slot];
+		if (st & SF_FINALIZE) {
+			const float4 p = W.prevAcc[slot];
+			foldSampleIntoFilm(W, W.pixel[slot], p.x + c.x, p.y + c.y, p.z + c.z, __float_as_uint(p.w));
+		} else if (!occluded) {
+			float4 acc = W.iterXYZ[slot];
+			acc.x += c.x;
+			acc.y += c.y;
+			acc.z += c.z;
+			W.iterXYZ[slot] = acc;
 		}
-		queuePush(W.counters + extendSel, W.qExtend[extendSel], push, slot);
-		const unsigned rmask = __ballot_sync(0xFFFFFFFFu, retired);
-		if ((threadIdx.x & 31) == 0 && rmask)
-			atomicAdd(W.counters + CNT_RETIRED, (uint32_t)__popc(rmask));
+		W.state[slot] = st & SF_ACTIVE;
 	}
-	statAdd(W.stats, ST_PIXEL_SAMPLE, nSamples);
-	statAdd(W.stats, ST_CAMERA_RAY, nSamples);
-	statAdd(W.stats, ST_PRIMARY, nSamples);
-}
-
-// ------------------------------------------------------------------ extend
-__global__ void __launch_bounds__(256) k_extend(DScene S, WFState W, int extendSel)
-{
-	const uint32_t n  = W.counters[extendSel];
-	const uint32_t* q = W.qExtend[extendSel];
-	for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-		const uint32_t slot = q[idx];
+	if (st & SF_ACTIVE) {
 		const float4 o = W.rayO[slot], d = W.rayD[slot];
 		HitRec h;
 		traverseScene<false>(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
@@ -200,20 +201,17 @@ PRB_DEV float rrProbability(const DScene& S, uint32_t pathLength, bool delta)
 	return __ldg(S.rrProb + min(pathLength, S.rrCount - 1));
 }
 
-__global__ void __launch_bounds__(128) k_shade(DScene S, WFState W, int extendSel)
+__global__ void __launch_bounds__(128) k_shade(DScene S, WFState W)
 {
-	const uint32_t n	   = W.counters[extendSel];
-	const uint32_t* q	   = W.qExtend[extendSel];
-	const int nextSel	   = 1 - extendSel;
 	const prb_settings& st = S.settings;
 	const bool power	   = st.mis_power;
 	uint32_t sEntity = 0, sBg = 0, sDepth = 0, sShadow = 0, sBounce = 0, sMono = 0;
-	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-		const uint32_t idx = base + threadIdx.x;
-		bool pushExtend = false, pushRegen = false, pushShadow = false;
-		uint32_t slot = 0;
-		if (idx < n) {
-			slot				= q[idx];
+	uint32_t sSamples = 0;
+	{
+		const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+		bool pushShadow		= false;
+		const uint32_t sst	= slot < W.nSlots ? W.state[slot] : 0u;
+		if (sst & SF_ACTIVE) {
 			const uint32_t pix	= W.pixel[slot];
 			const uint4 hraw	= W.hit[slot];
 			const float4 ro = W.rayO[slot], rd = W.rayD[slot];
@@ -479,16 +477,34 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, WFState W, int extendSe
 					W.rng[pix] = rnd.s;
 				}
 			}
-			W.iterXYZ[slot] = make_float4(acc[0], acc[1], acc[2], 0);
-			pushExtend		= alive;
-			pushRegen		= !alive;
+			uint32_t nst = pushShadow ? SF_SHADOW : 0u;
+			if (alive) {
+				W.iterXYZ[slot] = make_float4(acc[0], acc[1], acc[2], 0);
+				nst |= SF_ACTIVE;
+			} else {
+				// the path ended: fold the sample into the film -- now, or in the next k_trace when its last NEE shadow ray
+				// is still pending -- and refill the slot with the pixel's next camera sample
+				const uint32_t iterCount = W.iter[slot];
+				if (pushShadow) {
+					W.prevAcc[slot] = make_float4(acc[0], acc[1], acc[2], __uint_as_float(iterCount));
+					nst |= SF_FINALIZE;
+				} else {
+					foldSampleIntoFilm(W, pix, acc[0], acc[1], acc[2], iterCount);
+				}
+				W.iterXYZ[slot] = make_float4(0, 0, 0, 0);
+				if (startNextSample(S, W, slot, pix)) {
+					nst |= SF_ACTIVE;
+					++sSamples;
+				} else {
+					atomicAdd(W.counters + CNT_RETIRED, 1u);
+				}
+			}
+			W.state[slot] = nst;
 		}
-		queuePush(W.counters + nextSel, W.qExtend[nextSel], pushExtend, slot);
-		queuePush(W.counters + CNT_SHADOW, W.qShadow, pushShadow, slot);
-		// a path that ended while its last NEE shadow ray is still pending is regenerated only after the shadow
-		// kernel ran (the generate kernel of the NEXT wavefront iteration consumes the regen queue) -> ordering holds
-		queuePush(W.counters + CNT_REGEN, W.qRegen, pushRegen, slot);
 	}
+	statAdd(W.stats, ST_PIXEL_SAMPLE, sSamples);
+	statAdd(W.stats, ST_CAMERA_RAY, sSamples);
+	statAdd(W.stats, ST_PRIMARY, sSamples);
 	statAdd(W.stats, ST_ENTITY_HIT, sEntity);
 	statAdd(W.stats, ST_BG_HIT, sBg);
 	statAdd(W.stats, ST_CAMERA_DEPTH, sDepth);
@@ -496,26 +512,6 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, WFState W, int extendSe
 	statAdd(W.stats, ST_BOUNCE, sBounce);
 	statAdd(W.stats, ST_CAMERA_RAY, sBounce);
 	statAdd(W.stats, ST_MONO, sMono);
-}
-
-// ------------------------------------------------------------------ shadow
-__global__ void __launch_bounds__(256) k_shadow(DScene S, WFState W)
-{
-	const uint32_t n = W.counters[CNT_SHADOW];
-	for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-		const uint32_t slot = W.qShadow[idx];
-		const float4 o = W.shO[slot], d = W.shD[slot];
-		HitRec h;
-		const bool occluded = traverseScene<true>(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
-		if (!occluded) {
-			const float4 c = W.shXYZ[slot];
-			float4 acc	   = W.iterXYZ[slot];
-			acc.x += c.x;
-			acc.y += c.y;
-			acc.z += c.z;
-			W.iterXYZ[slot] = acc;
-		}
-	}
 }
 
 // ------------------------------------------------------------------ stream tracing (prb_trace_closest / _any)

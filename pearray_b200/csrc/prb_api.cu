@@ -80,8 +80,8 @@ struct prb_ctx {
 	DBuf<uint32_t> sampleCount;
 	DBuf<unsigned long long> stats;
 	// wavefront
-	DBuf<uint32_t> pixel, iter, flagsDepth, qExtend0, qExtend1, qRegen, qShadow, counters;
-	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ;
+	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters;
+	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ, prevAcc;
 	DBuf<uint4> hit;
 	DBuf<float> hitT;
 	std::vector<prb_tile> cachedTiles;
@@ -102,8 +102,8 @@ struct prb_ctx {
 	// per-stage profiling (prb_set_profiling)
 	bool profiling = false;
 	std::vector<cudaEvent_t> profEvents; // pairs
-	float stageMs[PRB_STAGE__COUNT] = { 0, 0, 0, 0 };
-	uint64_t stageLaunches[PRB_STAGE__COUNT] = { 0, 0, 0, 0 };
+	float stageMs[PRB_STAGE__COUNT] = {};
+	uint64_t stageLaunches[PRB_STAGE__COUNT] = {};
 };
 
 extern "C" {
@@ -163,13 +163,13 @@ void prb_destroy(prb_ctx* c)
 	if (c->graphExec)
 		cudaGraphExecDestroy(c->graphExec);
 	DBuf<uint32_t>* ub[] = { &c->entityMaterials, &c->faceIndices, &c->faceSlots, &c->tlasRefs, &c->sampleCount, &c->pixel, &c->iter, &c->flagsDepth,
-							 &c->qExtend0, &c->qExtend1, &c->qRegen, &c->qShadow, &c->counters, &c->scratchU };
+							 &c->slotState, &c->counters, &c->scratchU };
 	for (auto* b : ub)
 		b->release();
 	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->hitT, &c->scratchF };
 	for (auto* b : fb)
 		b->release();
-	DBuf<float4>* f4[] = { &c->bvhTris, &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ };
+	DBuf<float4>* f4[] = { &c->bvhTris, &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc };
 	for (auto* b : f4)
 		b->release();
 	c->nodes.release();
@@ -344,12 +344,9 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 	CU(c->pixel.upload(pix.data(), n, c->stream));
 	CU(c->iter.alloc(n));
 	CU(c->flagsDepth.alloc(n));
-	CU(c->qExtend0.alloc(n));
-	CU(c->qExtend1.alloc(n));
-	CU(c->qRegen.alloc(n));
-	CU(c->qShadow.alloc(n));
+	CU(c->slotState.alloc(n));
 	CU(c->counters.alloc(CNT__COUNT));
-	DBuf<float4>* f4[] = { &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ };
+	DBuf<float4>* f4[] = { &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc };
 	for (auto* b : f4)
 		CU(b->alloc(n));
 	CU(c->hit.alloc(n));
@@ -380,10 +377,8 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.shD		  = c->shD.p;
 	W.shXYZ		  = c->shXYZ.p;
 	W.iterXYZ	  = c->iterXYZ.p;
-	W.qExtend[0]  = c->qExtend0.p;
-	W.qExtend[1]  = c->qExtend1.p;
-	W.qRegen	  = c->qRegen.p;
-	W.qShadow	  = c->qShadow.p;
+	W.prevAcc	  = c->prevAcc.p;
+	W.state		  = c->slotState.p;
 	W.counters	  = c->counters.p;
 	W.rng		  = c->rng.p;
 	W.filmMean	  = c->filmMean.p;
@@ -409,69 +404,49 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 	if (st != PRB_OK)
 		return st;
 	cudaStream_t s = c->stream;
-	const WFState W = makeWF(c, first_iteration, iteration_count);
-	const int grid	= c->smCount * 4;
+	const WFState W	 = makeWF(c, first_iteration, iteration_count);
+	const int blocks = (int)((c->nSlots + 127) / 128);
 	CU(cudaEventRecord(c->evA, s));
 	CU(cudaMemsetAsync(c->counters.p, 0, CNT__COUNT * sizeof(uint32_t), s));
-	k_init_slots<<<grid, 256, 0, s>>>(W);
-	CU(cudaMemcpyAsync(c->counters.p + CNT_REGEN, &c->nSlots, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+	k_init_slots<<<blocks, 128, 0, s>>>(c->S, W);
 	c->kernelLaunches += 1;
-	// one wavefront iteration = generate -> extend -> shade -> shadow; 2 iterations (both queue parities) form one
-	// CUDA graph that is replayed; the retired-slot counter is polled every few replays.
-	auto enqueueIteration = [&](int sel) -> cudaError_t {
-		cudaError_t e = cudaMemsetAsync(c->counters.p + (1 - sel), 0, sizeof(uint32_t), s);
-		if (e != cudaSuccess)
-			return e;
-		k_generate<<<grid, 256, 0, s>>>(c->S, W, sel);
-		e = cudaMemsetAsync(c->counters.p + CNT_REGEN, 0, sizeof(uint32_t), s);
-		if (e != cudaSuccess)
-			return e;
-		k_extend<<<grid, 256, 0, s>>>(c->S, W, sel);
-		e = cudaMemsetAsync(c->counters.p + CNT_SHADOW, 0, sizeof(uint32_t), s);
-		if (e != cudaSuccess)
-			return e;
-		k_shade<<<c->smCount * 8, 128, 0, s>>>(c->S, W, sel);
-		k_shadow<<<grid, 256, 0, s>>>(c->S, W);
-		return cudaGetLastError();
-	};
-	// upper bound on wavefront iterations: every sample needs at most max_ray_depth+1 iterations
+	CU(cudaGetLastError());
+	// one wavefront iteration = k_trace + k_shade.  ITERS_PER_GRAPH iterations form one CUDA graph that is replayed;
+	// the retired-slot counter is read back every GRAPHS_PER_POLL replays.
+	constexpr int ITERS_PER_GRAPH = 8, GRAPHS_PER_POLL = 4;
+	// upper bound on wavefront iterations: every sample needs at most max_ray_depth + 1 iterations
 	const uint64_t maxIters = (uint64_t)iteration_count * (c->S.settings.max_ray_depth + 2) + 8;
-	const int replaysPerPoll = 16;
+	uint64_t done = 0;
+	bool finished = false;
+	auto poll = [&]() -> cudaError_t {
+		cudaError_t e = cudaMemcpyAsync(c->hostCounters, c->counters.p, CNT__COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(s);
+		finished = c->hostCounters[CNT_RETIRED] >= c->nSlots;
+		return e;
+	};
 	if (c->profiling) {
 		// same launch sequence without graph replay, every kernel bracketed by an event pair on the context stream
-		const size_t needEvents = (size_t)replaysPerPoll * 2 * PRB_STAGE__COUNT * 2;
+		const size_t needEvents = (size_t)ITERS_PER_GRAPH * GRAPHS_PER_POLL * PRB_STAGE__COUNT * 2;
 		while (c->profEvents.size() < needEvents) {
 			cudaEvent_t ev;
 			CU(cudaEventCreate(&ev));
 			c->profEvents.push_back(ev);
 		}
-		uint64_t done = 0;
-		bool finished = false;
-		while (!finished && done < maxIters + 2 * replaysPerPoll) {
+		while (!finished && done < maxIters + ITERS_PER_GRAPH * GRAPHS_PER_POLL) {
 			size_t ne = 0;
-			for (int r = 0; r < 2 * replaysPerPoll; ++r) {
-				const int sel = r & 1;
-				CU(cudaMemsetAsync(c->counters.p + (1 - sel), 0, sizeof(uint32_t), s));
+			for (int r = 0; r < ITERS_PER_GRAPH * GRAPHS_PER_POLL; ++r) {
 				CU(cudaEventRecord(c->profEvents[ne++], s));
-				k_generate<<<grid, 256, 0, s>>>(c->S, W, sel);
-				CU(cudaEventRecord(c->profEvents[ne++], s));
-				CU(cudaMemsetAsync(c->counters.p + CNT_REGEN, 0, sizeof(uint32_t), s));
-				CU(cudaEventRecord(c->profEvents[ne++], s));
-				k_extend<<<grid, 256, 0, s>>>(c->S, W, sel);
-				CU(cudaEventRecord(c->profEvents[ne++], s));
-				CU(cudaMemsetAsync(c->counters.p + CNT_SHADOW, 0, sizeof(uint32_t), s));
-				CU(cudaEventRecord(c->profEvents[ne++], s));
-				k_shade<<<c->smCount * 8, 128, 0, s>>>(c->S, W, sel);
+				k_trace<<<blocks, 128, 0, s>>>(c->S, W);
 				CU(cudaEventRecord(c->profEvents[ne++], s));
 				CU(cudaEventRecord(c->profEvents[ne++], s));
-				k_shadow<<<grid, 256, 0, s>>>(c->S, W);
+				k_shade<<<blocks, 128, 0, s>>>(c->S, W);
 				CU(cudaEventRecord(c->profEvents[ne++], s));
 				CU(cudaGetLastError());
 			}
-			done += 2 * replaysPerPoll;
-			c->kernelLaunches += 8 * replaysPerPoll;
-			CU(cudaMemcpyAsync(c->hostCounters, c->counters.p, CNT__COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-			CU(cudaStreamSynchronize(s));
+			done += ITERS_PER_GRAPH * GRAPHS_PER_POLL;
+			c->kernelLaunches += 2 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
+			CU(poll());
 			for (size_t i = 0; i + 1 < ne; i += 2) {
 				float ms = 0;
 				CU(cudaEventElapsedTime(&ms, c->profEvents[i], c->profEvents[i + 1]));
@@ -479,52 +454,43 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 				c->stageMs[stage] += ms;
 				c->stageLaunches[stage] += 1;
 			}
-			finished = c->hostCounters[CNT_RETIRED] >= c->nSlots;
 		}
-		c->wavefrontIterations += done;
-		CU(cudaEventRecord(c->evB, s));
-		CU(cudaEventSynchronize(c->evB));
-		CU(cudaEventElapsedTime(&c->lastMs, c->evA, c->evB));
-		if (!finished)
-			return fail(PRB_ERR_CUDA, "wavefront loop did not terminate within the iteration bound");
-		return PRB_OK;
-	}
-	cudaGraph_t graph = nullptr;
-	cudaGraphExec_t exec = nullptr;
-	CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-	cudaError_t ce = enqueueIteration(0);
-	if (ce == cudaSuccess)
-		ce = enqueueIteration(1);
-	cudaError_t ee = cudaStreamEndCapture(s, &graph);
-	if (ce != cudaSuccess || ee != cudaSuccess) {
-		if (graph)
-			cudaGraphDestroy(graph);
-		return fail(PRB_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
-	}
-	CU(cudaGraphInstantiate(&exec, graph, 0));
-	cudaGraphDestroy(graph);
-	uint64_t done = 0;
-	bool finished = false;
-	while (!finished && done < maxIters + 2 * replaysPerPoll) {
-		for (int r = 0; r < replaysPerPoll; ++r) {
-			cudaError_t e = cudaGraphLaunch(exec, s);
+	} else {
+		cudaGraph_t graph	 = nullptr;
+		cudaGraphExec_t exec = nullptr;
+		CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+		for (int r = 0; r < ITERS_PER_GRAPH; ++r) {
+			k_trace<<<blocks, 128, 0, s>>>(c->S, W);
+			k_shade<<<blocks, 128, 0, s>>>(c->S, W);
+		}
+		const cudaError_t ce = cudaGetLastError();
+		const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+		if (ce != cudaSuccess || ee != cudaSuccess) {
+			if (graph)
+				cudaGraphDestroy(graph);
+			return fail(PRB_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+		}
+		CU(cudaGraphInstantiate(&exec, graph, 0));
+		cudaGraphDestroy(graph);
+		while (!finished && done < maxIters + ITERS_PER_GRAPH * GRAPHS_PER_POLL) {
+			cudaError_t e = cudaSuccess;
+			for (int r = 0; r < GRAPHS_PER_POLL && e == cudaSuccess; ++r)
+				e = cudaGraphLaunch(exec, s);
+			done += ITERS_PER_GRAPH * GRAPHS_PER_POLL;
+			c->kernelLaunches += 2 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
+			if (e == cudaSuccess)
+				e = poll();
 			if (e != cudaSuccess) {
 				cudaGraphExecDestroy(exec);
-				return fail(PRB_ERR_CUDA, std::string("graph launch failed: ") + cudaGetErrorString(e));
+				return fail(PRB_ERR_CUDA, std::string("wavefront loop failed: ") + cudaGetErrorString(e));
 			}
 		}
-		done += 2 * replaysPerPoll;
-		c->kernelLaunches += 8 * replaysPerPoll;
-		cudaError_t e = cudaMemcpyAsync(c->hostCounters, c->counters.p, CNT__COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
-		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(s);
-		if (e != cudaSuccess) {
-			cudaGraphExecDestroy(exec);
-			return fail(PRB_ERR_CUDA, std::string("wavefront loop failed: ") + cudaGetErrorString(e));
-		}
-		finished = c->hostCounters[CNT_RETIRED] >= c->nSlots;
+		cudaGraphExecDestroy(exec);
 	}
-	cudaGraphExecDestroy(exec);
+	// flush: samples that ended with their last shadow ray in flight are folded into the film by k_trace
+	k_trace<<<blocks, 128, 0, s>>>(c->S, W);
+	c->kernelLaunches += 1;
+	CU(cudaGetLastError());
 	c->wavefrontIterations += done;
 	CU(cudaEventRecord(c->evB, s));
 	CU(cudaEventSynchronize(c->evB));
