@@ -327,13 +327,161 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- C5: triangle soup
+def run_soup(args, rank, world, local_rank):
+    """synthetic N-triangle soup (default 10 M), 2048x2048 pinhole, 16 jittered passes; three ray classes
+    timed separately through prb_trace_closest_device / prb_trace_any_device with the ray streams resident in HBM:
+    primary (coherent closest hit), shadow (any hit towards a point light at (0,3,0), tfar = dist - 1e-3) and incoherent
+    (cosine-hemisphere bounce from every primary hit, closest hit).  The only configuration that streams the BVH from HBM."""
+    import numpy as np
+    import torch
+    import pearray_b200 as prb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    res = args.soup_film
+    t0 = time.perf_counter()
+    scene = prb.Scene.soup(args.triangles, seed=1234, film=(res, res))
+    build_s = time.perf_counter() - t0
+    d = scene.desc.contents
+    ctx = prb.Context(local_rank)
+    ctx.upload_scene(scene)
+    ctx.upload_rng(scene.rng_map())
+    verts = torch.from_numpy(np.ctypeslib.as_array(d.vertices, shape=(d.n_vertices, 3)).copy()).to(dev).view(-1, 3, 3)
+    n = res * res
+    passes = args.passes
+    # weak scaling over ranks: every rank traces its own passes (pass index offset by rank) against the replicated scene
+    f32 = dict(dtype=torch.float32, device=dev)
+    ent = torch.empty(n, dtype=torch.int32, device=dev); prim = torch.empty_like(ent)
+    u = torch.empty(n, **f32); v = torch.empty(n, **f32); t = torch.empty(n, **f32)
+    occ = torch.empty(n, dtype=torch.uint8, device=dev)
+    light = torch.tensor([0.0, 3.0, 0.0], **f32)
+
+    def soa(x):  # (n,3) -> three contiguous columns
+        return [x[:, i].contiguous() for i in range(3)]
+
+    def ptrs(o, dd, tmin=None, tmax=None):
+        return [c.data_ptr() for c in o] + [c.data_ptr() for c in dd] + [tmin.data_ptr() if tmin is not None else None, tmax.data_ptr() if tmax is not None else None]
+
+    hitp = [ent.data_ptr(), prim.data_ptr(), u.data_ptr(), v.data_ptr(), t.data_ptr()]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    ms = {"primary": 0.0, "shadow": 0.0, "incoherent": 0.0}
+    rays = {"primary": 0, "shadow": 0, "incoherent": 0}
+    hits = {"primary": 0, "shadow": 0, "incoherent": 0}
+    sampler = ClockSampler(local_rank)
+
+    def one_pass(p, timed):
+        org, dr, _, _ = ctx.generate_camera_rays([(0, 0, res, res)], p)
+        o = soa(torch.from_numpy(org).to(dev)); dd = soa(torch.from_numpy(dr).to(dev))
+        torch.cuda.synchronize(dev)
+        ctx.trace_closest_device(ptrs(o, dd), n, hitp)
+        if timed:
+            ms["primary"] += ctx.last_device_ms(); rays["primary"] += n
+        hit = ent != -1
+        idx = hit.nonzero().squeeze(1)
+        m = int(idx.numel())
+        if timed:
+            hits["primary"] += m
+        O = torch.stack(o, 1)[idx]; D = torch.stack(dd, 1)[idx]
+        P = O + D * t[idx, None]
+        tri = verts[prim[idx].long()]
+        N = torch.linalg.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+        N = N / N.norm(dim=1, keepdim=True).clamp_min(1e-30)
+        N = torch.where((N * D).sum(1, keepdim=True) > 0, -N, N)  # face the incoming ray
+        # shadow rays (Scene::traceShadowRay semantics: tnear 1e-4, tfar = distance - 1e-3)
+        L = light - P
+        dist_l = L.norm(dim=1)
+        L = L / dist_l[:, None]
+        so = soa(P); sd = soa(L)
+        tmin = torch.full((m,), 1e-4, **f32); tmax = (dist_l - 1e-3).contiguous()
+        torch.cuda.synchronize(dev)
+        ctx.trace_any_device(ptrs(so, sd, tmin, tmax), m, occ.data_ptr())
+        if timed:
+            ms["shadow"] += ctx.last_device_ms(); rays["shadow"] += m; hits["shadow"] += int(occ[:m].sum())
+        # incoherent: cosine-hemisphere bounce around N
+        r1 = torch.rand(m, generator=gen, **f32); r2 = torch.rand(m, generator=gen, **f32)
+        ct = r1.sqrt(); st_ = (1 - r1).clamp_min(0).sqrt(); ph = 2 * np.pi * r2
+        a = torch.where(N[:, 0:1].abs() > 0.9, torch.tensor([0.0, 1.0, 0.0], **f32), torch.tensor([1.0, 0.0, 0.0], **f32)).expand(m, 3)
+        T = torch.linalg.cross(N, a); T = T / T.norm(dim=1, keepdim=True); B = torch.linalg.cross(N, T)
+        W = T * (st_ * ph.cos())[:, None] + B * (st_ * ph.sin())[:, None] + N * ct[:, None]
+        bo = soa(P); bd = soa(W)
+        torch.cuda.synchronize(dev)
+        ctx.trace_closest_device(ptrs(bo, bd, tmin, None), m, hitp)
+        if timed:
+            ms["incoherent"] += ctx.last_device_ms(); rays["incoherent"] += m; hits["incoherent"] += int((ent[:m] != -1).sum())
+
+    for w in range(max(args.warmup, 1)):
+        one_pass(1000 + w, False)
+    ctx.reset_stats()
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        for p in range(passes):
+            one_pass(rank * passes + p, True)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    if rank == 0:
+        sampler.stop()
+    tot_ms = sum(ms.values())
+    tot_rays = sum(rays.values())
+    if world > 1:
+        tt = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tot_ms_max = float(tt.item())
+        rr = torch.tensor([float(tot_rays)], dtype=torch.float64, device=dev)
+        dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+        all_rays = float(rr.item())
+    else:
+        tot_ms_max, all_rays = tot_ms, float(tot_rays)
+    if rank == 0:
+        n_tris = int(d.n_bvh_tris)
+        b_closest, b_any = bvh_depth_bytes(n_tris)
+        peak, peak_src = measured_peak_gbs()
+        per_class = {}
+        for k in ms:
+            bpr = b_any if k == "shadow" else b_closest
+            per_class[k] = {"mrays_per_s": rays[k] / (ms[k] * 1e-3) / 1e6, "hit_fraction": hits[k] / max(rays[k], 1), "ms": ms[k],
+                            "achieved_gbs": rays[k] * bpr / (ms[k] * 1e-3) / 1e9, "frac": rays[k] * bpr / (ms[k] * 1e-3) / 1e9 / peak, "bytes_per_ray": bpr}
+        dom = max(ms, key=lambda k: ms[k])
+        launches = args.steps * passes
+        roofline = {"bound": "hbm", "kernel": "k_trace_any" if dom == "shadow" else "k_trace_closest (%s rays)" % dom, "achieved": per_class[dom]["achieved_gbs"],
+                    "peak": peak, "unit": "GB/s", "frac": per_class[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "avg_launch_us": 1e3 * ms[dom] / launches, "launches": launches, "bytes_per_unit": per_class[dom]["bytes_per_ray"],
+                    "units_per_launch": rays[dom] / launches}
+        line = {"metric": "rays/s (primary+shadow+incoherent)", "value": all_rays / (tot_ms_max * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": "synthetic %d-triangle soup, %dx%d pinhole, %d passes/step, primary+shadow+1-bounce incoherent" % (n_tris, res, res, passes),
+                                                "bvh_nodes": int(d.n_bvh_nodes), "bvh_mbytes": (int(d.n_bvh_nodes) * 80 + n_tris * 48) / 1e6, "host_build_s": build_s,
+                                                "l2": "BVH + triangles (%.0f MB) exceed the 126 MB L2 for >= 2.4 M triangles" % ((int(d.n_bvh_nodes) * 80 + n_tris * 48) / 1e6)},
+                "classes": per_class, "roofline": roofline, "gpu_launches": int(ctx.stats().kernel_launches), "clocks": sampler.summary(),
+                "e2e": None, "cpu_baseline": None, "wall_s": wall}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scene", default="c2", choices=sorted(SCENES))
+    ap.add_argument("--scene", default="c2", choices=sorted(SCENES) + ["c5"])
+    ap.add_argument("--triangles", type=int, default=10000000, help="c5: soup size")
+    ap.add_argument("--soup-film", type=int, default=2048, help="c5: film resolution (square)")
+    ap.add_argument("--passes", type=int, default=16, help="c5: jittered passes per step")
     ap.add_argument("--spp", type=int, default=None, help="iterations per step (default: the scene's sample count)")
     ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -344,7 +492,12 @@ def main():
     import __graft_entry__ as g
     if rank == 0 and not os.path.exists(os.path.join(ROOT, "pearray_b200", "libprb200.so")):
         g.build()
-    if args.impl == "reference":
+    if args.scene == "c5":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "c5 is a GPU ray-stream workload; the CPU arm is defined for the path-tracing configs c1-c4"}))
+            return
+        run_soup(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

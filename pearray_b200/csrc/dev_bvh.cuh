@@ -141,49 +141,90 @@ PRB_DEV float safeInv(float d)
 	return 1.0f / a;
 }
 
-constexpr int BVH_STACK = 96;
-// stack entry .x encodings (.y = entry distance bits, used to cull popped subtrees behind the closest hit)
-//   00nn nnnn ...   internal node index
-//   1ccf ffff ...   leaf: (count-1) in bits 29..30, first primitive in bits 0..28 (triangle range in a BLAS, entity ref in the TLAS)
-//   0xFFFFFFFF      leave the current BLAS (restore the world-space ray)
-constexpr uint32_t STK_LEAF	 = 0x80000000u;
-constexpr uint32_t STK_EXIT	 = 0xFFFFFFFFu;
-constexpr uint32_t STK_NONE	 = 0xFFFFFFFEu;
+constexpr int BVH_STACK = 48;
+// Traversal stack entries are GROUPS (after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs Through
+// Compressed Wide BVHs", HPG 2017), 8 bytes each:
+//   node group      .x = child_base of the visited node            .y = hits (8 bit, octant-permuted slot space) | imask << 8
+//   primitive group .x = GRP_PRIM | prim_base of the visited node  .y = one bit per primitive of the node's hit leaf children
+//                   (BLAS: triangles; TLAS: entity references)
+//   exit marker     .x = GRP_EXIT                                  leave the current BLAS, restore the world-space ray
+// so a node visit pushes at most ONE entry (the not-yet-visited hit children) instead of up to seven.
+constexpr uint32_t GRP_PRIM = 0x80000000u;
+constexpr uint32_t GRP_EXIT = 0xFFFFFFFFu;
 
 // float(q) for a byte q without an int->float conversion: 0x4B000000 | q is 2^23 + q
 PRB_DEV float byteToFloat(uint32_t word, uint32_t sel) { return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f; }
 
-// Traverses TLAS + BLAS.  ANY: returns at the first accepted primitive.
-//
-// One loop iteration = at most one internal-node step followed by at most one leaf step, so the lanes of a warp
-// re-converge at both phases ("if-if" traversal).  A node step tests the 8 quantised child boxes branch-free, keeps
-// the nearest hit child in registers as the next entry and pushes the others; a leaf step runs the watertight test on
-// <= 4 triangles (BLAS) or enters an entity (TLAS: analytic sphere, or ray transformed into the mesh's local space).
-template <bool ANY>
-PRB_DEV bool traverseScene(const DScene& S, V3 wO, V3 wD, float tmin, float tmax, HitRec& best)
+// ray octant: bit a set when the direction is negative along axis a.  Children are stored by the builder so that
+// visiting slots in increasing (slot ^ octant) order is approximately front to back.
+PRB_DEV uint32_t rayOctant(V3 inv) { return (inv.x < 0 ? 1u : 0u) | (inv.y < 0 ? 2u : 0u) | (inv.z < 0 ? 4u : 0u); }
+// permutes an 8-bit slot mask m so that bit r of the result is bit (r ^ oct) of m
+PRB_DEV uint32_t permuteByOctant(uint32_t m, uint32_t oct)
 {
-	best.entity = PRB_INVALID_ID;
-	best.prim	= 0;
-	best.u = best.v = 0;
-	best.t			= tmax;
+	if (oct & 1u)
+		m = ((m & 0x55u) << 1) | ((m & 0xAAu) >> 1);
+	if (oct & 2u)
+		m = ((m & 0x33u) << 2) | ((m & 0xCCu) >> 2);
+	if (oct & 4u)
+		m = ((m & 0x0Fu) << 4) | ((m & 0xF0u) >> 4);
+	return m;
+}
+
+// Resumable traversal of TLAS + BLAS for ONE ray (one thread = one ray).
+//
+// advance() runs one round: a node step (fetch one 80-byte node with five 128-bit loads, test its 8 quantised child
+// boxes branch-free, emit a node group + a primitive group), the primitive phase (watertight triangle tests in a BLAS;
+// entity entry -- analytic sphere or ray transformed into the mesh's local space -- in the TLAS) and the pop.  Keeping the
+// state in a struct lets the persistent kernels leave the loop to refill idle lanes with new rays and come back.
+// Primitive groups are POSTPONED (pushed) while only a few lanes of the warp have primitives to test and node work is
+// available, so triangle tests run with fuller warps.
+constexpr int TRI_POSTPONE_LANES = 10;
+
+struct Trav {
+	V3 wO, wD, O, D, inv;
+	float tmin;
+	uint32_t oct, curEnt;
+	uint2 ng, pg;
+	int sp;
+	HitRec best;
 	uint2 stack[BVH_STACK];
-	int sp = 0;
-	V3 O = wO, D = wD;
-	V3 inv			= mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
-	uint32_t curEnt = PRB_INVALID_ID; // entity whose BLAS is being traversed (TLAS level when invalid)
-	uint32_t cur	= S.tlasRoot;
-	for (;;) {
-		// ---------------------------------------------------------------- internal node step
-		if (!(cur & STK_LEAF)) {
-			const uint4* np = S.bvhNodes + 5 * (size_t)cur;
+
+	PRB_DEV void begin(const DScene& S, V3 o, V3 d, float t0, float t1)
+	{
+		best.entity = PRB_INVALID_ID;
+		best.prim	= 0;
+		best.u = best.v = 0;
+		best.t			= t1;
+		wO = O = o;
+		wD = D = d;
+		tmin   = t0;
+		inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
+		oct	   = rayOctant(inv);
+		curEnt = PRB_INVALID_ID;							   // TLAS level
+		ng	   = make_uint2(S.tlasRoot, (1u << oct) | (1u << 8)); // the root as a one-child node group: slot 0, imask 1
+		pg	   = make_uint2(0, 0);
+		sp	   = 0;
+	}
+
+	// returns true when the ray is finished (ANY: as soon as one primitive was accepted)
+	template <bool ANY>
+	PRB_DEV bool advance(const DScene& S)
+	{
+		// ---------------------------------------------------------------- node step
+		if (ng.y & 0xFFu) {
+			const uint32_t r	= __ffs(ng.y & 0xFFu) - 1; // next child in octant order
+			const uint32_t slot = r ^ oct;
+			const uint32_t node = ng.x + __popc((ng.y >> 8) & ((1u << slot) - 1u));
+			ng.y &= ~(1u << r);
+			if ((ng.y & 0xFFu) && sp < BVH_STACK)
+				stack[sp++] = ng;
+			const uint4* np = S.bvhNodes + 5 * (size_t)node;
 			const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 			const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
 			const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
 						sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
-			const uint32_t childBase = n1.x, primBase = n1.y;
-			const float tcur = best.t; // == tmax until something was hit
-			uint32_t nearEntry = STK_NONE;
-			float nearDist	   = PRB_INF;
+			const float tcur  = best.t; // == tmax until something was hit
+			uint32_t nodeHits = 0, primBits = 0;
 #pragma unroll
 			for (int i = 0; i < 8; ++i) {
 				const uint32_t meta = ((i < 4 ? n1.z : n1.w) >> (8 * (i & 3))) & 0xFFu;
@@ -199,27 +240,26 @@ PRB_DEV bool traverseScene(const DScene& S, V3 wO, V3 wD, float tmin, float tmax
 				float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
 				tn		 = tn - fabsf(tn) * 4e-7f; // conservative: never cull what the triangle test could accept
 				tf		 = tf + fabsf(tf) * 4e-7f;
-				const bool hit = (meta != 0xFFu) && (fmaxf(tn, tmin) <= fminf(tf, tcur));
-				if (hit) {
-					const uint32_t entry = (meta & 0x80u) ? (childBase + (meta & 0x7Fu)) : (STK_LEAF | (((meta >> 5) & 3u) << 29) | (primBase + (meta & 0x1Fu)));
-					// keep the nearest child in registers, push the other one
-					const bool nearer	 = tn < nearDist;
-					const uint32_t pe	 = nearer ? nearEntry : entry;
-					const float pd		 = nearer ? nearDist : tn;
-					nearEntry			 = nearer ? entry : nearEntry;
-					nearDist			 = nearer ? tn : nearDist;
-					if (pe != STK_NONE && sp < BVH_STACK)
-						stack[sp++] = make_uint2(pe, __float_as_uint(pd));
-				}
+				const bool hit			= (meta != 0xFFu) && (fmaxf(tn, tmin) <= fminf(tf, tcur));
+				const uint32_t leafBits = ((2u << ((meta >> 5) & 3u)) - 1u) << (meta & 0x1Fu);
+				nodeHits |= (hit && (meta & 0x80u)) ? (1u << i) : 0u;
+				primBits |= (hit && !(meta & 0x80u)) ? leafBits : 0u;
 			}
-			cur = nearEntry;
+			ng = make_uint2(n1.x, permuteByOctant(nodeHits, oct) | ((n0.w >> 24) << 8));
+			pg = make_uint2(GRP_PRIM | n1.y, primBits);
 		}
-		// ---------------------------------------------------------------- leaf step
-		if (cur != STK_NONE && (cur & STK_LEAF)) {
-			const uint32_t first = cur & 0x1FFFFFFFu, count = ((cur >> 29) & 3u) + 1;
+		// ---------------------------------------------------------------- primitive phase
+		while (pg.y) {
+			if ((ng.y & 0xFFu) && sp < BVH_STACK && __popc(__activemask()) < TRI_POSTPONE_LANES) {
+				stack[sp++] = pg; // too few lanes have primitives: test them later, go on with the node group
+				pg.y		= 0;
+				break;
+			}
+			const uint32_t k = pg.x + (__ffs(pg.y) - 1); // GRP_PRIM | primitive index
+			pg.y &= pg.y - 1;
 			if (curEnt == PRB_INVALID_ID) {
-				// TLAS leaf = one entity (the TLAS is built with one reference per leaf)
-				const uint32_t e	 = __ldg(S.tlasRefs + first);
+				// TLAS: one entity per reference
+				const uint32_t e	 = __ldg(S.tlasRefs + (k & ~GRP_PRIM));
 				const prb_entity& en = S.entities[e];
 				const uint32_t type	 = en.type;
 				if (type == PRB_ENTITY_SPHERE) {
@@ -232,64 +272,94 @@ PRB_DEV bool traverseScene(const DScene& S, V3 wO, V3 wD, float tmin, float tmax
 						if (ANY)
 							return true;
 					}
-					cur = STK_NONE;
 				} else {
-					// enter the entity's BLAS; the matching exit marker restores the world-space ray
+					// enter the entity's BLAS: park the unfinished TLAS groups under an exit marker
+					if ((ng.y & 0xFFu) && sp < BVH_STACK)
+						stack[sp++] = ng;
+					if (pg.y && sp < BVH_STACK)
+						stack[sp++] = pg;
 					if (sp < BVH_STACK)
-						stack[sp++] = make_uint2(STK_EXIT, 0);
+						stack[sp++] = make_uint2(GRP_EXIT, 0);
 					curEnt = e;
 					if (type == PRB_ENTITY_MESH) { // planes are stored in world space: no transform (plane.cpp:71-94)
 						O	= xfPoint(en.world_to_local, wO);
 						D	= xfVec(en.world_to_local, wD);
 						inv = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
+						oct = rayOctant(inv);
 					}
-					cur = en.blas_root;
-					continue;
+					ng = make_uint2(en.blas_root, (1u << oct) | (1u << 8));
+					pg = make_uint2(0, 0);
 				}
 			} else {
-				for (uint32_t k = first; k < first + count; ++k) {
-					const float4* tp = S.bvhTris + 3 * (size_t)k;
-					const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-					float t, u, v;
-					if (triTest(O, D, tmin, best.t, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v)) {
-						const uint32_t prim = __float_as_uint(a.w);
-						if (betterHit(t, curEnt, prim, best)) {
-							if (__float_as_uint(b.w) & 1u) {
-								u = 1 - u;
-								v = 1 - v;
-							}
-							best.entity = curEnt;
-							best.prim	= prim;
-							best.t		= t;
-							best.u		= u;
-							best.v		= v;
-							if (ANY)
-								return true;
+				const float4* tp = S.bvhTris + 3 * (size_t)(k & ~GRP_PRIM);
+				const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+				float t, u, v;
+				if (triTest(O, D, tmin, best.t, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v)) {
+					const uint32_t prim = __float_as_uint(a.w);
+					if (betterHit(t, curEnt, prim, best)) {
+						if (__float_as_uint(b.w) & 1u) {
+							u = 1 - u;
+							v = 1 - v;
 						}
+						best.entity = curEnt;
+						best.prim	= prim;
+						best.t		= t;
+						best.u		= u;
+						best.v		= v;
+						if (ANY)
+							return true;
 					}
 				}
-				cur = STK_NONE;
 			}
 		}
 		// ---------------------------------------------------------------- pop
-		if (cur == STK_NONE) {
-			for (;;) {
-				if (sp == 0)
-					return best.entity != PRB_INVALID_ID;
-				const uint2 e = stack[--sp];
-				if (e.x == STK_EXIT) { // leave the BLAS: restore the world-space ray
-					O	   = wO;
-					D	   = wD;
-					inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
-					curEnt = PRB_INVALID_ID;
-					continue;
-				}
-				if (__uint_as_float(e.y) > best.t)
-					continue; // subtree entirely behind the current closest hit
-				cur = e.x;
-				break;
+		while (!(ng.y & 0xFFu)) {
+			if (sp == 0)
+				return true;
+			const uint2 e = stack[--sp];
+			if (e.x == GRP_EXIT) { // leave the BLAS: restore the world-space ray
+				O	   = wO;
+				D	   = wD;
+				inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
+				oct	   = rayOctant(inv);
+				curEnt = PRB_INVALID_ID;
+			} else if (e.x & GRP_PRIM) {
+				pg = e;
+				break; // next round: the node step is skipped (ng is empty), the primitive phase runs
+			} else {
+				ng = e;
 			}
 		}
+		return false;
 	}
+	PRB_DEV bool hit() const { return best.entity != PRB_INVALID_ID; }
+};
+
+template <bool ANY>
+PRB_DEV bool traverseScene(const DScene& S, V3 wO, V3 wD, float tmin, float tmax, HitRec& best)
+{
+	Trav tr;
+	tr.begin(S, wO, wD, tmin, tmax);
+	while (!tr.advance<ANY>(S)) {
+	}
+	best = tr.best;
+	return tr.hit();
 }
+
+// warp-aggregated fetch of the next work item from a global counter; every lane of the warp must call it.
+// Lanes with `need` get a unique index (>= limit when the pool is exhausted); others get 0xFFFFFFFF.
+PRB_DEV uint32_t fetchWork(uint32_t* counter, bool need)
+{
+	const unsigned mask = __ballot_sync(0xFFFFFFFFu, need);
+	if (mask == 0)
+		return 0xFFFFFFFFu;
+	const int lane	 = threadIdx.x & 31;
+	const int leader = __ffs(mask) - 1;
+	uint32_t base	 = 0;
+	if (lane == leader)
+		base = atomicAdd(counter, (uint32_t)__popc(mask));
+	base = __shfl_sync(0xFFFFFFFFu, base, leader);
+	return need ? base + __popc(mask & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
+}
+constexpr int REFILL_LANES = 20; // leave the traversal loop to refill idle lanes when fewer lanes than this are still tracing
 } // namespace prb

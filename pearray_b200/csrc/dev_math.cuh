@@ -10,6 +10,10 @@
 
 namespace prb {
 #define PRB_DEV __device__ __forceinline__
+// out-of-line: the microfacet / Fresnel kernels are called from many places (6 materials x eval/pdf/sample x 4
+// wavelengths); inlining every copy made k_shade ~1 MB of SASS and instruction-fetch bound (ncu: stall_no_instruction
+// 63 warps per issue).  One copy each keeps the hot code inside the instruction cache.
+#define PRB_DEV_NI __device__ __noinline__
 
 constexpr float PR_EPSILON	= 1.1920928955078125e-07f; // std::numeric_limits<float>::epsilon()
 constexpr float PR_PI		= 3.14159265358979323846f;
@@ -74,12 +78,12 @@ PRB_DEV float cos2Theta(V3 v) { return v.z * v.z; }
 PRB_DEV float absCosTheta(V3 v) { return fabsf(v.z); }
 PRB_DEV float sin2Theta(V3 v) { return fmaxf(0.0f, 1 - cos2Theta(v)); }
 PRB_DEV float tan2Theta(V3 v) { return absCosTheta(v) <= PR_EPSILON ? 0 : sin2Theta(v) / cos2Theta(v); }
-PRB_DEV float cos2Phi(V3 v)
+PRB_DEV_NI float cos2Phi(V3 v)
 {
 	const float s = sin2Theta(v);
 	return s <= PR_EPSILON ? 0 : fminf(1.0f, v.x * v.x / s);
 }
-PRB_DEV float sin2Phi(V3 v)
+PRB_DEV_NI float sin2Phi(V3 v)
 {
 	const float s = sin2Theta(v);
 	return s <= PR_EPSILON ? 0 : fminf(1.0f, v.y * v.y / s);
@@ -102,7 +106,7 @@ PRB_DEV V3 cos_hemi(float u1, float u2)
 PRB_DEV float cos_hemi_pdf(float NdotL) { return NdotL * PR_INV_PI; }
 
 // ---------------------------------------------------------------- Scattering (src/base/math/Scattering.h:49-183)
-PRB_DEV float refraction_angle(float cosI, float eta)
+PRB_DEV_NI float refraction_angle(float cosI, float eta)
 {
 	if (signbitf(cosI)) {
 		cosI = -cosI;
@@ -124,7 +128,7 @@ PRB_DEV V3 refractZ(float eta, V3 wIn)
 	V3 r			 = cosT < 0.0f ? reflectZ(wIn) : normalized(mk(-wIn.x * eta, -wIn.y * eta, -cosT));
 	return neg ? -r : r;
 }
-PRB_DEV V3 refractN(float eta, V3 wIn, V3 N, bool& total)
+PRB_DEV_NI V3 refractN(float eta, V3 wIn, V3 N, bool& total)
 {
 	float cosI	   = dot(wIn, N);
 	const bool neg = signbitf(cosI);
@@ -145,7 +149,7 @@ PRB_DEV float reflective_jacobian(float cosO)
 	const float denom = 4 * fabsf(cosO);
 	return denom <= PR_EPSILON ? 0.0f : 1 / denom;
 }
-PRB_DEV float refractive_jacobian(float eta, float cosI, float cosO)
+PRB_DEV_NI float refractive_jacobian(float eta, float cosI, float cosO)
 {
 	const float denom  = eta * cosI + cosO;
 	const float denom2 = denom * denom;
@@ -153,7 +157,7 @@ PRB_DEV float refractive_jacobian(float eta, float cosI, float cosO)
 }
 
 // ---------------------------------------------------------------- Fresnel (src/base/math/Fresnel.h:9-77)
-PRB_DEV float fresnel_dielectric(float cosI, float n_in, float n_out)
+PRB_DEV_NI float fresnel_dielectric(float cosI, float n_in, float n_out)
 {
 	if (signbitf(cosI)) { // negative hemisphere: dielectric(-cosI, n_out, n_in)
 		cosI		  = -cosI;
@@ -168,7 +172,7 @@ PRB_DEV float fresnel_dielectric(float cosI, float n_in, float n_out)
 	const float para = diffProd(n_out, cosI, n_in, cosT) / sumProd(n_out, cosI, n_in, cosT);
 	return fminf(fmaxf(sumProd(para, para, perp, perp) / 2.0f, 0.0f), 1.0f);
 }
-PRB_DEV float fresnel_conductor(float cosI, float n_in, float n_out, float k)
+PRB_DEV_NI float fresnel_conductor(float cosI, float n_in, float n_out, float k)
 {
 	if (cosI < 0)
 		cosI = -cosI;
@@ -198,21 +202,21 @@ PRB_DEV float schlick_term(float d)
 PRB_DEV float schlick(float d, float f0) { return f0 + (1 - f0) * schlick_term(d); }
 
 // ---------------------------------------------------------------- Microfacet (src/base/math/Microfacet.h)
-PRB_DEV float g_1_smith_opt(float NdotK, float roughness)
+PRB_DEV_NI float g_1_smith_opt(float NdotK, float roughness)
 {
 	const float a	  = roughness * roughness;
 	const float b	  = NdotK * NdotK;
 	const float denom = NdotK + sqrtf(a + b - a * b);
 	return (denom <= PR_EPSILON) ? 0.0f : 1.0f / denom;
 }
-PRB_DEV float g_1_smith1(V3 K, float roughness)
+PRB_DEV_NI float g_1_smith1(V3 K, float roughness)
 {
 	const float a	  = roughness * roughness;
 	const float b	  = tan2Theta(K);
 	const float denom = 1 + sqrtf(1 + a * b);
 	return (denom <= PR_EPSILON) ? 0.0f : 2.0f / denom;
 }
-PRB_DEV float g_1_smith2(V3 K, float rx, float ry)
+PRB_DEV_NI float g_1_smith2(V3 K, float rx, float ry)
 {
 	const float ax2	  = cos2Phi(K) * rx * rx;
 	const float ay2	  = sin2Phi(K) * ry * ry;
@@ -220,20 +224,20 @@ PRB_DEV float g_1_smith2(V3 K, float rx, float ry)
 	const float denom = 1 + sqrtf(1 + (ax2 + ay2) * b);
 	return (denom <= PR_EPSILON) ? 0.0f : 2.0f / denom;
 }
-PRB_DEV float g_1_smith_lambda1(V3 K, float roughness)
+PRB_DEV_NI float g_1_smith_lambda1(V3 K, float roughness)
 {
 	const float a = roughness * roughness;
 	const float b = tan2Theta(K);
 	return (sqrtf(1 + a * b) - 1) / 2;
 }
-PRB_DEV float g_1_smith_lambda2(V3 K, float rx, float ry)
+PRB_DEV_NI float g_1_smith_lambda2(V3 K, float rx, float ry)
 {
 	const float ax2 = cos2Phi(K) * rx * rx;
 	const float ay2 = sin2Phi(K) * ry * ry;
 	const float b	= tan2Theta(K);
 	return (sqrtf(1 + (ax2 + ay2) * b) - 1) / 2;
 }
-PRB_DEV float ndf_ggx1(V3 H, float roughness)
+PRB_DEV_NI float ndf_ggx1(V3 H, float roughness)
 {
 	const float sin2 = sin2Theta(H);
 	const float cos2 = cos2Theta(H);
@@ -248,7 +252,7 @@ PRB_DEV float ndf_ggx1(V3 H, float roughness)
 	const float denom = alpha2 * cos4 * (1 + e) * (1 + e);
 	return (denom <= PR_EPSILON) ? 0.0f : PR_INV_PI / denom;
 }
-PRB_DEV float ndf_ggx2(V3 H, float rx, float ry)
+PRB_DEV_NI float ndf_ggx2(V3 H, float rx, float ry)
 {
 	const float sin2 = sin2Theta(H);
 	const float cos2 = cos2Theta(H);
@@ -266,7 +270,7 @@ PRB_DEV float ndf_ggx2(V3 H, float rx, float ry)
 	return (denom <= PR_EPSILON) ? 0.0f : PR_INV_PI / denom;
 }
 PRB_DEV V3 spherical_cartesian(float thSin, float thCos, float phSin, float phCos) { return mk(thSin * phCos, thSin * phSin, thCos); }
-PRB_DEV V3 sample_ndf_ggx1(float u0, float u1, float roughness)
+PRB_DEV_NI V3 sample_ndf_ggx1(float u0, float u1, float roughness)
 {
 	const float alpha2 = roughness * roughness;
 	const float t2	   = alpha2 * u1 / (1 - u1);
@@ -276,7 +280,7 @@ PRB_DEV V3 sample_ndf_ggx1(float u0, float u1, float roughness)
 	sincosf(2 * PR_PI * u0, &sinPhi, &cosPhi);
 	return spherical_cartesian(sinT, cosT, sinPhi, cosPhi);
 }
-PRB_DEV V3 sample_ndf_ggx2(float u0, float u1, float rx, float ry)
+PRB_DEV_NI V3 sample_ndf_ggx2(float u0, float u1, float rx, float ry)
 {
 	const float phi = atanf(ry / rx * tanf(PR_PI + 2 * PR_PI * u0)) + PR_PI * floorf(2 * u0 + 0.5f);
 	float sinPhi, cosPhi;
@@ -289,11 +293,11 @@ PRB_DEV V3 sample_ndf_ggx2(float u0, float u1, float rx, float ry)
 	const float sinT   = sqrtf(1 - cosT * cosT);
 	return spherical_cartesian(sinT, cosT, sinPhi, cosPhi);
 }
-PRB_DEV float pdf_ggx_vndf(V3 V, V3 H, float rx, float ry)
+PRB_DEV_NI float pdf_ggx_vndf(V3 V, V3 H, float rx, float ry)
 {
 	return absCosTheta(V) <= PR_EPSILON ? 0.0f : g_1_smith2(V, rx, ry) * fabsf(dot(V, H)) * ndf_ggx2(H, rx, ry) / absCosTheta(V);
 }
-PRB_DEV V3 sample_vndf_ggx(float u0, float u1, V3 nV, float rx, float ry)
+PRB_DEV_NI V3 sample_vndf_ggx(float u0, float u1, V3 nV, float rx, float ry)
 { // Heitz 2018, Microfacet.h:261-330 (#if 1 branch)
 	const V3 Vh		  = normalized(mk(rx * nV.x, ry * nV.y, nV.z));
 	const float lensq = sumProd(Vh.x, Vh.x, Vh.y, Vh.y);
@@ -316,7 +320,7 @@ struct RoughDistribution { // src/base/math/RoughDistribution.h
 	float M1, M2;
 	bool aniso, vndf;
 	PRB_DEV bool isDelta() const { return M1 <= 1e-3f || M2 <= 1e-3f; }
-	PRB_DEV float G(V3 H, V3 V, V3 L) const
+	PRB_DEV_NI float G(V3 H, V3 V, V3 L) const
 	{
 		const bool chi_v = cosTheta(V) * dot(H, V) > PR_EPSILON;
 		const bool chi_l = cosTheta(L) * dot(H, L) > PR_EPSILON;
@@ -336,7 +340,7 @@ struct RoughDistribution { // src/base/math/RoughDistribution.h
 		return fabsf(dot(H, L)) / denom;
 	}
 	PRB_DEV float DGNorm(V3 H, V3 V, V3 L) const { return D(H) * G(H, V, L) * Norm(H, V, L); }
-	PRB_DEV float pdf(V3 H, V3 V) const
+	PRB_DEV_NI float pdf(V3 H, V3 V) const
 	{
 		if (isDelta())
 			return 1.0f;
@@ -344,7 +348,7 @@ struct RoughDistribution { // src/base/math/RoughDistribution.h
 			return pdf_ggx_vndf(makePositiveHemisphere(V), makePositiveHemisphere(H), M1, M2);
 		return (aniso ? ndf_ggx2(H, M1, M2) : ndf_ggx1(H, M1)) * absCosTheta(H);
 	}
-	PRB_DEV V3 sample(float r0, float r1, V3 V) const
+	PRB_DEV_NI V3 sample(float r0, float r1, V3 V) const
 	{
 		if (isDelta())
 			return mk(0, 0, 1);
@@ -356,7 +360,7 @@ struct RoughDistribution { // src/base/math/RoughDistribution.h
 struct MicrofacetReflection { // src/base/math/MicrofacetReflection.h
 	RoughDistribution D;
 	PRB_DEV bool isDelta() const { return D.isDelta(); }
-	PRB_DEV float evalDielectric(V3 wIn, V3 wOut, float n_in, float n_out) const
+	PRB_DEV_NI float evalDielectric(V3 wIn, V3 wOut, float n_in, float n_out) const
 	{
 		if (!sameHemisphere(wIn, wOut))
 			return 0.0f;
@@ -369,7 +373,7 @@ struct MicrofacetReflection { // src/base/math/MicrofacetReflection.h
 			return F;
 		return F * D.DGNorm(H, wIn, wOut) * reflective_jacobian(cosI);
 	}
-	PRB_DEV float evalConductor(V3 wIn, V3 wOut, float ior, float kappa) const
+	PRB_DEV_NI float evalConductor(V3 wIn, V3 wOut, float ior, float kappa) const
 	{
 		if (!sameHemisphere(wIn, wOut))
 			return 0.0f;
@@ -382,7 +386,7 @@ struct MicrofacetReflection { // src/base/math/MicrofacetReflection.h
 			return F;
 		return F * D.DGNorm(H, wIn, wOut) * reflective_jacobian(cosI);
 	}
-	PRB_DEV float eval(V3 wIn, V3 wOut) const
+	PRB_DEV_NI float eval(V3 wIn, V3 wOut) const
 	{
 		if (!sameHemisphere(wIn, wOut))
 			return 0.0f;
@@ -391,7 +395,7 @@ struct MicrofacetReflection { // src/base/math/MicrofacetReflection.h
 			return 1.0f;
 		return D.DGNorm(H, wIn, wOut) * reflective_jacobian(dot(H, wIn));
 	}
-	PRB_DEV float pdf(V3 wIn, V3 wOut) const
+	PRB_DEV_NI float pdf(V3 wIn, V3 wOut) const
 	{
 		if (!sameHemisphere(wIn, wOut))
 			return 0.0f;
@@ -400,7 +404,7 @@ struct MicrofacetReflection { // src/base/math/MicrofacetReflection.h
 			return 1.0f;
 		return reflective_jacobian(dot(H, wIn)) * D.pdf(H, wIn);
 	}
-	PRB_DEV V3 sample(float r0, float r1, V3 wIn) const
+	PRB_DEV_NI V3 sample(float r0, float r1, V3 wIn) const
 	{
 		const V3 H = D.sample(r0, r1, wIn);
 		if (isZero(H, PR_EPSILON))
@@ -413,7 +417,7 @@ struct MicrofacetTransmission { // src/base/math/MicrofacetTransmission.h
 	RoughDistribution D;
 	float InnerIOR, OuterIOR;
 	PRB_DEV bool isDelta() const { return D.isDelta(); }
-	PRB_DEV bool setup(V3 wIn, V3 wOut, V3& H, float& cosI, float& cosO, float& eta) const
+	PRB_DEV_NI bool setup(V3 wIn, V3 wOut, V3& H, float& cosI, float& cosO, float& eta) const
 	{
 		if (sameHemisphere(wIn, wOut))
 			return false;
@@ -429,7 +433,7 @@ struct MicrofacetTransmission { // src/base/math/MicrofacetTransmission.h
 		eta = in_ior / out_ior;
 		return true;
 	}
-	PRB_DEV float evalDielectric(V3 wIn, V3 wOut, bool isLightPath) const
+	PRB_DEV_NI float evalDielectric(V3 wIn, V3 wOut, bool isLightPath) const
 	{
 		V3 H;
 		float cosI, cosO, eta;
@@ -442,7 +446,7 @@ struct MicrofacetTransmission { // src/base/math/MicrofacetTransmission.h
 		const float spread	 = isLightPath ? 1 / (eta * eta) : 1.0f;
 		return (1 - F) * D.DGNorm(H, wIn, wOut) * jacobian * spread;
 	}
-	PRB_DEV float pdf(V3 wIn, V3 wOut) const
+	PRB_DEV_NI float pdf(V3 wIn, V3 wOut) const
 	{
 		V3 H;
 		float cosI, cosO, eta;
@@ -452,7 +456,7 @@ struct MicrofacetTransmission { // src/base/math/MicrofacetTransmission.h
 			return 1.0f;
 		return D.pdf(H, wIn) * refractive_jacobian(eta, cosI, cosO);
 	}
-	PRB_DEV V3 sample(float r0, float r1, V3 wIn) const
+	PRB_DEV_NI V3 sample(float r0, float r1, V3 wIn) const
 	{
 		const V3 H = D.sample(r0, r1, wIn);
 		if (isZero(H, PR_EPSILON))

@@ -19,7 +19,7 @@
 #include "dev_shade.cuh"
 
 namespace prb {
-enum { CNT_RETIRED = 0, CNT__COUNT = 4 };
+enum { CNT_RETIRED = 0, CNT_WORK = 1, CNT__COUNT = 4 };
 enum { ST_CAMERA_RAY = 0, ST_LIGHT_RAY, ST_PRIMARY, ST_BOUNCE, ST_SHADOW, ST_MONO, ST_PIXEL_SAMPLE, ST_ENTITY_HIT, ST_BG_HIT, ST_CAMERA_DEPTH, ST_LIGHT_DEPTH, ST__COUNT };
 
 constexpr uint32_t FD_DEPTH_MASK   = 0xFFFFu;
@@ -122,13 +122,20 @@ __global__ void __launch_bounds__(128) k_init_slots(DScene S, WFState W)
 		if (!ok)
 			atomicAdd(W.counters + CNT_RETIRED, 1u);
 	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		W.counters[CNT_WORK] = 0;
 	statAdd(W.stats, ST_PIXEL_SAMPLE, started);
 	statAdd(W.stats, ST_CAMERA_RAY, started);
 	statAdd(W.stats, ST_PRIMARY, started);
 }
 
 // ------------------------------------------------------------------ trace: pending shadow ray, then the path's next ray
-__global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
+// Persistent threads: lanes pull slots from a global counter (warp-aggregated atomic); a lane whose ray finished leaves
+// the traversal loop and, once fewer than REFILL_LANES lanes of the warp are still tracing, the warp refills its idle lanes
+// with new slots, so divergence in traversal length does not idle lanes until the longest ray of a warp is done.
+// static variant (slot == thread): no work counter, no refill.  Cheaper for scenes whose rays finish within a few steps
+// (a handful of primitives), where the bookkeeping of the persistent variant costs more than the idle lanes it avoids.
+__global__ void __launch_bounds__(128) k_trace_static(DScene S, WFState W)
 {
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	if (slot >= W.nSlots)
@@ -159,6 +166,76 @@ __global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
 		traverseScene<false>(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
 		W.hit[slot]	 = make_uint4(h.entity, h.prim, __float_as_uint(h.u), __float_as_uint(h.v));
 		W.hitT[slot] = h.t;
+	}
+}
+
+__global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
+{
+	Trav tr;
+	uint32_t slot = 0, st = 0;
+	int phase	  = 0; // 0 idle, 1 shadow ray in flight, 2 closest-hit ray in flight
+	bool pool	  = true;
+	for (;;) {
+		// ---- refill idle lanes (warp-uniform loop: a fetched slot may turn out to be retired, then the lane asks again)
+		for (;;) {
+			const bool need = (phase == 0) && pool;
+			if (!__any_sync(0xFFFFFFFFu, need))
+				break;
+			const uint32_t s = fetchWork(W.counters + CNT_WORK, need);
+			if (need) {
+				if (s >= W.nSlots) {
+					pool = false;
+				} else {
+					slot = s;
+					st	 = W.state[slot];
+					if (st & SF_SHADOW) {
+						const float4 o = W.shO[slot], d = W.shD[slot];
+						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w);
+						phase = 1;
+					} else if (st & SF_ACTIVE) {
+						const float4 o = W.rayO[slot], d = W.rayD[slot];
+						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w);
+						phase = 2;
+					}
+				}
+			}
+		}
+		if (__ballot_sync(0xFFFFFFFFu, phase != 0) == 0)
+			break;
+		// ---- trace
+		while (phase != 0) {
+			const bool done = (phase == 1) ? tr.advance<true>(S) : tr.advance<false>(S);
+			if (done) {
+				if (phase == 1) {
+					const bool occluded = tr.hit();
+					const float4 c		= occluded ? make_float4(0, 0, 0, 0) : W.shXYZ[slot];
+					if (st & SF_FINALIZE) {
+						const float4 p = W.prevAcc[slot];
+						foldSampleIntoFilm(W, W.pixel[slot], p.x + c.x, p.y + c.y, p.z + c.z, __float_as_uint(p.w));
+					} else if (!occluded) {
+						float4 acc = W.iterXYZ[slot];
+						acc.x += c.x;
+						acc.y += c.y;
+						acc.z += c.z;
+						W.iterXYZ[slot] = acc;
+					}
+					W.state[slot] = st & SF_ACTIVE;
+					if (st & SF_ACTIVE) { // the same lane goes on with the slot's path ray
+						const float4 o = W.rayO[slot], d = W.rayD[slot];
+						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w);
+						phase = 2;
+					} else {
+						phase = 0;
+					}
+				} else {
+					W.hit[slot]	 = make_uint4(tr.best.entity, tr.best.prim, __float_as_uint(tr.best.u), __float_as_uint(tr.best.v));
+					W.hitT[slot] = tr.best.t;
+					phase		 = 0;
+				}
+			}
+			if (pool && __popc(__activemask()) < REFILL_LANES)
+				break;
+		}
 	}
 }
 
@@ -502,6 +579,8 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, WFState W)
 			W.state[slot] = nst;
 		}
 	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		W.counters[CNT_WORK] = 0; // work counter of the next k_trace (stream order: this kernel runs after k_trace finished)
 	statAdd(W.stats, ST_PIXEL_SAMPLE, sSamples);
 	statAdd(W.stats, ST_CAMERA_RAY, sSamples);
 	statAdd(W.stats, ST_PRIMARY, sSamples);
@@ -515,29 +594,62 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, WFState W)
 }
 
 // ------------------------------------------------------------------ stream tracing (prb_trace_closest / _any)
-__global__ void __launch_bounds__(256) k_trace_closest(DScene S, const float* ox, const float* oy, const float* oz, const float* dx, const float* dy,
-														const float* dz, const float* tmin, const float* tmax, uint32_t n, uint32_t* ent, uint32_t* prim,
-														float* u, float* v, float* t)
+// persistent-thread ray-stream kernels: `counter` must be zero at launch
+template <bool ANY>
+PRB_DEV void traceStream(const DScene& S, const float* ox, const float* oy, const float* oz, const float* dx, const float* dy, const float* dz, const float* tmin,
+						 const float* tmax, uint32_t n, uint32_t* counter, uint32_t* ent, uint32_t* prim, float* u, float* v, float* t, uint8_t* occluded)
 {
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		HitRec h;
-		const float t0 = tmin ? tmin[i] : 0.0001f, t1 = tmax ? tmax[i] : PRB_INF;
-		const bool ok = traverseScene<false>(S, mk(ox[i], oy[i], oz[i]), mk(dx[i], dy[i], dz[i]), t0, t1, h);
-		ent[i]		  = ok ? h.entity : PRB_INVALID_ID;
-		prim[i]		  = ok ? h.prim : PRB_INVALID_ID;
-		u[i]		  = ok ? h.u : 0.0f;
-		v[i]		  = ok ? h.v : 0.0f;
-		t[i]		  = ok ? h.t : t1;
+	Trav tr;
+	uint32_t i	= 0;
+	bool active = false, pool = true;
+	float t1	= 0;
+	for (;;) {
+		{
+			const bool need	 = !active && pool;
+			const uint32_t k = fetchWork(counter, need);
+			if (need) {
+				if (k < n) {
+					i			   = k;
+					const float t0 = tmin ? tmin[i] : 0.0001f;
+					t1			   = tmax ? tmax[i] : PRB_INF;
+					tr.begin(S, mk(ox[i], oy[i], oz[i]), mk(dx[i], dy[i], dz[i]), t0, t1);
+					active = true;
+				} else {
+					pool = false;
+				}
+			}
+		}
+		if (__ballot_sync(0xFFFFFFFFu, active) == 0)
+			break;
+		while (active) {
+			if (tr.advance<ANY>(S)) {
+				const bool ok = tr.hit();
+				if (ANY) {
+					occluded[i] = ok ? 1 : 0;
+				} else {
+					ent[i]	= ok ? tr.best.entity : PRB_INVALID_ID;
+					prim[i] = ok ? tr.best.prim : PRB_INVALID_ID;
+					u[i]	= ok ? tr.best.u : 0.0f;
+					v[i]	= ok ? tr.best.v : 0.0f;
+					t[i]	= ok ? tr.best.t : t1;
+				}
+				active = false;
+			}
+			if (pool && __popc(__activemask()) < REFILL_LANES)
+				break;
+		}
 	}
 }
-__global__ void __launch_bounds__(256) k_trace_any(DScene S, const float* ox, const float* oy, const float* oz, const float* dx, const float* dy,
-													const float* dz, const float* tmin, const float* tmax, uint32_t n, uint8_t* occluded)
+__global__ void __launch_bounds__(128) k_trace_closest(DScene S, const float* ox, const float* oy, const float* oz, const float* dx, const float* dy,
+														const float* dz, const float* tmin, const float* tmax, uint32_t n, uint32_t* counter, uint32_t* ent,
+														uint32_t* prim, float* u, float* v, float* t)
 {
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		HitRec h;
-		const float t0 = tmin ? tmin[i] : 0.0001f, t1 = tmax ? tmax[i] : PRB_INF;
-		occluded[i]	   = traverseScene<true>(S, mk(ox[i], oy[i], oz[i]), mk(dx[i], dy[i], dz[i]), t0, t1, h) ? 1 : 0;
-	}
+	traceStream<false>(S, ox, oy, oz, dx, dy, dz, tmin, tmax, n, counter, ent, prim, u, v, t, nullptr);
+}
+__global__ void __launch_bounds__(128) k_trace_any(DScene S, const float* ox, const float* oy, const float* oz, const float* dx, const float* dy,
+													const float* dz, const float* tmin, const float* tmax, uint32_t n, uint32_t* counter, uint8_t* occluded)
+{
+	traceStream<true>(S, ox, oy, oz, dx, dy, dz, tmin, tmax, n, counter, nullptr, nullptr, nullptr, nullptr, nullptr, occluded);
 }
 
 // camera rays only (prb_generate_camera_rays): does not touch the RNG map

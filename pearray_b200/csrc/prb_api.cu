@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,6 +62,7 @@ struct prb_ctx {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t evA = nullptr, evB = nullptr;
 	int smCount = 148;
+	int gridTrace = 148 * 4, gridTraceClosest = 148 * 4, gridTraceAny = 148 * 4; // persistent grids: SMs x resident blocks
 	bool haveScene = false;
 	DScene S{};
 	// scene storage
@@ -99,6 +101,7 @@ struct prb_ctx {
 	cudaGraphExec_t graphExec = nullptr;
 	uint32_t graphSlots = 0;
 	bool wantAOV = true;
+	bool persistentTrace = true; // k_trace (persistent threads) vs k_trace_static, chosen per scene in prb_upload_scene
 	// per-stage profiling (prb_set_profiling)
 	bool profiling = false;
 	std::vector<cudaEvent_t> profEvents; // pairs
@@ -146,6 +149,16 @@ prb_status prb_create(int device, prb_ctx** out)
 		e = c->stats.alloc(ST__COUNT);
 	if (e == cudaSuccess)
 		e = cudaMemsetAsync(c->stats.p, 0, ST__COUNT * sizeof(unsigned long long), c->stream);
+	if (e == cudaSuccess) {
+		// persistent-thread kernels: one grid that exactly fills the machine (SM count x resident blocks per SM)
+		int nb = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace, 128, 0) == cudaSuccess && nb > 0)
+			c->gridTrace = c->smCount * nb;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_closest, 128, 0) == cudaSuccess && nb > 0)
+			c->gridTraceClosest = c->smCount * nb;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_any, 128, 0) == cudaSuccess && nb > 0)
+			c->gridTraceAny = c->smCount * nb;
+	}
 	if (e != cudaSuccess) {
 		delete c;
 		return fail(PRB_ERR_CUDA, std::string("context set-up failed: ") + cudaGetErrorString(e));
@@ -281,6 +294,15 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 		if (d->lights[i].type == PRB_LIGHT_ENV)
 			S.hasEnvLight = 1;
 	CU(cudaStreamSynchronize(s));
+	// trace-kernel variant: persistent threads pay off once rays take many traversal steps (measured: 2x on the 10 M
+	// triangle soup, 0.7x on the 32-triangle Cornell box, 0.95x on the 6 k-triangle bolts scene); PRB_TRACE_MODE=static|persistent overrides the heuristic
+	c->persistentTrace = d->n_bvh_tris > 262144;
+	if (const char* m = std::getenv("PRB_TRACE_MODE")) {
+		if (std::strcmp(m, "static") == 0)
+			c->persistentTrace = false;
+		else if (std::strcmp(m, "persistent") == 0)
+			c->persistentTrace = true;
+	}
 	c->haveScene = true;
 	c->cachedTiles.clear();
 	c->nSlots = 0;
@@ -355,6 +377,14 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 	c->cachedTiles.assign(tiles, tiles + n_tiles);
 	c->nSlots = (uint32_t)n;
 	return PRB_OK;
+}
+
+static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s)
+{
+	if (c->persistentTrace)
+		k_trace<<<c->gridTrace, 128, 0, s>>>(c->S, W);
+	else
+		k_trace_static<<<blocks, 128, 0, s>>>(c->S, W);
 }
 
 static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
@@ -437,7 +467,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 			size_t ne = 0;
 			for (int r = 0; r < ITERS_PER_GRAPH * GRAPHS_PER_POLL; ++r) {
 				CU(cudaEventRecord(c->profEvents[ne++], s));
-				k_trace<<<blocks, 128, 0, s>>>(c->S, W);
+				launchTrace(c, W, blocks, s);
 				CU(cudaEventRecord(c->profEvents[ne++], s));
 				CU(cudaEventRecord(c->profEvents[ne++], s));
 				k_shade<<<blocks, 128, 0, s>>>(c->S, W);
@@ -460,7 +490,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 		cudaGraphExec_t exec = nullptr;
 		CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
 		for (int r = 0; r < ITERS_PER_GRAPH; ++r) {
-			k_trace<<<blocks, 128, 0, s>>>(c->S, W);
+			launchTrace(c, W, blocks, s);
 			k_shade<<<blocks, 128, 0, s>>>(c->S, W);
 		}
 		const cudaError_t ce = cudaGetLastError();
@@ -488,7 +518,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 		cudaGraphExecDestroy(exec);
 	}
 	// flush: samples that ended with their last shadow ray in flight are folded into the film by k_trace
-	k_trace<<<blocks, 128, 0, s>>>(c->S, W);
+	launchTrace(c, W, blocks, s);
 	c->kernelLaunches += 1;
 	CU(cudaGetLastError());
 	c->wavefrontIterations += done;
@@ -583,13 +613,15 @@ prb_status prb_film_import_device(prb_ctx* c, const float* device_src)
 // ------------------------------------------------------------------ stream tracing
 static prb_status traceDevice(prb_ctx* c, const prb_ray_soa* r, size_t n, prb_hit_soa* hits, uint8_t* occluded)
 {
-	const int grid = c->smCount * 4;
+	CU(c->counters.alloc(CNT__COUNT));
+	CU(cudaMemsetAsync(c->counters.p + CNT_WORK, 0, sizeof(uint32_t), c->stream));
 	CU(cudaEventRecord(c->evA, c->stream));
 	if (hits)
-		k_trace_closest<<<grid, 256, 0, c->stream>>>(c->S, r->org_x, r->org_y, r->org_z, r->dir_x, r->dir_y, r->dir_z, r->tmin, r->tmax, (uint32_t)n,
-													  hits->entity_id, hits->primitive_id, hits->u, hits->v, hits->t);
+		k_trace_closest<<<c->gridTraceClosest, 128, 0, c->stream>>>(c->S, r->org_x, r->org_y, r->org_z, r->dir_x, r->dir_y, r->dir_z, r->tmin, r->tmax, (uint32_t)n,
+																	 c->counters.p + CNT_WORK, hits->entity_id, hits->primitive_id, hits->u, hits->v, hits->t);
 	else
-		k_trace_any<<<grid, 256, 0, c->stream>>>(c->S, r->org_x, r->org_y, r->org_z, r->dir_x, r->dir_y, r->dir_z, r->tmin, r->tmax, (uint32_t)n, occluded);
+		k_trace_any<<<c->gridTraceAny, 128, 0, c->stream>>>(c->S, r->org_x, r->org_y, r->org_z, r->dir_x, r->dir_y, r->dir_z, r->tmin, r->tmax, (uint32_t)n,
+															 c->counters.p + CNT_WORK, occluded);
 	c->kernelLaunches++;
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->evB, c->stream));

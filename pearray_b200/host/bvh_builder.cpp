@@ -217,6 +217,42 @@ BVH8 buildBVH8(const BVHBuildInput& in, int maxLeafPrims)
 		BoundingBox nb;
 		for (int i = 0; i < nk; ++i)
 			nb.combine(b2.nodes[kids[i]].box);
+		// Slot assignment for octant-ordered traversal (Ylitie et al. 2017, section 3.2): the child placed in slot s should
+		// lie towards the diagonal d_s = (s&1 ? + : -, s&2 ? + : -, s&4 ? + : -) of the node, so that a ray with octant o
+		// (bit a set = negative direction on axis a) meets the slots in increasing (s ^ o) order roughly front to back.
+		// Greedy maximisation of sum_c dot(centroid_c - centroid_node, d_slot(c)).
+		{
+			const Vector3f nc = nb.center();
+			float score[8][8];
+			for (int c = 0; c < nk; ++c) {
+				const Vector3f d = b2.nodes[kids[c]].box.center() - nc;
+				for (int sl = 0; sl < 8; ++sl)
+					score[c][sl] = ((sl & 1) ? d.x : -d.x) + ((sl & 2) ? d.y : -d.y) + ((sl & 4) ? d.z : -d.z);
+			}
+			int32 slotKid[8];
+			bool kidDone[8] = {}, slotDone[8] = {};
+			for (int sl = 0; sl < 8; ++sl)
+				slotKid[sl] = -1;
+			for (int round = 0; round < nk; ++round) {
+				int bc = -1, bs = -1;
+				float bv = -PR_INF;
+				for (int c = 0; c < nk; ++c) {
+					if (kidDone[c])
+						continue;
+					for (int sl = 0; sl < 8; ++sl)
+						if (!slotDone[sl] && score[c][sl] > bv) {
+							bv = score[c][sl];
+							bc = c;
+							bs = sl;
+						}
+				}
+				kidDone[bc]	 = true;
+				slotDone[bs] = true;
+				slotKid[bs]	 = kids[bc];
+			}
+			for (int sl = 0; sl < 8; ++sl)
+				kids[sl] = slotKid[sl];
+		}
 		node.px = nb.lo.x;
 		node.py = nb.lo.y;
 		node.pz = nb.lo.z;
@@ -243,7 +279,9 @@ BVH8 buildBVH8(const BVHBuildInput& in, int maxLeafPrims)
 		uint32 internalCount   = 0;
 		uint32 primOffset	   = 0;
 		uint8 imask			   = 0;
-		for (int i = 0; i < nk; ++i) {
+		for (int i = 0; i < 8; ++i) {
+			if (kids[i] < 0)
+				continue; // empty slot: meta stays 0xFF
 			const Node2& c = b2.nodes[kids[i]];
 			const float clo[3] = { c.box.lo.x, c.box.lo.y, c.box.lo.z }, chi[3] = { c.box.hi.x, c.box.hi.y, c.box.hi.z };
 			const float p[3] = { node.px, node.py, node.pz };
