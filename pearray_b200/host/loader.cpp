@@ -3,6 +3,10 @@
 #include "prh.h"
 
 #include <dlfcn.h>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <tuple>
 
 namespace PR {
 void registerNodePlugins(std::vector<std::shared_ptr<IPlugin>>& out);
@@ -426,7 +430,7 @@ void SceneLoader::setupEnvironment(const std::vector<DL::DataGroup>& groups, Sce
 		else if (id == "mesh")
 			addMesh(entry, ctx);
 		else if (id == "graph" || id == "embed")
-			PR_LOG(L_ERROR) << "[Loader] '" << id << "' archive loaders are out of scope (SURVEY row 24)" << std::endl;
+			addSubGraph(entry, ctx);
 		else if (id == "material")
 			addMaterial(entry, ctx);
 		else if (id == "emission")
@@ -867,6 +871,135 @@ void SceneLoader::addMesh(const DL::DataGroup& group, SceneLoadContext& ctx)
 	std::string err;
 	if (!me->isValid(&err)) {
 		PR_LOG(L_ERROR) << "Loaded mesh is invalid: " << err << std::endl;
+		return;
+	}
+	ctx.environment()->meshes[me->name] = me;
+}
+
+// Wavefront OBJ -> MeshBase.  The reference goes through tinyobjloader with triangulate = true
+// (src/loader/archives/WavefrontLoader.cpp:24-200): all shapes of the file are merged into one mesh, polygons become
+// triangles (tinyobj clips ears starting at the first corner, which for the convex polygons of the example data is the
+// fan (0,k,k+1)), materials are ignored.  tinyobj keeps one index list per attribute; the device mesh layout has one shared
+// index list, so corners are merged by their (v, vn, vt) triple -- same positions, normals and uvs at every face corner,
+// same face order and therefore the same primitive ids.
+static bool loadWavefront(const std::string& file, bool flipNormal, MeshBase& mesh)
+{
+	std::ifstream in(file);
+	if (!in) {
+		PR_LOG(L_ERROR) << "Wavefront file: Could not open file " << file << std::endl;
+		return false;
+	}
+	std::vector<float> P, N, T;
+	struct Corner {
+		int v, n, t;
+		bool operator<(const Corner& o) const { return std::tie(v, n, t) < std::tie(o.v, o.n, o.t); }
+	};
+	std::vector<std::vector<Corner>> polygons;
+	std::string line;
+	while (std::getline(in, line)) {
+		std::istringstream ls(line);
+		std::string tag;
+		if (!(ls >> tag) || tag[0] == '#')
+			continue;
+		if (tag == "v" || tag == "vn") {
+			float x = 0, y = 0, z = 0;
+			ls >> x >> y >> z;
+			std::vector<float>& dst = tag == "v" ? P : N;
+			dst.insert(dst.end(), { x, y, z });
+		} else if (tag == "vt") {
+			float u = 0, v = 0;
+			ls >> u >> v;
+			T.insert(T.end(), { u, v });
+		} else if (tag == "f") {
+			std::vector<Corner> poly;
+			std::string tok;
+			while (ls >> tok) {
+				// v | v/vt | v//vn | v/vt/vn ; 1-based, negative = relative to the elements read so far
+				int idx[3]	  = { 0, 0, 0 };
+				int field	  = 0;
+				size_t start  = 0;
+				for (size_t i = 0; i <= tok.size() && field < 3; ++i)
+					if (i == tok.size() || tok[i] == '/') {
+						if (i > start)
+							idx[field] = std::atoi(tok.substr(start, i - start).c_str());
+						++field;
+						start = i + 1;
+					}
+				auto fix = [](int i, size_t count) { return i > 0 ? i - 1 : (i < 0 ? (int)count + i : -1); };
+				poly.push_back(Corner{ fix(idx[0], P.size() / 3), fix(idx[2], N.size() / 3), fix(idx[1], T.size() / 2) });
+			}
+			if (poly.size() >= 3)
+				polygons.push_back(std::move(poly));
+		}
+	}
+	if (P.empty() || polygons.empty()) {
+		PR_LOG(L_ERROR) << "Wavefront file: No vertices or faces given in " << file << std::endl;
+		return false;
+	}
+	const bool hasN = !N.empty(), hasT = !T.empty();
+	std::map<Corner, uint32> merged;
+	auto cornerIndex = [&](Corner c) {
+		c.v = std::max(0, c.v);
+		c.n = hasN ? std::max(0, c.n) : -1;
+		c.t = hasT ? std::max(0, c.t) : -1;
+		auto it = merged.find(c);
+		if (it != merged.end())
+			return it->second;
+		const uint32 id = (uint32)mesh.vertexCount();
+		if ((size_t)c.v * 3 + 2 >= P.size() || (hasN && (size_t)c.n * 3 + 2 >= N.size()) || (hasT && (size_t)c.t * 2 + 1 >= T.size()))
+			return PR_INVALID_ID;
+		mesh.vertices.insert(mesh.vertices.end(), P.begin() + 3 * c.v, P.begin() + 3 * c.v + 3);
+		if (hasN)
+			for (int k = 0; k < 3; ++k)
+				mesh.normals.push_back(flipNormal ? -N[3 * c.n + k] : N[3 * c.n + k]);
+		if (hasT)
+			mesh.uvs.insert(mesh.uvs.end(), T.begin() + 2 * c.t, T.begin() + 2 * c.t + 2);
+		merged.emplace(c, id);
+		return id;
+	};
+	for (const auto& poly : polygons)
+		for (size_t k = 1; k + 1 < poly.size(); ++k) {
+			const uint32 tri[3] = { cornerIndex(poly[0]), cornerIndex(poly[k]), cornerIndex(poly[k + 1]) };
+			if (tri[0] == PR_INVALID_ID || tri[1] == PR_INVALID_ID || tri[2] == PR_INVALID_ID) {
+				PR_LOG(L_ERROR) << "Wavefront file: face index out of range in " << file << std::endl;
+				return false;
+			}
+			mesh.indices.insert(mesh.indices.end(), { tri[0], tri[1], tri[2], PR_INVALID_ID });
+		}
+	return true;
+}
+
+void SceneLoader::addSubGraph(const DL::DataGroup& group, SceneLoadContext& ctx)
+{ // SceneLoader.cpp:773-846
+	const DL::Data loaderD = group.getFromKey("loader");
+	const DL::Data fileD   = group.getFromKey("file");
+	if (fileD.type() != DL::DT_String) {
+		PR_LOG(L_ERROR) << "[Loader] Could not get file for subgraph entry." << std::endl;
+		return;
+	}
+	std::string loader;
+	if (loaderD.type() == DL::DT_String) {
+		loader = loaderD.getString();
+	} else {
+		PR_LOG(L_WARNING) << "[Loader] No valid loader set. Assuming 'obj'." << std::endl;
+		loader = "obj";
+	}
+	if (loader != "obj") { // 'ply' and 'mts' archives: not needed by the path's configurations
+		PR_LOG(L_ERROR) << "[Loader] Unknown " << loader << " loader." << std::endl;
+		return;
+	}
+	const std::string file	 = ctx.setupParametricPath(fileD.getString());
+	const DL::Data nameD	 = group.getFromKey("name");
+	const DL::Data flipD	 = group.getFromKey("flipNormal");
+	auto me					 = std::make_shared<MeshBase>();
+	if (!loadWavefront(file, flipD.type() == DL::DT_Bool && flipD.getBool(), *me))
+		return;
+	me->name = nameD.type() == DL::DT_String ? nameD.getString() : file;
+	if (ctx.environment()->meshes.count(me->name))
+		PR_LOG(L_ERROR) << "Mesh " << me->name << " already in use." << std::endl;
+	std::string err;
+	if (!me->isValid(&err)) {
+		PR_LOG(L_WARNING) << "Obj file could not construct a valid mesh data: " << err << std::endl;
 		return;
 	}
 	ctx.environment()->meshes[me->name] = me;

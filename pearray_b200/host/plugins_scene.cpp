@@ -571,39 +571,59 @@ private:
 };
 
 // ------------------------------------------------------------------ filters
-class MitchellFilter : public IFilter { // plugins/main/filter/MitchellFilter.cpp
+// All tabulated pixel filters of the reference share one construction (plugins/main/filter/{Mitchell,Triangle,Gaussian,
+// Lanczos}Filter.cpp): a radial profile sampled at integer pixel offsets of the first quadrant, normalised so that the
+// mirrored (2r+1)^2 table sums to one.  Only the profile differs.
+enum class FilterProfile { Mitchell, Triangle, Gaussian, Lanczos, Block };
+static float filterProfile(FilterProfile kind, float r, int radius)
+{ // r = distance in pixels
+	switch (kind) {
+	case FilterProfile::Mitchell: { // MitchellFilter.cpp: B = C = 1/3, argument 2 r / radius
+		const float B = 1 / 3.0f, C = 1 / 3.0f;
+		const float x = std::abs(2 * r / radius);
+		if (x < 1)
+			return ((12 - 9 * B - 6 * C) * x * x * x + (-18 + 12 * B + 6 * C) * x * x + (6 - 2 * B)) / 6;
+		if (x < 2)
+			return ((-B - 6 * C) * x * x * x + (6 * B + 30 * C) * x * x + (-12 * B - 48 * C) * x + (8 * B + 24 * C)) / 6;
+		return 0.0f;
+	}
+	case FilterProfile::Triangle: // TriangleFilter.cpp:45
+		return r <= radius ? 1 - r / (float)radius : 0.0f;
+	case FilterProfile::Gaussian: { // GaussianFilter.cpp:40-46: variance 0.2 on the normalised distance
+		const float x	  = r / (float)radius;
+		const float alpha = 1 / (2 * 0.2f);
+		return x <= 1.0f ? std::exp(-alpha * x * x) : 0.0f;
+	}
+	case FilterProfile::Lanczos: { // LanczosFilter.cpp:31-41
+		auto sinc = [](float x) { return PR_INV_PI * std::sin(PR_PI * x) / x; };
+		if (r <= PR_EPSILON)
+			return 1.0f;
+		return r <= radius ? sinc(r) * sinc(r / radius) : 0.0f;
+	}
+	default:
+		return 1.0f;
+	}
+}
+class TabulatedFilter : public IFilter {
 public:
-	explicit MitchellFilter(int radius)
+	TabulatedFilter(FilterProfile kind, int radius)
 		: mRadius(radius)
 	{
 		if (mRadius == 0)
 			return;
-		const int halfSize = mRadius + 1;
-		mCache.resize(halfSize * (size_t)halfSize);
-		auto mitchell = [](float x, float B, float C) {
-			x = std::abs(x);
-			if (x < 1)
-				return ((12 - 9 * B - 6 * C) * x * x * x + (-18 + 12 * B + 6 * C) * x * x + (6 - 2 * B)) / 6;
-			else if (x < 2)
-				return ((-B - 6 * C) * x * x * x + (6 * B + 30 * C) * x * x + (-12 * B - 48 * C) * x + (8 * B + 24 * C)) / 6;
-			return 0.0f;
-		};
-		float sum1 = 0, sum2 = 0, sum4 = 0;
-		for (int y = 0; y < halfSize; ++y)
-			for (int x = 0; x < halfSize; ++x) {
-				const float r			 = std::sqrt((float)(x * x + y * y));
-				const float val			 = mitchell(2 * r / mRadius, 1 / 3.0f, 1 / 3.0f);
-				mCache[y * halfSize + x] = val;
-				if (y == 0 && x == 0)
-					sum1 += val;
-				else if (y == 0 || x == 0)
-					sum2 += val;
-				else
-					sum4 += val;
+		const int half = mRadius + 1;
+		mTable.assign(half * (size_t)half, 0.0f);
+		// weights of the full table: centre once, axis entries twice, the rest four times
+		float centre = 0, axes = 0, quadrant = 0;
+		for (int y = 0; y < half; ++y)
+			for (int x = 0; x < half; ++x) {
+				const float w		 = filterProfile(kind, std::sqrt((float)(x * x + y * y)), mRadius);
+				mTable[y * half + x] = w;
+				(x == 0 && y == 0 ? centre : (x == 0 || y == 0 ? axes : quadrant)) += w;
 			}
-		const float norm = 1.0f / (sum1 + 2 * sum2 + 4 * sum4);
-		for (auto& v : mCache)
-			v *= norm;
+		const float norm = 1.0f / (centre + 2 * axes + 4 * quadrant);
+		for (float& w : mTable)
+			w *= norm;
 	}
 	int radius() const override { return mRadius; }
 	float evalWeight(float x, float y) const override
@@ -613,12 +633,12 @@ public:
 		// the reference clamps to mRadius+1 and indexes a (mRadius+1)^2 table with .at(); |x|,|y| <= mRadius here
 		const int ix = std::min((int)std::round(std::abs(x)), mRadius);
 		const int iy = std::min((int)std::round(std::abs(y)), mRadius);
-		return mCache[iy * (mRadius + 1) + ix];
+		return mTable[iy * (mRadius + 1) + ix];
 	}
 
 private:
 	int mRadius;
-	std::vector<float> mCache;
+	std::vector<float> mTable;
 };
 class BlockFilter : public IFilter { // plugins/main/filter/BlockFilter.cpp: constant weight 1/(2r+1)^2
 public:
@@ -634,43 +654,43 @@ private:
 };
 class FilterFactory : public IFilterFactory {
 public:
-	FilterFactory(bool mitchell, const ParameterGroup& p)
-		: mMitchell(mitchell)
+	FilterFactory(FilterProfile kind, const ParameterGroup& p)
+		: mKind(kind)
 		, mParams(p)
 	{
 	}
 	std::shared_ptr<IFilter> createInstance() const override
 	{
 		const int radius = (int)mParams.getInt("radius", 3);
-		if (mMitchell)
-			return std::make_shared<MitchellFilter>(radius);
-		return std::make_shared<BlockFilter>(radius);
+		if (mKind == FilterProfile::Block)
+			return std::make_shared<BlockFilter>(radius);
+		return std::make_shared<TabulatedFilter>(mKind, radius);
 	}
 
 private:
-	bool mMitchell;
+	FilterProfile mKind;
 	ParameterGroup mParams;
 };
 class FilterPlugin : public IFilterPlugin {
 public:
-	explicit FilterPlugin(bool mitchell)
-		: mMitchell(mitchell)
+	explicit FilterPlugin(FilterProfile kind)
+		: mKind(kind)
 	{
 	}
 	std::shared_ptr<IFilterFactory> create(const std::string&, const SceneLoadContext& ctx) override
 	{
-		return std::make_shared<FilterFactory>(mMitchell, ctx.parameters());
+		return std::make_shared<FilterFactory>(mKind, ctx.parameters());
 	}
 	const std::vector<std::string>& getNames() const override
 	{
-		static const std::vector<std::string> m({ "mitchell" });
-		static const std::vector<std::string> b({ "block", "blur" });
-		return mMitchell ? m : b;
+		static const std::vector<std::string> names[] = { { "mitchell", "default" }, { "tri", "triangle" }, { "gaussian", "gauss" }, { "lanczos", "sinc", "lancz" },
+														  { "block", "blur" } };
+		return names[(int)mKind];
 	}
 	std::string specification(const std::string&) const override { return "Pixel filter: radius"; }
 
 private:
-	bool mMitchell;
+	FilterProfile mKind;
 };
 
 // ------------------------------------------------------------------ spectral mappers
@@ -893,8 +913,8 @@ void registerScenePlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Sobol));
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::MJitt));
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Random));
-	out.push_back(std::make_shared<FilterPlugin>(true));
-	out.push_back(std::make_shared<FilterPlugin>(false));
+	for (FilterProfile k : { FilterProfile::Mitchell, FilterProfile::Triangle, FilterProfile::Gaussian, FilterProfile::Lanczos, FilterProfile::Block })
+		out.push_back(std::make_shared<FilterPlugin>(k));
 	out.push_back(std::make_shared<SPDSpectralMapperPlugin>());
 	out.push_back(std::make_shared<RandomSpectralMapperPlugin>());
 	out.push_back(std::make_shared<IntDirectFactoryFactory>());

@@ -736,6 +736,7 @@ private:
 	static void addNode(const DL::DataGroup& g, SceneLoadContext& ctx);
 	static void addMesh(const DL::DataGroup& g, SceneLoadContext& ctx);
 	static void addInclude(const DL::DataGroup& g, SceneLoadContext& ctx);
+	static void addSubGraph(const DL::DataGroup& g, SceneLoadContext& ctx); // (embed :loader 'obj' ...)
 	static uint32 addNodeInline(const DL::DataGroup& g, SceneLoadContext& ctx);
 	static Transformf extractTransform(const DL::DataGroup& g);
 	static ParameterGroup populateObjectParameters(const DL::DataGroup& g, SceneLoadContext& ctx);

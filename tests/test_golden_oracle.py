@@ -10,7 +10,7 @@ from conftest import ROOT, scene_path
 from oracle_binding import OracleScene
 from scene_strings import FURNACE, MATERIAL_ZOO
 
-GOLDEN = ["c1_sphere", "c2_cornellbox", "c3_cornellbox_glassy", "c4_boltsandgears", "material_zoo"]
+GOLDEN = ["c0_evaluation", "c1_sphere", "c2_cornellbox", "c3_cornellbox_glassy", "c4_boltsandgears", "c4b_complex_env", "material_zoo"]
 STAT_NAMES = ["camera_ray_count", "light_ray_count", "primary_ray_count", "bounce_ray_count", "shadow_ray_count", "monochrome_ray_count",
               "pixel_sample_count", "entity_hit_count", "background_hit_count", "camera_depth_count", "light_depth_count"]
 
@@ -86,3 +86,33 @@ def test_furnace_hero():
     assert abs(f[inside][:, 1].mean() - 1.0) < 0.03
     assert abs(f[outside][:, 1].mean() - 4.0) < 0.12
     assert (r["count"][inside] == 64).all() and (r["count"][outside] == 0).all()
+
+
+# ------------------------------------------------------------------ the reference's golden image
+XYZ_TO_LINEAR_SRGB = np.array([[3.2404542, -1.5371385, -0.4985314], [-0.9692660, 1.8760108, 0.0415560], [0.0556434, -0.2040259, 1.0572252]], np.float32)
+CBOX_LUMINANCE_TOL = 0.2   # relative RMSE of the 8x8-block luminance outside the luminaire
+CBOX_CHANNEL_TOL = 0.2     # relative difference of the per-channel image means
+
+
+def cbox_reference_error(xyz_film):
+    """Compare a render of scenes/c0_evaluation.prc with examples/evaluation/cbox.exr (tests/golden/cbox_reference_blocks.npz,
+    tools/make_golden.py:import_reference_image).  The image comes from another renderer (Mitsuba 2: CIE 1931 observer,
+    360-830 nm, different path-depth convention), so the bar is a sanity bound on block means, not bit parity."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cbox_reference_blocks.npz"))
+    rgb = xyz_film.astype(np.float32) @ XYZ_TO_LINEAR_SRGB.T
+    w = g["pixel_mask"].astype(np.float32)[..., None]
+    blocks = (rgb * w).reshape(32, 8, 32, 8, 3).sum(axis=(1, 3)) / np.maximum(w.reshape(32, 8, 32, 8, 1).sum(axis=(1, 3)), 1)
+    lum = np.array([0.2126, 0.7152, 0.0722], np.float32)
+    a, b = blocks @ lum, g["blocks"] @ lum
+    lum_err = float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(b))
+    ratio = blocks.sum(axis=(0, 1)) / g["blocks"].sum(axis=(0, 1))
+    return lum_err, ratio
+
+
+def test_oracle_vs_reference_golden_image():
+    scene = load_scene("c0_evaluation")
+    ora = OracleScene(scene)
+    r = ora.render(scene.tiles(8, 8), 0, 32, rng=scene.rng_map(), threads=os.cpu_count() or 1, aov=False)
+    lum_err, ratio = cbox_reference_error(r["filtered"])
+    assert lum_err < CBOX_LUMINANCE_TOL, lum_err
+    assert np.all(np.abs(ratio - 1) < CBOX_CHANNEL_TOL), ratio

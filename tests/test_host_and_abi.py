@@ -97,6 +97,41 @@ def test_loader_config_scenes():
     assert int(s.settings.max_ray_depth) == 6 and int(s.settings.soft_max_ray_depth) == 4 and int(s.settings.seed) == 42
 
 
+def test_loader_next_scenes():
+    """the evaluation scene of the reference's golden image and complex.prc (sky/sun replaced by a D65 env light)"""
+    s = prb.Scene.from_file(scene_path("c0_evaluation.prc"))
+    d = s.desc.contents
+    assert (s.width, s.height, int(s.settings.max_sample_count), int(d.n_entities), int(d.n_bvh_tris)) == (256, 256, 128, 8, 38)
+    assert int(s.settings.max_ray_depth) == 6 and int(s.settings.filter_radius) == 0
+    s = prb.Scene.from_file(scene_path("c4b_complex_env.prc"))
+    d = s.desc.contents
+    assert (s.width, s.height, int(s.settings.max_sample_count), int(d.n_entities), int(d.n_meshes)) == (1920, 1080, 4096, 68, 5)
+    assert int(d.n_lights) == 1 and int(d.n_faces) == 53428
+    assert [int(d.materials[i].type) for i in range(d.n_materials)] == [0, 1, 3, 5, 5, 1]  # diffuse, glass, rough conductor, principled x2, glass
+
+
+def test_wavefront_embed_and_filter_plugins(tmp_path):
+    """(embed :loader 'obj'), reference src/loader/archives/WavefrontLoader.cpp: quads are triangulated, corners with
+    different normal indices stay distinct vertices; all tabulated pixel filters of plugins/main/filter are registered"""
+    (tmp_path / "quad.obj").write_text("# unit quad with one shared normal, then a triangle without normal indices\n"
+                                       "vn 0 0 1\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1//1 2//1 3//1 4//1\nf -4//1 -3//1 -1//1\n")
+    src = ("(scene :name 'e' :render_width 8 :render_height 8 :camera 'C' (filter :slot 'pixel' :type '%s' :radius 1)"
+           " (camera :name 'C' :type 'standard' :position [0.5 0.5 2] :local_direction [0 0 -1])"
+           " (material :name 'm' :type 'diffuse' :albedo 0.5) (embed :loader 'obj' :file 'quad.obj' :name 'q')"
+           " (entity :name 'q' :type 'mesh' :mesh 'q' :materials 'm') (light :type 'env' :radiance 1))")
+    for flt in ("mitchell", "default", "triangle", "tri", "gaussian", "gauss", "lanczos", "sinc", "block"):
+        s = prb.Scene.from_string(src % flt, str(tmp_path / "scene.prc"))
+        d = s.desc.contents
+        assert int(d.n_bvh_tris) == 3 and int(d.n_faces) == 3 and int(d.n_vertices) == 4
+        r = int(s.settings.filter_radius)
+        assert r == 1
+        tab = np.array([d.pool[int(s.settings.filter_offset) + i] for i in range(9)], np.float32)
+        assert abs(float(tab.sum()) - 1.0) < 1e-5, flt  # normalised over the (2r+1)^2 footprint
+        assert np.array_equal(tab.reshape(3, 3), tab.reshape(3, 3).T)
+    idx = [int(d.face_indices[i]) for i in range(12)]
+    assert idx == [0, 1, 2, 0xFFFFFFFF, 0, 2, 3, 0xFFFFFFFF, 0, 1, 3, 0xFFFFFFFF]
+
+
 def test_loader_errors():
     with pytest.raises(prb.PrbError):
         prb.Scene.from_file("/nonexistent/scene.prc")
