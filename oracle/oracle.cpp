@@ -1427,7 +1427,7 @@ struct Integrator {
 		V3 o, n;
 		float z0, x0, y0, x1, y1, b0, b1, k, S;
 	};
-	static float safe_acos(float a) { return std::acos(std::max(-1.0f, std::min(1.0f, a))); }
+	static float safe_acos(float a) { return cr_acos(std::max(-1.0f, std::min(1.0f, a))); }
 	SQ computeSQ(const prb_entity& en, V3 o) const
 	{
 		SQ sq;
@@ -1527,7 +1527,7 @@ struct Integrator {
 			const SQ sq	   = computeSQ(en, ip.P);
 			const V3 mEx = ld3(en.geo + 3), mEy = ld3(en.geo + 6);
 			const float au = std::fma(rx, sq.S, sq.k);
-			const float fu = std::fma(std::cos(au), sq.b0, -sq.b1) / std::sin(au);
+			const float fu = std::fma(cr_cos(au), sq.b0, -sq.b1) / cr_sin(au);
 			const float cu = std::min(1.0f, std::max(-1.0f, std::copysign(1.0f, fu) / std::sqrt(sumProd(fu, fu, sq.b0, sq.b0))));
 			const float xu = std::min(sq.x1, std::max(sq.x0, -(cu * sq.z0) / std::max(1e-7f, std::sqrt(std::fma(-cu, cu, 1.0f)))));
 			const float dd = std::sqrt(sumProd(xu, xu, sq.z0, sq.z0));

@@ -88,14 +88,26 @@ inline bool isPositiveHemisphere(V3 a) { return !std::signbit(a.z); }
 inline V3 makeSameHemisphere(V3 self, V3 other) { return sameHemisphere(self, other) ? other : -other; }
 inline V3 makePositiveHemisphere(V3 a) { return isPositiveHemisphere(a) ? a : -a; }
 
+// ---------------------------------------------------------------- transcendental functions
+// The reference calls std::sin/cos/tan/atan/atan2/acos on float = the libm it links; glibc's float versions are within
+// 1 ulp but not correctly rounded (glibc 2.39: 1.3 % of sinf, 7.7 % of acosf, 15 % of atan2f results differ from the
+// correctly rounded value), so the reference's last bit is libm-version dependent.  The oracle (and the device code,
+// dev_math.cuh) use the correctly rounded fp32 value: evaluate in fp64, round once.
+inline float cr_sin(float x) { return (float)std::sin((double)x); }
+inline float cr_cos(float x) { return (float)std::cos((double)x); }
+inline float cr_tan(float x) { return (float)std::tan((double)x); }
+inline float cr_atan(float x) { return (float)std::atan((double)x); }
+inline float cr_atan2(float y, float x) { return (float)std::atan2((double)y, (double)x); }
+inline float cr_acos(float x) { return (float)std::acos((double)x); }
+
 // ---------------------------------------------------------------- Sampling, src/base/math/Sampling.h:38-57
 inline V3 cos_hemi(float u1, float u2)
 {
 	const float cosT   = std::sqrt(u1);
 	const float sinT   = std::sqrt(1 - u1);
 	const float phi	   = 2 * PR_PI * u2;
-	const float sinPhi = std::sin(phi);
-	const float cosPhi = std::cos(phi);
+	const float sinPhi = cr_sin(phi);
+	const float cosPhi = cr_cos(phi);
 	return mk(sinT * cosPhi, sinT * sinPhi, cosT);
 }
 inline float cos_hemi_pdf(float NdotL) { return NdotL * PR_INV_PI; }
@@ -271,15 +283,15 @@ inline V3 sample_ndf_ggx(float u0, float u1, float roughness) // :221-233
 	const float t2	   = alpha2 * u1 / (1 - u1);
 	const float cosT   = alpha2 <= PR_EPSILON ? 1.0f : std::max(0.001f, 1.0f / std::sqrt(1 + t2));
 	const float sinT   = std::sqrt(1 - cosT * cosT);
-	const float sinPhi = std::sin(2 * PR_PI * u0);
-	const float cosPhi = std::cos(2 * PR_PI * u0);
+	const float sinPhi = cr_sin(2 * PR_PI * u0);
+	const float cosPhi = cr_cos(2 * PR_PI * u0);
 	return spherical_cartesian(sinT, cosT, sinPhi, cosPhi);
 }
 inline V3 sample_ndf_ggx(float u0, float u1, float rx, float ry) // :234-249
 {
-	const float phi	   = std::atan(ry / rx * std::tan(PR_PI + 2 * PR_PI * u0)) + PR_PI * std::floor(2 * u0 + 0.5f);
-	const float sinPhi = std::sin(phi);
-	const float cosPhi = std::cos(phi);
+	const float phi	   = cr_atan(ry / rx * cr_tan(PR_PI + 2 * PR_PI * u0)) + PR_PI * std::floor(2 * u0 + 0.5f);
+	const float sinPhi = cr_sin(phi);
+	const float cosPhi = cr_cos(phi);
 	const float f1	   = cosPhi / rx;
 	const float f2	   = sinPhi / ry;
 	const float alpha2 = 1 / (f1 * f1 + f2 * f2);
@@ -300,8 +312,8 @@ inline V3 sample_vndf_ggx(float u0, float u1, V3 nV, float rx, float ry) // :261
 	const V3 T2		  = cross(Vh, T1);
 	const float r	  = std::sqrt(u0);
 	const float phi	  = 2.0f * PR_PI * u1;
-	const float t1	  = r * std::cos(phi);
-	float t2		  = r * std::sin(phi);
+	const float t1	  = r * cr_cos(phi);
+	float t2		  = r * cr_sin(phi);
 	const float s	  = 0.5f * (1.0f + Vh.z);
 	t2				  = (1.0f - s) * std::sqrt(1.0f - t1 * t1) + s * t2;
 	const V3 Nh		  = t1 * T1 + t2 * T2 + std::sqrt(std::max(0.0f, 1.0f + diffProd(-t1, t1, t2, t2))) * Vh;
@@ -536,9 +548,9 @@ inline V3 safePosition(V3 pos, V3 dir, V3 N)
 inline void spherical_from_direction(V3 D, float& theta, float& phi)
 {
 	const float x = (D.x == 0 && D.y == 0) ? 1e-5f : D.x;
-	phi			  = std::atan2(D.y, x);
+	phi			  = cr_atan2(D.y, x);
 	phi			  = phi < 0 ? phi + 2 * PR_PI : phi;
-	theta		  = std::acos(D.z);
+	theta		  = cr_acos(D.z);
 }
 inline void uv_from_normal(V3 N, float& u, float& v)
 {
@@ -551,6 +563,6 @@ inline void uv_from_normal(V3 N, float& u, float& v)
 inline V3 cartesian_from_uv(float u, float v)
 {
 	const float theta = v * PR_PI, phi = u * 2 * PR_PI;
-	return spherical_cartesian(std::sin(theta), std::cos(theta), std::sin(phi), std::cos(phi));
+	return spherical_cartesian(cr_sin(theta), cr_cos(theta), cr_sin(phi), cr_cos(phi));
 }
 } // namespace orc

@@ -93,6 +93,31 @@ PRB_DEV bool isPositiveHemisphere(V3 a) { return !signbitf(a.z); }
 PRB_DEV V3 makeSameHemisphere(V3 self, V3 other) { return sameHemisphere(self, other) ? other : -other; }
 PRB_DEV V3 makePositiveHemisphere(V3 a) { return isPositiveHemisphere(a) ? a : -a; }
 
+// IEEE division that survives the optimiser: under -ftz=true NVVM rewrites `x / constant` into `x * (1 / constant)`
+// (1 ulp off for constants that are not powers of two) even with -prec-div=true; the intrinsic is left alone.  Used
+// wherever the divisor is, or can become after inlining, a compile-time constant (checked by tools/check_ptx_div.sh).
+PRB_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// ---------------------------------------------------------------- transcendental functions
+// The reference calls std::sin/cos/tan/atan/atan2/acos on float, i.e. whatever libm the build links (glibc's are within
+// 1 ulp but not correctly rounded: 1.3 % of sinf and 15 % of atan2f results differ from the correctly rounded value),
+// so the last bit is libm-version dependent.  Device and oracle both use the CORRECTLY ROUNDED fp32 result instead
+// (evaluate in fp64, round once): libm-independent, and the two sides agree bit for bit, which keeps long specular
+// chains from diverging chaotically.
+PRB_DEV void cr_sincos(float x, float* s, float* c)
+{
+	double ds, dc;
+	sincos((double)x, &ds, &dc);
+	*s = (float)ds;
+	*c = (float)dc;
+}
+PRB_DEV float cr_sin(float x) { return (float)sin((double)x); }
+PRB_DEV float cr_cos(float x) { return (float)cos((double)x); }
+PRB_DEV float cr_tan(float x) { return (float)tan((double)x); }
+PRB_DEV float cr_atan(float x) { return (float)atan((double)x); }
+PRB_DEV float cr_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+PRB_DEV float cr_acos(float x) { return (float)acos((double)x); }
+
 // ---------------------------------------------------------------- Sampling (src/base/math/Sampling.h:38-57)
 PRB_DEV V3 cos_hemi(float u1, float u2)
 {
@@ -100,7 +125,7 @@ PRB_DEV V3 cos_hemi(float u1, float u2)
 	const float sinT = sqrtf(1 - u1);
 	const float phi	 = 2 * PR_PI * u2;
 	float sinPhi, cosPhi;
-	sincosf(phi, &sinPhi, &cosPhi);
+	cr_sincos(phi, &sinPhi, &cosPhi);
 	return mk(sinT * cosPhi, sinT * sinPhi, cosT);
 }
 PRB_DEV float cos_hemi_pdf(float NdotL) { return NdotL * PR_INV_PI; }
@@ -277,14 +302,14 @@ PRB_DEV_NI V3 sample_ndf_ggx1(float u0, float u1, float roughness)
 	const float cosT   = alpha2 <= PR_EPSILON ? 1.0f : fmaxf(0.001f, 1.0f / sqrtf(1 + t2));
 	const float sinT   = sqrtf(1 - cosT * cosT);
 	float sinPhi, cosPhi;
-	sincosf(2 * PR_PI * u0, &sinPhi, &cosPhi);
+	cr_sincos(2 * PR_PI * u0, &sinPhi, &cosPhi);
 	return spherical_cartesian(sinT, cosT, sinPhi, cosPhi);
 }
 PRB_DEV_NI V3 sample_ndf_ggx2(float u0, float u1, float rx, float ry)
 {
-	const float phi = atanf(ry / rx * tanf(PR_PI + 2 * PR_PI * u0)) + PR_PI * floorf(2 * u0 + 0.5f);
+	const float phi = cr_atan(ry / rx * cr_tan(PR_PI + 2 * PR_PI * u0)) + PR_PI * floorf(2 * u0 + 0.5f);
 	float sinPhi, cosPhi;
-	sincosf(phi, &sinPhi, &cosPhi);
+	cr_sincos(phi, &sinPhi, &cosPhi);
 	const float f1	   = cosPhi / rx;
 	const float f2	   = sinPhi / ry;
 	const float alpha2 = 1 / (f1 * f1 + f2 * f2);
@@ -306,7 +331,7 @@ PRB_DEV_NI V3 sample_vndf_ggx(float u0, float u1, V3 nV, float rx, float ry)
 	const float r	  = sqrtf(u0);
 	const float phi	  = 2.0f * PR_PI * u1;
 	float sp, cp;
-	sincosf(phi, &sp, &cp);
+	cr_sincos(phi, &sp, &cp);
 	const float t1 = r * cp;
 	float t2	   = r * sp;
 	const float s  = 0.5f * (1.0f + Vh.z);
@@ -523,9 +548,9 @@ PRB_DEV V3 safePosition(V3 pos, V3 dir, V3 N)
 PRB_DEV void uv_from_normal(V3 N, float& u, float& v)
 { // Spherical::uv_from_normal / from_direction, src/base/math/Spherical.h:9-31
 	const float x = (N.x == 0 && N.y == 0) ? 1e-5f : N.x;
-	float phi	  = atan2f(N.y, x);
+	float phi	  = cr_atan2(N.y, x);
 	phi			  = phi < 0 ? phi + 2 * PR_PI : phi;
-	const float theta = acosf(N.z);
+	const float theta = cr_acos(N.z);
 	const float tx = theta * PR_INV_PI, ty = phi * PR_INV_PI;
 	u = ty / 2;
 	v = tx;
@@ -534,8 +559,8 @@ PRB_DEV V3 cartesian_from_uv(float u, float v)
 {
 	const float theta = v * PR_PI, phi = u * 2 * PR_PI;
 	float st, ct, sp, cp;
-	sincosf(theta, &st, &ct);
-	sincosf(phi, &sp, &cp);
+	cr_sincos(theta, &st, &ct);
+	cr_sincos(phi, &sp, &cp);
 	return spherical_cartesian(st, ct, sp, cp);
 }
 

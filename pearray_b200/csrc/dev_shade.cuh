@@ -19,7 +19,7 @@ constexpr int CIE_N		   = 441;
 constexpr float CIE_Y_NORM = 113.042314572337f * (CIE_RANGE / (CIE_N - 1));
 PRB_DEV float cieEval(const DScene& S, int c, float w)
 { // CIE::eval_x/y/z, src/core/spectral/CIE.h:41-58
-	return tableLookup(S.pool + S.cieOffset + c * CIE_N, CIE_N, CIE_START, CIE_END, w) / CIE_Y_NORM * CIE_RANGE;
+	return fdiv(tableLookup(S.pool + S.cieOffset + c * CIE_N, CIE_N, CIE_START, CIE_END, w), CIE_Y_NORM) * CIE_RANGE;
 }
 
 // leaf node kinds; MUL / CHECKER reference other nodes.  The flattened graph is shallow (depth <= 3 in the
@@ -50,7 +50,7 @@ PRB_DEV Blob evalLeafNode(const DScene& S, const prb_node& n, const Blob& w)
 		const float* C = B + n.b;
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			const float qm	= w[i] / 1000;
+			const float qm	= fdiv(w[i], 1000.0f);
 			const float qm2 = qm * qm;
 			float value		= 1;
 			for (uint32_t k = 0; k < n.b; ++k)
@@ -322,7 +322,7 @@ struct Principled {
 		const Blob color = tintColor(S, wvl);
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			const float eta = HdotV < 0 ? AIR / IOR[i] : IOR[i] / AIR;
+			const float eta = HdotV < 0 ? AIR / IOR[i] : fdiv(IOR[i], AIR);
 			const float r0	= mixf(schlickR0(eta) * mixf(1.0f, color[i], SpecularTint), Base[i], Metallic);
 			const float f1	= fresnel_dielectric(HdotV, AIR, IOR[i]);
 			const float f2	= schlick(fabsf(HdotL), r0);
@@ -420,7 +420,7 @@ struct Principled {
 				if (c.rayFlags & PRB_RAY_LIGHT) {
 #pragma unroll
 					for (int i = 0; i < 4; ++i) {
-						const float eta = HdotL < 0.0f ? IOR[i] / AIR : AIR / IOR[i];
+						const float eta = HdotL < 0.0f ? fdiv(IOR[i], AIR) : AIR / IOR[i];
 						weight[i] *= eta * eta;
 					}
 				}
@@ -695,7 +695,7 @@ __device__ __noinline__ void materialSample(const DScene& S, uint32_t matID, con
 				out.weight = tWeight;
 			} else {
 				if (c.rayFlags & PRB_RAY_LIGHT) {
-					const float eta = isPositiveHemisphere(c.V) ? AIR / n2[0] : n2[0] / AIR;
+					const float eta = isPositiveHemisphere(c.V) ? AIR / n2[0] : fdiv(n2[0], AIR);
 					tWeight			= tWeight * (eta * eta);
 				}
 				out.L = refractZ(AIR / n2[0], c.V);
@@ -973,7 +973,7 @@ struct SQ { // spherical rectangle, plane.cpp:100-145
 	V3 o, n;
 	float z0, x0, y0, x1, y1, b0, b1, k, S;
 };
-PRB_DEV float safe_acos(float a) { return acosf(fmaxf(-1.0f, fminf(1.0f, a))); }
+PRB_DEV float safe_acos(float a) { return cr_acos(fmaxf(-1.0f, fminf(1.0f, a))); }
 PRB_DEV void computeSQ(const prb_entity& en, V3 o, SQ& sq)
 {
 	const V3 mS = ld3(en.geo), mEx = ld3(en.geo + 3), mEy = ld3(en.geo + 6), mEz = ld3(en.geo + 9);
@@ -1089,7 +1089,7 @@ __device__ __noinline__ void sampleLight(const DScene& S, const prb_light& l, V3
 		computeSQ(en, P, sq);
 		const V3 mEx = ld3(en.geo + 3), mEy = ld3(en.geo + 6);
 		const float au = fmaf(rx, sq.S, sq.k);
-		const float fu = fmaf(cosf(au), sq.b0, -sq.b1) / sinf(au);
+		const float fu = fmaf(cr_cos(au), sq.b0, -sq.b1) / cr_sin(au);
 		const float cu = fminf(1.0f, fmaxf(-1.0f, copysignf(1.0f, fu) / sqrtf(sumProd(fu, fu, sq.b0, sq.b0))));
 		const float xu = fminf(sq.x1, fmaxf(sq.x0, -(cu * sq.z0) / fmaxf(1e-7f, sqrtf(fmaf(-cu, cu, 1.0f)))));
 		const float dd = sqrtf(sumProd(xu, xu, sq.z0, sq.z0));
