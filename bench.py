@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
             "config": {"workload": label, "scene": fname, "note": "reference not buildable here (Eigen/Embree/TBB/OIIO absent): CPU oracle port, bounded sample"},
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -323,7 +323,7 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
                 "stage_ms": {k: v[0] for k, v in stage.items()} if stage else None}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -468,13 +468,30 @@ def run_soup(args, rank, world, local_rank):
                                                 "l2": "BVH + triangles (%.0f MB) exceed the 126 MB L2 for >= 2.4 M triangles" % ((int(d.n_bvh_nodes) * 80 + n_tris * 48) / 1e6)},
                 "classes": per_class, "roofline": roofline, "gpu_launches": int(ctx.stats().kernel_launches), "clocks": sampler.summary(),
                 "e2e": None, "cpu_baseline": None, "wall_s": wall}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was moved to stderr"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)  # NCCL prints its version banner on fd 1: keep stdout for the JSON line only
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -496,7 +513,7 @@ def main():
         g.build()
     if args.scene == "c5":
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "c5 is a GPU ray-stream workload; the CPU arm is defined for the path-tracing configs c1-c4"}))
+            emit({"impl": "reference", "unavailable": "c5 is a GPU ray-stream workload; the CPU arm is defined for the path-tracing configs c1-c4"})
             return
         run_soup(args, rank, world, local_rank)
     elif args.impl == "reference":
