@@ -142,6 +142,7 @@ PRB_DEV float safeInv(float d)
 }
 
 constexpr int BVH_STACK = 48;
+constexpr int BVH_STACK_ALLOC = BVH_STACK + 3; // + the world-space ray (origin, direction) parked while inside a BLAS
 // Traversal stack entries are GROUPS (after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs Through
 // Compressed Wide BVHs", HPG 2017), 8 bytes each:
 //   node group      .x = child_base of the visited node            .y = hits (8 bit, octant-permuted slot space) | imask << 8
@@ -170,34 +171,89 @@ PRB_DEV uint32_t permuteByOctant(uint32_t m, uint32_t oct)
 	return m;
 }
 
-// Resumable traversal of TLAS + BLAS for ONE ray (one thread = one ray).
+// Resumable, WARP-SYNCHRONOUS traversal of TLAS + BLAS: one lane = one ray, but all 32 lanes of the warp call round()
+// together (lanes without a ray pass live = false).
 //
-// advance() runs one round: a node step (fetch one 80-byte node with five 128-bit loads, test its 8 quantised child
-// boxes branch-free, emit a node group + a primitive group), the primitive phase (watertight triangle tests in a BLAS;
-// entity entry -- analytic sphere or ray transformed into the mesh's local space -- in the TLAS) and the pop.  Keeping the
-// state in a struct lets the persistent kernels leave the loop to refill idle lanes with new rays and come back.
-// Primitive groups are POSTPONED (pushed) while only a few lanes of the warp have primitives to test and node work is
-// available, so triangle tests run with fuller warps.
-constexpr int TRI_POSTPONE_LANES = 10;
+// round() runs, per lane, a node step (fetch one 80-byte node with five 128-bit loads, test its 8 quantised child boxes
+// branch-free, emit a node group + a primitive group), the TLAS primitive phase (analytic sphere, or the ray transformed
+// into the mesh's local space and the BLAS entered) and the pop.  Triangle tests are NOT done by the lane that owns the
+// ray: the pending (ray, triangle) pairs of the whole warp are counted, and once enough of them are waiting (or no lane has
+// node work left) they are dealt out one pair per lane -- the ray travels by shuffle -- so the watertight test runs on full
+// warps however few rays reached a leaf in this round (ncu on the 10 M soup: per-lane tests ran at 3.9 of 32 lanes and
+// took 47 % of the issue slots).  Accepted hits travel back to the owner by shuffle; closest-hit semantics are order
+// independent, so the result is bit-identical.
+#ifndef PRB_TRI_BATCH_MIN
+#define PRB_TRI_BATCH_MIN 16
+#endif
+constexpr int TRI_BATCH_MIN = PRB_TRI_BATCH_MIN; // fire a cooperative batch once this many (ray, triangle) pairs are pending in the warp
 
+PRB_DEV uint32_t nthSetBit(uint32_t m, uint32_t r)
+{ // position of the r-th (0-based) set bit of m; r < popc(m)
+	uint32_t pos = 0, c;
+	c = __popc(m & 0xFFFFu);
+	if (r >= c) {
+		r -= c;
+		pos = 16;
+		m >>= 16;
+	}
+	c = __popc(m & 0xFFu);
+	if (r >= c) {
+		r -= c;
+		pos += 8;
+		m >>= 8;
+	}
+	c = __popc(m & 0xFu);
+	if (r >= c) {
+		r -= c;
+		pos += 4;
+		m >>= 4;
+	}
+	c = __popc(m & 0x3u);
+	if (r >= c) {
+		r -= c;
+		pos += 2;
+		m >>= 2;
+	}
+	return pos + ((r >= (m & 1u)) ? 1u : 0u);
+}
+
+// The traversal stack (BVH_STACK entries of 8 bytes, local memory) is owned by the caller and passed to round(), so that
+// the scalar state below stays in registers.
 struct Trav {
-	V3 wO, wD, O, D, inv;
+	V3 O, D, inv;
 	float tmin;
 	uint32_t oct, curEnt;
 	uint2 ng, pg;
 	int sp;
+	bool any; // any-hit ray: finished as soon as one primitive was accepted
 	HitRec best;
-	uint2 stack[BVH_STACK];
 
-	PRB_DEV void begin(const DScene& S, V3 o, V3 d, float t0, float t1)
+	PRB_DEV void idle()
 	{
+		ng = pg = make_uint2(0, 0);
+		sp		= 0;
+		curEnt	= PRB_INVALID_ID;
+		any		= false;
+		tmin	= 0;
+		O = D = inv = mk(0, 0, 0);
+		oct					  = 0;
+		best.entity			  = PRB_INVALID_ID;
+		best.prim			  = 0;
+		best.u = best.v = best.t = 0;
+	}
+	PRB_DEV void begin(const DScene& S, V3 o, V3 d, float t0, float t1, bool anyHit, uint2* __restrict__ stack)
+	{
+		stack[BVH_STACK]	 = make_uint2(__float_as_uint(o.x), __float_as_uint(o.y));
+		stack[BVH_STACK + 1] = make_uint2(__float_as_uint(o.z), __float_as_uint(d.x));
+		stack[BVH_STACK + 2] = make_uint2(__float_as_uint(d.y), __float_as_uint(d.z));
 		best.entity = PRB_INVALID_ID;
 		best.prim	= 0;
 		best.u = best.v = 0;
 		best.t			= t1;
-		wO = O = o;
-		wD = D = d;
+		O = o;
+		D = d;
 		tmin   = t0;
+		any	   = anyHit;
 		inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
 		oct	   = rayOctant(inv);
 		curEnt = PRB_INVALID_ID;							   // TLAS level
@@ -205,13 +261,21 @@ struct Trav {
 		pg	   = make_uint2(0, 0);
 		sp	   = 0;
 	}
-
-	// returns true when the ray is finished (ANY: as soon as one primitive was accepted)
-	template <bool ANY>
-	PRB_DEV bool advance(const DScene& S)
+	PRB_DEV void finish()
 	{
+		ng.y = 0;
+		pg.y = 0;
+		sp	 = 0;
+	}
+
+	// All 32 lanes must call.  Returns true on the lanes whose ray finished in this round.
+	PRB_DEV bool round(const DScene& S, bool live, uint2* __restrict__ stack)
+	{
+		const unsigned FULL = 0xFFFFFFFFu;
+		const int lane		= threadIdx.x & 31;
+		bool fin			= false;
 		// ---------------------------------------------------------------- node step
-		if (ng.y & 0xFFu) {
+		if (live && (ng.y & 0xFFu)) {
 			const uint32_t r	= __ffs(ng.y & 0xFFu) - 1; // next child in octant order
 			const uint32_t slot = r ^ oct;
 			const uint32_t node = ng.x + __popc((ng.y >> 8) & ((1u << slot) - 1u));
@@ -220,45 +284,60 @@ struct Trav {
 				stack[sp++] = ng;
 			const uint4* np = S.bvhNodes + 5 * (size_t)node;
 			const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-			const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+			// Child planes in ray parameter space with ONE fused multiply-add per plane (after Ylitie et al.):
+			//   t = (p + q 2^e - O) inv = q adj + org,   adj = 2^e inv (exact),   org = (p - O) inv.
+			// The byte q becomes the float F = 2^15 + q with one PRMT (0x47000000 | q << 8), so t = F adj + (org - 2^15 adj).
+			// Rounding: |err(t)| <= 4 eps |t| + 2^-9 |adj| (the bias 2^15 adj costs 7 bits relative to one quantisation step);
+			// the test stays conservative through the absolute pad 2^-7 |adj| (1/128 step) on the near/far bias and the
+			// relative slack 2e-6 in the comparison (rounding above + the ulp slack of the watertight triangle test).
 			const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
 						sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+			const float adjx = sx * inv.x, adjy = sy * inv.y, adjz = sz * inv.z;
+			const float bx = fmaf(-32768.0f, adjx, (__uint_as_float(n0.x) - O.x) * inv.x);
+			const float by = fmaf(-32768.0f, adjy, (__uint_as_float(n0.y) - O.y) * inv.y);
+			const float bz = fmaf(-32768.0f, adjz, (__uint_as_float(n0.z) - O.z) * inv.z);
+			const float padx = fabsf(adjx) * 0.0078125f, pady = fabsf(adjy) * 0.0078125f, padz = fabsf(adjz) * 0.0078125f;
+			const float bnx = bx - padx, bfx = bx + padx, bny = by - pady, bfy = by + pady, bnz = bz - padz, bfz = bz + padz;
+			// near / far plane bytes by the sign of the direction: no per-child min/max
+			const bool negx = oct & 1u, negy = oct & 2u, negz = oct & 4u;
+			const uint32_t nx0 = negx ? n3.z : n2.x, nx1 = negx ? n3.w : n2.y, fx0 = negx ? n2.x : n3.z, fx1 = negx ? n2.y : n3.w;
+			const uint32_t ny0 = negy ? n4.x : n2.z, ny1 = negy ? n4.y : n2.w, fy0 = negy ? n2.z : n4.x, fy1 = negy ? n2.w : n4.y;
+			const uint32_t nz0 = negz ? n4.z : n3.x, nz1 = negz ? n4.w : n3.y, fz0 = negz ? n3.x : n4.z, fz1 = negz ? n3.y : n4.w;
 			const float tcur  = best.t; // == tmax until something was hit
-			uint32_t nodeHits = 0, primBits = 0;
+			uint32_t hitMask  = 0;
 #pragma unroll
 			for (int i = 0; i < 8; ++i) {
+				const uint32_t sel = 0x7404u | ((uint32_t)(i & 3) << 4); // bytes: 00, q, 00, 47  ->  2^15 + q
+				const float tnx	   = fmaf(__uint_as_float(__byte_perm(i < 4 ? nx0 : nx1, 0x47000000u, sel)), adjx, bnx);
+				const float tny	   = fmaf(__uint_as_float(__byte_perm(i < 4 ? ny0 : ny1, 0x47000000u, sel)), adjy, bny);
+				const float tnz	   = fmaf(__uint_as_float(__byte_perm(i < 4 ? nz0 : nz1, 0x47000000u, sel)), adjz, bnz);
+				const float tfx	   = fmaf(__uint_as_float(__byte_perm(i < 4 ? fx0 : fx1, 0x47000000u, sel)), adjx, bfx);
+				const float tfy	   = fmaf(__uint_as_float(__byte_perm(i < 4 ? fy0 : fy1, 0x47000000u, sel)), adjy, bfy);
+				const float tfz	   = fmaf(__uint_as_float(__byte_perm(i < 4 ? fz0 : fz1, 0x47000000u, sel)), adjz, bfz);
+				const float tn	   = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+				const float tf	   = fminf(fminf(tfx, tfy), fminf(tfz, tcur));
+				hitMask |= (tn <= fmaf(fabsf(tf), 2e-6f, tf)) ? (1u << i) : 0u;
+			}
+			// children: internal = imask bit, leaf = meta bit 7 clear, empty = meta 0xFF
+			const uint32_t imask = n0.w >> 24;
+			const uint32_t lz = (~n1.z & 0x80808080u) >> 7, lw = (~n1.w & 0x80808080u) >> 7;
+			const uint32_t leafMask = (((lz * 0x01020408u) >> 24) & 0xFu) | (((lw * 0x01020408u) >> 20) & 0xF0u);
+			const uint32_t nodeHits = hitMask & imask;
+			uint32_t leafHits = hitMask & leafMask, primBits = 0;
+			while (leafHits) { // typically 0..2 leaves
+				const int i = __ffs(leafHits) - 1;
+				leafHits &= leafHits - 1;
 				const uint32_t meta = ((i < 4 ? n1.z : n1.w) >> (8 * (i & 3))) & 0xFFu;
-				const uint32_t sel	= 0x7440u + (uint32_t)(i & 3); // byte (i&3) of the first operand into the low mantissa byte
-				// child box: lo = p + q_lo * 2^e (the product is exact, so the fused form rounds like the builder's decodeCoord)
-				const float lox = fmaf(byteToFloat(i < 4 ? n2.x : n2.y, sel), sx, px), loy = fmaf(byteToFloat(i < 4 ? n2.z : n2.w, sel), sy, py);
-				const float loz = fmaf(byteToFloat(i < 4 ? n3.x : n3.y, sel), sz, pz), hix = fmaf(byteToFloat(i < 4 ? n3.z : n3.w, sel), sx, px);
-				const float hiy = fmaf(byteToFloat(i < 4 ? n4.x : n4.y, sel), sy, py), hiz = fmaf(byteToFloat(i < 4 ? n4.z : n4.w, sel), sz, pz);
-				const float ax = (lox - O.x) * inv.x, bx = (hix - O.x) * inv.x;
-				const float ay = (loy - O.y) * inv.y, by = (hiy - O.y) * inv.y;
-				const float az = (loz - O.z) * inv.z, bz = (hiz - O.z) * inv.z;
-				float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-				float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-				tn		 = tn - fabsf(tn) * 4e-7f; // conservative: never cull what the triangle test could accept
-				tf		 = tf + fabsf(tf) * 4e-7f;
-				const bool hit			= (meta != 0xFFu) && (fmaxf(tn, tmin) <= fminf(tf, tcur));
-				const uint32_t leafBits = ((2u << ((meta >> 5) & 3u)) - 1u) << (meta & 0x1Fu);
-				nodeHits |= (hit && (meta & 0x80u)) ? (1u << i) : 0u;
-				primBits |= (hit && !(meta & 0x80u)) ? leafBits : 0u;
+				primBits |= ((2u << ((meta >> 5) & 3u)) - 1u) << (meta & 0x1Fu);
 			}
 			ng = make_uint2(n1.x, permuteByOctant(nodeHits, oct) | ((n0.w >> 24) << 8));
 			pg = make_uint2(GRP_PRIM | n1.y, primBits);
 		}
-		// ---------------------------------------------------------------- primitive phase
-		while (pg.y) {
-			if ((ng.y & 0xFFu) && sp < BVH_STACK && __popc(__activemask()) < TRI_POSTPONE_LANES) {
-				stack[sp++] = pg; // too few lanes have primitives: test them later, go on with the node group
-				pg.y		= 0;
-				break;
-			}
-			const uint32_t k = pg.x + (__ffs(pg.y) - 1); // GRP_PRIM | primitive index
-			pg.y &= pg.y - 1;
-			if (curEnt == PRB_INVALID_ID) {
-				// TLAS: one entity per reference
+		// ---------------------------------------------------------------- TLAS primitive phase (entity references), per lane
+		if (live && curEnt == PRB_INVALID_ID) {
+			while (pg.y) {
+				const uint32_t k = pg.x + (__ffs(pg.y) - 1);
+				pg.y &= pg.y - 1;
 				const uint32_t e	 = __ldg(S.tlasRefs + (k & ~GRP_PRIM));
 				const prb_entity& en = S.entities[e];
 				const uint32_t type	 = en.type;
@@ -269,8 +348,10 @@ struct Trav {
 						best.prim	= 0;
 						best.t		= t;
 						best.u = best.v = 0;
-						if (ANY)
-							return true;
+						if (any) {
+							finish();
+							fin = true;
+						}
 					}
 				} else {
 					// enter the entity's BLAS: park the unfinished TLAS groups under an exit marker
@@ -282,65 +363,141 @@ struct Trav {
 						stack[sp++] = make_uint2(GRP_EXIT, 0);
 					curEnt = e;
 					if (type == PRB_ENTITY_MESH) { // planes are stored in world space: no transform (plane.cpp:71-94)
-						O	= xfPoint(en.world_to_local, wO);
-						D	= xfVec(en.world_to_local, wD);
+						O	= xfPoint(en.world_to_local, O); // at TLAS level (O, D) is the world-space ray
+						D	= xfVec(en.world_to_local, D);
 						inv = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
 						oct = rayOctant(inv);
 					}
 					ng = make_uint2(en.blas_root, (1u << oct) | (1u << 8));
 					pg = make_uint2(0, 0);
 				}
-			} else {
-				const float4* tp = S.bvhTris + 3 * (size_t)(k & ~GRP_PRIM);
-				const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-				float t, u, v;
-				if (triTest(O, D, tmin, best.t, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v)) {
-					const uint32_t prim = __float_as_uint(a.w);
-					if (betterHit(t, curEnt, prim, best)) {
-						if (__float_as_uint(b.w) & 1u) {
-							u = 1 - u;
-							v = 1 - v;
+			}
+		}
+		// ---------------------------------------------------------------- cooperative triangle phase (warp-uniform)
+		{
+			const bool has		 = live && !fin && curEnt != PRB_INVALID_ID && pg.y != 0;
+			const bool nodeWork	 = live && !fin && (ng.y & 0xFFu);
+			const uint32_t cnt	 = has ? __popc(pg.y) : 0u;
+			const unsigned hasM	 = __ballot_sync(FULL, has);
+			if (hasM) {
+				uint32_t incl = cnt; // inclusive prefix sum of the pair counts
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t n = __shfl_up_sync(FULL, incl, d);
+					if (lane >= d)
+						incl += n;
+				}
+				const uint32_t total = __shfl_sync(FULL, incl, 31);
+				const bool mustNow	 = has && nodeWork && sp >= BVH_STACK; // cannot postpone: no room to park the group
+				const bool fire		 = total >= TRI_BATCH_MIN || __ballot_sync(FULL, nodeWork) == 0 || __any_sync(FULL, mustNow);
+				if (!fire) {
+					if (has && nodeWork) { // park the group, go on with the node group; lanes without node work keep theirs and wait
+						stack[sp++] = pg;
+						pg.y		= 0;
+					}
+				} else {
+					const uint32_t excl = incl - cnt;
+					for (uint32_t base = 0; base < total; base += 32) {
+						const uint32_t q = base + lane;
+						// owner of pair q: the first lane whose inclusive count exceeds q
+						uint32_t o = 0;
+#pragma unroll
+						for (int step = 16; step >= 1; step >>= 1) {
+							const uint32_t v = __shfl_sync(FULL, incl, (o + step - 1) & 31);
+							if (v <= q)
+								o += step;
 						}
-						best.entity = curEnt;
-						best.prim	= prim;
-						best.t		= t;
-						best.u		= u;
-						best.v		= v;
-						if (ANY)
-							return true;
+						const bool valid = q < total;
+						o &= 31;
+						const uint32_t r	 = q - __shfl_sync(FULL, excl, o);
+						const uint32_t bits	 = __shfl_sync(FULL, pg.y, o);
+						const uint32_t pbase = __shfl_sync(FULL, pg.x, o) & ~GRP_PRIM;
+						const V3 rO			 = mk(__shfl_sync(FULL, O.x, o), __shfl_sync(FULL, O.y, o), __shfl_sync(FULL, O.z, o));
+						const V3 rD			 = mk(__shfl_sync(FULL, D.x, o), __shfl_sync(FULL, D.y, o), __shfl_sync(FULL, D.z, o));
+						const float rt0 = __shfl_sync(FULL, tmin, o), rt1 = __shfl_sync(FULL, best.t, o);
+						bool hit		= false;
+						float t = 0, u = 0, v = 0;
+						uint32_t prim = 0;
+						if (valid) {
+							const uint32_t k = pbase + nthSetBit(bits, r);
+							const float4* tp = S.bvhTris + 3 * (size_t)k;
+							const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+							hit	 = triTest(rO, rD, rt0, rt1, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v);
+							prim = __float_as_uint(a.w);
+							if (hit && (__float_as_uint(b.w) & 1u)) {
+								u = 1 - u;
+								v = 1 - v;
+							}
+						}
+						// accepted hits go back to the ray's lane; the owner keeps the smallest (t, entity, prim)
+						unsigned hm = __ballot_sync(FULL, hit);
+						while (hm) {
+							const int src = __ffs(hm) - 1;
+							hm &= hm - 1;
+							const uint32_t ow = __shfl_sync(FULL, o, src);
+							const float ht	  = __shfl_sync(FULL, t, src);
+							const uint32_t hp = __shfl_sync(FULL, prim, src);
+							const float hu = __shfl_sync(FULL, u, src), hv = __shfl_sync(FULL, v, src);
+							if ((uint32_t)lane == ow && betterHit(ht, curEnt, hp, best)) {
+								best.entity = curEnt;
+								best.prim	= hp;
+								best.t		= ht;
+								best.u		= hu;
+								best.v		= hv;
+							}
+						}
+					}
+					if (has) {
+						pg.y = 0;
+						if (any && best.entity != PRB_INVALID_ID) {
+							finish();
+							fin = true;
+						}
 					}
 				}
 			}
 		}
 		// ---------------------------------------------------------------- pop
-		while (!(ng.y & 0xFFu)) {
-			if (sp == 0)
-				return true;
-			const uint2 e = stack[--sp];
-			if (e.x == GRP_EXIT) { // leave the BLAS: restore the world-space ray
-				O	   = wO;
-				D	   = wD;
-				inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
-				oct	   = rayOctant(inv);
-				curEnt = PRB_INVALID_ID;
-			} else if (e.x & GRP_PRIM) {
-				pg = e;
-				break; // next round: the node step is skipped (ng is empty), the primitive phase runs
-			} else {
-				ng = e;
+		if (live && !fin && pg.y == 0) {
+			while (!(ng.y & 0xFFu)) {
+				if (sp == 0) {
+					fin = true;
+					break;
+				}
+				const uint2 e = stack[--sp];
+				if (e.x == GRP_EXIT) { // leave the BLAS: restore the world-space ray
+					const uint2 w0 = stack[BVH_STACK], w1 = stack[BVH_STACK + 1], w2 = stack[BVH_STACK + 2];
+					O	   = mk(__uint_as_float(w0.x), __uint_as_float(w0.y), __uint_as_float(w1.x));
+					D	   = mk(__uint_as_float(w1.y), __uint_as_float(w2.x), __uint_as_float(w2.y));
+					inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
+					oct	   = rayOctant(inv);
+					curEnt = PRB_INVALID_ID;
+				} else if (e.x & GRP_PRIM) {
+					pg = e;
+					break; // next round: the node step is skipped (ng is empty), the primitive phases see the group
+				} else {
+					ng = e;
+				}
 			}
 		}
-		return false;
+		return fin;
 	}
 	PRB_DEV bool hit() const { return best.entity != PRB_INVALID_ID; }
 };
 
-template <bool ANY>
-PRB_DEV bool traverseScene(const DScene& S, V3 wO, V3 wD, float tmin, float tmax, HitRec& best)
+// warp-synchronous: every lane of the warp must call (lanes without a ray pass live = false)
+PRB_DEV bool traverseScene(const DScene& S, bool live, bool anyHit, V3 wO, V3 wD, float tmin, float tmax, HitRec& best)
 {
 	Trav tr;
-	tr.begin(S, wO, wD, tmin, tmax);
-	while (!tr.advance<ANY>(S)) {
+	uint2 stack[BVH_STACK_ALLOC];
+	if (live)
+		tr.begin(S, wO, wD, tmin, tmax, anyHit, stack);
+	else
+		tr.idle();
+	bool act = live;
+	while (__any_sync(0xFFFFFFFFu, act)) {
+		if (tr.round(S, act, stack))
+			act = false;
 	}
 	best = tr.best;
 	return tr.hit();

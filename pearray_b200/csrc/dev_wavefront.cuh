@@ -137,41 +137,55 @@ __global__ void __launch_bounds__(128) k_init_slots(DScene S, WFState W)
 // (a handful of primitives), where the bookkeeping of the persistent variant costs more than the idle lanes it avoids.
 __global__ void __launch_bounds__(128) k_trace_static(DScene S, WFState W)
 {
+	// no early return: the traversal is warp-synchronous, lanes without a ray take part with live = false
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if (slot >= W.nSlots)
-		return;
-	const uint32_t st = W.state[slot];
-	if (st == 0)
-		return;
-	if (st & SF_SHADOW) {
-		const float4 o = W.shO[slot], d = W.shD[slot];
-		HitRec h;
-		const bool occluded = traverseScene<true>(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
-		const float4 c		= occluded ? make_float4(0, 0, 0, 0) : W.shXYZ[slot];
-		if (st & SF_FINALIZE) {
-			const float4 p = W.prevAcc[slot];
-			foldSampleIntoFilm(W, W.pixel[slot], p.x + c.x, p.y + c.y, p.z + c.z, __float_as_uint(p.w));
-		} else if (!occluded) {
-			float4 acc = W.iterXYZ[slot];
-			acc.x += c.x;
-			acc.y += c.y;
-			acc.z += c.z;
-			W.iterXYZ[slot] = acc;
+	const bool inRange	= slot < W.nSlots;
+	const uint32_t st	= inRange ? W.state[slot] : 0u;
+	{
+		const bool live = (st & SF_SHADOW) != 0;
+		float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
+		if (live) {
+			o = W.shO[slot];
+			d = W.shD[slot];
 		}
-		W.state[slot] = st & SF_ACTIVE;
-	}
-	if (st & SF_ACTIVE) {
-		const float4 o = W.rayO[slot], d = W.rayD[slot];
 		HitRec h;
-		traverseScene<false>(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
-		W.hit[slot]	 = make_uint4(h.entity, h.prim, __float_as_uint(h.u), __float_as_uint(h.v));
-		W.hitT[slot] = h.t;
+		const bool occluded = traverseScene(S, live, true, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
+		if (live) {
+			const float4 c = occluded ? make_float4(0, 0, 0, 0) : W.shXYZ[slot];
+			if (st & SF_FINALIZE) {
+				const float4 p = W.prevAcc[slot];
+				foldSampleIntoFilm(W, W.pixel[slot], p.x + c.x, p.y + c.y, p.z + c.z, __float_as_uint(p.w));
+			} else if (!occluded) {
+				float4 acc = W.iterXYZ[slot];
+				acc.x += c.x;
+				acc.y += c.y;
+				acc.z += c.z;
+				W.iterXYZ[slot] = acc;
+			}
+			W.state[slot] = st & SF_ACTIVE;
+		}
+	}
+	{
+		const bool live = (st & SF_ACTIVE) != 0;
+		float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
+		if (live) {
+			o = W.rayO[slot];
+			d = W.rayD[slot];
+		}
+		HitRec h;
+		traverseScene(S, live, false, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, h);
+		if (live) {
+			W.hit[slot]	 = make_uint4(h.entity, h.prim, __float_as_uint(h.u), __float_as_uint(h.v));
+			W.hitT[slot] = h.t;
+		}
 	}
 }
 
 __global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
 {
 	Trav tr;
+	uint2 stack[BVH_STACK_ALLOC];
+	tr.idle();
 	uint32_t slot = 0, st = 0;
 	int phase	  = 0; // 0 idle, 1 shadow ray in flight, 2 closest-hit ray in flight
 	bool pool	  = true;
@@ -190,11 +204,11 @@ __global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
 					st	 = W.state[slot];
 					if (st & SF_SHADOW) {
 						const float4 o = W.shO[slot], d = W.shD[slot];
-						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w);
+						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, true, stack);
 						phase = 1;
 					} else if (st & SF_ACTIVE) {
 						const float4 o = W.rayO[slot], d = W.rayD[slot];
-						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w);
+						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, false, stack);
 						phase = 2;
 					}
 				}
@@ -202,9 +216,9 @@ __global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
 		}
 		if (__ballot_sync(0xFFFFFFFFu, phase != 0) == 0)
 			break;
-		// ---- trace
-		while (phase != 0) {
-			const bool done = (phase == 1) ? tr.advance<true>(S) : tr.advance<false>(S);
+		// ---- trace: warp-synchronous rounds (Trav::round), left to refill once too few lanes are still tracing
+		for (;;) {
+			const bool done = tr.round(S, phase != 0, stack);
 			if (done) {
 				if (phase == 1) {
 					const bool occluded = tr.hit();
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
 					W.state[slot] = st & SF_ACTIVE;
 					if (st & SF_ACTIVE) { // the same lane goes on with the slot's path ray
 						const float4 o = W.rayO[slot], d = W.rayD[slot];
-						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w);
+						tr.begin(S, mk(o.x, o.y, o.z), mk(d.x, d.y, d.z), o.w, d.w, false, stack);
 						phase = 2;
 					} else {
 						phase = 0;
@@ -233,7 +247,8 @@ __global__ void __launch_bounds__(128) k_trace(DScene S, WFState W)
 					phase		 = 0;
 				}
 			}
-			if (pool && __popc(__activemask()) < REFILL_LANES)
+			const unsigned am = __ballot_sync(0xFFFFFFFFu, phase != 0);
+			if (am == 0 || (__popc(am) < REFILL_LANES && __any_sync(0xFFFFFFFFu, pool && phase == 0)))
 				break;
 		}
 	}
@@ -600,6 +615,8 @@ PRB_DEV void traceStream(const DScene& S, const float* ox, const float* oy, cons
 						 const float* tmax, uint32_t n, uint32_t* counter, uint32_t* ent, uint32_t* prim, float* u, float* v, float* t, uint8_t* occluded)
 {
 	Trav tr;
+	uint2 stack[BVH_STACK_ALLOC];
+	tr.idle();
 	uint32_t i	= 0;
 	bool active = false, pool = true;
 	float t1	= 0;
@@ -612,7 +629,7 @@ PRB_DEV void traceStream(const DScene& S, const float* ox, const float* oy, cons
 					i			   = k;
 					const float t0 = tmin ? tmin[i] : 0.0001f;
 					t1			   = tmax ? tmax[i] : PRB_INF;
-					tr.begin(S, mk(ox[i], oy[i], oz[i]), mk(dx[i], dy[i], dz[i]), t0, t1);
+					tr.begin(S, mk(ox[i], oy[i], oz[i]), mk(dx[i], dy[i], dz[i]), t0, t1, ANY, stack);
 					active = true;
 				} else {
 					pool = false;
@@ -621,8 +638,8 @@ PRB_DEV void traceStream(const DScene& S, const float* ox, const float* oy, cons
 		}
 		if (__ballot_sync(0xFFFFFFFFu, active) == 0)
 			break;
-		while (active) {
-			if (tr.advance<ANY>(S)) {
+		for (;;) { // warp-synchronous rounds
+			if (tr.round(S, active, stack)) {
 				const bool ok = tr.hit();
 				if (ANY) {
 					occluded[i] = ok ? 1 : 0;
@@ -635,7 +652,8 @@ PRB_DEV void traceStream(const DScene& S, const float* ox, const float* oy, cons
 				}
 				active = false;
 			}
-			if (pool && __popc(__activemask()) < REFILL_LANES)
+			const unsigned am = __ballot_sync(0xFFFFFFFFu, active);
+			if (am == 0 || (__popc(am) < REFILL_LANES && __any_sync(0xFFFFFFFFu, pool && !active)))
 				break;
 		}
 	}
