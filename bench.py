@@ -39,6 +39,7 @@ SCENES = {
     "c3": ("c3_cornellbox_glassy.prc", "cornellbox_glassy.prc 256x256 direct(depth 16, power MIS) mjitt 128spp"),
     "c4": ("c4_boltsandgears.prc", "boltsandgears.prc 1000x1000 direct mjitt 256spp"),
     "c4b": ("c4b_complex_env.prc", "complex.prc 1920x1080 direct sobol 4096spp (sky+sun replaced by a D65 env light)"),
+    "c4c": ("c4c_complex.prc", "complex.prc 1920x1080 direct sobol 4096spp (as shipped: Hosek-Wilkie sky + sun)"),
     "c0": ("c0_evaluation.prc", "evaluation/scene.prc 256x256 direct(depth 6) sobol 128spp"),
 }
 

@@ -205,7 +205,16 @@ typedef struct prb_bvh_tri {
 } prb_bvh_tri;
 
 /* ---------------------------------------------------------------- lights */
-enum { PRB_LIGHT_AREA = 0, PRB_LIGHT_ENV = 1 };
+enum {
+	PRB_LIGHT_AREA		= 0,
+	PRB_LIGHT_ENV		= 1, /* plugins/main/infinitelights/environment.cpp (no-distribution branches) */
+	PRB_LIGHT_SKY		= 2, /* plugins/main/infinitelights/sky.cpp:27-173 (Hosek-Wilkie table + Distribution2D) */
+	PRB_LIGHT_SUN		= 3, /* plugins/main/infinitelights/sun.cpp:27-140 (cone) */
+	PRB_LIGHT_SUN_DELTA = 4	 /* plugins/main/infinitelights/sun.cpp:142-240 (radius <= eps: delta direction) */
+};
+#define PRB_SKY_BANDS 11		 /* AR_SPECTRAL_BANDS, src/skysun/skysun/SkySunConfig.h:6-9 */
+#define PRB_SKY_BAND_START 320.0f /* AR_SPECTRAL_START */
+#define PRB_SKY_BAND_DELTA 40.0f	 /* AR_SPECTRAL_DELTA */
 typedef struct prb_light { /* src/core/light/Light.cpp, LightSampler.cpp:11-132 */
 	uint32_t type;
 	uint32_t entity_id;	   /* AREA */
@@ -215,8 +224,20 @@ typedef struct prb_light { /* src/core/light/Light.cpp, LightSampler.cpp:11-132 
 	uint32_t env_split;
 	float select_pdf; /* discretePdf(lightID) */
 	float scene_radius;
-	float normal_matrix[9];		/* ENV: ITransformable normalMatrix() */
-	float inv_normal_matrix[9]; /* ENV: invNormalMatrix() */
+	float normal_matrix[9];		/* ENV/SKY: ITransformable normalMatrix() */
+	float inv_normal_matrix[9]; /* ENV/SKY: invNormalMatrix() */
+	/* SKY: SkyModel::mData [elevation][azimuth][PRB_SKY_BANDS] floats at table_offset in the pool (SkyModel.cpp:19-60);
+	 * SUN / SUN_DELTA: the EquidistantSpectrum (table_count samples over [table_start, table_end] nm) */
+	uint32_t table_offset;
+	uint32_t table_count;
+	float table_start, table_end;
+	uint32_t az_count, el_count; /* SKY */
+	/* SKY: Distribution2D (core/sampler/Distribution2D.cpp) at dist_offset in the pool: marginal CDF (dist_h + 1 floats)
+	 * followed by dist_h conditional CDFs of (dist_w + 1) floats each */
+	uint32_t dist_offset, dist_w, dist_h;
+	uint32_t sky_extend; /* SkyLight<ExtendToGround> */
+	float sun_dir[3], sun_dx[3], sun_dy[3]; /* SUN: mDirection and its tangent frame */
+	float sun_cos_theta, sun_pdf;			 /* SUN: cos(SUN_VIS_RADIUS * radius), uniform_cone_pdf */
 } prb_light;
 
 /* ---------------------------------------------------------------- samplers, mapper, camera */

@@ -1463,12 +1463,161 @@ struct Integrator {
 		Blob radiance;
 		V3 outgoing, lightPos;
 		float posPDF, dirPDF_S, cosLight;
-		bool posIsArea, infinite;
+		bool posIsArea, infinite, delta;
 	};
+	// ---- sky / sun (plugins/main/infinitelights/sky.cpp, sun.cpp; tables precomputed by the host, see prb200_abi.h)
+	static constexpr float SKY_ELEVATION_RANGE = PR_PI * 0.5f; // skysun/ElevationAzimuth.h:6-7
+	static constexpr float SKY_AZIMUTH_RANGE   = PR_PI * 2;
+	float skyModelRadiance(const prb_light& l, int band, float el, float az) const
+	{ // SkyModel::radiance, skysun/SkyModel.h:19-24
+		const int azc = (int)l.az_count, elc = (int)l.el_count;
+		const int az_in = std::max(0, std::min<int>(azc - 1, int(az / SKY_AZIMUTH_RANGE * (float)azc)));
+		const int el_in = std::max(0, std::min<int>(elc - 1, int(el / SKY_ELEVATION_RANGE * (float)elc)));
+		return sc.d->pool[l.table_offset + ((size_t)el_in * azc + az_in) * PRB_SKY_BANDS + band];
+	}
+	Blob skyRadiance(const prb_light& l, const Blob& wvls, float el, float az) const
+	{ // SkyLight::radiance, sky.cpp:168-184
+		Blob b;
+		for (int i = 0; i < 4; ++i) {
+			const float af	= std::max(0.0f, (wvls[i] - PRB_SKY_BAND_START) / PRB_SKY_BAND_DELTA);
+			const int index = (int)std::min<float>(PRB_SKY_BANDS - 2, af);
+			const float t	= std::min<float>(PRB_SKY_BANDS - 1, af) - index;
+			b[i]			= skyModelRadiance(l, index, el, az) * (1 - t) + skyModelRadiance(l, index + 1, el, az) * t;
+		}
+		return b;
+	}
+	// Distribution2D::sampleContinuous / continuousPdf, core/sampler/Distribution2D.cpp:13-31
+	void dist2DSampleContinuous(const prb_light& l, float u0, float u1, float& d0, float& d1, float& pdf) const
+	{
+		const float* marginal = sc.d->pool + l.dist_offset;
+		const int h = (int)l.dist_h, w = (int)l.dist_w;
+		float pdf1, pdf0;
+		d1 = sampleContinuous(marginal, h + 1, u1, pdf1);
+		// offset found by the marginal's sampleDiscrete
+		int first = 0, len = h + 1;
+		while (len > 0) {
+			const int half = len / 2, middle = first + half;
+			if (marginal[middle] <= u1) {
+				first = middle + 1;
+				len -= half + 1;
+			} else {
+				len = half;
+			}
+		}
+		const int moff		   = std::max(0, std::min(first - 1, h - 1));
+		const float* conditional = marginal + (h + 1) + (size_t)moff * (w + 1);
+		d0					   = sampleContinuous(conditional, w + 1, u0, pdf0);
+		pdf					   = pdf0 * pdf1;
+	}
+	float dist2DContinuousPdf(const prb_light& l, float x0, float x1) const
+	{ // Distribution1D::continuousPdf, Distribution1D.inl:93-99
+		const float* marginal = sc.d->pool + l.dist_offset;
+		const size_t h = l.dist_h, w = l.dist_w;
+		const size_t moff		 = std::min<size_t>(h - 1, (size_t)(x1 * (float)h));
+		const float pdf1		 = (marginal[moff + 1] - marginal[moff]) * (float)h;
+		const float* conditional = marginal + (h + 1) + moff * (w + 1);
+		const size_t off		 = std::min<size_t>(w - 1, (size_t)(x0 * (float)w));
+		const float pdf0		 = (conditional[off + 1] - conditional[off]) * (float)w;
+		return pdf0 * pdf1;
+	}
+	// IInfiniteLight::eval for every infinite light type
+	void infLightEval(const prb_light& l, const RayS& ray, Blob& rad, float& pdfS) const
+	{
+		if (l.type == PRB_LIGHT_SKY) { // SkyLight::eval, sky.cpp:53-80
+			float theta, phi;
+			spherical_from_direction(m3mul(l.inv_normal_matrix, ray.D), theta, phi);
+			const float el = 0.5f * PR_PI - theta; // ElevationAzimuth::fromThetaPhi (phi is already in [0, 2 pi))
+			float az	   = phi;
+			if (az < 0)
+				az += 2 * PR_PI;
+			if (!l.sky_extend && el < 0) {
+				rad	 = blob(0);
+				pdfS = 0;
+				return;
+			}
+			rad = skyRadiance(l, ray.wvl, el, az);
+			pdfS = l.sky_extend ? dist2DContinuousPdf(l, az / SKY_AZIMUTH_RANGE, el / (2 * SKY_ELEVATION_RANGE) + 0.5f)
+								: dist2DContinuousPdf(l, az / SKY_AZIMUTH_RANGE, el / SKY_ELEVATION_RANGE);
+			const float f	  = cr_cos(el);
+			const float denom = 2 * PR_PI * PR_PI * f;
+			pdfS *= (denom <= PR_EPSILON) ? 0.0f : 1.0f / denom;
+		} else if (l.type == PRB_LIGHT_SUN) { // SunLight::eval, sun.cpp:60-75
+			const float cosine = std::max(0.0f, dot(ray.D, ld3(l.sun_dir)));
+			if (cosine < l.sun_cos_theta) {
+				rad	 = blob(0);
+				pdfS = 0;
+			} else {
+				for (int i = 0; i < 4; ++i)
+					rad[i] = tableLookup(sc.d->pool + l.table_offset, l.table_count, l.table_start, l.table_end, ray.wvl[i]);
+				pdfS = l.sun_pdf;
+			}
+		} else {
+			envEval(l, ray, rad, pdfS);
+		}
+	}
+	static bool isInfLight(const prb_light& l) { return l.type != PRB_LIGHT_AREA; }
+	static bool isDeltaLight(const prb_light& l) { return l.type == PRB_LIGHT_SUN_DELTA; }
+
 	// Light::sample with SamplingInfo + Point (NEE), src/core/light/Light.cpp:108-226
 	void sampleLight(const prb_light& l, const IP& ip, Rng& rnd, LightSample& o)
 	{
 		const prb_scene_desc& d = *sc.d;
+		o.delta = false;
+		if (l.type == PRB_LIGHT_SKY) { // SkyLight::sampleDir / samplePosDir, sky.cpp:82-113
+			float dx, dy, px, py;
+			rnd.get2D(dx, dy);
+			rnd.get2D(px, py);
+			float pdf;
+			float u0, u1;
+			dist2DSampleContinuous(l, dx, dy, u0, u1, pdf);
+			float el, az;
+			if (l.sky_extend) {
+				el = 2 * SKY_ELEVATION_RANGE * (u1 - 0.5f);
+				az = SKY_AZIMUTH_RANGE * u0;
+			} else {
+				el = SKY_ELEVATION_RANGE * u1;
+				az = SKY_AZIMUTH_RANGE * u0;
+			}
+			const float theta = 0.5f * PR_PI - el; // ElevationAzimuth::toDirection
+			o.outgoing		  = m3mul(l.normal_matrix, spherical_cartesian(cr_sin(theta), cr_cos(theta), cr_sin(az), cr_cos(az)));
+			const float f	  = cr_cos(el);
+			const float denom = 2 * PR_PI * PR_PI * f;
+			o.dirPDF_S		  = pdf * ((denom <= PR_EPSILON) ? 0.0f : 1.0f / denom);
+			o.radiance		  = skyRadiance(l, ip.ray.wvl, el, az);
+			o.lightPos		  = ip.P + l.scene_radius * o.outgoing;
+			o.posPDF		  = 1;
+			o.posIsArea		  = true;
+			o.cosLight		  = 1;
+			o.infinite		  = true;
+			return;
+		}
+		if (l.type == PRB_LIGHT_SUN || l.type == PRB_LIGHT_SUN_DELTA) { // SunLight / SunDeltaLight::sampleDir, sun.cpp:77-99,177-199
+			float dx, dy, px, py;
+			rnd.get2D(dx, dy);
+			rnd.get2D(px, py);
+			const V3 sunDir = ld3(l.sun_dir);
+			if (l.type == PRB_LIGHT_SUN) {
+				// Sampling::uniform_cone, src/base/math/Sampling.h:101-107
+				const float cosTheta = std::fma(dx, l.sun_cos_theta, 1 - dx);
+				const float sinTheta = std::sqrt(std::max(0.0f, diffProd(1, 1, cosTheta, cosTheta)));
+				const float phi		 = 2 * PR_PI * dy;
+				const V3 local		 = mk(cr_cos(phi) * sinTheta, cr_sin(phi) * sinTheta, cosTheta);
+				o.outgoing			 = fromTangentSpace(sunDir, ld3(l.sun_dx), ld3(l.sun_dy), local);
+				o.dirPDF_S			 = l.sun_pdf;
+			} else {
+				o.outgoing = sunDir;
+				o.dirPDF_S = 1;
+				o.delta	   = true;
+			}
+			for (int i = 0; i < 4; ++i)
+				o.radiance[i] = tableLookup(sc.d->pool + l.table_offset, l.table_count, l.table_start, l.table_end, ip.ray.wvl[i]);
+			o.lightPos	= ip.P + l.scene_radius * o.outgoing;
+			o.posPDF	= 0; // Position_PDF_A is left at its default (0) when a point is given, InfiniteLightSamplePosDirOutput
+			o.posIsArea = true;
+			o.cosLight	= 1;
+			o.infinite	= true;
+			return;
+		}
 		if (l.type == PRB_LIGHT_ENV) { // environment.cpp sampleDir/samplePosDir, non-distribution branch
 			float dx, dy, px, py;
 			rnd.get2D(dx, dy);
@@ -1610,16 +1759,20 @@ struct Integrator {
 		const Blob connectionW = ls.radiance * mout.weight;
 		const bool worthACheck = !blobIsZero(connectionW, PR_EPSILON);
 		float lightPdfS		   = 0;
-		if (ls.infinite) {
-			lightPdfS = ls.dirPDF_S;
+		if (ls.delta) { // light->hasDeltaDistribution(), direct.cpp:288-289
+			lightPdfS = 1;
 		} else {
-			lightPdfS = ls.posPDF;
-			if (ls.posIsArea)
-				lightPdfS = lightPdfS * sqrD / cosL; // IS::toSolidAngle
+			if (ls.infinite) {
+				lightPdfS = ls.dirPDF_S;
+			} else {
+				lightPdfS = ls.posPDF;
+				if (ls.posIsArea)
+					lightPdfS = lightPdfS * sqrD / cosL; // IS::toSolidAngle
+			}
+			lightPdfS *= selPdf;
+			if (!std::isnormal(lightPdfS) || lightPdfS <= 1e-6f)
+				return;
 		}
-		lightPdfS *= selPdf;
-		if (!std::isnormal(lightPdfS) || lightPdfS <= 1e-6f)
-			return;
 		const Blob lightPdfS2 = rayHeroFactor * lightPdfS; // lightPdfS * Wavelength_PDF(=1) * rayHeroFactor
 		if (allLE(lightPdfS2, 1e-6f))
 			return;
@@ -1630,7 +1783,8 @@ struct Integrator {
 			const float cameraRoulette		= rrProbability(cameraPathLength, false);
 			const Blob bsdfPdfS				= bsdfWvlPdfS * cameraRoulette;
 			const float denom				= bsum(misTerm(power, cur.PathPDF * lightPdfS2)) + bsum(misTerm(power, cur.PathPDF * bsdfPdfS));
-			mis = blob(misTerm(power, cur.PathPDF[0] * lightPdfS2[0])) / ((heroFactor * denom) * misTerm(power, cur.WavelengthPDF));
+			mis = ls.delta ? heroFactor / bsum(heroFactor)
+						   : blob(misTerm(power, cur.PathPDF[0] * lightPdfS2[0])) / ((heroFactor * denom) * misTerm(power, cur.WavelengthPDF));
 		} else {
 			mis = heroFactor / (cur.WavelengthPDF * bsum(heroFactor));
 		}
@@ -1740,7 +1894,7 @@ struct Integrator {
 		const Blob heroFactor = mono ? heroOnly() : blob(1);
 		bool hasInf			  = false;
 		for (uint32_t i = 0; i < d.n_lights; ++i)
-			if (d.lights[i].type == PRB_LIGHT_ENV)
+			if (isInfLight(d.lights[i])) // HasInfLights = infiniteLightCount() != 0 (delta lights included), direct.cpp:487
 				hasInf = true;
 		if (!hasInf || !d.settings.do_direct) { // handleZero
 			pushSpectralFragment(heroFactor / (cur.WavelengthPDF * bsum(heroFactor)), cur.Throughput, blob(0), ray.flags);
@@ -1751,11 +1905,11 @@ struct Integrator {
 		Blob radiance	 = blob(0);
 		for (uint32_t i = 0; i < d.n_lights; ++i) {
 			const prb_light& l = d.lights[i];
-			if (l.type != PRB_LIGHT_ENV)
+			if (!isInfLight(l) || isDeltaLight(l))
 				continue;
 			Blob rad;
 			float pdfS;
-			envEval(l, ray, rad, pdfS);
+			infLightEval(l, ray, rad, pdfS);
 			const float pdf_S = pdfS * l.select_pdf;
 			radiance		  = radiance + rad;
 			denom_mis += bsum(misTerm(power, cur.PrevPathPDF * pdf_S));
@@ -1820,12 +1974,12 @@ struct Integrator {
 			bool illuminated = false;
 			for (uint32_t i = 0; i < d.n_lights; ++i) {
 				const prb_light& l = d.lights[i];
-				if (l.type != PRB_LIGHT_ENV)
+				if (!isInfLight(l) || isDeltaLight(l))
 					continue;
 				illuminated = true;
 				Blob rad;
 				float pdfS;
-				envEval(l, ray, rad, pdfS);
+				infLightEval(l, ray, rad, pdfS);
 				pushSpectralFragment(blob(1), blob(1), rad, ray.flags);
 			}
 			if (!illuminated)

@@ -84,7 +84,11 @@ class Entity(C.Structure):
 class Light(C.Structure):
     _fields_ = [("type", C.c_uint32), ("entity_id", C.c_uint32), ("emission_id", C.c_uint32), ("radiance_node", C.c_uint32),
                 ("background_node", C.c_uint32), ("env_split", C.c_uint32), ("select_pdf", C.c_float), ("scene_radius", C.c_float),
-                ("normal_matrix", C.c_float * 9), ("inv_normal_matrix", C.c_float * 9)]
+                ("normal_matrix", C.c_float * 9), ("inv_normal_matrix", C.c_float * 9),
+                ("table_offset", C.c_uint32), ("table_count", C.c_uint32), ("table_start", C.c_float), ("table_end", C.c_float),
+                ("az_count", C.c_uint32), ("el_count", C.c_uint32), ("dist_offset", C.c_uint32), ("dist_w", C.c_uint32),
+                ("dist_h", C.c_uint32), ("sky_extend", C.c_uint32), ("sun_dir", C.c_float * 3), ("sun_dx", C.c_float * 3),
+                ("sun_dy", C.c_float * 3), ("sun_cos_theta", C.c_float), ("sun_pdf", C.c_float)]
 
 
 class SceneDesc(C.Structure):

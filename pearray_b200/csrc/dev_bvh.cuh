@@ -39,7 +39,7 @@ struct DScene { // device pointers + by-value small structs; passed to kernels b
 	const float* pool;
 	const float* rrProb; // RussianRoulette::probability(len) table
 	uint32_t nMaterials, nEmissions, nEntities, nLights, nMeshes, tlasRoot, cieOffset, rrCount;
-	uint32_t hasEnvLight;
+	uint32_t hasInfLight;
 };
 
 struct HitRec {

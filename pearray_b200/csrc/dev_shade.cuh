@@ -1024,11 +1024,109 @@ struct LightSample {
 	Blob radiance;
 	V3 outgoing, lightPos;
 	float posPDF, dirPDF_S, cosLight;
-	bool infinite;
+	bool infinite, delta;
 };
+// ---- sky / sun (plugins/main/infinitelights/sky.cpp, sun.cpp; tables precomputed by the host, see prb200_abi.h)
+constexpr float SKY_ELEVATION_RANGE = PR_PI * 0.5f; // skysun/ElevationAzimuth.h:6-7
+constexpr float SKY_AZIMUTH_RANGE	= PR_PI * 2;
+PRB_DEV float skyModelRadiance(const DScene& S, const prb_light& l, int band, float el, float az)
+{ // SkyModel::radiance, skysun/SkyModel.h:19-24
+	const int azc = (int)l.az_count, elc = (int)l.el_count;
+	const int az_in = max(0, min(azc - 1, (int)(fdiv(az, SKY_AZIMUTH_RANGE) * (float)azc)));
+	const int el_in = max(0, min(elc - 1, (int)(fdiv(el, SKY_ELEVATION_RANGE) * (float)elc)));
+	return __ldg(S.pool + l.table_offset + ((size_t)el_in * azc + az_in) * PRB_SKY_BANDS + band);
+}
+PRB_DEV Blob skyRadiance(const DScene& S, const prb_light& l, const Blob& wvls, float el, float az)
+{ // SkyLight::radiance, sky.cpp:168-184
+	Blob b;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const float af	= fmaxf(0.0f, fdiv(wvls[i] - PRB_SKY_BAND_START, PRB_SKY_BAND_DELTA));
+		const int index = (int)fminf((float)(PRB_SKY_BANDS - 2), af);
+		const float t	= fminf((float)(PRB_SKY_BANDS - 1), af) - index;
+		b[i]			= skyModelRadiance(S, l, index, el, az) * (1 - t) + skyModelRadiance(S, l, index + 1, el, az) * t;
+	}
+	return b;
+}
+// Distribution2D::sampleContinuous / continuousPdf, core/sampler/Distribution2D.cpp:13-31
+PRB_DEV void dist2DSampleContinuous(const DScene& S, const prb_light& l, float u0, float u1, float& d0, float& d1, float& pdf)
+{
+	const float* marginal = S.pool + l.dist_offset;
+	const int h = (int)l.dist_h, w = (int)l.dist_w;
+	float pdf1, pdf0;
+	d1						 = sampleContinuous(marginal, h + 1, u1, pdf1);
+	const int moff			 = cdfSearch(marginal, h + 1, u1);
+	const float* conditional = marginal + (h + 1) + (size_t)moff * (w + 1);
+	d0						 = sampleContinuous(conditional, w + 1, u0, pdf0);
+	pdf						 = pdf0 * pdf1;
+}
+PRB_DEV float dist2DContinuousPdf(const DScene& S, const prb_light& l, float x0, float x1)
+{ // Distribution1D::continuousPdf, Distribution1D.inl:93-99
+	const float* marginal = S.pool + l.dist_offset;
+	const uint32_t h = l.dist_h, w = l.dist_w;
+	const uint32_t moff		 = min(h - 1, (uint32_t)(x1 * (float)h));
+	const float pdf1		 = (__ldg(marginal + moff + 1) - __ldg(marginal + moff)) * (float)h;
+	const float* conditional = marginal + (h + 1) + (size_t)moff * (w + 1);
+	const uint32_t off		 = min(w - 1, (uint32_t)(x0 * (float)w));
+	const float pdf0		 = (__ldg(conditional + off + 1) - __ldg(conditional + off)) * (float)w;
+	return pdf0 * pdf1;
+}
+PRB_DEV bool isInfLight(const prb_light& l) { return l.type != PRB_LIGHT_AREA; }
+PRB_DEV bool isDeltaLight(const prb_light& l) { return l.type == PRB_LIGHT_SUN_DELTA; }
+
 // Light::sample with SamplingInfo + Point (NEE), src/core/light/Light.cpp:108-226
 __device__ __noinline__ void sampleLight(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o)
 {
+	o.delta = false;
+	if (l.type == PRB_LIGHT_SKY) { // SkyLight::sampleDir / samplePosDir, sky.cpp:82-113
+		float dx, dy, px, py;
+		rnd.get2D(dx, dy);
+		rnd.get2D(px, py);
+		float pdf, u0, u1;
+		dist2DSampleContinuous(S, l, dx, dy, u0, u1, pdf);
+		const float el	  = l.sky_extend ? 2 * SKY_ELEVATION_RANGE * (u1 - 0.5f) : SKY_ELEVATION_RANGE * u1;
+		const float az	  = SKY_AZIMUTH_RANGE * u0;
+		const float theta = 0.5f * PR_PI - el; // ElevationAzimuth::toDirection
+		float st, ct, sp, cp;
+		cr_sincos(theta, &st, &ct);
+		cr_sincos(az, &sp, &cp);
+		o.outgoing		  = m3mul(l.normal_matrix, spherical_cartesian(st, ct, sp, cp));
+		const float f	  = cr_cos(el);
+		const float denom = 2 * PR_PI * PR_PI * f;
+		o.dirPDF_S		  = pdf * ((denom <= PR_EPSILON) ? 0.0f : 1.0f / denom);
+		o.radiance		  = skyRadiance(S, l, wvl, el, az);
+		o.lightPos		  = P + l.scene_radius * o.outgoing;
+		o.posPDF		  = 1;
+		o.cosLight		  = 1;
+		o.infinite		  = true;
+		return;
+	}
+	if (l.type == PRB_LIGHT_SUN || l.type == PRB_LIGHT_SUN_DELTA) { // SunLight / SunDeltaLight::sampleDir, sun.cpp:77-99,177-199
+		float dx, dy, px, py;
+		rnd.get2D(dx, dy);
+		rnd.get2D(px, py);
+		const V3 sunDir = ld3(l.sun_dir);
+		if (l.type == PRB_LIGHT_SUN) { // Sampling::uniform_cone, src/base/math/Sampling.h:101-107
+			const float cosTheta = fmaf(dx, l.sun_cos_theta, 1 - dx);
+			const float sinTheta = sqrtf(fmaxf(0.0f, diffProd(1, 1, cosTheta, cosTheta)));
+			float sp, cp;
+			cr_sincos(2 * PR_PI * dy, &sp, &cp);
+			o.outgoing = fromTangentSpace(sunDir, ld3(l.sun_dx), ld3(l.sun_dy), mk(cp * sinTheta, sp * sinTheta, cosTheta));
+			o.dirPDF_S = l.sun_pdf;
+		} else {
+			o.outgoing = sunDir;
+			o.dirPDF_S = 1;
+			o.delta	   = true;
+		}
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			o.radiance[i] = tableLookup(S.pool + l.table_offset, l.table_count, l.table_start, l.table_end, wvl[i]);
+		o.lightPos = P + l.scene_radius * o.outgoing;
+		o.posPDF   = 0;
+		o.cosLight = 1;
+		o.infinite = true;
+		return;
+	}
 	if (l.type == PRB_LIGHT_ENV) { // environment.cpp sampleDir / samplePosDir (no distribution)
 		float dx, dy, px, py;
 		rnd.get2D(dx, dy);
@@ -1125,5 +1223,40 @@ PRB_DEV void envEval(const DScene& S, const prb_light& l, V3 dir, uint32_t depth
 	const uint32_t node = (l.env_split && depth == 0) ? l.background_node : l.radiance_node;
 	rad					= evalNode(S, node, wvl, u, v);
 	pdfS				= cos_hemi_pdf(fabsf(ld.z));
+}
+// IInfiniteLight::eval for every infinite light type
+__device__ __noinline__ void infLightEval(const DScene& S, const prb_light& l, V3 dir, uint32_t depth, const Blob& wvl, Blob& rad, float& pdfS)
+{
+	if (l.type == PRB_LIGHT_SKY) { // SkyLight::eval, sky.cpp:53-80
+		const V3 ld	  = m3mul(l.inv_normal_matrix, dir);
+		const float x = (ld.x == 0 && ld.y == 0) ? 1e-5f : ld.x; // Spherical::from_direction
+		float az	  = cr_atan2(ld.y, x);
+		az			  = az < 0 ? az + 2 * PR_PI : az;
+		const float el = 0.5f * PR_PI - cr_acos(ld.z);
+		if (!l.sky_extend && el < 0) {
+			rad	 = blob(0);
+			pdfS = 0;
+			return;
+		}
+		rad	 = skyRadiance(S, l, wvl, el, az);
+		pdfS = l.sky_extend ? dist2DContinuousPdf(S, l, fdiv(az, SKY_AZIMUTH_RANGE), fdiv(el, 2 * SKY_ELEVATION_RANGE) + 0.5f)
+							: dist2DContinuousPdf(S, l, fdiv(az, SKY_AZIMUTH_RANGE), fdiv(el, SKY_ELEVATION_RANGE));
+		const float f	  = cr_cos(el);
+		const float denom = 2 * PR_PI * PR_PI * f;
+		pdfS *= (denom <= PR_EPSILON) ? 0.0f : 1.0f / denom;
+	} else if (l.type == PRB_LIGHT_SUN) { // SunLight::eval, sun.cpp:60-75
+		const float cosine = fmaxf(0.0f, dot(dir, ld3(l.sun_dir)));
+		if (cosine < l.sun_cos_theta) {
+			rad	 = blob(0);
+			pdfS = 0;
+		} else {
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				rad[i] = tableLookup(S.pool + l.table_offset, l.table_count, l.table_start, l.table_end, wvl[i]);
+			pdfS = l.sun_pdf;
+		}
+	} else {
+		envEval(S, l, dir, depth, wvl, rad, pdfS);
+	}
 }
 } // namespace prb

@@ -62,6 +62,7 @@ struct prb_ctx {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t evA = nullptr, evB = nullptr;
 	int smCount = 148;
+	bool mixedMaterials = false; // the scene mixes material types: k_shade sorts larger windows (launchShade)
 	int gridTrace = 148 * 4, gridTraceClosest = 148 * 4, gridTraceAny = 148 * 4; // persistent grids: SMs x resident blocks
 	bool haveScene = false;
 	DScene S{};
@@ -289,10 +290,14 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	S.nMeshes		  = d->n_meshes;
 	S.tlasRoot		  = d->tlas_root;
 	S.cieOffset		  = d->cie_offset;
-	S.hasEnvLight	  = 0;
+	c->mixedMaterials = false;
+	for (uint32_t i = 1; i < d->n_materials; ++i)
+		if (d->materials[i].type != d->materials[0].type)
+			c->mixedMaterials = true;
+	S.hasInfLight	  = 0;
 	for (uint32_t i = 0; i < d->n_lights; ++i)
-		if (d->lights[i].type == PRB_LIGHT_ENV)
-			S.hasEnvLight = 1;
+		if (d->lights[i].type != PRB_LIGHT_AREA)
+			S.hasInfLight = 1;
 	CU(cudaStreamSynchronize(s));
 	// trace-kernel variant: persistent threads pay off once rays take many traversal steps (measured: 2x on the 10 M
 	// triangle soup, 0.7x on the 32-triangle Cornell box, 0.95x on the 6 k-triangle bolts scene); PRB_TRACE_MODE=static|persistent overrides the heuristic
@@ -379,6 +384,19 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 	return PRB_OK;
 }
 
+// k_shade sorts a window of rounds * block slots by material per thread block; larger windows give more uniform warps but
+// fewer blocks, so rounds is chosen such that the grid still holds >= 4 blocks per resident block slot
+static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
+{
+	if (!c->mixedMaterials) {
+		k_shade<SHADE_BLOCK_UNIFORM, 1><<<(int)((c->nSlots + SHADE_BLOCK_UNIFORM - 1) / SHADE_BLOCK_UNIFORM), SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
+		return;
+	}
+	const size_t perRound = (size_t)512 * c->smCount * 4;
+	const int rounds	  = (int)std::max<size_t>(1, std::min<size_t>(SHADE_ROUNDS_MIXED, c->nSlots / perRound));
+	const size_t window	  = (size_t)rounds * SHADE_BLOCK_MIXED;
+	k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED><<<(int)((c->nSlots + window - 1) / window), SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
+}
 static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s)
 {
 	if (c->persistentTrace)
@@ -470,7 +488,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 				launchTrace(c, W, blocks, s);
 				CU(cudaEventRecord(c->profEvents[ne++], s));
 				CU(cudaEventRecord(c->profEvents[ne++], s));
-				k_shade<<<blocks, 128, 0, s>>>(c->S, W);
+				launchShade(c, W, s);
 				CU(cudaEventRecord(c->profEvents[ne++], s));
 				CU(cudaGetLastError());
 			}
@@ -491,7 +509,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 		CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
 		for (int r = 0; r < ITERS_PER_GRAPH; ++r) {
 			launchTrace(c, W, blocks, s);
-			k_shade<<<blocks, 128, 0, s>>>(c->S, W);
+			launchShade(c, W, s);
 		}
 		const cudaError_t ce = cudaGetLastError();
 		const cudaError_t ee = cudaStreamEndCapture(s, &graph);

@@ -12,7 +12,31 @@ struct SceneHandle {
 thread_local std::string g_err;
 } // namespace
 
+namespace PR {
+double hosekSkyRadiance(double solarElevation, double turbidity, double albedo, double theta, double gamma, double wavelength);
+void sunElevationAzimuth(int year, int month, int day, int hour, int minute, float seconds, float latitude, float longitude, float timezone, float* elevation,
+						 float* azimuth);
+float sunRadiance(float wavelength, float theta, float turbidity);
+}
+
 extern "C" {
+// sky / sun host models (skysun.cpp), exposed for the known-answer tests
+double prh_hosek_sky_radiance(double solar_elevation, double turbidity, double albedo, double theta, double gamma, double wavelength)
+{
+	try {
+		return hosekSkyRadiance(solar_elevation, turbidity, albedo, theta, gamma, wavelength);
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return -1.0;
+	}
+}
+void prh_sun_position(int year, int month, int day, int hour, int minute, float seconds, float latitude, float longitude, float timezone, float* elevation,
+					  float* azimuth)
+{
+	sunElevationAzimuth(year, month, day, hour, minute, seconds, latitude, longitude, timezone, elevation, azimuth);
+}
+float prh_sun_radiance(float wavelength, float theta, float turbidity) { return sunRadiance(wavelength, theta, turbidity); }
+
 const char* prh_last_error() { return g_err.c_str(); }
 void prh_set_verbosity(int level) { logVerbosity() = level; }
 

@@ -12,11 +12,14 @@ namespace PR {
 void registerNodePlugins(std::vector<std::shared_ptr<IPlugin>>& out);
 void registerMaterialPlugins(std::vector<std::shared_ptr<IPlugin>>& out);
 void registerScenePlugins(std::vector<std::shared_ptr<IPlugin>>& out);
+std::vector<std::shared_ptr<IPlugin>> createSkySunPlugins(); // skysun.cpp
 void registerEmbeddedPlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 {
 	registerNodePlugins(out);
 	registerMaterialPlugins(out);
 	registerScenePlugins(out);
+	for (const auto& p : createSkySunPlugins())
+		out.push_back(p);
 }
 
 // ------------------------------------------------------------------ PluginManager
@@ -84,7 +87,7 @@ bool PluginManager::tryLoad(const std::string& path)
 }
 
 // ------------------------------------------------------------------ Environment
-static std::string dataDirectory()
+std::string dataDirectory()
 {
 	if (const char* e = std::getenv("PRB200_DATA_DIR"))
 		return e;

@@ -47,3 +47,28 @@ FURNACE = """
  (light :type 'env' :radiance 1)
 )
 """
+
+# sky / sun infinite lights (SURVEY 8(f)-1): the Hosek-Wilkie sky WITHOUT ground extension and with a rotated frame, a cone
+# sun given by direction, a delta sun (radius 0, hasDeltaDistribution) given by date/time, over diffuse / glossy / glass spheres;
+# together with scenes/c4c_complex.prc (extended sky + cone sun by hour) this covers every branch of sky.cpp / sun.cpp
+SKYSUN_ZOO = """
+(scene :name 'skysun' :render_width 48 :render_height 48 :camera 'Camera'
+ (integrator :type 'direct' :max_ray_depth 6)
+ (sampler :slot 'aa' :type 'mjitt' :sample_count 16)
+ (camera :name 'Camera' :type 'standard' :width 1.4 :height 1.4 :local_direction [0,0,-1] :local_up [0,1,0] :local_right [1,0,0]
+   :near 0.1 :far 100 :transform [1,0,0,0, 0,0.7071068,0.7071068,3, 0,-0.7071068,0.7071068,3, 0,0,0,1])
+ (material :name 'm_ground' :type 'diffuse' :albedo (refl 0.5 0.45 0.4))
+ (material :name 'm_diffuse' :type 'diffuse' :albedo (refl 0.8 0.2 0.3))
+ (material :name 'm_metal' :type 'roughconductor' :eta 0.2 :k 3.0 :roughness 0.2)
+ (material :name 'm_glass' :type 'glass' :index (lookup_index "bk7"))
+ (entity :name 'ground' :type 'plane' :centering true :width 8 :height 8 :material 'm_ground' :position [0,0,0])
+ (entity :name 's0' :type 'sphere' :radius 0.5 :material 'm_diffuse' :position [-1.1,0,0.5])
+ (entity :name 's1' :type 'sphere' :radius 0.5 :material 'm_metal' :position [0,0,0.5])
+ (entity :name 's2' :type 'sphere' :radius 0.5 :material 'm_glass' :position [1.1,0,0.5])
+ (light :name 'sky' :type 'sky' :turbidity 4.5 :albedo 0.3 :extend false :elevation 0.6 :azimuth 2.0
+   :azimuth_resolution 64 :elevation_resolution 32 :transform [0.9800666,-0.1986693,0,0, 0.1986693,0.9800666,0,0, 0,0,1,0, 0,0,0,1])
+ (light :name 'sun' :type 'sun' :turbidity 4.5 :radius 8 :direction [0.4,-0.3,0.85])
+ (light :name 'sun_delta' :type 'sun' :turbidity 2 :radius 0 :power_scale 0.5 :year 2021 :month 7 :day 14 :hour 10 :minute 30
+   :latitude 48.2 :longitude 16.4 :timezone 2)
+)
+"""

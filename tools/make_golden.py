@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pearray_b200 as prb  # noqa: E402
 from oracle_binding import OracleScene  # noqa: E402
-from scene_strings import MATERIAL_ZOO  # noqa: E402
+from scene_strings import MATERIAL_ZOO, SKYSUN_ZOO  # noqa: E402
 
 GOLDEN_ITER = 4
 GOLDEN_TILE = 48
@@ -100,6 +100,7 @@ def import_reference_image():
 
 if __name__ == "__main__":
     import_reference_image()
-    for n in ("c0_evaluation", "c1_sphere", "c2_cornellbox", "c3_cornellbox_glassy", "c4_boltsandgears", "c4b_complex_env"):
+    for n in ("c0_evaluation", "c1_sphere", "c2_cornellbox", "c3_cornellbox_glassy", "c4_boltsandgears", "c4b_complex_env", "c4c_complex"):
         make(n, prb.Scene.from_file(os.path.join(ROOT, "scenes", n + ".prc")))
     make("material_zoo", prb.Scene.from_string(MATERIAL_ZOO))
+    make("skysun_zoo", prb.Scene.from_string(SKYSUN_ZOO))

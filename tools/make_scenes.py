@@ -8,6 +8,7 @@
   c4_boltsandgears.prc   examples/boltsandgears.prc (+ inlined meshes), as shipped
   c4b_complex_env.prc    examples/complex.prc with the 'sky' and 'sun' lights replaced by one constant D65 environment light
                          (interim form until the sky/sun rows of 8(f) land), everything else as shipped
+  c4c_complex.prc        examples/complex.prc (+ inlined meshes), as shipped: 'sky' and 'sun' infinite lights
   c0_evaluation.prc      examples/evaluation/scene.prc with the eight (embed :loader 'obj') meshes inlined as (mesh ...) blocks;
                          this is the scene of the reference's golden image examples/evaluation/cbox.exr
 
@@ -157,6 +158,7 @@ build("boltsandgears.prc", "c4_boltsandgears.prc")
 build("complex.prc", "c4b_complex_env.prc", [
     lambda s: replace_all_blocks(s, "light", "(light :name 'env' :type 'env' :radiance (illuminant 'D65'))"),
 ])
+build("complex.prc", "c4c_complex.prc")  # as shipped: Hosek-Wilkie 'sky' + 'sun' lights
 build("evaluation/scene.prc", "c0_evaluation.prc", [
     lambda s: inline_embeds(s, os.path.join(EX, "evaluation")),
 ])
