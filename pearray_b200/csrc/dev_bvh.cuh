@@ -142,7 +142,7 @@ PRB_DEV float safeInv(float d)
 }
 
 constexpr int BVH_STACK = 48;
-constexpr int BVH_STACK_ALLOC = BVH_STACK + 3; // + the world-space ray (origin, direction) parked while inside a BLAS
+constexpr int BVH_STACK_ALLOC = BVH_STACK + 5; // + the world-space ray (origin, direction, 1/direction, octant) parked while inside a BLAS
 // Traversal stack entries are GROUPS (after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs Through
 // Compressed Wide BVHs", HPG 2017), 8 bytes each:
 //   node group      .x = child_base of the visited node            .y = hits (8 bit, octant-permuted slot space) | imask << 8
@@ -243,9 +243,7 @@ struct Trav {
 	}
 	PRB_DEV void begin(const DScene& S, V3 o, V3 d, float t0, float t1, bool anyHit, uint2* __restrict__ stack)
 	{
-		stack[BVH_STACK]	 = make_uint2(__float_as_uint(o.x), __float_as_uint(o.y));
-		stack[BVH_STACK + 1] = make_uint2(__float_as_uint(o.z), __float_as_uint(d.x));
-		stack[BVH_STACK + 2] = make_uint2(__float_as_uint(d.y), __float_as_uint(d.z));
+
 		best.entity = PRB_INVALID_ID;
 		best.prim	= 0;
 		best.u = best.v = 0;
@@ -257,6 +255,12 @@ struct Trav {
 		inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
 		oct	   = rayOctant(inv);
 		curEnt = PRB_INVALID_ID;							   // TLAS level
+		// the world-space ray, reloaded (not recomputed: the compiler hoists this path above the pop) when a BLAS is left
+		stack[BVH_STACK]	 = make_uint2(__float_as_uint(o.x), __float_as_uint(o.y));
+		stack[BVH_STACK + 1] = make_uint2(__float_as_uint(o.z), __float_as_uint(d.x));
+		stack[BVH_STACK + 2] = make_uint2(__float_as_uint(d.y), __float_as_uint(d.z));
+		stack[BVH_STACK + 3] = make_uint2(__float_as_uint(inv.x), __float_as_uint(inv.y));
+		stack[BVH_STACK + 4] = make_uint2(__float_as_uint(inv.z), oct);
 		ng	   = make_uint2(S.tlasRoot, (1u << oct) | (1u << 8)); // the root as a one-child node group: slot 0, imask 1
 		pg	   = make_uint2(0, 0);
 		sp	   = 0;
@@ -469,8 +473,9 @@ struct Trav {
 					const uint2 w0 = stack[BVH_STACK], w1 = stack[BVH_STACK + 1], w2 = stack[BVH_STACK + 2];
 					O	   = mk(__uint_as_float(w0.x), __uint_as_float(w0.y), __uint_as_float(w1.x));
 					D	   = mk(__uint_as_float(w1.y), __uint_as_float(w2.x), __uint_as_float(w2.y));
-					inv	   = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
-					oct	   = rayOctant(inv);
+					const uint2 w3 = stack[BVH_STACK + 3], w4 = stack[BVH_STACK + 4];
+					inv	   = mk(__uint_as_float(w3.x), __uint_as_float(w3.y), __uint_as_float(w4.x));
+					oct	   = w4.y;
 					curEnt = PRB_INVALID_ID;
 				} else if (e.x & GRP_PRIM) {
 					pg = e;
