@@ -101,6 +101,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(scene_key, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture of this
+    workload (profiles/traffic.json, written by hand from profiles/r01_ncu_*.txt); None when no capture is on file"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[scene_key][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def bvh_depth_bytes(n_tris):
     """minimal-path bytes of one closest-hit / any-hit ray, SURVEY 8(d): 32 + (24|4) + 80*ceil(log8(N/4)) + 4*48"""
     import math
@@ -290,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = measured_peak_gbs()
         achieved = bytes_total[dom] / (ms_dom * 1e-3) / 1e9 if ms_dom > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_us": 1e3 * ms_dom / max(n_dom, 1), "launches": n_dom,
+                    "traffic": ncu_traffic(args.scene, "k_" + dom), "peak_source": peak_src, "avg_launch_us": 1e3 * ms_dom / max(n_dom, 1), "launches": n_dom,
                     "bytes_per_unit": per_unit[dom], "units_per_launch": units[dom] / max(n_dom, 1),
                     "stage_share": {k: v[0] / total for k, v in stage.items()},
                     "note": "scene is L2-resident (%d triangles): HBM is not the binding resource, see DESIGN.md" % n_tris}
@@ -459,7 +469,7 @@ def run_soup(args, rank, world, local_rank):
         dom = max(ms, key=lambda k: ms[k])
         launches = args.steps * passes
         roofline = {"bound": "hbm", "kernel": "k_trace_any" if dom == "shadow" else "k_trace_closest (%s rays)" % dom, "achieved": per_class[dom]["achieved_gbs"],
-                    "peak": peak, "unit": "GB/s", "frac": per_class[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "peak": peak, "unit": "GB/s", "frac": per_class[dom]["frac"], "traffic": ncu_traffic("c5", "k_trace_any" if dom == "shadow" else "k_trace_closest"), "peak_source": peak_src,
                     "avg_launch_us": 1e3 * ms[dom] / launches, "launches": launches, "bytes_per_unit": per_class[dom]["bytes_per_ray"],
                     "units_per_launch": rays[dom] / launches}
         line = {"metric": "rays/s (primary+shadow+incoherent)", "value": all_rays / (tot_ms_max * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,

@@ -109,7 +109,7 @@ PRB_DEV bool startNextSample(const DScene& S, const WFState& W, uint32_t slot, u
 	return true;
 }
 
-__global__ void __launch_bounds__(128) k_init_slots(DScene S, WFState W)
+__global__ void __launch_bounds__(128) k_init_slots(const __grid_constant__ DScene S, WFState W)
 {
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t started	= 0;
@@ -322,7 +322,7 @@ PRB_DEV uint32_t shadeSortKey(const DScene& S, const WFState& W, uint32_t slot)
 }
 
 template <int SHADE_BLOCK, int SHADE_ROUNDS_MAX>
-__global__ void __launch_bounds__(SHADE_BLOCK, 512 / SHADE_BLOCK) k_shade(DScene S, WFState W, int roundsArg)
+__global__ void __launch_bounds__(SHADE_BLOCK, 512 / SHADE_BLOCK) k_shade(const __grid_constant__ DScene S, WFState W, int roundsArg)
 {
 	const int rounds = SHADE_ROUNDS_MAX == 1 ? 1 : roundsArg; // compile-time 1 for the uniform instantiation: no loop
 
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(128) k_trace_any(DScene S, const float* ox, co
 }
 
 // camera rays only (prb_generate_camera_rays): does not touch the RNG map
-__global__ void k_camera_rays(DScene S, const uint64_t* rng, const uint32_t* pixels, uint32_t n, uint32_t iteration, float* org, float* dir, float* wvl)
+__global__ void k_camera_rays(const __grid_constant__ DScene S, const uint64_t* rng, const uint32_t* pixels, uint32_t n, uint32_t iteration, float* org, float* dir, float* wvl)
 {
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint32_t pix = pixels[i];
@@ -756,7 +756,7 @@ __global__ void k_camera_rays(DScene S, const uint64_t* rng, const uint32_t* pix
 }
 
 // unit-level material calls (IMaterial::eval / ::sample)
-__global__ void k_material_eval(DScene S, const prb_material_query* q, uint32_t n, prb_material_result* out)
+__global__ void k_material_eval(const __grid_constant__ DScene S, const prb_material_query* q, uint32_t n, prb_material_result* out)
 {
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		MatCtx c;
@@ -779,7 +779,7 @@ __global__ void k_material_eval(DScene S, const prb_material_query* q, uint32_t 
 		out[i].rng_state						= q[i].rng_state;
 	}
 }
-__global__ void k_material_sample(DScene S, const prb_material_query* q, uint32_t n, prb_material_result* out)
+__global__ void k_material_sample(const __grid_constant__ DScene S, const prb_material_query* q, uint32_t n, prb_material_result* out)
 {
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		MatCtx c;
