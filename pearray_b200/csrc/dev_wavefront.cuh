@@ -321,8 +321,11 @@ PRB_DEV uint32_t shadeSortKey(const DScene& S, const WFState& W, uint32_t slot)
 	return min(mat, (uint32_t)SHADE_BINS - 3);
 }
 
+#ifndef PRB_SHADE_MINB
+#define PRB_SHADE_MINB 4 /* resident 128-thread blocks per SM the uniform instantiation is compiled for */
+#endif
 template <int SHADE_BLOCK, int SHADE_ROUNDS_MAX>
-__global__ void __launch_bounds__(SHADE_BLOCK, 512 / SHADE_BLOCK) k_shade(const __grid_constant__ DScene S, WFState W, int roundsArg)
+__global__ void __launch_bounds__(SHADE_BLOCK, SHADE_BLOCK == 128 ? PRB_SHADE_MINB : 512 / SHADE_BLOCK) k_shade(const __grid_constant__ DScene S, WFState W, int roundsArg)
 {
 	const int rounds = SHADE_ROUNDS_MAX == 1 ? 1 : roundsArg; // compile-time 1 for the uniform instantiation: no loop
 

@@ -300,8 +300,8 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 			S.hasInfLight = 1;
 	CU(cudaStreamSynchronize(s));
 	// trace-kernel variant: persistent threads pay off once rays take many traversal steps (measured: 2x on the 10 M
-	// triangle soup, 0.7x on the 32-triangle Cornell box, 0.95x on the 6 k-triangle bolts scene); PRB_TRACE_MODE=static|persistent overrides the heuristic
-	c->persistentTrace = d->n_bvh_tris > 262144;
+	// triangle soup, 0.7x on the 32-triangle Cornell box, 1.0x on the 6 k-triangle bolts scene, 1.09x on complex.prc with 53 k); PRB_TRACE_MODE=static|persistent overrides the heuristic
+	c->persistentTrace = d->n_bvh_tris > 32768;
 	if (const char* m = std::getenv("PRB_TRACE_MODE")) {
 		if (std::strcmp(m, "static") == 0)
 			c->persistentTrace = false;
