@@ -90,7 +90,9 @@ enum {
 	PRB_MAT_CONDUCTOR		= 2, /* conductor.cpp:16-95     node[0]=eta node[1]=k node[2]=specularity */
 	PRB_MAT_ROUGHCONDUCTOR	= 3, /* roughconductor.cpp:16-143  nodes as CONDUCTOR, f[0]=roughness_x f[1]=roughness_y */
 	PRB_MAT_ROUGHDIELECTRIC = 4, /* roughdielectric.cpp:42-279 nodes as DIELECTRIC, f[0],f[1] roughness */
-	PRB_MAT_PRINCIPLED		= 5	 /* principled.cpp:34-631   node[0]=base node[1]=ior, f[] see PRB_PR_* */
+	PRB_MAT_PRINCIPLED		= 5, /* principled.cpp:34-631   node[0]=base node[1]=ior, f[] see PRB_PR_* */
+	PRB_MAT_MIRROR			= 6, /* mirror.cpp:14-65        node[0]=specularity (only-delta) */
+	PRB_MAT_ORENNAYAR		= 7	 /* orennayar.cpp:16-86     node[0]=albedo, f[0]=roughness (scalar, squared on use) */
 };
 #define PRB_MATF_TWO_SIDED 0x001u		  /* lambert two_sided (default true) */
 #define PRB_MATF_THIN 0x002u			  /* dielectric / principled 'thin' */

@@ -570,6 +570,22 @@ struct RoughDielectric {
 	}
 };
 
+// OrenNayarMaterial::calc (improved Oren-Nayar), orennayar.cpp:29-49
+PRB_DEV Blob orenNayarCalc(const DScene& S, const prb_material& m, const MatCtx& c, V3 L, float NdotL)
+{
+	float roughness = m.f[0];
+	roughness *= roughness;
+	Blob weight = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+	if (roughness > PR_EPSILON) {
+		const float s = -NdotL * c.V.z + dot(c.V, L);
+		const float t = s < PR_EPSILON ? 1.0f : fmaxf(NdotL, c.V.z);
+		const Blob A  = blob(1 - 0.5f * roughness / (roughness + 0.33f)) + ((weight * 0.17f) * roughness) / (roughness + 0.13f);
+		const float B = 0.45f * roughness / (roughness + 0.09f);
+		weight		  = weight * (A + blob(B * s / t));
+	}
+	return weight;
+}
+
 __device__ __noinline__ void materialEval(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
 {
 	const prb_material m = S.materials[matID];
@@ -589,6 +605,18 @@ __device__ __noinline__ void materialEval(const DScene& S, uint32_t matID, const
 		out.type   = 3;
 		out.flags  = MSF_Delta | contribFlags(m);
 		break;
+	case PRB_MAT_MIRROR: // mirror.cpp:27-37
+		out.pdf	   = blob(0);
+		out.weight = blob(0);
+		out.type   = 1;
+		out.flags  = MSF_Delta;
+		break;
+	case PRB_MAT_ORENNAYAR: { // orennayar.cpp:51-60
+		const float d = fmaxf(0.0f, c.L.z);
+		out.weight	  = (orenNayarCalc(S, m, c, c.L, d) * PR_INV_PI) * d;
+		out.pdf		  = blob(cos_hemi_pdf(d));
+		break;
+	}
 	case PRB_MAT_CONDUCTOR:
 		out.pdf	   = blob(0);
 		out.weight = blob(0);
@@ -709,6 +737,21 @@ __device__ __noinline__ void materialSample(const DScene& S, uint32_t matID, con
 			}
 		}
 		out.flags = MSF_Delta | contribFlags(m);
+		break;
+	}
+	case PRB_MAT_MIRROR: // mirror.cpp:50-61
+		out.weight = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+		out.type   = 1;
+		out.pdf	   = blob(1);
+		out.L	   = reflectZ(c.V);
+		out.flags  = MSF_Delta;
+		break;
+	case PRB_MAT_ORENNAYAR: { // orennayar.cpp:72-84
+		const float u2 = rnd.getFloat(); // cos_hemi(RND.getFloat(), RND.getFloat()): second argument drawn first
+		const float u1 = rnd.getFloat();
+		out.L		   = cos_hemi(u1, u2);
+		out.weight	   = orenNayarCalc(S, m, c, out.L, fmaxf(0.0f, out.L.z));
+		out.pdf		   = blob(cos_hemi_pdf(out.L.z));
 		break;
 	}
 	case PRB_MAT_CONDUCTOR: { // conductor.cpp:56-74

@@ -354,6 +354,76 @@ public:
 			   "specular_tint, flatness|subsurface, metallic, sheen, sheen_tint, clearcoat, clearcoat_gloss (0), vndf (true), thin (false)";
 	}
 };
+class MirrorMaterial : public IMaterial { // mirror.cpp:14-65
+public:
+	explicit MirrorMaterial(const std::shared_ptr<FloatSpectralNode>& spec)
+		: mSpecularity(spec)
+	{
+	}
+	bool hasOnlyDeltaDistribution() const override { return true; }
+	void describe(prb_material& out, NodeEmitter& e) const override
+	{
+		out.type	= PRB_MAT_MIRROR;
+		out.flags	= PRB_MATF_ONLY_DELTA;
+		out.node[0] = mSpecularity->emit(e);
+	}
+	std::string dumpInformation() const override { return "  <MirrorMaterial>:\n    Specularity: " + mSpecularity->dumpInformation() + "\n"; }
+
+private:
+	std::shared_ptr<FloatSpectralNode> mSpecularity;
+};
+class MirrorMaterialPlugin : public IMaterialPlugin {
+public:
+	std::shared_ptr<IMaterial> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		return std::make_shared<MirrorMaterial>(ctx.lookupSpectralNode("specularity", 1));
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> names({ "mirror", "reflection" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Delta Mirror BSDF: specularity (spectral, 1)"; }
+};
+
+class OrenNayarMaterial : public IMaterial { // orennayar.cpp:16-86
+public:
+	OrenNayarMaterial(const std::shared_ptr<FloatSpectralNode>& alb, float roughness)
+		: mAlbedo(alb)
+		, mRoughness(roughness)
+	{
+	}
+	void describe(prb_material& out, NodeEmitter& e) const override
+	{
+		out.type	= PRB_MAT_ORENNAYAR;
+		out.flags	= 0;
+		out.node[0] = mAlbedo->emit(e);
+		out.f[0]	= mRoughness;
+	}
+	std::string dumpInformation() const override
+	{
+		std::stringstream s;
+		s << "  <OrenNayarMaterial>:\n    Albedo: " << mAlbedo->dumpInformation() << "\n    Roughness: " << mRoughness << "\n";
+		return s.str();
+	}
+
+private:
+	std::shared_ptr<FloatSpectralNode> mAlbedo;
+	float mRoughness;
+};
+class OrenNayarMaterialPlugin : public IMaterialPlugin {
+public:
+	std::shared_ptr<IMaterial> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		return std::make_shared<OrenNayarMaterial>(ctx.lookupSpectralNode("albedo", 1), constScalar(ctx.lookupScalarNode("roughness", 0.5f), "roughness"));
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> names({ "orennayar", "oren", "rough" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "OrenNayar BSDF: albedo (spectral, 1), roughness (scalar, 0.5)"; }
+};
 } // namespace
 
 void registerMaterialPlugins(std::vector<std::shared_ptr<IPlugin>>& out)
@@ -364,5 +434,7 @@ void registerMaterialPlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 	out.push_back(std::make_shared<RoughConductorMaterialPlugin>());
 	out.push_back(std::make_shared<RoughDielectricMaterialPlugin>());
 	out.push_back(std::make_shared<PrincipledMaterialPlugin>());
+	out.push_back(std::make_shared<MirrorMaterialPlugin>());
+	out.push_back(std::make_shared<OrenNayarMaterialPlugin>());
 }
 } // namespace PR

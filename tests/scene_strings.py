@@ -72,3 +72,28 @@ SKYSUN_ZOO = """
    :latitude 48.2 :longitude 16.4 :timezone 2)
 )
 """
+
+# SURVEY 8(f)-3: the cheap materials of the other example scenes -- delta mirror (mirror.cpp) and improved Oren-Nayar
+# (orennayar.cpp; roughness 0 must reduce to its albedo / pi like Lambert without the two-sided handling)
+MATERIAL_ZOO2 = """
+(scene :name 'zoo2' :render_width 32 :render_height 32 :camera 'Camera'
+ (integrator :type 'direct' :max_ray_depth 8)
+ (sampler :slot 'aa' :type 'mjitt' :sample_count 16)
+ (camera :name 'Camera' :type 'standard' :width 1 :height 1 :local_direction [0,0,-1] :local_up [0,1,0] :local_right [1,0,0]
+   :near 0.1 :far 100 :transform [1,0,0,0, 0,1,0,0, 0,0,1,4, 0,0,0,1])
+ (emission :name 'em' :type 'standard' :radiance (illuminant "D65"))
+ (material :name 'm_floor' :type 'orennayar' :albedo (refl 0.7 0.7 0.6) :roughness 0.8)
+ (material :name 'm_mirror' :type 'mirror')
+ (material :name 'm_mirror_tint' :type 'reflection' :specularity (refl 0.9 0.6 0.2))
+ (material :name 'm_oren' :type 'orennayar' :albedo (refl 0.2 0.5 0.8) :roughness 0.5)
+ (material :name 'm_oren0' :type 'rough' :albedo (refl 0.8 0.3 0.3) :roughness 0)
+ (material :name 'm_lamp' :type 'diffuse' :albedo 0.5)
+ (entity :name 'floor' :type 'plane' :centering true :width 4 :height 4 :material 'm_floor' :position [0,0,-1])
+ (entity :name 's0' :type 'sphere' :radius 0.5 :material 'm_mirror' :position [-0.9,0.7,0])
+ (entity :name 's1' :type 'sphere' :radius 0.5 :material 'm_mirror_tint' :position [0.9,0.7,0])
+ (entity :name 's2' :type 'sphere' :radius 0.5 :material 'm_oren' :position [-0.9,-0.7,0])
+ (entity :name 's3' :type 'sphere' :radius 0.5 :material 'm_oren0' :position [0.9,-0.7,0])
+ (entity :name 'lamp' :type 'plane' :centering true :width 1 :height 1 :material 'm_lamp' :emission 'em' :transform [1,0,0,0, 0,-1,0,0, 0,0,-1,3, 0,0,0,1])
+ (light :type 'env' :radiance (illuminant "D65"))
+)
+"""

@@ -11,7 +11,7 @@ import pytest
 
 import pearray_b200 as prb
 import oracle_binding as ob
-from scene_strings import MATERIAL_ZOO
+from scene_strings import MATERIAL_ZOO, MATERIAL_ZOO2
 
 EPS = 2 * np.finfo(np.float32).eps
 
@@ -267,9 +267,9 @@ def test_upsampler_golden_through_oracle_nodes():
 
 
 # ---------------------------------------------------------------- src/tests/materials.cpp:13-165 (eval/pdf/sample self-consistency)
-@pytest.fixture(scope="module")
-def zoo():
-    scene = prb.Scene.from_string(MATERIAL_ZOO)
+@pytest.fixture(scope="module", params=["zoo", "zoo2"])
+def zoo(request):
+    scene = prb.Scene.from_string(MATERIAL_ZOO if request.param == "zoo" else MATERIAL_ZOO2)
     return scene, ob.OracleScene(scene)
 
 
@@ -312,3 +312,46 @@ def test_materials_sample_matches_eval(zoo, backside):
             for k in range(4):
                 tol = 5e-4 * max(1.0, abs(e.weight[k]))
                 assert abs(s.weight[k] * s.pdf_s[0] - e.weight[k]) <= tol, (mat, d.materials[mat].type, k, s.weight[k] * s.pdf_s[0], e.weight[k])
+
+
+# ---------------------------------------------------------------- mirror.cpp / orennayar.cpp
+def _zoo2_material(scene, mtype, nth=0):
+    d = scene.desc.contents
+    ids = [i for i in range(d.n_materials) if d.materials[i].type == mtype]
+    return ids[nth]
+
+
+def test_mirror_reflects_and_tints():
+    scene = prb.Scene.from_string(MATERIAL_ZOO2)
+    ora = ob.OracleScene(scene)
+    V = nrm(0.3, -0.2, 0.9)
+    plain, tinted = _zoo2_material(scene, 6, 0), _zoo2_material(scene, 6, 1)
+    s = ora.material_sample(_query(scene, plain, V))[0]
+    assert s.flags & 0x2 and list(s.pdf_s) == [1.0] * 4 and list(s.weight) == [1.0] * 4
+    assert np.allclose(list(s.L), [-V[0], -V[1], V[2]], atol=0)  # Scattering::reflect in shading space
+    t = ora.material_sample(_query(scene, tinted, V))[0]
+    node = scene.desc.contents.materials[tinted].node[0]
+    assert np.allclose(list(t.weight), [ora.eval_node(node, w) for w in (560.0, 540.0, 400.0, 600.0)], atol=1e-6)
+
+
+def test_orennayar_roughness_zero_is_lambert_and_energy_is_bounded():
+    scene = prb.Scene.from_string(MATERIAL_ZOO2)
+    ora = ob.OracleScene(scene)
+    d = scene.desc.contents
+    ids = [i for i in range(d.n_materials) if d.materials[i].type == 7]
+    smooth = [i for i in ids if d.materials[i].f[0] == 0.0][0]
+    rough = [i for i in ids if d.materials[i].f[0] == 0.5][0]
+    V = nrm(0.5, 0.1, 0.8)
+    albedo = [ora.eval_node(d.materials[smooth].node[0], w) for w in (560.0, 540.0, 400.0, 600.0)]
+    rs = np.random.RandomState(3)
+    n, acc = 4000, np.zeros(4)
+    for _ in range(n):
+        u1, u2 = rs.rand(2)  # uniform hemisphere directions, pdf 1 / (2 pi)
+        L = np.array([np.sqrt(1 - u1 * u1) * np.cos(2 * np.pi * u2), np.sqrt(1 - u1 * u1) * np.sin(2 * np.pi * u2), u1])
+        e0 = ora.material_eval(_query(scene, smooth, V, L))[0]
+        assert np.allclose(list(e0.weight), np.array(albedo) * L[2] / np.pi, rtol=2e-6, atol=1e-7)
+        assert np.allclose(list(e0.pdf_s), [L[2] / np.pi] * 4, rtol=2e-6)
+        acc += np.array(list(ora.material_eval(_query(scene, rough, V, L))[0].weight)) * 2 * np.pi
+    assert np.all(acc / n < 1.0) and np.all(acc / n > 0.05)  # directional albedo of the rough lobe stays below one
+    below = ora.material_eval(_query(scene, rough, V, [0.3, 0.1, -0.9]))[0]
+    assert list(below.weight) == [0.0] * 4 and list(below.pdf_s) == [0.0] * 4
