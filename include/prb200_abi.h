@@ -243,7 +243,13 @@ typedef struct prb_light { /* src/core/light/Light.cpp, LightSampler.cpp:11-132 
 } prb_light;
 
 /* ---------------------------------------------------------------- samplers, mapper, camera */
-enum { PRB_SAMPLER_RANDOM = 0, PRB_SAMPLER_MJITT = 1, PRB_SAMPLER_SOBOL = 2 };
+enum {
+	PRB_SAMPLER_RANDOM	   = 0,
+	PRB_SAMPLER_MJITT	   = 1,
+	PRB_SAMPLER_SOBOL	   = 2,
+	PRB_SAMPLER_STRATIFIED = 3, /* StratifiedSampler.cpp:12-41: bins_1d = groups, m2d_x = (uint32)sqrt(groups) */
+	PRB_SAMPLER_UNIFORM	   = 4	/* UniformSampler.cpp:11-29: always 0.5 */
+};
 typedef struct prb_sampler { /* src/plugins/main/sampler/ */
 	uint32_t type;
 	uint32_t max_samples; /* ISampler::maxSamples() */

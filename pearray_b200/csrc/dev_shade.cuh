@@ -904,6 +904,15 @@ PRB_DEV void sampler2D(const DScene& S, const prb_sampler& s, Rng& rnd, uint32_t
 		y					= (index + jy) / maxS;
 		break;
 	}
+	case PRB_SAMPLER_STRATIFIED: { // StratifiedSampler.cpp:29-36, Projection::stratified
+		const float range = 1.0f / (int)s.m2d_x;
+		const float ux	  = rnd.getFloat();
+		x				  = ux * range + (int)(index % s.m2d_x) * range;
+		const float uy	  = rnd.getFloat();
+		y				  = uy * range + (int)(index / s.m2d_x) * range;
+		break;
+	}
+	case PRB_SAMPLER_UNIFORM: x = y = 0.5f; break;
 	default: rnd.get2D(x, y); break;
 	}
 }
@@ -918,6 +927,11 @@ PRB_DEV float sampler1D(const DScene& S, const prb_sampler& s, Rng& rnd, uint32_
 		const float j = rnd.getFloat();
 		return (index % s.bins_1d + j) / s.bins_1d;
 	}
+	case PRB_SAMPLER_STRATIFIED: { // StratifiedSampler.cpp:22-26
+		const float range = 1.0f / (int)s.bins_1d;
+		return rnd.getFloat() * range + (int)index * range;
+	}
+	case PRB_SAMPLER_UNIFORM: return 0.5f;
 	default: return rnd.getFloat();
 	}
 }

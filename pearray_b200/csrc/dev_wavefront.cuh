@@ -137,12 +137,26 @@ __global__ void __launch_bounds__(128) k_init_slots(const __grid_constant__ DSce
 // (a handful of primitives), where the bookkeeping of the persistent variant costs more than the idle lanes it avoids.
 __global__ void __launch_bounds__(128) k_trace_static(DScene S, WFState W)
 {
-	// no early return: the traversal is warp-synchronous, lanes without a ray take part with live = false
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool inRange	= slot < W.nSlots;
-	const uint32_t st	= inRange ? W.state[slot] : 0u;
+	// The traversal is warp-synchronous (lanes without a ray take part with live = false), so idle lanes cost issue
+	// slots: slots retire at different times (a pixel's samples are sequential, short paths finish early -- about a third
+	// of the slots are idle over a Cornell-box render) and not every active slot has a shadow ray.  Each phase therefore
+	// first compacts the block's slots that have a ray of that kind into a list in shared memory and traces the list
+	// with dense warps; warps past the end of the list leave immediately.
+	__shared__ uint16_t list[128];
+	__shared__ uint32_t count[2];
+	const uint32_t base = blockIdx.x * blockDim.x;
+	const uint32_t own	= base + threadIdx.x;
+	const uint32_t st0	= own < W.nSlots ? W.state[own] : 0u;
+	if (threadIdx.x < 2)
+		count[threadIdx.x] = 0;
+	__syncthreads();
+	if (st0 & SF_SHADOW)
+		list[atomicAdd(&count[0], 1u)] = (uint16_t)threadIdx.x;
+	__syncthreads();
 	{
-		const bool live = (st & SF_SHADOW) != 0;
+		const bool live		= threadIdx.x < count[0];
+		const uint32_t slot = base + (live ? list[threadIdx.x] : 0u);
+		const uint32_t st	= live ? W.state[slot] : 0u;
 		float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
 		if (live) {
 			o = W.shO[slot];
@@ -165,8 +179,13 @@ __global__ void __launch_bounds__(128) k_trace_static(DScene S, WFState W)
 			W.state[slot] = st & SF_ACTIVE;
 		}
 	}
+	__syncthreads(); // the list is rebuilt for the path rays (the SF_ACTIVE bit of a slot is not touched by the shadow phase)
+	if (st0 & SF_ACTIVE)
+		list[atomicAdd(&count[1], 1u)] = (uint16_t)threadIdx.x;
+	__syncthreads();
 	{
-		const bool live = (st & SF_ACTIVE) != 0;
+		const bool live		= threadIdx.x < count[1];
+		const uint32_t slot = base + (live ? list[threadIdx.x] : 0u);
 		float4 o = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 1, 0);
 		if (live) {
 			o = W.rayO[slot];

@@ -515,7 +515,49 @@ private:
 	std::vector<float> mSamples1D;
 	std::vector<Vector2f> mSamples2D;
 };
-enum class SamplerKind { Random, MJitt, Sobol };
+class StratifiedSampler : public ISampler { // StratifiedSampler.cpp:12-41, Projection::stratified (src/base/math/Projection.h:14-18)
+public:
+	StratifiedSampler(uint32 samples, uint32 groups)
+		: ISampler(samples)
+		, m2D_X(static_cast<uint32>(std::sqrt(groups)))
+		, mGroups(groups)
+	{
+	}
+	static float stratified(float u, int index, int groups)
+	{
+		const float range = 1.0f / groups;
+		return u * range + index * range;
+	}
+	float generate1D(Random& rnd, uint32 index) override { return stratified(rnd.getFloat(), (int)index, (int)mGroups); }
+	Vector2f generate2D(Random& rnd, uint32 index) override
+	{
+		const float x = stratified(rnd.getFloat(), (int)(index % m2D_X), (int)m2D_X);
+		const float y = stratified(rnd.getFloat(), (int)(index / m2D_X), (int)m2D_X);
+		return Vector2f(x, y);
+	}
+	void describe(prb_sampler& out, std::vector<float>&) const override
+	{
+		out.type		= PRB_SAMPLER_STRATIFIED;
+		out.max_samples = maxSamples();
+		out.bins_1d		= mGroups;
+		out.m2d_x		= m2D_X;
+	}
+
+private:
+	uint32 m2D_X, mGroups;
+};
+class UniformSampler : public ISampler { // UniformSampler.cpp:11-29 ("a very bad sampler for test purposes")
+public:
+	using ISampler::ISampler;
+	float generate1D(Random&, uint32) override { return 0.5f; }
+	Vector2f generate2D(Random&, uint32) override { return Vector2f(0.5f, 0.5f); }
+	void describe(prb_sampler& out, std::vector<float>&) const override
+	{
+		out.type		= PRB_SAMPLER_UNIFORM;
+		out.max_samples = maxSamples();
+	}
+};
+enum class SamplerKind { Random, MJitt, Sobol, Stratified, Uniform };
 class SamplerFactory : public ISamplerFactory {
 public:
 	SamplerFactory(SamplerKind k, const ParameterGroup& params)
@@ -535,6 +577,8 @@ public:
 														  (uint32)mParams.getUInt("seed", defSeed));
 		}
 		case SamplerKind::Sobol: return std::make_shared<SobolSampler>(rnd, sample_count);
+		case SamplerKind::Stratified: return std::make_shared<StratifiedSampler>(sample_count, (uint32)mParams.getUInt("bins", std::max(1u, sample_count)));
+		case SamplerKind::Uniform: return std::make_shared<UniformSampler>(sample_count);
 		default: return std::make_shared<RandomSampler>(sample_count);
 		}
 	}
@@ -562,7 +606,15 @@ public:
 		static const std::vector<std::string> rnd({ "random" });
 		static const std::vector<std::string> sob({ "sobol" });
 		static const std::vector<std::string> mj({ "multijittered", "multi_jittered", "jittered", "multijitter", "multi_jitter", "jitter", "mjitt", "jitt" });
-		return mKind == SamplerKind::Random ? rnd : (mKind == SamplerKind::Sobol ? sob : mj);
+		static const std::vector<std::string> strat({ "stratified" });
+		static const std::vector<std::string> uni({ "uniform" });
+		switch (mKind) {
+		case SamplerKind::Random: return rnd;
+		case SamplerKind::Sobol: return sob;
+		case SamplerKind::Stratified: return strat;
+		case SamplerKind::Uniform: return uni;
+		default: return mj;
+		}
 	}
 	std::string specification(const std::string&) const override { return "Sampler: sample_count (128) [bins, seed for mjitt]"; }
 
@@ -913,6 +965,8 @@ void registerScenePlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Sobol));
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::MJitt));
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Random));
+	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Stratified));
+	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Uniform));
 	for (FilterProfile k : { FilterProfile::Mitchell, FilterProfile::Triangle, FilterProfile::Gaussian, FilterProfile::Lanczos, FilterProfile::Block })
 		out.push_back(std::make_shared<FilterPlugin>(k));
 	out.push_back(std::make_shared<SPDSpectralMapperPlugin>());

@@ -12,10 +12,13 @@ import pytest
 import pearray_b200 as prb
 from conftest import scene_path
 from oracle_binding import OracleScene
-from scene_strings import FURNACE, MATERIAL_ZOO
+from scene_strings import FURNACE, MATERIAL_ZOO, MATERIAL_ZOO2
 from test_golden_oracle import CBOX_CHANNEL_TOL, CBOX_LUMINANCE_TOL, GOLDEN, STAT_NAMES, cbox_reference_error, load_golden, load_scene
 
 pytestmark = pytest.mark.gpu
+
+ZOO2_WITH_SAMPLER = MATERIAL_ZOO2.replace("(sampler :slot 'aa' :type 'mjitt' :sample_count 16)",
+                                          "(sampler :slot 'aa' :type '{0}' :sample_count 36) (sampler :slot 'lens' :type '{0}' :sample_count 36)")
 
 # Same-seed renders are BIT EXACT against the oracle on every scene: all fp32 arithmetic on the device rounds like the
 # oracle's (-fmad=false, IEEE div/sqrt, FTZ, explicit fma only where the reference has std::fma, correctly rounded
@@ -105,6 +108,23 @@ def test_sobol_and_mjitt_camera_rays_bit_exact(name):
         b = ora.generate_camera_rays(tiles, it)
         for x, y in zip(a, b):
             assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+
+
+@pytest.mark.parametrize("sampler", ["stratified", "uniform"])
+def test_stratified_and_uniform_samplers_bit_exact(sampler):
+    """StratifiedSampler.cpp / UniformSampler.cpp: camera rays and a short render against the oracle"""
+    scene = prb.Scene.from_string(ZOO2_WITH_SAMPLER.format(sampler))
+    ctx = make_ctx(scene)
+    ora = OracleScene(scene)
+    tiles = [(0, 0, 32, 32)]
+    for it in (0, 5, 40):  # 40 >= sample_count: indices beyond the strata
+        for x, y in zip(ctx.generate_camera_rays(tiles, it), ora.generate_camera_rays(tiles, it)):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+    ctx.render_tiles(tiles, 0, 4)
+    xyz, cnt = ctx.film()
+    ref = ora.render(tiles, 0, 4)
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
 
 
 def test_material_unit_calls_vs_oracle():
