@@ -231,6 +231,8 @@ def host_lib():
         lib.prh_render_context_device.restype = C.c_void_p
         lib.prh_render_context_device.argtypes = [C.c_void_p]
         lib.prh_render_context_destroy.argtypes = [C.c_void_p]
+        lib.prh_render_context_save_outputs.restype = C.c_int
+        lib.prh_render_context_save_outputs.argtypes = [C.c_void_p, C.c_char_p]
         _host = lib
     return _host
 

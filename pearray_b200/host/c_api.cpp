@@ -75,6 +75,31 @@ void* prh_make_soup(uint32_t triangles, uint64_t seed, uint32_t film_w, uint32_t
 {
 	return new SceneHandle{ nullptr, makeSoupScene(triangles, seed, film_w, film_h) };
 }
+// (output ...) blocks of the scene: number of files, and <dir>/results[_index]/<name>.exr written from host film buffers
+// (xyz: 3 floats / pixel, count: 1 u32 / pixel, aov: 10 floats / pixel or NULL), as prb_film_download / prb_film_aov return them
+uint32_t prh_output_file_count(void* h)
+{
+	auto* s = static_cast<SceneHandle*>(h);
+	return s->env ? (uint32_t)s->env->outputSpecification().files().size() : 0u;
+}
+int prh_save_outputs(void* h, const char* dir, const float* xyz, const uint32_t* count, const float* aov, uint32_t context_index)
+{
+	auto* s = static_cast<SceneHandle*>(h);
+	if (!s->env) {
+		g_err = "scene has no loader environment (synthetic scene)";
+		return -1;
+	}
+	const prb_settings& st = s->scene->desc.settings;
+	FilmView film;
+	film.width		 = st.film_width;
+	film.height		 = st.film_height;
+	film.fullWidth	 = st.film_width;
+	film.fullHeight	 = st.film_height;
+	film.xyz		 = xyz;
+	film.sampleCount = count;
+	film.aov		 = aov;
+	return s->env->outputSpecification().save(dir ? dir : "", film, context_index);
+}
 void prh_free_scene(void* h) { delete static_cast<SceneHandle*>(h); }
 const prb_scene_desc* prh_scene_desc(void* h) { return &static_cast<SceneHandle*>(h)->scene->desc; }
 prb_scene_desc* prh_scene_desc_mutable(void* h) { return &static_cast<SceneHandle*>(h)->scene->desc; }
@@ -184,6 +209,7 @@ int prh_render_context_start(void* rc, uint32_t rtx, uint32_t rty, uint32_t iter
 {
 	return static_cast<RenderContext*>(rc)->start(rtx, rty, iterations) ? 0 : -1;
 }
+int prh_render_context_save_outputs(void* rc, const char* dir) { return static_cast<RenderContext*>(rc)->saveOutputs(dir ? dir : ""); }
 void prh_render_context_wait(void* rc) { static_cast<RenderContext*>(rc)->waitForFinish(); }
 prb_ctx* prh_render_context_device(void* rc) { return static_cast<RenderContext*>(rc)->deviceContext(); }
 void prh_render_context_destroy(void* rc) { delete static_cast<RenderContext*>(rc); }

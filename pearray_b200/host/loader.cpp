@@ -446,9 +446,8 @@ void SceneLoader::setupEnvironment(const std::vector<DL::DataGroup>& groups, Sce
 			addCamera(entry, ctx);
 		else if (id == "spectral_mapper")
 			addSpectralMapper(entry, ctx);
-		else if (id == "output") {
-			// channel layout is fixed on the device path (XYZ + sample count + first-hit AOVs): SURVEY 8(f)-2
-		}
+		else if (id == "output")
+			ctx.environment()->outputSpecification().parse(entry); // SceneLoader.cpp: OutputSpecification::parse
 	}
 }
 

@@ -635,6 +635,41 @@ struct RenderSettings { // reference src/core/renderer/RenderSettings.cpp:11-33
 	uint32 cropOffsetY() const { return (uint32)(cropMinY * filmHeight); }
 };
 
+// ------------------------------------------------------------------ output specification + image writer (image_io.cpp)
+enum class ToneColorMode { SRGB, XYZ, XYZNorm, Luminance }; // reference src/core/spectral/ToneMapper.h
+enum OutputVariable { OV_Unsupported = -1, OV_Output = 0, OV_Position, OV_Normal, OV_UVW, OV_Depth, OV_EntityID, OV_SampleCount };
+struct OutputChannel { // reference IM_ChannelSetting{Spec,3D,1D,Counter}, src/loader/output/io/ImageWriter.h
+	enum Kind { Spectral, ThreeD, OneD, Counter } kind = Spectral;
+	int variable	  = OV_Output;
+	ToneColorMode tcm = ToneColorMode::SRGB;
+	std::string name; // empty for the plain colour channel ("R", "G", "B")
+};
+struct OutputFile {
+	std::string name;
+	std::vector<OutputChannel> channels;
+};
+struct FilmView { // what prb_film_download / prb_film_aov return for one context
+	uint32 width = 0, height = 0;		  // view size
+	uint32 offsetX = 0, offsetY = 0;	  // view offset inside the film
+	uint32 fullWidth = 0, fullHeight = 0; // film size
+	const float* xyz		  = nullptr;  // 3 per pixel
+	const uint32* sampleCount = nullptr;  // 1 per pixel
+	const float* aov		  = nullptr;  // 10 per pixel (N, P, u, v, depth, entity id), sums over the samples; may be null
+};
+class OutputSpecification { // reference src/loader/output/io/OutputSpecification.h
+public:
+	void parse(const DL::DataGroup& entry);
+	const std::vector<OutputFile>& files() const { return mFiles; }
+	// writes <workingDir>/results[_<contextIndex>]/<name>.exr for every (output ...) block; returns the number written
+	int save(const std::string& workingDir, const FilmView& film, uint32 contextIndex = 0) const;
+
+private:
+	std::vector<OutputFile> mFiles;
+};
+bool saveImage(const std::string& path, const OutputFile& file, const FilmView& film);
+bool writeEXR(const std::string& path, const std::vector<std::string>& channelNames, const std::vector<const float*>& planes, uint32 width, uint32 height,
+			  int32_t offX, int32_t offY, uint32 fullWidth, uint32 fullHeight);
+
 class Environment { // reference src/loader/Environment.h:45-134
 public:
 	explicit Environment(const std::string& pluginPath = "");
@@ -643,6 +678,8 @@ public:
 	SceneDatabase* sceneDatabase() { return &mDatabase; }
 	const SceneDatabase* sceneDatabase() const { return &mDatabase; }
 	const std::shared_ptr<SpectralUpsampler>& defaultSpectralUpsampler() const { return mUpsampler; }
+	OutputSpecification& outputSpecification() { return mOutputSpecification; }
+	const OutputSpecification& outputSpecification() const { return mOutputSpecification; }
 
 	AbstractManager<ICameraPlugin> cameraManager;
 	AbstractManager<IEmissionPlugin> emissionManager;
@@ -668,6 +705,7 @@ private:
 	RenderSettings mRenderSettings;
 	SceneDatabase mDatabase;
 	std::shared_ptr<SpectralUpsampler> mUpsampler;
+	OutputSpecification mOutputSpecification;
 };
 
 class SceneLoadContext { // reference src/loader/SceneLoadContext.h / .cpp:196-326
@@ -866,6 +904,8 @@ public:
 	const std::shared_ptr<CompiledScene>& compiledScene() const { return mScene; }
 	prb_ctx* deviceContext() const { return mCtx; }
 	std::vector<float> filmXYZ();
+	// writes <workingDir>/results[_<rank>]/<name>.exr for every (output ...) block of the scene; returns the number of files
+	int saveOutputs(const std::string& workingDir);
 	prb_stats statistics() const;
 	const RenderSettings& settings() const { return mEnv->renderSettings(); }
 	const std::vector<RenderTile>& ownedTiles() const { return mOwnedTiles; }

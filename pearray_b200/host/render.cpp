@@ -83,6 +83,26 @@ std::vector<float> RenderContext::filmXYZ()
 		PR_LOG(L_ERROR) << "prb_film_download failed: " << prb_last_error() << std::endl;
 	return xyz;
 }
+int RenderContext::saveOutputs(const std::string& workingDir)
+{ // Environment::save -> OutputSpecification::save (reference src/loader/Environment.cpp, OutputSpecification.cpp:439-464)
+	const prb_settings& st = mScene->desc.settings;
+	const size_t n		   = (size_t)st.film_width * st.film_height;
+	std::vector<float> xyz(n * 3), aov;
+	std::vector<uint32> count(n);
+	if (!mCtx || prb_film_download(mCtx, xyz.data(), count.data()) != PRB_OK) {
+		PR_LOG(L_ERROR) << "prb_film_download failed: " << prb_last_error() << std::endl;
+		return -1;
+	}
+	FilmView film;
+	film.width = film.fullWidth = st.film_width;
+	film.height = film.fullHeight = st.film_height;
+	film.xyz					  = xyz.data();
+	film.sampleCount			  = count.data();
+	aov.resize(n * 10);
+	if (prb_film_download_aov(mCtx, aov.data()) == PRB_OK) // AOVs are optional (prb_settings.enable_aov)
+		film.aov = aov.data();
+	return mEnv->outputSpecification().save(workingDir, film, mRank);
+}
 prb_stats RenderContext::statistics() const
 {
 	prb_stats s{};

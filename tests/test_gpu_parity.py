@@ -325,6 +325,31 @@ def test_host_render_context_matches_abi_path():
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_host_render_context_writes_the_output_files(tmp_path):
+    """RenderContext::saveOutputs: results/<name>.exr of the scene's (output ...) blocks holds the film the C ABI returns
+    (SURVEY 8(f)-2; reference OutputSpecification::save + ImageWriter::save)"""
+    from test_image_output import SCENE, read_exr
+    h = prb.host_lib()
+    scene = prb.Scene.from_string(SCENE)
+    rc = h.prh_render_context_create(scene._h, 0, 0, 1)
+    assert rc, h.prh_last_error()
+    assert h.prh_render_context_start(rc, 8, 8, 4) == 0
+    h.prh_render_context_wait(rc)
+    dev = h.prh_render_context_device(rc)
+    xyz = np.empty((scene.height, scene.width, 3), np.float32)
+    cnt = np.empty((scene.height, scene.width), np.uint32)
+    assert prb.device_lib().prb_film_download(dev, xyz.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p)) == 0
+    assert h.prh_render_context_save_outputs(rc, str(tmp_path).encode()) == 2
+    h.prh_render_context_destroy(rc)
+    _, _, pl = read_exr(str(tmp_path / "results" / "aovs.exr"))
+    for k, c in enumerate("RGB"):  # :color 'xyz'
+        assert np.array_equal(pl[c], xyz[..., k])
+    assert np.array_equal(pl["sample_count"], cnt.astype(np.float32))
+    assert cnt.max() == 4 and xyz.max() > 0
+    _, chans, _ = read_exr(str(tmp_path / "results" / "image.exr"))
+    assert chans == ["B", "G", "R"]
+
+
 def test_invalid_arguments_on_device():
     scene = load_scene("c2_cornellbox")
     ctx = make_ctx(scene)
