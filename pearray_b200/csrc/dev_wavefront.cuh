@@ -321,7 +321,10 @@ PRB_DEV float rrProbability(const DScene& S, uint32_t pathLength, bool delta)
 // (nothing to gain from larger windows; small blocks balance better), SHADE_BLOCK_MIXED threads sorting a window of up to
 // SHADE_ROUNDS_MIXED * SHADE_BLOCK_MIXED slots, shaded in that many passes, for scenes that mix material types
 // (boltsandgears: 1006 ms -> 447 ms of k_shade per 64 spp).
-constexpr int SHADE_BLOCK_UNIFORM = 128;
+#ifndef PRB_SHADE_BLOCK_UNIFORM
+#define PRB_SHADE_BLOCK_UNIFORM 128
+#endif
+constexpr int SHADE_BLOCK_UNIFORM = PRB_SHADE_BLOCK_UNIFORM;
 constexpr int SHADE_BLOCK_MIXED	  = 512;
 constexpr int SHADE_ROUNDS_MIXED	  = 4;
 constexpr int SHADE_BINS		  = 64; // materials 0..61 (ids beyond share bin 61), 62 = miss, 63 = no work
@@ -344,7 +347,7 @@ PRB_DEV uint32_t shadeSortKey(const DScene& S, const WFState& W, uint32_t slot)
 #define PRB_SHADE_MINB 4 /* resident 128-thread blocks per SM the uniform instantiation is compiled for */
 #endif
 template <int SHADE_BLOCK, int SHADE_ROUNDS_MAX>
-__global__ void __launch_bounds__(SHADE_BLOCK, SHADE_BLOCK == 128 ? PRB_SHADE_MINB : 512 / SHADE_BLOCK) k_shade(const __grid_constant__ DScene S, WFState W, int roundsArg)
+__global__ void __launch_bounds__(SHADE_BLOCK, SHADE_BLOCK <= 128 ? (PRB_SHADE_MINB * 128) / SHADE_BLOCK : 512 / SHADE_BLOCK) k_shade(const __grid_constant__ DScene S, WFState W, int roundsArg)
 {
 	const int rounds = SHADE_ROUNDS_MAX == 1 ? 1 : roundsArg; // compile-time 1 for the uniform instantiation: no loop
 

@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -m gpu -x -q) > gpurun_out/gpu_tests.log 2>&1; tail -8 gpurun_out/gpu_tests.log
-for sc in "c1 16" "c2 256" "c3 128" "c4 64" "c4c 16"; do set -- $sc
-  timeout 300 python bench.py --scene $1 --no-cpu --steps 1 --warmup 1 --spp $2 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1', round(d['value']/1e6,1), d['stage_ms'])"
+cp pearray_b200/libprb200.so /tmp/lib_base.so
+for v in base u256; do
+  if [ $v != base ]; then cp gpurun_variants/lib_$v.so pearray_b200/libprb200.so; else cp /tmp/lib_base.so pearray_b200/libprb200.so; fi
+  echo "== variant $v"
+  for i in 1 2; do timeout 200 python bench.py --scene c2 --no-cpu --steps 1 --warmup 1 --spp 256 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('c2', round(d['value']/1e6,1), d['stage_ms'])"; done
 done
+cp /tmp/lib_base.so pearray_b200/libprb200.so
