@@ -260,12 +260,19 @@ typedef struct prb_sampler { /* src/plugins/main/sampler/ */
 	uint32_t _pad;
 } prb_sampler;
 
-enum { PRB_MAPPER_RANDOM = 0, PRB_MAPPER_SPD_CMIS = 1, PRB_MAPPER_SPD_HERO = 2 };
-typedef struct prb_spectral_mapper { /* src/plugins/main/spectralmapper/spd.cpp, random.cpp */
+enum {
+	PRB_MAPPER_RANDOM	= 0,
+	PRB_MAPPER_SPD_CMIS = 1,
+	PRB_MAPPER_SPD_HERO = 2,
+	PRB_MAPPER_CIE		= 3 /* cie.cpp:13-83: four independent samples of the CIE Y or X+Y+Z CDF, truncated to the camera range */
+};
+typedef struct prb_spectral_mapper { /* src/plugins/main/spectralmapper/spd.cpp, random.cpp, cie.cpp */
 	uint32_t type;
-	uint32_t cdf_offset; /* pool offset of cdf_size floats (Distribution1D mCDF) */
+	uint32_t cdf_offset; /* pool offset of cdf_size floats (Distribution1D mCDF / StaticCDF) */
 	uint32_t cdf_size;
-	uint32_t _pad;
+	/* CIE: evalContinuous of the CDF at the normalised ends of the camera range (CIE::sample_trunc, CIE.h:117-127);
+	 * 0 and 1 for the full range */
+	float trunc_cdf_start, trunc_cdf_end;
 } prb_spectral_mapper;
 
 typedef struct prb_camera { /* plugins/main/cameras/perspective.cpp:45-113, no-DOF branch */

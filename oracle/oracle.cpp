@@ -1327,6 +1327,16 @@ void constructCameraRay(const Scene& sc, uint32_t px, uint32_t py, uint32_t iter
 				o.wvlPDF[i]	  = pdf;
 			}
 			break;
+		case PRB_MAPPER_CIE: // cie.cpp:24-31,61-69 + CIE::sample_trunc, CIE.h:117-127 (0..1 for the full range)
+			for (int i = 0; i < 4; ++i) {
+				float pdf;
+				const float cs = d.pixel_mapper.trunc_cdf_start, ce = d.pixel_mapper.trunc_cdf_end;
+				const float v  = sampleContinuous(d.pool + d.pixel_mapper.cdf_offset, (int)d.pixel_mapper.cdf_size, cs + rnd.getFloat() * (ce - cs), pdf);
+				pdf /= (ce - cs);
+				o.wvl[i]	= v * (end - start) + start;
+				o.wvlPDF[i] = pdf;
+			}
+			break;
 		case PRB_MAPPER_SPD_HERO: { // spd.cpp:104-112
 			float pdf;
 			const float u	 = rnd.getFloat();

@@ -54,7 +54,8 @@ class Sampler(C.Structure):
 
 
 class SpectralMapper(C.Structure):
-    _fields_ = [("type", C.c_uint32), ("cdf_offset", C.c_uint32), ("cdf_size", C.c_uint32), ("_pad", C.c_uint32)]
+    _fields_ = [("type", C.c_uint32), ("cdf_offset", C.c_uint32), ("cdf_size", C.c_uint32), ("trunc_cdf_start", C.c_float),
+                ("trunc_cdf_end", C.c_float)]
 
 
 class Node(C.Structure):

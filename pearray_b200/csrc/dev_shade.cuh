@@ -991,6 +991,17 @@ __device__ __noinline__ void constructCameraRay(const DScene& S, uint32_t px, ui
 				o.wvlPDF[i]	  = pdf;
 			}
 			break;
+		case PRB_MAPPER_CIE: // cie.cpp:24-31,61-69 + CIE::sample_trunc, CIE.h:117-127 (0..1 for the full range)
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				float pdf;
+				const float cs = S.mapper.trunc_cdf_start, ce = S.mapper.trunc_cdf_end;
+				const float v  = sampleContinuous(S.pool + S.mapper.cdf_offset, (int)S.mapper.cdf_size, cs + rnd.getFloat() * (ce - cs), pdf);
+				pdf /= (ce - cs);
+				o.wvl[i]	= v * (end - start) + start;
+				o.wvlPDF[i] = pdf;
+			}
+			break;
 		case PRB_MAPPER_SPD_HERO: { // spd.cpp:104-112 + Standard.h:8-21
 			float pdf;
 			const float u	 = rnd.getFloat();

@@ -761,6 +761,64 @@ public:
 	std::string specification(const std::string&) const override { return "Random Spectral Mapper"; }
 };
 
+class CIESpectralMapperFactory : public ISpectralMapperFactory { // spectralmapper/cie.cpp:13-99, CIE::sample_(trunc_)xyz / _y (CIE.h:66-127)
+public:
+	explicit CIESpectralMapperFactory(bool onlyY)
+		: mOnlyY(onlyY)
+	{
+	}
+	void describe(const SpectralMapperBuildInput& in, prb_spectral_mapper& out, std::vector<float>& pool) override
+	{
+		const SpectralRange range = in.cameraRange;
+		if (!(range.Start >= PR_CIE_WAVELENGTH_START && range.End <= PR_CIE_WAVELENGTH_END))
+			throw std::runtime_error("cie spectral mapper: the camera range must lie inside the CIE range"); // createInstance returns nullptr
+		// StaticCDF (src/base/math/Distribution1D.h:11-46): running sum of data / N in fp32, normalised, last entry forced to 1
+		constexpr size_t N = PR_CIE_SAMPLE_COUNT;
+		std::vector<float> cdf(N + 1);
+		const float *X = CIE::table(0), *Y = CIE::table(1), *Z = CIE::table(2);
+		cdf[0] = 0.0f;
+		for (size_t i = 1; i < N + 1; ++i)
+			cdf[i] = mOnlyY ? cdf[i - 1] + Y[i - 1] / N : cdf[i - 1] + (X[i - 1] + Y[i - 1] + Z[i - 1]) / N;
+		if (cdf[N] < PR_EPSILON) {
+			for (size_t i = 1; i < N + 1; ++i)
+				cdf[i] = float(i) / float(N);
+		} else {
+			for (size_t i = 1; i < N + 1; ++i)
+				cdf[i] /= cdf[N];
+		}
+		cdf[N] = 1.0f;
+		const auto evalContinuous = [&](float x) { // Distribution1D::evalContinuous, Distribution1D.inl:106-112
+			const size_t size = N + 1;
+			const size_t off  = std::min<size_t>(size - 2, (size_t)(x * (size - 1)));
+			const float dt	  = x * (size - 1) - off;
+			return cdf[off] * (1 - dt) + cdf[off + 1] * dt;
+		};
+		out.type			= PRB_MAPPER_CIE;
+		out.cdf_offset		= (uint32)pool.size();
+		out.cdf_size		= (uint32)cdf.size();
+		out.trunc_cdf_start = evalContinuous((range.Start - PR_CIE_WAVELENGTH_START) / PR_CIE_WAVELENGTH_RANGE);
+		out.trunc_cdf_end	= evalContinuous((range.End - PR_CIE_WAVELENGTH_START) / PR_CIE_WAVELENGTH_RANGE);
+		pool.insert(pool.end(), cdf.begin(), cdf.end());
+	}
+
+private:
+	bool mOnlyY;
+};
+class CIESpectralMapperPlugin : public ISpectralMapperPlugin {
+public:
+	std::shared_ptr<ISpectralMapperFactory> create(const std::string& type_name, const SceneLoadContext& ctx) override
+	{
+		const bool onlyY = type_name == "cie_y" || type_name == "visible_y" || ctx.parameters().getBool("only_y", false);
+		return std::make_shared<CIESpectralMapperFactory>(onlyY);
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> names({ "cie", "cie_y", "visible", "visible_y" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "CIE Spectral Mapper: only_y (bool, false)"; }
+};
+
 struct SPDParameters { // spd.cpp:161-176
 	uint32 NumberOfBins			= (uint32)PR_CIE_WAVELENGTH_RANGE;
 	int Method					= 2; // 0 none, 1 Y, 2 XYZ, 3 sRGB
@@ -971,6 +1029,7 @@ void registerScenePlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 		out.push_back(std::make_shared<FilterPlugin>(k));
 	out.push_back(std::make_shared<SPDSpectralMapperPlugin>());
 	out.push_back(std::make_shared<RandomSpectralMapperPlugin>());
+	out.push_back(std::make_shared<CIESpectralMapperPlugin>());
 	out.push_back(std::make_shared<IntDirectFactoryFactory>());
 }
 } // namespace PR

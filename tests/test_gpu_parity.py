@@ -127,6 +127,28 @@ def test_stratified_and_uniform_samplers_bit_exact(sampler):
     assert np.array_equal(ctx.download_rng(), ref["rng"])
 
 
+@pytest.mark.parametrize("mapper", ["cie", "cie_y"])
+def test_cie_spectral_mapper_bit_exact(mapper):
+    """spectralmapper/cie.cpp: four independent wavelengths from the CIE X+Y+Z / Y CDF"""
+    src = MATERIAL_ZOO2.replace("(sampler :slot 'aa'", "(spectral_mapper :slot 'pixel' :type '%s') (sampler :slot 'aa'" % mapper)
+    scene = prb.Scene.from_string(src)
+    assert scene.desc.contents.pixel_mapper.type == 3
+    ctx = make_ctx(scene)
+    ora = OracleScene(scene)
+    tiles = [(0, 0, 32, 32)]
+    for it in (0, 9):
+        a, b = ctx.generate_camera_rays(tiles, it), ora.generate_camera_rays(tiles, it)
+        for x, y in zip(a, b):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+        wvl = a[2]
+        assert wvl.min() >= 390.0 and wvl.max() <= 830.0
+    ctx.render_tiles(tiles, 0, 4)
+    xyz, cnt = ctx.film()
+    ref = ora.render(tiles, 0, 4)
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
+
+
 def test_material_unit_calls_vs_oracle():
     """IMaterial::eval / ::sample through prb_material_eval / prb_material_sample for every material of the zoo"""
     scene = prb.Scene.from_string(MATERIAL_ZOO)

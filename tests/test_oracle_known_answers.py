@@ -355,3 +355,31 @@ def test_orennayar_roughness_zero_is_lambert_and_energy_is_bounded():
     assert np.all(acc / n < 1.0) and np.all(acc / n > 0.05)  # directional albedo of the rough lobe stays below one
     below = ora.material_eval(_query(scene, rough, V, [0.3, 0.1, -0.9]))[0]
     assert list(below.weight) == [0.0] * 4 and list(below.pdf_s) == [0.0] * 4
+
+
+# ---------------------------------------------------------------- spectralmapper/cie.cpp
+@pytest.mark.parametrize("mapper,channels", [("cie", (0, 1, 2)), ("cie_y", (1,))])
+def test_cie_mapper_cdf_is_the_static_cdf_of_the_cie_tables(mapper, channels):
+    """the CDF handed to the device is StaticCDF(NM_TO_X + NM_TO_Y + NM_TO_Z) resp. StaticCDF(NM_TO_Y) (CIE.cpp:431-433),
+    and wavelengths drawn from it follow that density"""
+    src = MATERIAL_ZOO2.replace("(sampler :slot 'aa'", "(spectral_mapper :slot 'pixel' :type '%s') (sampler :slot 'aa'" % mapper)
+    scene = prb.Scene.from_string(src)
+    d = scene.desc.contents
+    m = d.pixel_mapper
+    assert (m.type, m.cdf_size, m.trunc_cdf_start, m.trunc_cdf_end) == (3, 442, 0.0, 1.0)
+    pool = np.ctypeslib.as_array(d.pool, shape=(d.n_pool,))
+    cdf = pool[m.cdf_offset:m.cdf_offset + m.cdf_size]
+    h = prb.host_lib()
+    h.prh_cie_eval.restype = C.c_float
+    h.prh_cie_eval.argtypes = [C.c_int, C.c_float]
+    wl = np.arange(390, 831, dtype=np.float32)
+    dens = sum(np.array([h.prh_cie_eval(c, float(w)) for w in wl]) for c in channels)
+    want = np.concatenate([[0.0], np.cumsum(dens)])
+    want /= want[-1]
+    assert cdf[0] == 0 and cdf[-1] == 1 and np.all(np.diff(cdf) >= 0)
+    np.testing.assert_allclose(cdf, want, atol=2e-5)
+    ora = ob.OracleScene(scene)
+    _, _, wvl, _ = ora.generate_camera_rays([(0, 0, 32, 32)], 0)
+    hist, _ = np.histogram(wvl.ravel(), bins=11, range=(390, 830))
+    expect = np.diff(np.interp(np.linspace(0, 1, 12), np.linspace(0, 1, 442), want)) * wvl.size
+    assert np.all(np.abs(hist - expect) < 5 * np.sqrt(expect + 1) + 4)
