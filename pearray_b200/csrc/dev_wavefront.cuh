@@ -138,10 +138,10 @@ __global__ void __launch_bounds__(128) k_init_slots(const __grid_constant__ DSce
 __global__ void __launch_bounds__(128) k_trace_static(DScene S, WFState W)
 {
 	// The traversal is warp-synchronous (lanes without a ray take part with live = false), so idle lanes cost issue
-	// slots: slots retire at different times (a pixel's samples are sequential, short paths finish early -- about a third
-	// of the slots are idle over a Cornell-box render) and not every active slot has a shadow ray.  Each phase therefore
-	// first compacts the block's slots that have a ray of that kind into a list in shared memory and traces the list
-	// with dense warps; warps past the end of the list leave immediately.
+	// slots.  Each phase therefore first compacts the block's slots that have a ray of that kind (not every active slot
+	// has a shadow ray; slots whose pixel ran out of samples have none) into a list in shared memory and traces the list
+	// with dense warps; warps past the end of the list leave immediately.  (Measured on the Cornell box: neutral -- idle
+	// slots there already come in whole warps because neighbouring pixels retire together -- kept for scenes where they do not.)
 	__shared__ uint16_t list[128];
 	__shared__ uint32_t count[2];
 	const uint32_t base = blockIdx.x * blockDim.x;
