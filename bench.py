@@ -215,9 +215,15 @@ def run_ours(args, rank, world, local_rank):
         ev1.synchronize()
         return ev0.elapsed_time(ev1)
 
+    split_ms = [0.0, 0.0]  # render, film reduce (the reduce of a rank that finished early includes waiting for the slowest rank)
+
     def step_resident():
         ctx.render_tiles(tiles, first_iter, spp)  # returns when the wavefront retired every sample
-        return ctx.last_device_ms() + reduce_films()
+        r = ctx.last_device_ms()
+        f = reduce_films()
+        split_ms[0] += r
+        split_ms[1] += f
+        return r + f
 
     def step_e2e():
         t0 = time.perf_counter()
@@ -247,6 +253,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step_resident()
     ctx.reset_stats()
+    split_ms[0] = split_ms[1] = 0.0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -259,6 +266,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
     dev_ms = max_over_ranks(dev_ms)
+    rank_ms = None
+    if world > 1:  # per-rank split of the timed region, for the scaling analysis
+        t = torch.tensor(split_ms, dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [{"render": float(x[0]) / args.steps, "film_reduce": float(x[1]) / args.steps} for x in allt]
     st = ctx.stats()
     launches = int(st.kernel_launches)
     rays_rank = st.ray_count
@@ -333,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
                            "l2": "wavefront state (%d paths x ~250 B) and film are re-written every wavefront iteration; scene is L2-resident by nature" % npix_rank},
                 "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-                "stage_ms": {k: v[0] for k, v in stage.items()} if stage else None}
+                "stage_ms": {k: v[0] for k, v in stage.items()} if stage else None, "rank_ms_per_step": rank_ms}
         emit(line)
     if world > 1:
         dist.barrier()
