@@ -248,7 +248,10 @@ enum {
 	PRB_SAMPLER_MJITT	   = 1,
 	PRB_SAMPLER_SOBOL	   = 2,
 	PRB_SAMPLER_STRATIFIED = 3, /* StratifiedSampler.cpp:12-41: bins_1d = groups, m2d_x = (uint32)sqrt(groups) */
-	PRB_SAMPLER_UNIFORM	   = 4	/* UniformSampler.cpp:11-29: always 0.5 */
+	PRB_SAMPLER_UNIFORM	   = 4, /* UniformSampler.cpp:11-29: always 0.5 */
+	/* HaltonSampler.cpp:14-121 (halton and hammersley): tables like SOBOL at table_offset; past max_samples the radical
+	 * inverse of (index + seed) in base m2d_x (x) / m2d_y (y; 47 for hammersley) is computed on the fly; seed = burn-in */
+	PRB_SAMPLER_HALTON	   = 5
 };
 typedef struct prb_sampler { /* src/plugins/main/sampler/ */
 	uint32_t type;

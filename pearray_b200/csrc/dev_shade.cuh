@@ -880,6 +880,17 @@ PRB_DEV uint32_t mjPermute(uint32_t i, uint32_t l, uint32_t p)
 	} while (!pow2 && i >= l);
 	return pow2 ? ((i + p) & w) : ((i + p) % l);
 }
+PRB_DEV float haltonValue(uint32_t index, uint32_t base)
+{ // HaltonSampler.cpp:14-25
+	float result = 0;
+	float f		 = 1;
+	for (uint32_t i = index; i > 0;) {
+		f = f / (float)base;
+		result += f * (float)(i % base);
+		i = (uint32_t)floorf((float)i / (float)base);
+	}
+	return result;
+}
 PRB_DEV void sampler2D(const DScene& S, const prb_sampler& s, Rng& rnd, uint32_t index, float& x, float& y)
 {
 	switch (s.type) {
@@ -904,6 +915,16 @@ PRB_DEV void sampler2D(const DScene& S, const prb_sampler& s, Rng& rnd, uint32_t
 		y					= (index + jy) / maxS;
 		break;
 	}
+	case PRB_SAMPLER_HALTON: // HaltonSampler.cpp:52-60,100-108
+		if (index < s.max_samples) {
+			const float* t = S.pool + s.table_offset + s.max_samples;
+			x			   = __ldg(t + 2 * index);
+			y			   = __ldg(t + 2 * index + 1);
+		} else {
+			x = haltonValue(index + s.seed, s.m2d_x);
+			y = haltonValue(index + s.seed, s.m2d_y);
+		}
+		break;
 	case PRB_SAMPLER_STRATIFIED: { // StratifiedSampler.cpp:29-36, Projection::stratified
 		const float range = 1.0f / (int)s.m2d_x;
 		const float ux	  = rnd.getFloat();
@@ -927,6 +948,8 @@ PRB_DEV float sampler1D(const DScene& S, const prb_sampler& s, Rng& rnd, uint32_
 		const float j = rnd.getFloat();
 		return (index % s.bins_1d + j) / s.bins_1d;
 	}
+	case PRB_SAMPLER_HALTON:
+		return index < s.max_samples ? __ldg(S.pool + s.table_offset + index) : haltonValue(index + s.seed, s.m2d_x);
 	case PRB_SAMPLER_STRATIFIED: { // StratifiedSampler.cpp:22-26
 		const float range = 1.0f / (int)s.bins_1d;
 		return rnd.getFloat() * range + (int)index * range;

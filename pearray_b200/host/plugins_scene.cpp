@@ -557,7 +557,59 @@ public:
 		out.max_samples = maxSamples();
 	}
 };
-enum class SamplerKind { Random, MJitt, Sobol, Stratified, Uniform };
+inline float haltonValue(uint32 index, uint32 base)
+{ // radical inverse as the reference computes it (fp32), HaltonSampler.cpp:14-25
+	float result = 0;
+	float f		 = 1;
+	for (uint32 i = index; i > 0;) {
+		f = f / base;
+		result += f * (i % base);
+		i = static_cast<uint32>(std::floor(i / static_cast<float>(base)));
+	}
+	return result;
+}
+class HaltonSampler : public ISampler { // HaltonSampler (:30-72) and HammersleySampler (:77-121): y = (0.5 + i) / samples inside the table
+public:
+	HaltonSampler(uint32 samples, uint32 baseX, uint32 baseY, uint32 burnin, bool hammersley)
+		: ISampler(samples)
+		, mX(samples)
+		, mY(samples)
+		, mBaseX(baseX)
+		, mBaseY(hammersley ? 47u /* HAMMERSLEY_EVASIVE_BASE_Y */ : baseY)
+		, mBurnin(burnin)
+	{
+		for (uint32 i = 0; i < samples; ++i) {
+			mX[i] = haltonValue(i + burnin, baseX);
+			mY[i] = hammersley ? (0.5f + i) / samples : haltonValue(i + burnin, baseY);
+		}
+	}
+	float generate1D(Random&, uint32 index) override { return index < maxSamples() ? mX[index] : haltonValue(index + mBurnin, mBaseX); }
+	Vector2f generate2D(Random&, uint32 index) override
+	{
+		if (index < maxSamples())
+			return Vector2f(mX[index], mY[index]);
+		return Vector2f(haltonValue(index + mBurnin, mBaseX), haltonValue(index + mBurnin, mBaseY));
+	}
+	void describe(prb_sampler& out, std::vector<float>& pool) const override
+	{
+		out.type		 = PRB_SAMPLER_HALTON;
+		out.max_samples	 = maxSamples();
+		out.m2d_x		 = mBaseX;
+		out.m2d_y		 = mBaseY;
+		out.seed		 = mBurnin;
+		out.table_offset = (uint32)pool.size();
+		pool.insert(pool.end(), mX.begin(), mX.end());
+		for (uint32 i = 0; i < maxSamples(); ++i) {
+			pool.push_back(mX[i]);
+			pool.push_back(mY[i]);
+		}
+	}
+
+private:
+	std::vector<float> mX, mY;
+	uint32 mBaseX, mBaseY, mBurnin;
+};
+enum class SamplerKind { Random, MJitt, Sobol, Stratified, Uniform, Halton, Hammersley };
 class SamplerFactory : public ISamplerFactory {
 public:
 	SamplerFactory(SamplerKind k, const ParameterGroup& params)
@@ -579,6 +631,14 @@ public:
 		case SamplerKind::Sobol: return std::make_shared<SobolSampler>(rnd, sample_count);
 		case SamplerKind::Stratified: return std::make_shared<StratifiedSampler>(sample_count, (uint32)mParams.getUInt("bins", std::max(1u, sample_count)));
 		case SamplerKind::Uniform: return std::make_shared<UniformSampler>(sample_count);
+		case SamplerKind::Halton: { // HaltonSamplerFactory::createInstance, HaltonSampler.cpp:135-141
+			const uint32 bx = (uint32)mParams.getUInt("base_x", 13), by = (uint32)mParams.getUInt("base_y", 47);
+			return std::make_shared<HaltonSampler>(sample_count, bx, by, (uint32)mParams.getUInt("burnin", std::max(bx, by)), false);
+		}
+		case SamplerKind::Hammersley: { // HammersleySamplerFactory::createInstance, :159-164
+			const uint32 bx = (uint32)mParams.getUInt("base_x", 13);
+			return std::make_shared<HaltonSampler>(sample_count, bx, 47, (uint32)mParams.getUInt("burnin", bx), true);
+		}
 		default: return std::make_shared<RandomSampler>(sample_count);
 		}
 	}
@@ -595,8 +655,8 @@ public:
 	}
 	std::shared_ptr<ISamplerFactory> create(const std::string&, const SceneLoadContext& ctx) override
 	{
-		if (mKind == SamplerKind::Sobol && ctx.environment()->renderSettings().progressive) {
-			PR_LOG(L_WARNING) << "Sobol sampler does not support progressive rendering. Using 'mjitt' instead" << std::endl;
+		if ((mKind == SamplerKind::Sobol || mKind == SamplerKind::Halton || mKind == SamplerKind::Hammersley) && ctx.environment()->renderSettings().progressive) {
+			PR_LOG(L_WARNING) << "Sobol, halton and hammersley samplers do not support progressive rendering. Using 'mjitt' instead" << std::endl;
 			return ctx.loadSamplerFactory("mjitt", ctx.parameters());
 		}
 		return std::make_shared<SamplerFactory>(mKind, ctx.parameters());
@@ -608,11 +668,15 @@ public:
 		static const std::vector<std::string> mj({ "multijittered", "multi_jittered", "jittered", "multijitter", "multi_jitter", "jitter", "mjitt", "jitt" });
 		static const std::vector<std::string> strat({ "stratified" });
 		static const std::vector<std::string> uni({ "uniform" });
+		static const std::vector<std::string> hal({ "halton" });
+		static const std::vector<std::string> ham({ "hammersley" });
 		switch (mKind) {
 		case SamplerKind::Random: return rnd;
 		case SamplerKind::Sobol: return sob;
 		case SamplerKind::Stratified: return strat;
 		case SamplerKind::Uniform: return uni;
+		case SamplerKind::Halton: return hal;
+		case SamplerKind::Hammersley: return ham;
 		default: return mj;
 		}
 	}
@@ -1025,6 +1089,8 @@ void registerScenePlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Random));
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Stratified));
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Uniform));
+	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Halton));
+	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Hammersley));
 	for (FilterProfile k : { FilterProfile::Mitchell, FilterProfile::Triangle, FilterProfile::Gaussian, FilterProfile::Lanczos, FilterProfile::Block })
 		out.push_back(std::make_shared<FilterPlugin>(k));
 	out.push_back(std::make_shared<SPDSpectralMapperPlugin>());

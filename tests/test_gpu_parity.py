@@ -110,14 +110,14 @@ def test_sobol_and_mjitt_camera_rays_bit_exact(name):
             assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
 
 
-@pytest.mark.parametrize("sampler", ["stratified", "uniform"])
+@pytest.mark.parametrize("sampler", ["stratified", "uniform", "halton", "hammersley"])
 def test_stratified_and_uniform_samplers_bit_exact(sampler):
-    """StratifiedSampler.cpp / UniformSampler.cpp: camera rays and a short render against the oracle"""
+    """StratifiedSampler.cpp / UniformSampler.cpp / HaltonSampler.cpp: camera rays and a short render against the oracle"""
     scene = prb.Scene.from_string(ZOO2_WITH_SAMPLER.format(sampler))
     ctx = make_ctx(scene)
     ora = OracleScene(scene)
     tiles = [(0, 0, 32, 32)]
-    for it in (0, 5, 40):  # 40 >= sample_count: indices beyond the strata
+    for it in (0, 5, 40):  # 40 >= sample_count: indices beyond the strata / the precomputed table
         for x, y in zip(ctx.generate_camera_rays(tiles, it), ora.generate_camera_rays(tiles, it)):
             assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
     ctx.render_tiles(tiles, 0, 4)

@@ -383,3 +383,36 @@ def test_cie_mapper_cdf_is_the_static_cdf_of_the_cie_tables(mapper, channels):
     hist, _ = np.histogram(wvl.ravel(), bins=11, range=(390, 830))
     expect = np.diff(np.interp(np.linspace(0, 1, 12), np.linspace(0, 1, 442), want)) * wvl.size
     assert np.all(np.abs(hist - expect) < 5 * np.sqrt(expect + 1) + 4)
+
+
+# ---------------------------------------------------------------- sampler/HaltonSampler.cpp
+def test_halton_and_hammersley_tables_are_radical_inverses():
+    def table(kind, extra):
+        src = MATERIAL_ZOO2.replace("(sampler :slot 'aa' :type 'mjitt' :sample_count 16)", "(sampler :slot 'aa' :type '%s' :sample_count 8 %s)" % (kind, extra))
+        scene = prb.Scene.from_string(src)
+        d = scene.desc.contents
+        s = d.aa_sampler
+        pool = np.ctypeslib.as_array(d.pool, shape=(d.n_pool,))
+        one = pool[s.table_offset:s.table_offset + s.max_samples].copy()
+        two = pool[s.table_offset + s.max_samples:s.table_offset + 3 * s.max_samples].reshape(-1, 2).copy()
+        return s, one, two
+
+    def radical_inverse(i, b):
+        r, f = 0.0, 1.0
+        while i > 0:
+            f /= b
+            r += f * (i % b)
+            i //= b
+        return r
+    s, one, two = table("halton", ":base_x 2 :base_y 3 :burnin 0")
+    assert (s.type, s.max_samples, s.m2d_x, s.m2d_y, s.seed) == (5, 8, 2, 3, 0)
+    assert np.allclose(one, [0, .5, .25, .75, .125, .625, .375, .875], atol=1e-7)
+    assert np.array_equal(two[:, 0], one)
+    assert np.allclose(two[:, 1], [radical_inverse(i, 3) for i in range(8)], atol=1e-6)
+    s, one, two = table("halton", "")  # defaults: bases 13 / 47, burn-in max(13, 47)
+    assert (s.m2d_x, s.m2d_y, s.seed) == (13, 47, 47)
+    assert np.allclose(two[:, 0], [radical_inverse(i + 47, 13) for i in range(8)], atol=1e-6)
+    s, one, two = table("hammersley", ":base_x 2")
+    assert (s.m2d_x, s.m2d_y, s.seed) == (2, 47, 2)  # burn-in defaults to base_x; base 47 only past the table
+    assert np.allclose(two[:, 1], (0.5 + np.arange(8)) / 8, atol=1e-7)
+    assert np.allclose(two[:, 0], [radical_inverse(i + 2, 2) for i in range(8)], atol=1e-7)
