@@ -92,7 +92,11 @@ enum {
 	PRB_MAT_ROUGHDIELECTRIC = 4, /* roughdielectric.cpp:42-279 nodes as DIELECTRIC, f[0],f[1] roughness */
 	PRB_MAT_PRINCIPLED		= 5, /* principled.cpp:34-631   node[0]=base node[1]=ior, f[] see PRB_PR_* */
 	PRB_MAT_MIRROR			= 6, /* mirror.cpp:14-65        node[0]=specularity (only-delta) */
-	PRB_MAT_ORENNAYAR		= 7	 /* orennayar.cpp:16-86     node[0]=albedo, f[0]=roughness (scalar, squared on use) */
+	PRB_MAT_ORENNAYAR		= 7, /* orennayar.cpp:16-86     node[0]=albedo, f[0]=roughness (scalar, squared on use) */
+	/* blend.cpp:20-148 / add.cpp:20-122: node[0], node[1] = MATERIAL ids of the two children (leaf materials only, no nesting
+	 * on the device path), f[0] = blend factor; PRB_MATF_CHILD0_DELTA / CHILD1_DELTA give the MaterialDelta variant */
+	PRB_MAT_BLEND = 8,
+	PRB_MAT_ADD	  = 9
 };
 #define PRB_MATF_TWO_SIDED 0x001u		  /* lambert two_sided (default true) */
 #define PRB_MATF_THIN 0x002u			  /* dielectric / principled 'thin' */
@@ -102,6 +106,8 @@ enum {
 #define PRB_MATF_ONLY_DELTA 0x020u		  /* IMaterial::hasOnlyDeltaDistribution() */
 #define PRB_MATF_SPECTRAL_VARYING 0x040u  /* mNodeContribFlags & SpectralVarying (hero collapse when delta) */
 #define PRB_MATF_HAS_TRANSMISSION 0x080u  /* principled: diffuse_/specular_transmission present */
+#define PRB_MATF_CHILD0_DELTA 0x100u	  /* blend / add: material1 has only delta distributions */
+#define PRB_MATF_CHILD1_DELTA 0x200u	  /* blend / add: material2 has only delta distributions */
 
 /* principled scalar slots (principled.cpp:50-62) */
 enum {

@@ -906,7 +906,7 @@ Blob orenNayarCalc(const Scene& sc, const prb_material& m, const MatCtx& c, V3 L
 	return weight;
 }
 
-void materialEval(const Scene& sc, uint32_t matID, const MatCtx& c, MatEval& out)
+void materialEvalLeaf(const Scene& sc, uint32_t matID, const MatCtx& c, MatEval& out)
 {
 	const prb_material& m = sc.d->materials[matID];
 	out.flags			  = 0;
@@ -999,7 +999,7 @@ void materialEval(const Scene& sc, uint32_t matID, const MatCtx& c, MatEval& out
 	}
 }
 
-void materialSample(const Scene& sc, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
+void materialSampleLeaf(const Scene& sc, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
 {
 	const prb_material& m = sc.d->materials[matID];
 	out.flags			  = 0;
@@ -1154,6 +1154,62 @@ void materialSample(const Scene& sc, uint32_t matID, const MatCtx& c, Rng& rnd, 
 		break;
 	}
 	}
+}
+
+// blend.cpp:20-148 / add.cpp:20-122 over two LEAF materials (node[0], node[1] hold their ids); everything else is a leaf
+inline bool isCombination(const prb_material& m) { return m.type == PRB_MAT_BLEND || m.type == PRB_MAT_ADD; }
+void materialEval(const Scene& sc, uint32_t matID, const MatCtx& c, MatEval& out)
+{
+	const prb_material& m = sc.d->materials[matID];
+	if (!isCombination(m)) {
+		materialEvalLeaf(sc, matID, c, out);
+		return;
+	}
+	const bool add = m.type == PRB_MAT_ADD;
+	const bool d0 = m.flags & PRB_MATF_CHILD0_DELTA, d1 = m.flags & PRB_MATF_CHILD1_DELTA;
+	const float prob = std::min(1.0f, std::max(0.0f, m.f[0]));
+	if (d0 && d1) { // MaterialDelta::All: never evaluated by the integrator
+		out.pdf	   = blob(0);
+		out.weight = blob(0);
+		out.type   = 3;
+		out.flags  = 0;
+	} else if (d0 || d1) { // the non-delta child alone, scaled by its share
+		materialEvalLeaf(sc, m.node[d0 ? 1 : 0], c, out);
+		const float share = add ? 0.5f : (d0 ? prob : 1 - prob);
+		out.pdf			  = out.pdf * share;
+		if (!add)
+			out.weight = out.weight * share;
+	} else {
+		MatEval o1, o2;
+		materialEvalLeaf(sc, m.node[0], c, o1);
+		materialEvalLeaf(sc, m.node[1], c, o2);
+		out.flags = 0;
+		if (add) {
+			out.pdf	   = (o1.pdf + o2.pdf) / 2.0f;
+			out.weight = o1.weight + o2.weight;
+			out.type   = o1.type;
+		} else {
+			out.pdf	   = o1.pdf * (1 - prob) + o2.pdf * prob;
+			out.weight = o1.weight * (1 - prob) + o2.weight * prob;
+			out.type   = prob <= 0.5f ? o1.type : o2.type;
+		}
+	}
+}
+void materialSample(const Scene& sc, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
+{
+	const prb_material& m = sc.d->materials[matID];
+	if (!isCombination(m)) {
+		materialSampleLeaf(sc, matID, c, rnd, out);
+		return;
+	}
+	const bool add	 = m.type == PRB_MAT_ADD;
+	const float prob = add ? 0.5f : std::min(1.0f, std::max(0.0f, m.f[0]));
+	const bool first = rnd.getFloat() < (add ? 0.5f : 1 - prob);
+	materialSampleLeaf(sc, m.node[first ? 0 : 1], c, rnd, out);
+	const float share = add ? 0.5f : (first ? 1 - prob : prob);
+	if (!add)
+		out.weight = out.weight * share;
+	out.pdf = out.pdf * share;
 }
 
 // ------------------------------------------------------------------ samplers / mapper / camera

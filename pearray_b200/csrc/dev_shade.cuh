@@ -586,7 +586,7 @@ PRB_DEV Blob orenNayarCalc(const DScene& S, const prb_material& m, const MatCtx&
 	return weight;
 }
 
-__device__ __noinline__ void materialEval(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
+__device__ __noinline__ void materialEvalLeaf(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
 {
 	const prb_material m = S.materials[matID];
 	out.flags			 = 0;
@@ -684,7 +684,7 @@ __device__ __noinline__ void materialEval(const DScene& S, uint32_t matID, const
 	}
 }
 
-__device__ __noinline__ void materialSample(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
+__device__ __noinline__ void materialSampleLeaf(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
 {
 	const prb_material m = S.materials[matID];
 	out.flags			 = 0;
@@ -842,6 +842,72 @@ __device__ __noinline__ void materialSample(const DScene& S, uint32_t matID, con
 	}
 	default: rejectSample(out, 0, 0); break;
 	}
+}
+
+// blend.cpp:20-148 / add.cpp:20-122 over two LEAF materials (node[0], node[1] hold their ids); everything else is a leaf.
+// No recursion: the host rejects nested combinations, so the device stack stays statically sized.
+PRB_DEV bool isCombination(uint32_t type) { return type == PRB_MAT_BLEND || type == PRB_MAT_ADD; }
+__device__ __noinline__ void materialEvalCombined(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
+{ // out of line: its two child results only occupy stack while a combination is evaluated
+	const prb_material& m = S.materials[matID];
+	const uint32_t type	  = m.type;
+	const bool add		  = type == PRB_MAT_ADD;
+	const bool d0 = m.flags & PRB_MATF_CHILD0_DELTA, d1 = m.flags & PRB_MATF_CHILD1_DELTA;
+	const float prob = fminf(1.0f, fmaxf(0.0f, m.f[0]));
+	if (d0 && d1) { // MaterialDelta::All: never evaluated by the integrator
+		out.pdf	   = blob(0);
+		out.weight = blob(0);
+		out.type   = 3;
+		out.flags  = 0;
+	} else if (d0 || d1) { // the non-delta child alone, scaled by its share
+		materialEvalLeaf(S, m.node[d0 ? 1 : 0], c, out);
+		const float share = add ? 0.5f : (d0 ? prob : 1 - prob);
+		out.pdf			  = out.pdf * share;
+		if (!add)
+			out.weight = out.weight * share;
+	} else {
+		MatEval o1, o2;
+		materialEvalLeaf(S, m.node[0], c, o1);
+		materialEvalLeaf(S, m.node[1], c, o2);
+		out.flags = 0;
+		if (add) {
+			out.pdf	   = (o1.pdf + o2.pdf) * 0.5f; // (a + b) / 2
+			out.weight = o1.weight + o2.weight;
+			out.type   = o1.type;
+		} else {
+			out.pdf	   = o1.pdf * (1 - prob) + o2.pdf * prob;
+			out.weight = o1.weight * (1 - prob) + o2.weight * prob;
+			out.type   = prob <= 0.5f ? o1.type : o2.type;
+		}
+	}
+}
+PRB_DEV void materialEval(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
+{
+	if (isCombination(S.materials[matID].type))
+		materialEvalCombined(S, matID, c, out);
+	else
+		materialEvalLeaf(S, matID, c, out);
+}
+__device__ __noinline__ void materialSampleCombined(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
+{
+	const prb_material& m = S.materials[matID];
+	const uint32_t type	  = m.type;
+	const bool add		  = type == PRB_MAT_ADD;
+	const float prob	  = add ? 0.5f : fminf(1.0f, fmaxf(0.0f, m.f[0]));
+	const bool first	  = rnd.getFloat() < (add ? 0.5f : 1 - prob);
+	materialSampleLeaf(S, m.node[first ? 0 : 1], c, rnd, out);
+	const float share = add ? 0.5f : (first ? 1 - prob : prob);
+	if (!add)
+		out.weight = out.weight * share;
+	out.pdf = out.pdf * share;
+}
+
+PRB_DEV void materialSample(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
+{
+	if (isCombination(S.materials[matID].type))
+		materialSampleCombined(S, matID, c, rnd, out);
+	else
+		materialSampleLeaf(S, matID, c, rnd, out);
 }
 
 // ------------------------------------------------------------------ samplers / mapper / camera

@@ -424,6 +424,71 @@ public:
 	}
 	std::string specification(const std::string&) const override { return "OrenNayar BSDF: albedo (spectral, 1), roughness (scalar, 0.5)"; }
 };
+class CombineMaterial : public IMaterial { // blend.cpp:20-148 (BlendMaterial<Delta>) and add.cpp:20-122 (AddMaterial<Delta>)
+public:
+	CombineMaterial(bool add, const std::shared_ptr<IMaterial>& m0, const std::shared_ptr<IMaterial>& m1, float factor)
+		: mAdd(add)
+		, mMaterials{ m0, m1 }
+		, mFactor(factor)
+	{
+	}
+	bool hasOnlyDeltaDistribution() const override { return mMaterials[0]->hasOnlyDeltaDistribution() && mMaterials[1]->hasOnlyDeltaDistribution(); }
+	void describe(prb_material& out, NodeEmitter&) const override
+	{
+		out.type	= mAdd ? PRB_MAT_ADD : PRB_MAT_BLEND;
+		out.flags	= (mMaterials[0]->hasOnlyDeltaDistribution() ? PRB_MATF_CHILD0_DELTA : 0) | (mMaterials[1]->hasOnlyDeltaDistribution() ? PRB_MATF_CHILD1_DELTA : 0)
+					| (hasOnlyDeltaDistribution() ? PRB_MATF_ONLY_DELTA : 0);
+		out.node[0] = mMaterials[0]->id();
+		out.node[1] = mMaterials[1]->id();
+		out.f[0]	= mFactor;
+	}
+	std::string dumpInformation() const override
+	{
+		return std::string(mAdd ? "  <AddMaterial>:\n" : "  <BlendMaterial>:\n") + "    [0]: " + mMaterials[0]->dumpInformation() + "    [1]: " + mMaterials[1]->dumpInformation();
+	}
+
+private:
+	bool mAdd;
+	std::shared_ptr<IMaterial> mMaterials[2];
+	float mFactor;
+};
+class CombineMaterialPlugin : public IMaterialPlugin {
+public:
+	explicit CombineMaterialPlugin(bool add)
+		: mAdd(add)
+	{
+	}
+	std::shared_ptr<IMaterial> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		const ParameterGroup& params = ctx.parameters();
+		const uint32 id1 = ctx.lookupMaterialID(params.getParameter("material1")), id2 = ctx.lookupMaterialID(params.getParameter("material2"));
+		const auto& db	 = ctx.environment()->sceneDatabase()->Materials;
+		const auto mat1 = id1 != PR_INVALID_ID ? db.getSafe(id1) : nullptr, mat2 = id2 != PR_INVALID_ID ? db.getSafe(id2) : nullptr;
+		if (!mat1 || !mat2) {
+			PR_LOG(L_ERROR) << "Valid material1 or material2 parameters for blend material missing" << std::endl;
+			return nullptr;
+		}
+		if (std::dynamic_pointer_cast<CombineMaterial>(mat1) || std::dynamic_pointer_cast<CombineMaterial>(mat2)) {
+			PR_LOG(L_ERROR) << "blend / add of a blend / add material is not supported on the device path (no nested material evaluation)" << std::endl;
+			return nullptr;
+		}
+		const float factor = mAdd ? 0.5f : constScalar(ctx.lookupScalarNode("factor", 0.5f), "factor");
+		return std::make_shared<CombineMaterial>(mAdd, mat1, mat2, factor);
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> blend({ "blend", "mix" });
+		static const std::vector<std::string> add({ "add" });
+		return mAdd ? add : blend;
+	}
+	std::string specification(const std::string&) const override
+	{
+		return mAdd ? "Add BSDF: material1, material2 (material references)" : "Blend BSDF: material1, material2 (material references), factor (scalar, 0.5)";
+	}
+
+private:
+	bool mAdd;
+};
 } // namespace
 
 void registerMaterialPlugins(std::vector<std::shared_ptr<IPlugin>>& out)
@@ -436,5 +501,7 @@ void registerMaterialPlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 	out.push_back(std::make_shared<PrincipledMaterialPlugin>());
 	out.push_back(std::make_shared<MirrorMaterialPlugin>());
 	out.push_back(std::make_shared<OrenNayarMaterialPlugin>());
+	out.push_back(std::make_shared<CombineMaterialPlugin>(false));
+	out.push_back(std::make_shared<CombineMaterialPlugin>(true));
 }
 } // namespace PR

@@ -97,3 +97,34 @@ MATERIAL_ZOO2 = """
  (light :type 'env' :radiance (illuminant "D65"))
 )
 """
+
+# blend.cpp / add.cpp (SURVEY 8(f)-3): every MaterialDelta variant -- None, First, Second, All -- over leaf materials
+MATERIAL_ZOO3 = """
+(scene :name 'zoo3' :render_width 32 :render_height 32 :camera 'Camera'
+ (integrator :type 'direct' :max_ray_depth 8)
+ (sampler :slot 'aa' :type 'mjitt' :sample_count 16)
+ (camera :name 'Camera' :type 'standard' :width 1 :height 1 :local_direction [0,0,-1] :local_up [0,1,0] :local_right [1,0,0]
+   :near 0.1 :far 100 :transform [1,0,0,0, 0,1,0,0, 0,0,1,4, 0,0,0,1])
+ (emission :name 'em' :type 'standard' :radiance (illuminant "D65"))
+ (material :name 'm_diffuse' :type 'diffuse' :albedo (refl 0.8 0.4 0.2))
+ (material :name 'm_metal' :type 'roughconductor' :eta 0.2 :k 3.0 :roughness 0.2)
+ (material :name 'm_mirror' :type 'mirror' :specularity (refl 0.9 0.9 0.8))
+ (material :name 'm_glass' :type 'glass' :index 1.55)
+ (material :name 'm_oren' :type 'orennayar' :albedo (refl 0.3 0.6 0.4) :roughness 0.6)
+ (material :name 'b_none' :type 'blend' :material1 'm_diffuse' :material2 'm_metal' :factor 0.3)
+ (material :name 'b_first' :type 'mix' :material1 'm_mirror' :material2 'm_diffuse' :factor 0.6)
+ (material :name 'b_second' :type 'blend' :material1 'm_oren' :material2 'm_glass' :factor 0.4)
+ (material :name 'b_all' :type 'blend' :material1 'm_mirror' :material2 'm_glass')
+ (material :name 'a_none' :type 'add' :material1 'm_diffuse' :material2 'm_metal')
+ (material :name 'a_first' :type 'add' :material1 'm_mirror' :material2 'm_oren')
+ (entity :name 'floor' :type 'plane' :centering true :width 4 :height 4 :material 'm_diffuse' :position [0,0,-1])
+ (entity :name 's0' :type 'sphere' :radius 0.4 :material 'b_none' :position [-1.0,0.7,0])
+ (entity :name 's1' :type 'sphere' :radius 0.4 :material 'b_first' :position [0,0.7,0])
+ (entity :name 's2' :type 'sphere' :radius 0.4 :material 'b_second' :position [1.0,0.7,0])
+ (entity :name 's3' :type 'sphere' :radius 0.4 :material 'b_all' :position [-1.0,-0.5,0])
+ (entity :name 's4' :type 'sphere' :radius 0.4 :material 'a_none' :position [0,-0.5,0])
+ (entity :name 's5' :type 'sphere' :radius 0.4 :material 'a_first' :position [1.0,-0.5,0])
+ (entity :name 'lamp' :type 'plane' :centering true :width 1 :height 1 :material 'm_diffuse' :emission 'em' :transform [1,0,0,0, 0,-1,0,0, 0,0,-1,3, 0,0,0,1])
+ (light :type 'env' :radiance (illuminant "D65"))
+)
+"""

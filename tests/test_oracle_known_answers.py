@@ -416,3 +416,64 @@ def test_halton_and_hammersley_tables_are_radical_inverses():
     assert (s.m2d_x, s.m2d_y, s.seed) == (2, 47, 2)  # burn-in defaults to base_x; base 47 only past the table
     assert np.allclose(two[:, 1], (0.5 + np.arange(8)) / 8, atol=1e-7)
     assert np.allclose(two[:, 0], [radical_inverse(i + 2, 2) for i in range(8)], atol=1e-7)
+
+
+# ---------------------------------------------------------------- materials/blend.cpp, add.cpp
+def test_blend_and_add_follow_their_children():
+    from scene_strings import MATERIAL_ZOO3
+    scene = prb.Scene.from_string(MATERIAL_ZOO3)
+    ora = ob.OracleScene(scene)
+    d = scene.desc.contents
+    mats = {}
+    for i in range(d.n_materials):
+        mats.setdefault((d.materials[i].type, d.materials[i].flags & 0x300), []).append(i)
+    V, L = nrm(0.3, 0.2, 0.9), nrm(-0.4, 0.1, 0.8)
+    ev = lambda m: ora.material_eval(_query(scene, m, V, L))[0]
+    arr = lambda x: np.array(list(x), np.float32)
+    # blend, no delta child: (1 - f) * m0 + f * m1 for weight and pdf (blend.cpp:66-76)
+    b = mats[(8, 0)][0]
+    m0, m1, f = d.materials[b].node[0], d.materials[b].node[1], np.float32(d.materials[b].f[0])
+    e, e0, e1 = ev(b), ev(m0), ev(m1)
+    assert np.array_equal(arr(e.weight), (1 - f) * arr(e0.weight) + f * arr(e1.weight))
+    assert np.array_equal(arr(e.pdf_s), (1 - f) * arr(e0.pdf_s) + f * arr(e1.pdf_s))
+    # blend, first child delta: the second child scaled by f (blend.cpp:53-58); second child delta: the first by 1 - f
+    b = mats[(8, 0x100)][0]
+    f = np.float32(d.materials[b].f[0])
+    e, e1 = ev(b), ev(d.materials[b].node[1])
+    assert np.array_equal(arr(e.weight), arr(e1.weight) * f) and np.array_equal(arr(e.pdf_s), arr(e1.pdf_s) * f)
+    b = mats[(8, 0x200)][0]
+    f = np.float32(d.materials[b].f[0])
+    e, e0 = ev(b), ev(d.materials[b].node[0])
+    assert np.array_equal(arr(e.weight), arr(e0.weight) * (1 - f)) and np.array_equal(arr(e.pdf_s), arr(e0.pdf_s) * (1 - f))
+    # both delta: only-delta material, its samples are delta
+    b = mats[(8, 0x300)][0]
+    assert d.materials[b].flags & 0x20
+    assert ora.material_sample(_query(scene, b, V))[0].flags & 0x2
+    # add: weights add, pdfs average (add.cpp:53-62); with a delta child the other one with half the pdf (:47-52)
+    a = mats[(9, 0)][0]
+    e, e0, e1 = ev(a), ev(d.materials[a].node[0]), ev(d.materials[a].node[1])
+    assert np.array_equal(arr(e.weight), arr(e0.weight) + arr(e1.weight))
+    assert np.array_equal(arr(e.pdf_s), (arr(e0.pdf_s) + arr(e1.pdf_s)) / 2)
+    a = mats[(9, 0x100)][0]
+    e, e1 = ev(a), ev(d.materials[a].node[1])
+    assert np.array_equal(arr(e.weight), arr(e1.weight)) and np.array_equal(arr(e.pdf_s), arr(e1.pdf_s) * np.float32(0.5))
+    # sampling draws one number to pick a child, samples it with the following numbers and scales by its share (blend.cpp:106-122)
+    h = prb.host_lib()
+    h.prh_random_advance.restype = C.c_uint64
+    h.prh_random_advance.argtypes = [C.c_uint64, C.c_uint64]
+    b = mats[(8, 0)][0]
+    f = np.float32(d.materials[b].f[0])
+    picked = []
+    for seed in [(0x9E3779B97F4A7C15 * k) & 0xFFFFFFFFFFFFFFFF for k in range(1, 41)]:  # well mixed states (an MCG outputs ~0 for tiny ones)
+        s = ora.material_sample(_query(scene, b, V, seed=seed))[0]
+        matches = []
+        for k, share in ((0, 1 - f), (1, f)):
+            q = _query(scene, d.materials[b].node[k], V, seed=seed)
+            q[0].rng_state = h.prh_random_advance(seed | 3, 1)
+            c = ora.material_sample(q)[0]
+            if np.array_equal(arr(s.L), arr(c.L)) and np.array_equal(arr(s.weight), arr(c.weight) * share) and np.array_equal(arr(s.pdf_s), arr(c.pdf_s) * share):
+                matches.append(k)
+        assert len(matches) == 1, (seed, matches)
+        picked.append(matches[0])
+    assert 0 < sum(picked) < len(picked)  # both children get picked; f = 0.3 -> mostly the first
+    assert sum(picked) < len(picked) / 2

@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pearray_b200 as prb  # noqa: E402
 from oracle_binding import OracleScene  # noqa: E402
-from scene_strings import MATERIAL_ZOO, MATERIAL_ZOO2, SKYSUN_ZOO  # noqa: E402
+from scene_strings import MATERIAL_ZOO, MATERIAL_ZOO2, MATERIAL_ZOO3, SKYSUN_ZOO  # noqa: E402
 
 GOLDEN_ITER = 4
 GOLDEN_TILE = 48
@@ -105,3 +105,4 @@ if __name__ == "__main__":
     make("material_zoo", prb.Scene.from_string(MATERIAL_ZOO))
     make("skysun_zoo", prb.Scene.from_string(SKYSUN_ZOO))
     make("material_zoo2", prb.Scene.from_string(MATERIAL_ZOO2))
+    make("material_zoo3", prb.Scene.from_string(MATERIAL_ZOO3))
