@@ -40,6 +40,7 @@ struct DScene { // device pointers + by-value small structs; passed to kernels b
 	const float* rrProb; // RussianRoulette::probability(len) table
 	uint32_t nMaterials, nEmissions, nEntities, nLights, nMeshes, tlasRoot, cieOffset, rrCount;
 	uint32_t hasInfLight;
+	uint32_t hasCombined; // any blend / add material in the scene (keeps the check off the path of scenes without them)
 };
 
 struct HitRec {

@@ -294,6 +294,10 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	for (uint32_t i = 1; i < d->n_materials; ++i)
 		if (d->materials[i].type != d->materials[0].type)
 			c->mixedMaterials = true;
+	S.hasCombined	  = 0;
+	for (uint32_t i = 0; i < d->n_materials; ++i)
+		if (d->materials[i].type == PRB_MAT_BLEND || d->materials[i].type == PRB_MAT_ADD)
+			S.hasCombined = 1;
 	S.hasInfLight	  = 0;
 	for (uint32_t i = 0; i < d->n_lights; ++i)
 		if (d->lights[i].type != PRB_LIGHT_AREA)
@@ -388,14 +392,19 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 // fewer blocks, so rounds is chosen such that the grid still holds >= 4 blocks per resident block slot
 static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
 {
-	if (!c->mixedMaterials) {
-		k_shade<SHADE_BLOCK_UNIFORM, 1><<<(int)((c->nSlots + SHADE_BLOCK_UNIFORM - 1) / SHADE_BLOCK_UNIFORM), SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
+	const bool combined = c->S.hasCombined != 0; // a scene with blend / add materials always mixes material types
+	if (!c->mixedMaterials && !combined) {
+		k_shade<SHADE_BLOCK_UNIFORM, 1, false><<<(int)((c->nSlots + SHADE_BLOCK_UNIFORM - 1) / SHADE_BLOCK_UNIFORM), SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
 		return;
 	}
 	const size_t perRound = (size_t)512 * c->smCount * 4;
 	const int rounds	  = (int)std::max<size_t>(1, std::min<size_t>(SHADE_ROUNDS_MIXED, c->nSlots / perRound));
 	const size_t window	  = (size_t)rounds * SHADE_BLOCK_MIXED;
-	k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED><<<(int)((c->nSlots + window - 1) / window), SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
+	const int grid		  = (int)((c->nSlots + window - 1) / window);
+	if (combined)
+		k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED, true><<<grid, SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
+	else
+		k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED, false><<<grid, SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
 }
 static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s)
 {
