@@ -11,4 +11,8 @@ timeout 500 ncu --set full --clock-control none --import-source on -k regex:k_tr
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_shade|k_trace" -s 60 -c 2 -o gpurun_out/r01_c2_final -f python bench.py --scene c2 --no-cpu --steps 1 --warmup 1 --spp 16 > gpurun_out/ncu_c2.log 2>&1
 timeout 400 python bench.py > gpurun_out/bench_c2_final.json 2> gpurun_out/bench_c2_final.err; cat gpurun_out/bench_c2_final.json | cut -c1-300
 timeout 300 python bench.py --scene c5 --no-cpu > gpurun_out/bench_c5_final.json 2>/dev/null; cat gpurun_out/bench_c5_final.json | cut -c1-200
-for sc in c1 c3 c4 c4c; do timeout 900 python bench.py --scene $sc --no-cpu --steps 1 --warmup 1 > gpurun_out/bench_${sc}_final.json 2>/dev/null; python -c "import json; d=json.load(open('gpurun_out/bench_${sc}_final.json')); print('$sc', round(d['value']/1e6,1), round(d['e2e']['value']/1e6,1), d['stage_ms'])"; done
+for sc in "c1 0" "c3 0" "c4 0" "c4c 512"; do set -- $sc  # complex.prc: 512 of its 4096 spp (a full render is 140 s, the bench runs four)
+  if [ "$2" = 0 ]; then spp=""; else spp="--spp $2"; fi
+  timeout 900 python bench.py --scene $1 --no-cpu --steps 1 --warmup 1 $spp > gpurun_out/bench_$1_final.json 2>/dev/null
+  python -c "import json; d=json.load(open('gpurun_out/bench_$1_final.json')); print('$1', round(d['value']/1e6,1), round(d['e2e']['value']/1e6,1), d['stage_ms'])"
+done
