@@ -273,7 +273,11 @@ enum {
 	PRB_MAPPER_RANDOM	= 0,
 	PRB_MAPPER_SPD_CMIS = 1,
 	PRB_MAPPER_SPD_HERO = 2,
-	PRB_MAPPER_CIE		= 3 /* cie.cpp:13-83: four independent samples of the CIE Y or X+Y+Z CDF, truncated to the camera range */
+	PRB_MAPPER_CIE		= 3, /* cie.cpp:13-83: four independent samples of the CIE Y or X+Y+Z CDF, truncated to the camera range */
+	/* agh.cpp:14-121 ("An Improved Technique for Full Spectral Rendering"): lambda = B - atanh(C - N u) / A with A = 0.0072,
+	 * B = 538; trunc_cdf_start holds C = tanh(A (B - start)), trunc_cdf_end holds N = C - tanh(A (B - end)) */
+	PRB_MAPPER_AGH_CMIS = 4, /* four independent samples */
+	PRB_MAPPER_AGH_HERO = 5	 /* one sample + hero rotation (Standard.h:8-21) */
 };
 typedef struct prb_spectral_mapper { /* src/plugins/main/spectralmapper/spd.cpp, random.cpp, cie.cpp */
 	uint32_t type;

@@ -1416,6 +1416,25 @@ void constructCameraRay(const Scene& sc, uint32_t px, uint32_t py, uint32_t iter
 				o.wvlPDF[i] = pdf;
 			}
 			break;
+		case PRB_MAPPER_AGH_CMIS: // agh.cpp:49-57: aghSample / aghPDF per wavelength
+			for (int i = 0; i < 4; ++i) {
+				const float C = d.pixel_mapper.trunc_cdf_start, N = d.pixel_mapper.trunc_cdf_end;
+				o.wvl[i]	  = 538.0f - cr_atanh(C - N * rnd.getFloat()) / 0.0072f;
+				const float K = cr_cosh(0.0072f * (o.wvl[i] - 538.0f));
+				o.wvlPDF[i]	  = 1 / (K * K * N);
+			}
+			break;
+		case PRB_MAPPER_AGH_HERO: { // agh.cpp:98-103 + Standard.h:8-21
+			const float C = d.pixel_mapper.trunc_cdf_start, N = d.pixel_mapper.trunc_cdf_end;
+			const float hero = 538.0f - cr_atanh(C - N * rnd.getFloat()) / 0.0072f;
+			const float K	 = cr_cosh(0.0072f * (hero - 538.0f));
+			const float span = end - start, delta = span / 4, s = hero - start;
+			o.wvl[0] = hero;
+			for (int i = 1; i < 4; ++i)
+				o.wvl[i] = start + std::fmod(s + i * delta, span);
+			o.wvlPDF = blob(1 / (K * K * N));
+			break;
+		}
 		case PRB_MAPPER_SPD_HERO: { // spd.cpp:104-112
 			float pdf;
 			const float u	 = rnd.getFloat();

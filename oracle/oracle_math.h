@@ -96,6 +96,8 @@ inline V3 makePositiveHemisphere(V3 a) { return isPositiveHemisphere(a) ? a : -a
 inline float cr_sin(float x) { return (float)std::sin((double)x); }
 inline float cr_cos(float x) { return (float)std::cos((double)x); }
 inline float cr_tan(float x) { return (float)std::tan((double)x); }
+inline float cr_atanh(float x) { return (float)std::atanh((double)x); }
+inline float cr_cosh(float x) { return (float)std::cosh((double)x); }
 inline float cr_atan(float x) { return (float)std::atan((double)x); }
 inline float cr_atan2(float y, float x) { return (float)std::atan2((double)y, (double)x); }
 inline float cr_acos(float x) { return (float)std::acos((double)x); }

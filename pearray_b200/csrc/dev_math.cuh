@@ -114,6 +114,8 @@ PRB_DEV void cr_sincos(float x, float* s, float* c)
 PRB_DEV float cr_sin(float x) { return (float)sin((double)x); }
 PRB_DEV float cr_cos(float x) { return (float)cos((double)x); }
 PRB_DEV float cr_tan(float x) { return (float)tan((double)x); }
+PRB_DEV float cr_atanh(float x) { return (float)atanh((double)x); }
+PRB_DEV float cr_cosh(float x) { return (float)cosh((double)x); }
 PRB_DEV float cr_atan(float x) { return (float)atan((double)x); }
 PRB_DEV float cr_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
 PRB_DEV float cr_acos(float x) { return (float)acos((double)x); }

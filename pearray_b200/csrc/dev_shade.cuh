@@ -1095,6 +1095,27 @@ __device__ __noinline__ void constructCameraRay(const DScene& S, uint32_t px, ui
 				o.wvlPDF[i] = pdf;
 			}
 			break;
+		case PRB_MAPPER_AGH_CMIS: // agh.cpp:49-57: aghSample / aghPDF per wavelength
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const float C = S.mapper.trunc_cdf_start, N = S.mapper.trunc_cdf_end;
+				o.wvl[i]	  = 538.0f - fdiv(cr_atanh(C - N * rnd.getFloat()), 0.0072f);
+				const float K = cr_cosh(0.0072f * (o.wvl[i] - 538.0f));
+				o.wvlPDF[i]	  = 1 / (K * K * N);
+			}
+			break;
+		case PRB_MAPPER_AGH_HERO: { // agh.cpp:98-103 + Standard.h:8-21
+			const float C = S.mapper.trunc_cdf_start, N = S.mapper.trunc_cdf_end;
+			const float hero = 538.0f - fdiv(cr_atanh(C - N * rnd.getFloat()), 0.0072f);
+			const float K	 = cr_cosh(0.0072f * (hero - 538.0f));
+			const float span = end - start, delta = span / 4, s = hero - start;
+			o.wvl[0] = hero;
+#pragma unroll
+			for (int i = 1; i < 4; ++i)
+				o.wvl[i] = start + fmodf(s + i * delta, span);
+			o.wvlPDF = blob(1 / (K * K * N));
+			break;
+		}
 		case PRB_MAPPER_SPD_HERO: { // spd.cpp:104-112 + Standard.h:8-21
 			float pdf;
 			const float u	 = rnd.getFloat();

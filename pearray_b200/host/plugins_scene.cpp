@@ -883,6 +883,38 @@ public:
 	std::string specification(const std::string&) const override { return "CIE Spectral Mapper: only_y (bool, false)"; }
 };
 
+class AGHSpectralMapperFactory : public ISpectralMapperFactory { // spectralmapper/agh.cpp:14-155
+public:
+	explicit AGHSpectralMapperFactory(bool cmis)
+		: mCMIS(cmis)
+	{
+	}
+	void describe(const SpectralMapperBuildInput& in, prb_spectral_mapper& out, std::vector<float>&) override
+	{
+		constexpr float AStd = 0.0072f, BStd = 538;
+		const auto single	= [&](float lambda) { return std::tanh(AStd * (BStd - lambda)); }; // aghSingle
+		out.type			= mCMIS ? PRB_MAPPER_AGH_CMIS : PRB_MAPPER_AGH_HERO;
+		out.trunc_cdf_start = single(in.cameraRange.Start);									 // mCameraC
+		out.trunc_cdf_end	= single(in.cameraRange.Start) - single(in.cameraRange.End); // mCameraN
+	}
+
+private:
+	bool mCMIS;
+};
+class AGHSpectralMapperPlugin : public ISpectralMapperPlugin {
+public:
+	std::shared_ptr<ISpectralMapperFactory> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		return std::make_shared<AGHSpectralMapperFactory>(ctx.parameters().getBool("cmis", true));
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static const std::vector<std::string> names({ "agh" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "AGH Spectral Mapper: cmis (bool, true)"; }
+};
+
 struct SPDParameters { // spd.cpp:161-176
 	uint32 NumberOfBins			= (uint32)PR_CIE_WAVELENGTH_RANGE;
 	int Method					= 2; // 0 none, 1 Y, 2 XYZ, 3 sRGB
@@ -1096,6 +1128,7 @@ void registerScenePlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 	out.push_back(std::make_shared<SPDSpectralMapperPlugin>());
 	out.push_back(std::make_shared<RandomSpectralMapperPlugin>());
 	out.push_back(std::make_shared<CIESpectralMapperPlugin>());
+	out.push_back(std::make_shared<AGHSpectralMapperPlugin>());
 	out.push_back(std::make_shared<IntDirectFactoryFactory>());
 }
 } // namespace PR

@@ -127,12 +127,13 @@ def test_stratified_and_uniform_samplers_bit_exact(sampler):
     assert np.array_equal(ctx.download_rng(), ref["rng"])
 
 
-@pytest.mark.parametrize("mapper", ["cie", "cie_y"])
-def test_cie_spectral_mapper_bit_exact(mapper):
-    """spectralmapper/cie.cpp: four independent wavelengths from the CIE X+Y+Z / Y CDF"""
-    src = MATERIAL_ZOO2.replace("(sampler :slot 'aa'", "(spectral_mapper :slot 'pixel' :type '%s') (sampler :slot 'aa'" % mapper)
+@pytest.mark.parametrize("mapper,kind", [("'cie'", 3), ("'cie_y'", 3), ("'agh'", 4), ("'agh' :cmis false", 5)])
+def test_cie_and_agh_spectral_mappers_bit_exact(mapper, kind):
+    """spectralmapper/cie.cpp (four independent wavelengths from the CIE X+Y+Z / Y CDF) and agh.cpp (lambda = B - atanh(C - N u) / A,
+    CMIS and hero form; its pdf 1 / (cosh^2 N) is restated as the reference writes it) -- SURVEY 8(f)-3"""
+    src = MATERIAL_ZOO2.replace("(sampler :slot 'aa'", "(spectral_mapper :slot 'pixel' :type %s) (sampler :slot 'aa'" % mapper)
     scene = prb.Scene.from_string(src)
-    assert scene.desc.contents.pixel_mapper.type == 3
+    assert scene.desc.contents.pixel_mapper.type == kind
     ctx = make_ctx(scene)
     ora = OracleScene(scene)
     tiles = [(0, 0, 32, 32)]

@@ -477,3 +477,27 @@ def test_blend_and_add_follow_their_children():
         picked.append(matches[0])
     assert 0 < sum(picked) < len(picked)  # both children get picked; f = 0.3 -> mostly the first
     assert sum(picked) < len(picked) / 2
+
+
+# ---------------------------------------------------------------- spectralmapper/agh.cpp
+@pytest.mark.parametrize("cmis", [True, False])
+def test_agh_mapper_follows_its_closed_form(cmis):
+    """lambda = B - atanh(C - N u) / A with A = 0.0072, B = 538 (agh.cpp:19-36): wavelengths stay inside the camera range, are
+    densest around B, and the pdf handed on is 1 / (cosh^2(A (lambda - B)) N); the hero form rotates one sample by span / 4"""
+    extra = "(spectral_mapper :slot 'pixel' :type 'agh'%s)" % ("" if cmis else " :cmis false")
+    scene = prb.Scene.from_string(MATERIAL_ZOO2.replace("(sampler :slot 'aa'", extra + " (sampler :slot 'aa'"))
+    m = scene.desc.contents.pixel_mapper
+    A, B = 0.0072, 538.0
+    C, N = np.tanh(A * (B - 390.0)), np.tanh(A * (B - 390.0)) - np.tanh(A * (B - 830.0))
+    assert m.type == (4 if cmis else 5)
+    assert abs(m.trunc_cdf_start - C) < 1e-6 and abs(m.trunc_cdf_end - N) < 1e-6
+    ora = ob.OracleScene(scene)
+    _, _, wvl, _ = ora.generate_camera_rays([(0, 0, 32, 32)], 0)
+    assert wvl.min() >= 390.0 and wvl.max() <= 830.0
+    hero = wvl[:, 0] if not cmis else wvl.ravel()
+    inner = np.mean(np.abs(hero - B) < 70)  # P(|lambda - B| < 70) = 2 tanh(0.504) / N = 0.529
+    assert abs(inner - 2 * np.tanh(A * 70) / N) < 0.06
+    if not cmis:
+        span = 440.0
+        for k in range(1, 4):
+            assert np.allclose(wvl[:, k], 390.0 + np.mod(wvl[:, 0] - 390.0 + k * span / 4, span), atol=2e-3)
