@@ -570,6 +570,28 @@ struct RoughDielectric {
 	}
 };
 
+// LambertMaterial::eval / ::sample (lambert.cpp:33-43, :53-73); inline so that k_shade's all-Lambert instantiation can use
+// them without the out-of-line material dispatch
+PRB_DEV void lambertEval(const DScene& S, const prb_material& m, const MatCtx& c, MatEval& out)
+{
+	const bool two = m.flags & PRB_MATF_TWO_SIDED;
+	const float d  = sameHemisphere(c.V, c.L) ? (two ? fabsf(c.L.z) : fmaxf(0.0f, c.L.z)) : 0;
+	out.weight	   = evalNode(S, m.node[0], c.wvl, c.u, c.v) * d * PR_INV_PI;
+	out.pdf		   = blob(cos_hemi_pdf(d));
+}
+PRB_DEV void lambertSample(const DScene& S, const prb_material& m, const MatCtx& c, Rng& rnd, MatSample& out)
+{
+	if (!(m.flags & PRB_MATF_TWO_SIDED) && c.V.z < 0.0f) {
+		rejectSample(out, 0, 0);
+		return;
+	}
+	const float u2 = rnd.getFloat(); // cos_hemi(RND.getFloat(), RND.getFloat()): second argument drawn first
+	const float u1 = rnd.getFloat();
+	out.L		   = cos_hemi(u1, u2);
+	out.weight	   = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+	out.pdf		   = blob(cos_hemi_pdf(out.L.z));
+	out.L		   = makeSameHemisphere(c.V, out.L);
+}
 // OrenNayarMaterial::calc (improved Oren-Nayar), orennayar.cpp:29-49
 PRB_DEV Blob orenNayarCalc(const DScene& S, const prb_material& m, const MatCtx& c, V3 L, float NdotL)
 {
@@ -592,13 +614,7 @@ __device__ __noinline__ void materialEvalLeaf(const DScene& S, uint32_t matID, c
 	out.flags			 = 0;
 	out.type			 = 0;
 	switch (m.type) {
-	case PRB_MAT_DIFFUSE: { // lambert.cpp:33-43
-		const bool two = m.flags & PRB_MATF_TWO_SIDED;
-		const float d  = sameHemisphere(c.V, c.L) ? (two ? fabsf(c.L.z) : fmaxf(0.0f, c.L.z)) : 0;
-		out.weight	   = evalNode(S, m.node[0], c.wvl, c.u, c.v) * d * PR_INV_PI;
-		out.pdf		   = blob(cos_hemi_pdf(d));
-		break;
-	}
+	case PRB_MAT_DIFFUSE: lambertEval(S, m, c, out); break;
 	case PRB_MAT_DIELECTRIC:
 		out.pdf	   = blob(0);
 		out.weight = blob(0);
@@ -690,19 +706,7 @@ __device__ __noinline__ void materialSampleLeaf(const DScene& S, uint32_t matID,
 	out.flags			 = 0;
 	out.type			 = 0;
 	switch (m.type) {
-	case PRB_MAT_DIFFUSE: { // lambert.cpp:53-73
-		if (!(m.flags & PRB_MATF_TWO_SIDED) && c.V.z < 0.0f) {
-			rejectSample(out, 0, 0);
-			return;
-		}
-		const float u2 = rnd.getFloat(); // cos_hemi(RND.getFloat(), RND.getFloat()): second argument drawn first
-		const float u1 = rnd.getFloat();
-		out.L		   = cos_hemi(u1, u2);
-		out.weight	   = evalNode(S, m.node[0], c.wvl, c.u, c.v);
-		out.pdf		   = blob(cos_hemi_pdf(out.L.z));
-		out.L		   = makeSameHemisphere(c.V, out.L);
-		break;
-	}
+	case PRB_MAT_DIFFUSE: lambertSample(S, m, c, rnd, out); break;
 	case PRB_MAT_DIELECTRIC: { // dielectric.cpp:60-114
 		out.pdf		  = blob(1);
 		const Blob n2 = evalNode(S, m.node[2], c.wvl, c.u, c.v);
@@ -881,15 +885,21 @@ __device__ __noinline__ void materialEvalCombined(const DScene& S, uint32_t matI
 		}
 	}
 }
-// COMBINED = false compiles the plain leaf call: k_shade is instantiated without the combination path for scenes that
-// have no blend / add material (merely having the call in the kernel cost 4-5 % of k_shade on C2 / C4).
-template <bool COMBINED>
+// k_shade is instantiated per KIND: without the combination path for scenes that have no blend / add material (merely having
+// the call in the kernel cost 4-5 % of k_shade on C2 / C4), and with the Lambert code inline for all-Lambert scenes.
+enum { SHADE_MATERIALS_LEAF = 0, SHADE_MATERIALS_COMBINED = 1, SHADE_MATERIALS_LAMBERT = 2 };
+template <int KIND>
 PRB_DEV void materialEval(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
 {
-	if (COMBINED && isCombination(S.materials[matID].type))
+	if (KIND == SHADE_MATERIALS_LAMBERT) { // every material of the scene is a Lambert material (Cornell box)
+		out.flags = 0;
+		out.type  = 0;
+		lambertEval(S, S.materials[matID], c, out);
+	} else if (KIND == SHADE_MATERIALS_COMBINED && isCombination(S.materials[matID].type)) {
 		materialEvalCombined(S, matID, c, out);
-	else
+	} else {
 		materialEvalLeaf(S, matID, c, out);
+	}
 }
 __device__ __noinline__ void materialSampleCombined(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
 {
@@ -905,13 +915,18 @@ __device__ __noinline__ void materialSampleCombined(const DScene& S, uint32_t ma
 	out.pdf = out.pdf * share;
 }
 
-template <bool COMBINED>
+template <int KIND>
 PRB_DEV void materialSample(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
 {
-	if (COMBINED && isCombination(S.materials[matID].type))
+	if (KIND == SHADE_MATERIALS_LAMBERT) {
+		out.flags = 0;
+		out.type  = 0;
+		lambertSample(S, S.materials[matID], c, rnd, out);
+	} else if (KIND == SHADE_MATERIALS_COMBINED && isCombination(S.materials[matID].type)) {
 		materialSampleCombined(S, matID, c, rnd, out);
-	else
+	} else {
 		materialSampleLeaf(S, matID, c, rnd, out);
+	}
 }
 
 // ------------------------------------------------------------------ samplers / mapper / camera

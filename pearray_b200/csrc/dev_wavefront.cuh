@@ -346,7 +346,7 @@ PRB_DEV uint32_t shadeSortKey(const DScene& S, const WFState& W, uint32_t slot)
 #ifndef PRB_SHADE_MINB
 #define PRB_SHADE_MINB 4 /* resident 128-thread blocks per SM the uniform instantiation is compiled for */
 #endif
-template <int SHADE_BLOCK, int SHADE_ROUNDS_MAX, bool COMBINED>
+template <int SHADE_BLOCK, int SHADE_ROUNDS_MAX, int MATERIALS>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_BLOCK <= 128 ? (PRB_SHADE_MINB * 128) / SHADE_BLOCK : 512 / SHADE_BLOCK) k_shade(const __grid_constant__ DScene S, WFState W, int roundsArg)
 {
 	const int rounds = SHADE_ROUNDS_MAX == 1 ? 1 : roundsArg; // compile-time 1 for the uniform instantiation: no loop
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_BLOCK <= 128 ? (PRB_SHADE_M
 						if (cosC * cosL > 1e-5f && sqrD > 1e-5f) { // GEOMETRY_EPS / DISTANCE_EPS
 							mc.L = toTangentSpace(g.N, g.Nx, g.Ny, L);
 							MatEval mout;
-							materialEval<COMBINED>(S, matID, mc, mout);
+							materialEval<MATERIALS>(S, matID, mc, mout);
 							if (!(mout.flags & MSF_Delta)) {
 								const bool rayMono		 = rayFlags & PRB_RAY_MONOCHROME;
 								const bool bsdfMono		 = rayMono; // a non-delta eval result is never hero collapsing
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_BLOCK <= 128 ? (PRB_SHADE_M
 					if (scatter) {
 						MatSample sout;
 						mc.L = mk(0, 0, 0);
-						materialSample<COMBINED>(S, matID, mc, rnd, sout);
+						materialSample<MATERIALS>(S, matID, mc, rnd, sout);
 						const V3 L	 = normalized(fromTangentSpace(g.N, g.Nx, g.Ny, sout.L)); // MaterialSampleOutput::globalL
 						LastWasDelta = sout.isDelta();
 						PrevPathPDF	 = PathPDF;
@@ -810,7 +810,7 @@ __global__ void k_material_eval(const __grid_constant__ DScene S, const prb_mate
 		c.v		   = q[i].uv[1];
 		c.rayFlags = q[i].ray_flags;
 		MatEval e;
-		materialEval<true>(S, q[i].material_id, c, e);
+		materialEval<SHADE_MATERIALS_COMBINED>(S, q[i].material_id, c, e);
 		for (int k = 0; k < 4; ++k) {
 			out[i].weight[k] = e.weight[k];
 			out[i].pdf_s[k]	 = e.pdf[k];
@@ -834,7 +834,7 @@ __global__ void k_material_sample(const __grid_constant__ DScene S, const prb_ma
 		c.rayFlags = q[i].ray_flags;
 		Rng rnd{ q[i].rng_state };
 		MatSample e;
-		materialSample<true>(S, q[i].material_id, c, rnd, e);
+		materialSample<SHADE_MATERIALS_COMBINED>(S, q[i].material_id, c, rnd, e);
 		for (int k = 0; k < 4; ++k) {
 			out[i].weight[k] = e.weight[k];
 			out[i].pdf_s[k]	 = e.pdf[k];

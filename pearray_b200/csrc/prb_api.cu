@@ -62,6 +62,7 @@ struct prb_ctx {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t evA = nullptr, evB = nullptr;
 	int smCount = 148;
+	bool allLambert = false;	 // every material is PRB_MAT_DIFFUSE: k_shade with the Lambert code inline
 	bool mixedMaterials = false; // the scene mixes material types: k_shade sorts larger windows (launchShade)
 	int gridTrace = 148 * 4, gridTraceClosest = 148 * 4, gridTraceAny = 148 * 4; // persistent grids: SMs x resident blocks
 	bool haveScene = false;
@@ -291,6 +292,7 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	S.tlasRoot		  = d->tlas_root;
 	S.cieOffset		  = d->cie_offset;
 	c->mixedMaterials = false;
+	c->allLambert	  = d->n_materials > 0 && d->materials[0].type == PRB_MAT_DIFFUSE;
 	for (uint32_t i = 1; i < d->n_materials; ++i)
 		if (d->materials[i].type != d->materials[0].type)
 			c->mixedMaterials = true;
@@ -394,7 +396,11 @@ static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
 {
 	const bool combined = c->S.hasCombined != 0; // a scene with blend / add materials always mixes material types
 	if (!c->mixedMaterials && !combined) {
-		k_shade<SHADE_BLOCK_UNIFORM, 1, false><<<(int)((c->nSlots + SHADE_BLOCK_UNIFORM - 1) / SHADE_BLOCK_UNIFORM), SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
+		const int grid = (int)((c->nSlots + SHADE_BLOCK_UNIFORM - 1) / SHADE_BLOCK_UNIFORM);
+		if (c->allLambert)
+			k_shade<SHADE_BLOCK_UNIFORM, 1, SHADE_MATERIALS_LAMBERT><<<grid, SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
+		else
+			k_shade<SHADE_BLOCK_UNIFORM, 1, SHADE_MATERIALS_LEAF><<<grid, SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
 		return;
 	}
 	const size_t perRound = (size_t)512 * c->smCount * 4;
@@ -402,9 +408,9 @@ static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
 	const size_t window	  = (size_t)rounds * SHADE_BLOCK_MIXED;
 	const int grid		  = (int)((c->nSlots + window - 1) / window);
 	if (combined)
-		k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED, true><<<grid, SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
+		k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED, SHADE_MATERIALS_COMBINED><<<grid, SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
 	else
-		k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED, false><<<grid, SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
+		k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED, SHADE_MATERIALS_LEAF><<<grid, SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
 }
 static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s)
 {
