@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """bench.py -- spectral path samples/s of the 'direct' (unidirectional PT) hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene c2] [--partition samples|tiles]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene c2|c1|c3|c4|c4b|c4c|c0|c5] [--spp S]
+                  [--partition samples|tiles]
 
 Workload (BASELINE.json configs[1]): cornellbox.prc, 500x500, 'direct' integrator depth 6, mjitt sampler,
 1024 spp, diffuse materials + one area light.  One "step" = one complete render of that configuration
