@@ -84,7 +84,7 @@ struct prb_ctx {
 	DBuf<uint32_t> sampleCount;
 	DBuf<unsigned long long> stats;
 	// wavefront
-	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters;
+	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters, regenList;
 	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ, prevAcc;
 	DBuf<uint4> hit;
 	DBuf<float> hitT;
@@ -178,7 +178,7 @@ void prb_destroy(prb_ctx* c)
 	if (c->graphExec)
 		cudaGraphExecDestroy(c->graphExec);
 	DBuf<uint32_t>* ub[] = { &c->entityMaterials, &c->faceIndices, &c->faceSlots, &c->tlasRefs, &c->sampleCount, &c->pixel, &c->iter, &c->flagsDepth,
-							 &c->slotState, &c->counters, &c->scratchU };
+							 &c->slotState, &c->counters, &c->regenList, &c->scratchU };
 	for (auto* b : ub)
 		b->release();
 	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->hitT, &c->scratchF };
@@ -378,6 +378,7 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 	CU(c->iter.alloc(n));
 	CU(c->flagsDepth.alloc(n));
 	CU(c->slotState.alloc(n));
+	CU(c->regenList.alloc(n));
 	CU(c->counters.alloc(CNT__COUNT));
 	DBuf<float4>* f4[] = { &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc };
 	for (auto* b : f4)
@@ -392,12 +393,22 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 
 // k_shade sorts a window of rounds * block slots by material per thread block; larger windows give more uniform warps but
 // fewer blocks, so rounds is chosen such that the grid still holds >= 4 blocks per resident block slot
+static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s);
+// shade + regenerate: k_regen starts the next camera sample of every path that k_shade ended (dense list, see k_shade)
 static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
 {
+	launchShadeOnly(c, W, s);
+	k_regen<<<(int)((c->nSlots + 127) / 128), 128, 0, s>>>(c->S, W);
+}
+static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s)
+{
 	const bool combined = c->S.hasCombined != 0; // a scene with blend / add materials always mixes material types
-	if (!c->mixedMaterials && !combined) {
+	// small films (fewer slots than two 512-thread blocks per SM) keep the 128-thread blocks even with mixed materials: the
+	// large sort window is worth less than filling the machine (cornellbox_glassy, 256x256: 65 k slots = 128 blocks of 512)
+	const bool smallFilm = c->nSlots < (size_t)SHADE_BLOCK_MIXED * c->smCount * 2;
+	if ((!c->mixedMaterials || smallFilm) && !combined) {
 		const int grid = (int)((c->nSlots + SHADE_BLOCK_UNIFORM - 1) / SHADE_BLOCK_UNIFORM);
-		if (c->allLambert)
+		if (c->allLambert && !c->mixedMaterials)
 			k_shade<SHADE_BLOCK_UNIFORM, 1, SHADE_MATERIALS_LAMBERT><<<grid, SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
 		else
 			k_shade<SHADE_BLOCK_UNIFORM, 1, SHADE_MATERIALS_LEAF><<<grid, SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
@@ -443,6 +454,7 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.prevAcc	  = c->prevAcc.p;
 	W.state		  = c->slotState.p;
 	W.counters	  = c->counters.p;
+	W.regenList	  = c->regenList.p;
 	W.rng		  = c->rng.p;
 	W.filmMean	  = c->filmMean.p;
 	W.sampleCount = c->sampleCount.p;
@@ -508,7 +520,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 				CU(cudaGetLastError());
 			}
 			done += ITERS_PER_GRAPH * GRAPHS_PER_POLL;
-			c->kernelLaunches += 2 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
+			c->kernelLaunches += 3 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
 			CU(poll());
 			for (size_t i = 0; i + 1 < ne; i += 2) {
 				float ms = 0;
@@ -540,7 +552,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 			for (int r = 0; r < GRAPHS_PER_POLL && e == cudaSuccess; ++r)
 				e = cudaGraphLaunch(exec, s);
 			done += ITERS_PER_GRAPH * GRAPHS_PER_POLL;
-			c->kernelLaunches += 2 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
+			c->kernelLaunches += 3 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
 			if (e == cudaSuccess)
 				e = poll();
 			if (e != cudaSuccess) {
