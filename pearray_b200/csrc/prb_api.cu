@@ -403,12 +403,9 @@ static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
 static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s)
 {
 	const bool combined = c->S.hasCombined != 0; // a scene with blend / add materials always mixes material types
-	// small films (fewer slots than two 512-thread blocks per SM) keep the 128-thread blocks even with mixed materials: the
-	// large sort window is worth less than filling the machine (cornellbox_glassy, 256x256: 65 k slots = 128 blocks of 512)
-	const bool smallFilm = c->nSlots < (size_t)SHADE_BLOCK_MIXED * c->smCount * 2;
-	if ((!c->mixedMaterials || smallFilm) && !combined) {
+	if (!c->mixedMaterials && !combined) {
 		const int grid = (int)((c->nSlots + SHADE_BLOCK_UNIFORM - 1) / SHADE_BLOCK_UNIFORM);
-		if (c->allLambert && !c->mixedMaterials)
+		if (c->allLambert)
 			k_shade<SHADE_BLOCK_UNIFORM, 1, SHADE_MATERIALS_LAMBERT><<<grid, SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
 		else
 			k_shade<SHADE_BLOCK_UNIFORM, 1, SHADE_MATERIALS_LEAF><<<grid, SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
