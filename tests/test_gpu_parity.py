@@ -300,6 +300,44 @@ def test_full_frame_c2_vs_oracle_and_stats():
     assert np.array_equal(aov.view(np.uint32), ref["aov"].view(np.uint32))
 
 
+@pytest.mark.parametrize("name,iters", [("c4_boltsandgears", 2), ("c4c_complex", 1)])
+def test_full_frame_large_films_vs_oracle(name, iters):
+    """whole 1000x1000 / 1920x1080 films: the only sizes at which k_shade sorts multi-pass windows (3 and 4 passes of 512
+    slots per block) and, for complex.prc, the persistent k_trace runs over every pixel; same bits, RNG states and counters
+    as the oracle"""
+    scene = load_scene(name)
+    ctx = make_ctx(scene)
+    ctx.reset_stats()
+    tiles = scene.tiles(8, 8)
+    ctx.render_tiles(tiles, 0, iters)
+    xyz, cnt = ctx.film()
+    ref = OracleScene(scene).render(tiles, 0, iters)
+    assert np.array_equal(cnt, ref["count"])
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
+    st = ctx.stats()
+    assert {k: int(getattr(st, k)) for k in STAT_NAMES} == ref["stats"]
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
+
+
+def test_uniform_non_lambert_scene_uses_the_generic_single_pass_kernel():
+    """all materials of one non-Lambert type: k_shade<128, 1, leaf dispatch> (the Cornell box takes the all-Lambert
+    instantiation, mixed scenes the 512-thread one)"""
+    src = MATERIAL_ZOO2
+    for m in ("'mirror'", "'reflection' :specularity (refl 0.9 0.6 0.2)", "'diffuse' :albedo 0.5"):
+        src = src.replace(":type %s" % m, ":type 'orennayar' :albedo (refl 0.6 0.5 0.4) :roughness 0.4")
+    src = src.replace(":type 'rough' ", ":type 'orennayar' ")
+    scene = prb.Scene.from_string(src)
+    d = scene.desc.contents
+    assert {d.materials[i].type for i in range(d.n_materials)} == {7}
+    ctx = make_ctx(scene)
+    tiles = [(0, 0, 32, 32)]
+    ctx.render_tiles(tiles, 0, 4)
+    xyz, _ = ctx.film()
+    ref = OracleScene(scene).render(tiles, 0, 4)
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
+
+
 def test_furnace_on_gpu():
     scene = prb.Scene.from_string(FURNACE % dict(hero="true"))
     ctx = make_ctx(scene)
