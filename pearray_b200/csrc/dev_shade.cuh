@@ -1076,7 +1076,7 @@ struct CameraSampleOut {
 	Blob wvl, wvlPDF;
 	bool mono;
 };
-__device__ __noinline__ void constructCameraRay(const DScene& S, uint32_t px, uint32_t py, uint32_t iteration, Rng& rnd, CameraSampleOut& o)
+PRB_DEV void constructCameraRay(const DScene& S, uint32_t px, uint32_t py, uint32_t iteration, Rng& rnd, CameraSampleOut& o)
 { // RenderTile::constructCameraRay, RenderTile.cpp:71-132 + PerspectiveCamera::constructRay, perspective.cpp:45-82
 	const prb_settings& st = S.settings;
 	float ax, ay, lx, ly;
@@ -1272,7 +1272,7 @@ PRB_DEV bool isInfLight(const prb_light& l) { return l.type != PRB_LIGHT_AREA; }
 PRB_DEV bool isDeltaLight(const prb_light& l) { return l.type == PRB_LIGHT_SUN_DELTA; }
 
 // Light::sample with SamplingInfo + Point (NEE), src/core/light/Light.cpp:108-226
-__device__ __noinline__ void sampleLight(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o)
+PRB_DEV void sampleLightInline(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o)
 {
 	o.delta = false;
 	if (l.type == PRB_LIGHT_SKY) { // SkyLight::sampleDir / samplePosDir, sky.cpp:82-113
@@ -1412,6 +1412,7 @@ __device__ __noinline__ void sampleLight(const DScene& S, const prb_light& l, V3
 	o.posPDF   = pdfA;
 	o.lightPos = pos;
 }
+__device__ __noinline__ void sampleLight(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o) { sampleLightInline(S, l, P, wvl, rnd, o); }
 PRB_DEV void envEval(const DScene& S, const prb_light& l, V3 dir, uint32_t depth, const Blob& wvl, Blob& rad, float& pdfS)
 { // EnvironmentLight::eval (no distribution), environment.cpp
 	const V3 ld = m3mul(l.inv_normal_matrix, dir);
