@@ -392,7 +392,8 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 }
 
 // k_shade sorts a window of rounds * block slots by material per thread block; larger windows give more uniform warps but
-// fewer blocks, so rounds is chosen such that the grid still holds >= 4 blocks per resident block slot
+// fewer blocks, so rounds is chosen such that the grid still holds >= PRB_SHADE_FILL blocks per SM (measured on complex.prc,
+// 2 M slots: windows of 8 x 512 slots with 2 blocks per SM shade 10 % faster than 4 x 512 with 4)
 static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s);
 // shade + regenerate: k_regen starts the next camera sample of every path that k_shade ended (dense list, see k_shade)
 static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
@@ -411,7 +412,10 @@ static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s)
 			k_shade<SHADE_BLOCK_UNIFORM, 1, SHADE_MATERIALS_LEAF><<<grid, SHADE_BLOCK_UNIFORM, 0, s>>>(c->S, W, 1);
 		return;
 	}
-	const size_t perRound = (size_t)512 * c->smCount * 4;
+#ifndef PRB_SHADE_FILL
+#define PRB_SHADE_FILL 2 /* blocks per SM the grid must still hold when a window spans several passes */
+#endif
+	const size_t perRound = (size_t)512 * c->smCount * PRB_SHADE_FILL;
 	const int rounds	  = (int)std::max<size_t>(1, std::min<size_t>(SHADE_ROUNDS_MIXED, c->nSlots / perRound));
 	const size_t window	  = (size_t)rounds * SHADE_BLOCK_MIXED;
 	const int grid		  = (int)((c->nSlots + window - 1) / window);
