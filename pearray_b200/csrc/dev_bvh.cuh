@@ -529,5 +529,8 @@ PRB_DEV uint32_t fetchWork(uint32_t* counter, bool need)
 	base = __shfl_sync(0xFFFFFFFFu, base, leader);
 	return need ? base + __popc(mask & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
 }
-constexpr int REFILL_LANES = 20; // leave the traversal loop to refill idle lanes when fewer lanes than this are still tracing
+#ifndef PRB_REFILL_LANES
+#define PRB_REFILL_LANES 20
+#endif
+constexpr int REFILL_LANES = PRB_REFILL_LANES; // leave the traversal loop to refill idle lanes when fewer lanes than this are still tracing
 } // namespace prb
