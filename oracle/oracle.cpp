@@ -2392,6 +2392,39 @@ static MatCtx ctxOf(const prb_material_query& q)
 	c.rayFlags = q.ray_flags;
 	return c;
 }
+// Light::sample (NEE form) of light `light_id` for a point P, followed by IInfiniteLight::eval in the sampled direction.
+// out: outgoing[3], sampled Direction_PDF_S, sampled radiance[4], evaluated Direction_PDF_S, evaluated radiance[4], delta flag.
+void orc_light_sample_and_eval(orc_scene* s, uint32_t light_id, const float* P, const float* wvl4, uint64_t* rng_state, float* out14)
+{
+	setFTZ();
+	Film film{};
+	Stats stats;
+	Integrator in{ s->sc, s->accel, film, stats, 0, Group{} };
+	IP ip{};
+	ip.P = ld3(P);
+	for (int k = 0; k < 4; ++k)
+		ip.ray.wvl[k] = wvl4[k];
+	Rng rnd{ *rng_state };
+	Integrator::LightSample ls;
+	const prb_light& l = s->sc.d->lights[light_id];
+	in.sampleLight(l, ip, rnd, ls);
+	*rng_state = rnd.s;
+	out14[0] = ls.outgoing.x, out14[1] = ls.outgoing.y, out14[2] = ls.outgoing.z;
+	out14[3] = ls.dirPDF_S;
+	for (int k = 0; k < 4; ++k)
+		out14[4 + k] = ls.radiance[k];
+	RayS ray{};
+	ray.D	= ls.outgoing;
+	ray.wvl = ip.ray.wvl;
+	Blob rad = blob(0);
+	float pdf = 0;
+	if (l.type != PRB_LIGHT_AREA && l.type != PRB_LIGHT_SUN_DELTA)
+		in.infLightEval(l, ray, rad, pdf);
+	out14[8] = pdf;
+	for (int k = 0; k < 4; ++k)
+		out14[9 + k] = rad[k];
+	out14[13] = ls.delta ? 1.0f : 0.0f;
+}
 void orc_material_eval(orc_scene* s, const prb_material_query* q, size_t n, prb_material_result* out)
 {
 	setFTZ();

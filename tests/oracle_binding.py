@@ -144,6 +144,20 @@ class OracleScene:
         lib().orc_material_sample(self._h, queries, len(queries), out)
         return out
 
+    def light_sample_and_eval(self, light_id, P, wavelengths, rng_state):
+        """Light::sample for a point (NEE form) + IInfiniteLight::eval in the sampled direction; returns a dict and the new RNG state"""
+        f = lib().orc_light_sample_and_eval
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
+        p = (C.c_float * 3)(*[float(x) for x in P])
+        w = (C.c_float * 4)(*[float(x) for x in wavelengths])
+        st = C.c_uint64(int(rng_state))
+        out = (C.c_float * 14)()
+        f(self._h, light_id, p, w, C.byref(st), out)
+        o = list(out)
+        return {"outgoing": np.array(o[0:3], np.float32), "pdf": o[3], "radiance": np.array(o[4:8], np.float32), "eval_pdf": o[8],
+                "eval_radiance": np.array(o[9:13], np.float32), "delta": bool(o[13])}, st.value
+
     def eval_node(self, node, wavelength, u=0.0, v=0.0):
         return float(lib().orc_eval_node(self._h, node, wavelength, u, v))
 

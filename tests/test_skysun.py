@@ -106,3 +106,43 @@ def test_sky_tables_in_the_scene_description(which):
             assert s.sun_cos_theta == 1.0
         else:
             assert 0.99 < s.sun_cos_theta < 1.0 and abs(s.sun_pdf - 1 / (2 * np.pi * (1 - s.sun_cos_theta))) / s.sun_pdf < 1e-3
+
+
+@pytest.mark.parametrize("which", ["complex", "zoo"])
+def test_infinite_light_sampling_is_consistent_with_its_evaluation(which):
+    """the analogue of src/tests/materials.cpp for lights: a direction drawn by SkyLight / SunLight::sampleDir evaluates (eval)
+    to the same radiance and the same solid-angle pdf it was drawn with; the sky pdf integrates to one over the sphere and
+    its samples stay above the horizon as far as the ground penalty allows; the delta sun returns its fixed direction"""
+    from oracle_binding import OracleScene
+    scene = prb.Scene.from_file(scene_path("c4c_complex.prc")) if which == "complex" else prb.Scene.from_string(SKYSUN_ZOO)
+    d = scene.desc.contents
+    ora = OracleScene(scene)
+    wvl = [560.0, 540.0, 400.0, 600.0]
+    for li in range(d.n_lights):
+        l = d.lights[li]
+        state, up, inv_pdf = 0x853C49E6748FEA9B | 3, 0, []
+        for _ in range(3000):
+            r, state = ora.light_sample_and_eval(li, (0.0, 0.0, 0.5), wvl, state)
+            if l.type == 4:  # delta sun: its direction, pdf 1, never evaluated
+                assert r["delta"] and r["pdf"] == 1.0 and np.allclose(r["outgoing"], list(l.sun_dir), atol=1e-6)
+                continue
+            assert not r["delta"] and abs(np.linalg.norm(r["outgoing"]) - 1) < 1e-5
+            if r["pdf"] == 0:
+                continue
+            # cell-boundary samples may land in the neighbouring table cell when re-evaluated: compare with a tolerance and
+            # allow a few such samples
+            ok = abs(r["pdf"] - r["eval_pdf"]) <= 2e-3 * r["pdf"] and np.allclose(r["radiance"], r["eval_radiance"], rtol=2e-3, atol=1e-6)
+            up += ok
+            inv_pdf.append(1.0 / r["pdf"])
+            if l.type == 3:  # cone sun: inside the cone, uniform pdf
+                assert np.dot(r["outgoing"], list(l.sun_dir)) >= l.sun_cos_theta - 1e-6 and abs(r["pdf"] - l.sun_pdf) <= 1e-6 * l.sun_pdf
+        if l.type == 4:
+            continue
+        assert up >= 0.97 * len(inv_pdf), (li, l.type, up, len(inv_pdf))
+        if l.type == 2:
+            # E[1 / pdf] = measure of the support = 4 pi for the extended sky.  The non-extended sky maps v to [0, pi/2] but keeps
+            # the extended form's Jacobian 2 pi^2 cos(el) (sky.cpp:69-70,97-99), i.e. half the true density: 2 x 2 pi as well.
+            want = 4 * np.pi
+            assert abs(np.mean(inv_pdf) - want) < 0.35 * want
+        if l.type == 3:
+            assert abs(np.mean(inv_pdf) - 2 * np.pi * (1 - l.sun_cos_theta)) < 1e-3 * np.mean(inv_pdf)
