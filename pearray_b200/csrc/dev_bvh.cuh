@@ -532,5 +532,12 @@ PRB_DEV uint32_t fetchWork(uint32_t* counter, bool need)
 #ifndef PRB_REFILL_LANES
 #define PRB_REFILL_LANES 20
 #endif
-constexpr int REFILL_LANES = PRB_REFILL_LANES; // leave the traversal loop to refill idle lanes when fewer lanes than this are still tracing
+#ifndef PRB_REFILL_LANES_STREAM
+#define PRB_REFILL_LANES_STREAM 26
+#endif
+// A persistent warp leaves the traversal loop to refill its idle lanes when fewer lanes than this are still tracing.
+// Measured (gpurun_out/refill_sweep.log): the wavefront k_trace on complex.prc is flat between 12 and 26 (20 best by 1 %);
+// the ray-stream kernels on the 10 M-triangle soup gain steadily with the threshold (12: 933, 20: 966, 26: 1007 Mrays/s primary).
+constexpr int REFILL_LANES		  = PRB_REFILL_LANES;
+constexpr int REFILL_LANES_STREAM = PRB_REFILL_LANES_STREAM;
 } // namespace prb
