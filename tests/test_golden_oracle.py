@@ -95,6 +95,29 @@ def test_furnace_hero():
     assert (r["count"][inside] == 64).all() and (r["count"][outside] == 0).all()
 
 
+def test_furnace_non_hero_and_single_wavelength():
+    """The other two modes of the reference furnace test (whitefurnance.py: `:spectral_hero false`, `:spectral_domain 520`).
+    Both force monochrome camera rays (RenderTile.cpp:123-128): only the hero wavelength carries importance, so a camera ray
+    that misses everything is splatted once instead of four times.  With a single-wavelength domain the sample is
+    deterministic (wavelength 520 nm, pdf 1), so every background pixel holds the same value.  On the sphere the
+    per-wavelength MIS weight of a monochrome NEE fragment divides by heroFactor = (1,0,0,0) (direct.cpp:318), its non-hero
+    lanes are NaN and LocalFrameOutputDevice.cpp:128-144 drops the fragment: only BSDF-sampled background hits remain,
+    the same fraction of the background value in both modes.  Known deviation: the reference's
+    monotonic film stores the unweighted hero sample in all three channels, this path stores its CIE-weighted XYZ."""
+    ys, xs = np.mgrid[0:48, 0:48]
+    rad = np.hypot(xs - 23.5, ys - 23.5)
+    inside, outside = rad < 12, rad > 22
+    nonhero = OracleScene(prb.Scene.from_string(FURNACE % dict(hero="false"))).render([(0, 0, 48, 48)], 0, 64)["filtered"]
+    assert abs(nonhero[outside][:, 1].mean() - 1.0) < 0.05
+    mono_src = (FURNACE % dict(hero="true")).replace(":spectral_hero true", ":spectral_hero true :spectral_domain 520")
+    mono = OracleScene(prb.Scene.from_string(mono_src)).render([(0, 0, 48, 48)], 0, 64)["filtered"]
+    bg = mono[outside]
+    assert np.ptp(bg, axis=0).max() <= 1e-5 * bg.max() and bg[0, 1] > bg[0, 0] and bg[0, 1] > bg[0, 2]  # 520 nm: Y dominates
+    r_mono = mono[inside][:, 1].mean() / bg[:, 1].mean()
+    r_nonhero = nonhero[inside][:, 1].mean() / nonhero[outside][:, 1].mean()
+    assert 0.05 < r_mono < 0.5 and abs(r_mono - r_nonhero) < 0.15 * r_mono
+
+
 # ------------------------------------------------------------------ the reference's golden image
 XYZ_TO_LINEAR_SRGB = np.array([[3.2404542, -1.5371385, -0.4985314], [-0.9692660, 1.8760108, 0.0415560], [0.0556434, -0.2040259, 1.0572252]], np.float32)
 CBOX_LUMINANCE_TOL = 0.2   # relative RMSE of the 8x8-block luminance outside the luminaire
