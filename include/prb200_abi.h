@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 1u
+#define PRB_ABI_VERSION 2u
 #define PRB_INVALID_ID 0xFFFFFFFFu /* reference PR_INVALID_ID, src/base/config/Constants.inl */
 #define PRB_SPECTRAL_BLOB_SIZE 4	/* reference SpectralBlob, src/core/spectral/SpectralBlob.h:7-20 */
 
@@ -288,12 +288,18 @@ typedef struct prb_spectral_mapper { /* src/plugins/main/spectralmapper/spd.cpp,
 	float trunc_cdf_start, trunc_cdf_end;
 } prb_spectral_mapper;
 
-typedef struct prb_camera { /* plugins/main/cameras/perspective.cpp:45-113, no-DOF branch */
+enum {
+	PRB_CAMERA_PERSPECTIVE	= 0, /* plugins/main/cameras/perspective.cpp:45-113, no-DOF branch: origin fixed, dir = normalize(right nx + up ny + dir) */
+	PRB_CAMERA_ORTHOGRAPHIC = 1	 /* plugins/main/cameras/ortho.cpp:47-66: origin + right nx + up ny, dir = mDirection_Cache (unit) */
+};
+typedef struct prb_camera {
 	float origin[3];
 	float right[3]; /* mRight_Cache (already * 0.5 * width) */
 	float up[3];	/* mUp_Cache */
-	float dir[3];	/* mFocalDistance_Cache */
+	float dir[3];	/* perspective: mFocalDistance_Cache; orthographic: mDirection_Cache (normalised) */
 	float near_t, far_t;
+	uint32_t type; /* PRB_CAMERA_* */
+	uint32_t _pad;
 } prb_camera;
 
 typedef struct prb_settings { /* RenderSettings.cpp:11-33 + DiParameters direct.cpp:34-39 */
@@ -311,6 +317,10 @@ typedef struct prb_settings { /* RenderSettings.cpp:11-33 + DiParameters direct.
 	float time_alpha, time_beta; /* RenderTile.cpp:44-63 */
 	int32_t filter_radius;		 /* FilterCache table (2r+1)^2 at filter_offset in the pool */
 	uint32_t filter_offset;
+	/* monotonic film: FrameOutputDevice(filter, size, 3, spectralMono) (loader/Environment.cpp:194-198) -> every fragment
+	 * stores its unweighted hero sample in all three channels (mapSpectral<true>, LocalFrameOutputDevice.cpp:76-85) */
+	uint32_t film_monotonic;
+	uint32_t _pad;
 } prb_settings;
 
 /* ---------------------------------------------------------------- the scene */
@@ -417,7 +427,9 @@ prb_status prb_download_rng(prb_ctx* ctx, uint64_t* states, size_t n);
  * (src/plugins/main/integrators/direct.cpp:153-166) over a batch of tiles, for iterations
  * [first_iteration, first_iteration + iteration_count).  Film cells of the tiles are updated
  * (running mean over iterations as FrameOutputDevice::onEndOfIteration, FrameOutputDevice.cpp:202-221).
- * Asynchronous; prb_sync / prb_film_download wait. */
+ * Blocks until every sample of the call has been folded into the film (the wavefront loop polls a device counter).
+ * first_iteration == 0 starts the listed pixels from scratch (sample counts, AOV sums and feedback bits are cleared);
+ * tiles must not overlap; prb_upload_rng must have been called since the last prb_upload_scene. */
 prb_status prb_render_tiles(prb_ctx* ctx, const prb_tile* tiles, size_t n_tiles,
 							uint32_t first_iteration, uint32_t iteration_count);
 prb_status prb_sync(prb_ctx* ctx);
@@ -430,6 +442,12 @@ prb_status prb_film_download(prb_ctx* ctx, float* xyz, uint32_t* sample_count);
 /* optional first-hit AOVs (sums over samples as commitShadingPoints, LocalFrameOutputDevice.cpp:252-302):
  * normal (3), position (3), uv (2), depth (1), entity id (1) -> 10 floats per pixel, may be NULL */
 prb_status prb_film_download_aov(prb_ctx* ctx, float* aov10);
+/* AOV_Feedback (LocalFrameOutputDevice.cpp:125-143, FrameOutputDevice.cpp:150-153): per pixel the OR of the PRB_FEEDBACK_*
+ * bits of every fragment that was rejected there; W*H words */
+#define PRB_FEEDBACK_NAN 0x1u		/* OutputFeedback::NaN, src/core/output/Feedback.h:6-12 */
+#define PRB_FEEDBACK_INFINITE 0x2u	/* OutputFeedback::Infinite */
+#define PRB_FEEDBACK_NEGATIVE 0x4u	/* OutputFeedback::Negative */
+prb_status prb_film_download_feedback(prb_ctx* ctx, uint32_t* feedback);
 /* copy the UNFILTERED film (xyz mean, 3 floats/pixel, then sample counts as float) into a caller
  * provided DEVICE buffer of W*H*4 floats -- the buffer handed to the NCCL reduce in multi-GPU runs. */
 prb_status prb_film_export_device(prb_ctx* ctx, float* device_dst);

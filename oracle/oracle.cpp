@@ -11,6 +11,7 @@
 #include "oracle_math.h"
 
 #include <atomic>
+#include <cstring>
 #include <thread>
 #include <vector>
 #include <xmmintrin.h>
@@ -1457,9 +1458,14 @@ void constructCameraRay(const Scene& sc, uint32_t px, uint32_t py, uint32_t iter
 	// PerspectiveCamera::constructRay, plugins/main/cameras/perspective.cpp:45-82
 	const float nx = 2 * (pixx / (float)st.film_width - 0.5f);
 	const float ny = -(2 * (pixy / (float)st.film_height - 0.5f));
-	const V3 dir   = (ld3(d.camera.right) * nx + ld3(d.camera.up) * ny) + ld3(d.camera.dir);
-	o.origin	   = ld3(d.camera.origin);
-	o.dir		   = normalized(dir);
+	if (d.camera.type == PRB_CAMERA_ORTHOGRAPHIC) { // OrthoCamera::constructRay, plugins/main/cameras/ortho.cpp:47-66
+		o.origin = (ld3(d.camera.origin) + ld3(d.camera.right) * nx) + ld3(d.camera.up) * ny;
+		o.dir	 = ld3(d.camera.dir);
+	} else {
+		const V3 dir = (ld3(d.camera.right) * nx + ld3(d.camera.up) * ny) + ld3(d.camera.dir);
+		o.origin	 = ld3(d.camera.origin);
+		o.dir		 = normalized(dir);
+	}
 	o.tmin		   = d.camera.near_t;
 	o.tmax		   = d.camera.far_t;
 	o.importance   = blob(1.0f);
@@ -1474,7 +1480,7 @@ struct Film {
 	float* mean;				// running mean, W*H*3 (FrameOutputDevice::onEndOfIteration)
 	uint32_t* sampleCount;
 	float* aov; // 10 floats/pixel or null
-	std::atomic<uint32_t>* feedback = nullptr;
+	uint32_t* feedback = nullptr; // AOV_Feedback, W*H words or null
 };
 struct Stats {
 	uint64_t c[11] = {};
@@ -1506,6 +1512,24 @@ struct IP { // IntersectionPoint, src/core/trace/IntersectionPoint.h:40-138
 inline float misTerm(bool power, float a) { return power ? a * a : a; } // vcm/MIS.h:7-30
 inline Blob misTerm(bool power, Blob a) { return power ? a * a : a; }
 
+// Test instrumentation: every fragment the integrator pushes, together with the path state and the pdfs its MIS weight was
+// computed from, so that tests/test_mis_independent.py can recompute the weights from the text of direct.cpp alone.
+enum { FK_BACKGROUND = 0, FK_DIRECT_HIT = 1, FK_NEE = 2, FK_INF_LIGHT = 3, FK_ZERO = 4 };
+enum { FF_RAY_MONO = 1, FF_BSDF_MONO = 2, FF_LIGHT_DELTA = 4, FF_LAST_DELTA = 8, FF_LAST_EMISSIVE = 16, FF_FROM_BEHIND = 32, FF_VISIBLE = 64, FF_LIGHT_INFINITE = 128 };
+struct FragLog { // 48 floats
+	float kind, flags, depth, pixel;
+	float mis[4], importance[4], radiance[4];
+	float pathPDF[4], prevPathPDF[4], wvlPDF[4], bsdfPDF[4];
+	float lightPdfS;   // NEE: the sampled light pdf (solid angle, x selection probability); direct hit: posPDF_S; inf light: sum_l pdf_S(l) is in extra
+	float roulette;	   // NEE: mCameraRR.probability(pathLength)
+	float extra;	   // inf light: number of non-delta infinite lights evaluated
+	float accepted;	   // 1 when the film took the fragment, else -(feedback bits)
+	float infPdfS[4];  // inf light: pdf_S (x selection probability) of up to four infinite lights
+	float wvl[4];
+	float groupImportance[4]; // RayGroup::Importance (HeroOnly for forced-monochrome renders)
+};
+static_assert(sizeof(FragLog) == 48 * sizeof(float), "FragLog layout is mirrored in tests/oracle_binding.py");
+
 struct Integrator {
 	const Scene& sc;
 	const Accel& A;
@@ -1513,26 +1537,74 @@ struct Integrator {
 	Stats& stats;
 	uint32_t pixelIndex;
 	Group grp;
+	std::vector<FragLog>* log = nullptr;
+	FragLog pending{}; // filled by the handlers before pushSpectralFragment
 
 	// LocalFrameOutputDevice::commitSpectrals2, src/loader/output/LocalFrameOutputDevice.cpp:88-164 (filter applied later)
 	void pushSpectralFragment(const Blob& mis, const Blob& importance, const Blob& radiance, uint32_t rayFlags)
 	{
-		const bool isMono	  = rayFlags & PRB_RAY_MONOCHROME;
+		// a monotonic film (FrameOutputDevice(..., spectralMono), loader/Environment.cpp:194-198) instantiates
+		// commitSpectrals2<IsMono = true>: every fragment is hero-only and mapSpectral<true> (:76-85) stores the unweighted
+		// hero sample in all three channels
+		const bool monotonic  = sc.d->settings.film_monotonic;
+		const bool isMono	  = monotonic || (rayFlags & PRB_RAY_MONOCHROME);
 		const Blob heroFactor = isMono ? heroOnly() : blob(1);
 		const Blob imp		  = grp.importance * importance;
 		const Blob contrib	  = heroFactor * ((mis * imp) * radiance);
-		bool invalid		  = false;
-		for (int i = 0; i < 4; ++i)
-			if (std::isinf(contrib[i]) || std::isnan(contrib[i]) || contrib[i] < -PR_EPSILON)
-				invalid = true;
-		if (invalid)
+		uint32_t feedback	  = 0; // LocalFrameOutputDevice.cpp:125-143
+		for (int i = 0; i < 4; ++i) {
+			if (std::isnan(contrib[i]))
+				feedback |= PRB_FEEDBACK_NAN;
+			if (std::isinf(contrib[i]))
+				feedback |= PRB_FEEDBACK_INFINITE;
+			if (contrib[i] < -PR_EPSILON)
+				feedback |= PRB_FEEDBACK_NEGATIVE;
+		}
+		if (log) {
+			FragLog e  = pending;
+			e.pixel	   = (float)pixelIndex;
+			e.accepted = feedback ? -(float)feedback : 1.0f;
+			for (int i = 0; i < 4; ++i) {
+				e.mis[i]		= mis[i];
+				e.importance[i] = imp[i];
+				e.radiance[i]	= radiance[i];
+				e.wvl[i]		= grp.wvl[i];
+				e.groupImportance[i] = grp.importance[i];
+			}
+			if (rayFlags & PRB_RAY_MONOCHROME)
+				e.flags = (float)((uint32_t)e.flags | FF_RAY_MONO);
+			log->push_back(e);
+			pending = FragLog{};
+		}
+		if (feedback) {
+			if (film.feedback)
+				film.feedback[pixelIndex] |= feedback;
 			return;
+		}
 		float xyz[3] = { 0, 0, 0 };
-		for (int k = 0; k < 4; ++k)
-			for (int c = 0; c < 3; ++c)
-				xyz[c] += contrib[k] * cieEval(sc, c, grp.wvl[k]);
+		if (monotonic) {
+			xyz[0] = xyz[1] = xyz[2] = contrib[0];
+		} else {
+			for (int k = 0; k < 4; ++k)
+				for (int c = 0; c < 3; ++c)
+					xyz[c] += contrib[k] * cieEval(sc, c, grp.wvl[k]);
+		}
 		for (int c = 0; c < 3; ++c)
 			film.iterXYZ[3 * (size_t)pixelIndex + c] += grp.blendWeight * xyz[c];
+	}
+	void logState(int kind, uint32_t flags, uint32_t depth, const PathState& cur)
+	{
+		if (!log)
+			return;
+		pending		  = FragLog{};
+		pending.kind  = (float)kind;
+		pending.flags = (float)(flags | (cur.LastWasDelta ? FF_LAST_DELTA : 0) | (cur.LastWasEmissive ? FF_LAST_EMISSIVE : 0));
+		pending.depth = (float)depth;
+		for (int i = 0; i < 4; ++i) {
+			pending.pathPDF[i]	   = cur.PathPDF[i];
+			pending.prevPathPDF[i] = cur.PrevPathPDF[i];
+			pending.wvlPDF[i]	   = cur.WavelengthPDF[i];
+		}
 	}
 	float rrProbability(uint32_t pathLength, bool delta) const
 	{ // RussianRoulette::probability, vcm/RussianRoulette.h:22-34
@@ -1553,6 +1625,7 @@ struct Integrator {
 		const Blob radiance		 = hitFromBehind ? blob(0) : evalNode(sc, d.emissions[ip.g.emission].radiance_node, ip.ray.wvl, ip.g.u, ip.g.v);
 		const bool mono			 = ip.ray.flags & PRB_RAY_MONOCHROME;
 		const Blob heroFactor	 = mono ? heroOnly() : blob(1);
+		logState(FK_DIRECT_HIT, hitFromBehind ? FF_FROM_BEHIND : 0, ip.ray.depth, cur);
 		if (!d.settings.do_nee || hitFromBehind || cur.LastWasDelta) {
 			pushSpectralFragment(heroFactor / (cur.WavelengthPDF * bsum(heroFactor)), cur.Throughput, radiance, ip.ray.flags);
 			return;
@@ -1571,6 +1644,7 @@ struct Integrator {
 		const bool power	 = d.settings.mis_power;
 		const float denom	 = bsum(misTerm(power, cur.PrevPathPDF * posPDF_S)) + bsum(misTerm(power, cur.PathPDF));
 		const Blob mis		 = (heroFactor * misTerm(power, cur.PathPDF[0])) / (misTerm(power, cur.WavelengthPDF) * denom);
+		pending.lightPdfS	 = posPDF_S;
 		pushSpectralFragment(mis, cur.Throughput, radiance, ip.ray.flags);
 	}
 
@@ -1968,6 +2042,13 @@ struct Integrator {
 			stats.c[S_BG_HIT]++;
 		else
 			stats.c[S_ENTITY_HIT]++;
+		logState(FK_NEE, (bsdfMono ? FF_BSDF_MONO : 0) | (ls.delta ? FF_LIGHT_DELTA : 0) | (isVisible ? FF_VISIBLE : 0) | (ls.infinite ? FF_LIGHT_INFINITE : 0), ip.ray.depth, cur);
+		if (log) {
+			pending.lightPdfS = lightPdfS;
+			pending.roulette  = rrProbability(ip.ray.depth + 1, false);
+			for (int i = 0; i < 4; ++i)
+				pending.bsdfPDF[i] = mout.pdf[i];
+		}
 		pushSpectralFragment(mis, cur.Throughput, contrib, shadow.flags);
 	}
 
@@ -2064,12 +2145,15 @@ struct Integrator {
 			if (isInfLight(d.lights[i])) // HasInfLights = infiniteLightCount() != 0 (delta lights included), direct.cpp:487
 				hasInf = true;
 		if (!hasInf || !d.settings.do_direct) { // handleZero
+			logState(FK_ZERO, 0, ray.depth, cur);
 			pushSpectralFragment(heroFactor / (cur.WavelengthPDF * bsum(heroFactor)), cur.Throughput, blob(0), ray.flags);
 			return;
 		}
 		const bool power = d.settings.mis_power;
 		float denom_mis	 = 0;
 		Blob radiance	 = blob(0);
+		logState(FK_INF_LIGHT, 0, ray.depth, cur);
+		int nInf = 0;
 		for (uint32_t i = 0; i < d.n_lights; ++i) {
 			const prb_light& l = d.lights[i];
 			if (!isInfLight(l) || isDeltaLight(l))
@@ -2080,7 +2164,11 @@ struct Integrator {
 			const float pdf_S = pdfS * l.select_pdf;
 			radiance		  = radiance + rad;
 			denom_mis += bsum(misTerm(power, cur.PrevPathPDF * pdf_S));
+			if (nInf < 4)
+				pending.infPdfS[nInf] = pdf_S;
+			++nInf;
 		}
+		pending.extra = (float)nInf;
 		if (!d.settings.do_nee || cur.LastWasDelta) {
 			pushSpectralFragment(heroFactor / (cur.WavelengthPDF * bsum(heroFactor)), cur.Throughput, radiance, ray.flags);
 			return;
@@ -2147,6 +2235,7 @@ struct Integrator {
 				Blob rad;
 				float pdfS;
 				infLightEval(l, ray, rad, pdfS);
+				logState(FK_BACKGROUND, 0, 0, PathState{});
 				pushSpectralFragment(blob(1), blob(1), rad, ray.flags);
 			}
 			if (!illuminated)
@@ -2225,9 +2314,10 @@ orc_scene* orc_scene_create(const prb_scene_desc* d)
 void orc_scene_destroy(orc_scene* s) { delete s; }
 
 // Render iterations [first, first+count) of the given tiles.  rng: W*H states (updated in place).
-// film_mean: W*H*3 running mean (unfiltered; updated), sample_count: W*H, aov: W*H*10 or NULL, stats: 11 counters.
+// film_mean: W*H*3 running mean (unfiltered; updated), sample_count: W*H, aov: W*H*10 or NULL, stats: 11 counters,
+// feedback: W*H words (OR of PRB_FEEDBACK_* bits, updated) or NULL.
 void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count,
-				float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads)
+				float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback)
 {
 	const prb_settings& st = s->sc.d->settings;
 	const uint32_t W	   = st.film_width;
@@ -2236,6 +2326,7 @@ void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_til
 	film.mean		 = film_mean;
 	film.sampleCount = sample_count;
 	film.aov		 = aov;
+	film.feedback	 = feedback;
 	// pixel list (pixels are independent: own RNG stream, own film cell)
 	std::vector<uint32_t> pixels;
 	for (size_t t = 0; t < n_tiles; ++t)
@@ -2282,6 +2373,38 @@ void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_til
 		for (int t = 0; t < threads; ++t)
 			for (int i = 0; i < 11; ++i)
 				stats11[i] += tstats[t].c[i];
+}
+
+// Test instrumentation: renders iterations [first, first + count) of the listed pixels single-threaded WITHOUT touching a
+// film and returns the fragment log (FragLog records of 48 floats); returns the number of records (<= capacity kept).
+size_t orc_log_fragments(orc_scene* s, const uint64_t* rng, const uint32_t* pixels, size_t n_pixels, uint32_t first_iteration, uint32_t iteration_count,
+						 float* out48, size_t capacity)
+{
+	setFTZ();
+	const prb_settings& st = s->sc.d->settings;
+	const uint32_t W	   = st.film_width;
+	Film film;
+	film.iterXYZ.assign((size_t)W * st.film_height * 3, 0.0f);
+	std::vector<float> mean((size_t)W * st.film_height * 3, 0.0f);
+	std::vector<uint32_t> cnt((size_t)W * st.film_height, 0);
+	film.mean		 = mean.data();
+	film.sampleCount = cnt.data();
+	film.aov		 = nullptr;
+	Stats stats;
+	std::vector<FragLog> log;
+	Integrator I{ s->sc, s->accel, film, stats, 0, Group{} };
+	I.log = &log;
+	for (size_t i = 0; i < n_pixels; ++i) {
+		const uint32_t p = pixels[i];
+		Rng rnd{ rng[p] };
+		for (uint32_t it = first_iteration; it < first_iteration + iteration_count; ++it) {
+			I.pixelIndex = p;
+			I.renderSample(p % W, p / W, it, rnd);
+		}
+	}
+	const size_t n = std::min(log.size(), capacity);
+	std::memcpy(out48, log.data(), n * sizeof(FragLog));
+	return log.size();
 }
 
 // pixel filter as a post pass (zero padded convolution with the FilterCache table)

@@ -40,12 +40,12 @@ class Settings(C.Structure):
                 ("spectral_start", C.c_float), ("spectral_end", C.c_float),
                 ("light_range_start", C.c_float), ("light_range_end", C.c_float),
                 ("time_alpha", C.c_float), ("time_beta", C.c_float),
-                ("filter_radius", C.c_int32), ("filter_offset", C.c_uint32)]
+                ("filter_radius", C.c_int32), ("filter_offset", C.c_uint32), ("film_monotonic", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class Camera(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("right", C.c_float * 3), ("up", C.c_float * 3), ("dir", C.c_float * 3),
-                ("near_t", C.c_float), ("far_t", C.c_float)]
+                ("near_t", C.c_float), ("far_t", C.c_float), ("type", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class Sampler(C.Structure):
@@ -144,7 +144,7 @@ _host = None
 # every symbol include/prb200_abi.h declares
 ABI_SYMBOLS = ["prb_create", "prb_destroy", "prb_last_error", "prb_device_count", "prb_upload_scene", "prb_upload_rng",
                "prb_download_rng", "prb_render_tiles", "prb_sync", "prb_film_clear", "prb_film_download",
-               "prb_film_download_aov", "prb_film_export_device", "prb_film_import_device", "prb_trace_closest",
+               "prb_film_download_aov", "prb_film_download_feedback", "prb_film_export_device", "prb_film_import_device", "prb_trace_closest",
                "prb_trace_any", "prb_trace_closest_device", "prb_trace_any_device", "prb_generate_camera_rays",
                "prb_material_eval", "prb_material_sample", "prb_get_stats", "prb_reset_stats", "prb_last_device_ms",
                "prb_set_profiling", "prb_get_stage_times"]
@@ -170,6 +170,7 @@ def device_lib():
         lib.prb_film_clear.argtypes = [C.c_void_p]
         lib.prb_film_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.prb_film_download_aov.argtypes = [C.c_void_p, C.c_void_p]
+        lib.prb_film_download_feedback.argtypes = [C.c_void_p, C.c_void_p]
         lib.prb_film_export_device.argtypes = [C.c_void_p, C.c_void_p]
         lib.prb_film_import_device.argtypes = [C.c_void_p, C.c_void_p]
         for n in ("prb_trace_closest", "prb_trace_closest_device"):
@@ -225,6 +226,8 @@ def host_lib():
         lib.prh_random_advance.argtypes = [C.c_uint64, C.c_uint64]
         lib.prh_list_plugins.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
         lib.prh_set_verbosity.argtypes = [C.c_int]
+        lib.prh_abi_sizeof.restype = C.c_uint32
+        lib.prh_abi_sizeof.argtypes = [C.c_char_p]
         lib.prh_render_context_create.restype = C.c_void_p
         lib.prh_render_context_create.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]
         lib.prh_render_context_start.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -376,6 +379,12 @@ class Context:
         aov = np.empty((h, w, 10), dtype=np.float32)
         self._chk(self._lib.prb_film_download_aov(self._h, _ptr(aov)), "prb_film_download_aov")
         return aov
+
+    def film_feedback(self):
+        """AOV_Feedback: per pixel the OR of the PRB_FEEDBACK_* bits of rejected fragments"""
+        fb = np.empty((self.scene.height, self.scene.width), dtype=np.uint32)
+        self._chk(self._lib.prb_film_download_feedback(self._h, _ptr(fb)), "prb_film_download_feedback")
+        return fb
 
     def film_export_device(self, device_ptr):
         self._chk(self._lib.prb_film_export_device(self._h, C.c_void_p(device_ptr)), "prb_film_export_device")

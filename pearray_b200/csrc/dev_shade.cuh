@@ -1157,9 +1157,14 @@ PRB_DEV void constructCameraRay(const DScene& S, uint32_t px, uint32_t py, uint3
 	}
 	const float nx = 2 * (pixx / (float)st.film_width - 0.5f);
 	const float ny = -(2 * (pixy / (float)st.film_height - 0.5f));
-	const V3 dir   = (ld3(S.camera.right) * nx + ld3(S.camera.up) * ny) + ld3(S.camera.dir);
-	o.origin	   = ld3(S.camera.origin);
-	o.dir		   = normalized(dir);
+	if (S.camera.type == PRB_CAMERA_ORTHOGRAPHIC) { // OrthoCamera::constructRay, plugins/main/cameras/ortho.cpp:47-66
+		o.origin = (ld3(S.camera.origin) + ld3(S.camera.right) * nx) + ld3(S.camera.up) * ny;
+		o.dir	 = ld3(S.camera.dir);
+	} else {
+		const V3 dir = (ld3(S.camera.right) * nx + ld3(S.camera.up) * ny) + ld3(S.camera.dir);
+		o.origin	 = ld3(S.camera.origin);
+		o.dir		 = normalized(dir);
+	}
 	o.tmin		   = S.camera.near_t;
 	o.tmax		   = S.camera.far_t;
 	o.mono		   = st.spectral_mono || !st.spectral_hero;

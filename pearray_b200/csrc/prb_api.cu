@@ -81,8 +81,9 @@ struct prb_ctx {
 	// film
 	DBuf<uint64_t> rng;
 	DBuf<float> filmMean, filmTmp, aov;
-	DBuf<uint32_t> sampleCount;
+	DBuf<uint32_t> sampleCount, feedback;
 	DBuf<unsigned long long> stats;
+	bool rngUploaded = false;
 	// wavefront
 	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters, regenList;
 	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ, prevAcc;
@@ -100,8 +101,10 @@ struct prb_ctx {
 	// bookkeeping
 	uint64_t kernelLaunches = 0, wavefrontIterations = 0;
 	float lastMs = 0;
+	// the wavefront graph (ITERS_PER_GRAPH x k_trace, k_shade, k_regen) is instantiated once and replayed by every
+	// prb_render_tiles call until something baked into its kernel parameters changes (scene, slot buffers, variant)
 	cudaGraphExec_t graphExec = nullptr;
-	uint32_t graphSlots = 0;
+	uint64_t graphKey = 0, stateVersion = 1; // stateVersion: bumped whenever the scene or the slot buffers change
 	bool wantAOV = true;
 	bool persistentTrace = true; // k_trace (persistent threads) vs k_trace_static, chosen per scene in prb_upload_scene
 	// per-stage profiling (prb_set_profiling)
@@ -177,7 +180,7 @@ void prb_destroy(prb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	if (c->graphExec)
 		cudaGraphExecDestroy(c->graphExec);
-	DBuf<uint32_t>* ub[] = { &c->entityMaterials, &c->faceIndices, &c->faceSlots, &c->tlasRefs, &c->sampleCount, &c->pixel, &c->iter, &c->flagsDepth,
+	DBuf<uint32_t>* ub[] = { &c->entityMaterials, &c->faceIndices, &c->faceSlots, &c->tlasRefs, &c->sampleCount, &c->feedback, &c->pixel, &c->iter, &c->flagsDepth,
 							 &c->slotState, &c->counters, &c->regenList, &c->scratchU };
 	for (auto* b : ub)
 		b->release();
@@ -210,12 +213,57 @@ void prb_destroy(prb_ctx* c)
 	delete c;
 }
 
+// number of BVH8 levels below (and including) `root`; 0 when an index is out of range or the tree is deeper than `limit`
+static uint32_t bvhLevels(const prb_scene_desc* d, uint32_t root, uint32_t limit)
+{
+	struct Item {
+		uint32_t node, level;
+	};
+	std::vector<Item> todo{ { root, 1 } };
+	uint32_t deepest = 0;
+	while (!todo.empty()) {
+		const Item it = todo.back();
+		todo.pop_back();
+		if (it.node >= d->n_bvh_nodes || it.level > limit)
+			return 0;
+		deepest					= std::max(deepest, it.level);
+		const prb_bvh8_node& n = d->bvh_nodes[it.node];
+		for (int i = 0; i < 8; ++i)
+			if (n.meta[i] != 0xFF && (n.meta[i] & 0x80))
+				todo.push_back({ n.child_base + (n.meta[i] & 0x7Fu), it.level + 1 });
+	}
+	return deepest;
+}
+
 prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 {
 	if (!c || !d)
 		return fail(PRB_ERR_INVALID_ARG, "null argument");
 	if (d->abi_version != PRB_ABI_VERSION)
 		return fail(PRB_ERR_INVALID_ARG, "scene descriptor ABI version mismatch");
+	{
+		// The traversal stack holds BVH_STACK groups per ray.  A node visit parks at most two groups (the unvisited hit
+		// children and the hit leaf primitives), entering a BLAS three (both TLAS groups and the exit marker), so a scene
+		// needs 2 x TLAS levels + 3 + 2 x deepest BLAS levels entries; a deeper BVH would silently drop subtrees, so it is
+		// rejected here instead.
+		const uint32_t limit = BVH_STACK;
+		const uint32_t tlas	 = bvhLevels(d, d->tlas_root, limit);
+		uint32_t blas		 = 0;
+		bool ok				 = tlas != 0;
+		std::vector<uint32_t> seen;
+		for (uint32_t i = 0; ok && i < d->n_entities; ++i) {
+			const uint32_t r = d->entities[i].blas_root;
+			if (d->entities[i].type == PRB_ENTITY_SPHERE || r == PRB_INVALID_ID || std::find(seen.begin(), seen.end(), r) != seen.end())
+				continue;
+			seen.push_back(r);
+			const uint32_t l = bvhLevels(d, r, limit);
+			ok				 = l != 0;
+			blas			 = std::max(blas, l);
+		}
+		if (!ok || 2 * tlas + 3 + 2 * blas > (uint32_t)BVH_STACK)
+			return fail(PRB_ERR_UNSUPPORTED, "BVH too deep for the " + std::to_string(BVH_STACK) + "-entry traversal stack (or a node index is out of range): TLAS " +
+												 std::to_string(tlas) + " levels, deepest BLAS " + std::to_string(blas) + " levels");
+	}
 	static_assert(sizeof(prb_bvh8_node) == 80, "node must be 80 bytes");
 	static_assert(sizeof(prb_bvh_tri) == 48, "triangle must be 48 bytes");
 	CU(cudaSetDevice(c->device));
@@ -254,6 +302,8 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	CU(c->filmTmp.alloc(npix * 4));
 	CU(c->sampleCount.alloc(npix));
 	CU(c->aov.alloc(npix * 10));
+	CU(c->feedback.alloc(npix));
+	CU(cudaMemsetAsync(c->feedback.p, 0, npix * sizeof(uint32_t), s));
 	CU(cudaMemsetAsync(c->filmMean.p, 0, npix * 3 * sizeof(float), s));
 	CU(cudaMemsetAsync(c->sampleCount.p, 0, npix * sizeof(uint32_t), s));
 	CU(cudaMemsetAsync(c->aov.p, 0, npix * 10 * sizeof(float), s));
@@ -314,9 +364,11 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 		else if (std::strcmp(m, "persistent") == 0)
 			c->persistentTrace = true;
 	}
-	c->haveScene = true;
+	c->haveScene   = true;
+	c->rngUploaded = false; // the RNG map was zeroed above: state 0 of the pcg32_fast MCG stays 0 forever
 	c->cachedTiles.clear();
 	c->nSlots = 0;
+	c->stateVersion++;
 	return PRB_OK;
 }
 
@@ -331,6 +383,7 @@ prb_status prb_upload_rng(prb_ctx* c, const uint64_t* states, size_t n)
 	CU(cudaSetDevice(c->device));
 	CU(cudaMemcpyAsync(c->rng.p, states, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
+	c->rngUploaded = true;
 	return PRB_OK;
 }
 prb_status prb_download_rng(prb_ctx* c, uint64_t* states, size_t n)
@@ -356,6 +409,7 @@ prb_status prb_film_clear(prb_ctx* c)
 	CU(cudaMemsetAsync(c->filmMean.p, 0, npix * 3 * sizeof(float), c->stream));
 	CU(cudaMemsetAsync(c->sampleCount.p, 0, npix * sizeof(uint32_t), c->stream));
 	CU(cudaMemsetAsync(c->aov.p, 0, npix * 10 * sizeof(float), c->stream));
+	CU(cudaMemsetAsync(c->feedback.p, 0, npix * sizeof(uint32_t), c->stream));
 	return PRB_OK;
 }
 
@@ -366,12 +420,17 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 		return PRB_OK;
 	const uint32_t W = c->S.settings.film_width, H = c->S.settings.film_height;
 	std::vector<uint32_t> pix;
+	std::vector<uint8_t> owned((size_t)W * H, 0); // slot == pixel: a pixel listed twice would race on its RNG state and film cell
 	for (size_t t = 0; t < n_tiles; ++t) {
 		if (tiles[t].ex > W || tiles[t].ey > H || tiles[t].sx >= tiles[t].ex || tiles[t].sy >= tiles[t].ey)
 			return fail(PRB_ERR_INVALID_ARG, "tile outside the film");
 		for (uint32_t y = tiles[t].sy; y < tiles[t].ey; ++y)
-			for (uint32_t x = tiles[t].sx; x < tiles[t].ex; ++x)
+			for (uint32_t x = tiles[t].sx; x < tiles[t].ex; ++x) {
+				if (owned[(size_t)y * W + x])
+					return fail(PRB_ERR_INVALID_ARG, "tiles overlap: a film pixel may be listed only once per call");
+				owned[(size_t)y * W + x] = 1;
 				pix.push_back(y * W + x);
+			}
 	}
 	const size_t n = pix.size();
 	CU(c->pixel.upload(pix.data(), n, c->stream));
@@ -388,6 +447,7 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 	CU(cudaStreamSynchronize(c->stream));
 	c->cachedTiles.assign(tiles, tiles + n_tiles);
 	c->nSlots = (uint32_t)n;
+	c->stateVersion++;
 	return PRB_OK;
 }
 
@@ -460,6 +520,7 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.filmMean	  = c->filmMean.p;
 	W.sampleCount = c->sampleCount.p;
 	W.aov		  = c->wantAOV ? c->aov.p : nullptr;
+	W.feedback	  = c->feedback.p;
 	W.stats		  = c->stats.p;
 	W.nSlots	  = c->nSlots;
 	W.firstIter	  = first;
@@ -475,6 +536,8 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
 	if (n_tiles == 0 || iteration_count == 0)
 		return PRB_OK;
+	if (!c->rngUploaded)
+		return fail(PRB_ERR_INVALID_ARG, "prb_upload_rng has not been called for this scene (all-zero pcg32_fast states never advance)");
 	CU(cudaSetDevice(c->device));
 	prb_status st = setupSlots(c, tiles, n_tiles);
 	if (st != PRB_OK)
@@ -532,36 +595,46 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 			}
 		}
 	} else {
-		cudaGraph_t graph	 = nullptr;
-		cudaGraphExec_t exec = nullptr;
-		CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-		for (int r = 0; r < ITERS_PER_GRAPH; ++r) {
-			launchTrace(c, W, blocks, s);
-			launchShade(c, W, s);
+		// the kernels of the graph read the iteration range from device memory (CNT_END_ITER, written by k_init_slots), so one
+		// instantiated graph serves every call until the scene, the slot buffers or the kernel variant change
+		const uint64_t key = (c->stateVersion << 2) | (c->persistentTrace ? 1u : 0u) | (c->wantAOV ? 2u : 0u);
+		if (!c->graphExec || c->graphKey != key) {
+			if (c->graphExec) {
+				cudaGraphExecDestroy(c->graphExec);
+				c->graphExec = nullptr;
+			}
+			cudaGraph_t graph = nullptr;
+			CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+			for (int r = 0; r < ITERS_PER_GRAPH; ++r) {
+				launchTrace(c, W, blocks, s);
+				launchShade(c, W, s);
+			}
+			const cudaError_t ce = cudaGetLastError();
+			const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+			if (ce != cudaSuccess || ee != cudaSuccess) {
+				if (graph)
+					cudaGraphDestroy(graph);
+				return fail(PRB_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+			}
+			const cudaError_t ie = cudaGraphInstantiate(&c->graphExec, graph, 0);
+			cudaGraphDestroy(graph);
+			if (ie != cudaSuccess) {
+				c->graphExec = nullptr;
+				return fail(PRB_ERR_CUDA, std::string("graph instantiation failed: ") + cudaGetErrorString(ie));
+			}
+			c->graphKey = key;
 		}
-		const cudaError_t ce = cudaGetLastError();
-		const cudaError_t ee = cudaStreamEndCapture(s, &graph);
-		if (ce != cudaSuccess || ee != cudaSuccess) {
-			if (graph)
-				cudaGraphDestroy(graph);
-			return fail(PRB_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
-		}
-		CU(cudaGraphInstantiate(&exec, graph, 0));
-		cudaGraphDestroy(graph);
 		while (!finished && done < maxIters + ITERS_PER_GRAPH * GRAPHS_PER_POLL) {
 			cudaError_t e = cudaSuccess;
 			for (int r = 0; r < GRAPHS_PER_POLL && e == cudaSuccess; ++r)
-				e = cudaGraphLaunch(exec, s);
+				e = cudaGraphLaunch(c->graphExec, s);
 			done += ITERS_PER_GRAPH * GRAPHS_PER_POLL;
 			c->kernelLaunches += 3 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
 			if (e == cudaSuccess)
 				e = poll();
-			if (e != cudaSuccess) {
-				cudaGraphExecDestroy(exec);
+			if (e != cudaSuccess)
 				return fail(PRB_ERR_CUDA, std::string("wavefront loop failed: ") + cudaGetErrorString(e));
-			}
 		}
-		cudaGraphExecDestroy(exec);
 	}
 	// flush: samples that ended with their last shadow ray in flight are folded into the film by k_trace
 	launchTrace(c, W, blocks, s);
@@ -628,6 +701,16 @@ prb_status prb_film_download_aov(prb_ctx* c, float* aov10)
 	CU(cudaSetDevice(c->device));
 	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
 	CU(cudaMemcpyAsync(aov10, c->aov.p, npix * 10 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_film_download_feedback(prb_ctx* c, uint32_t* feedback)
+{
+	if (!c || !c->haveScene || !feedback)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded / null buffer");
+	CU(cudaSetDevice(c->device));
+	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
+	CU(cudaMemcpyAsync(feedback, c->feedback.p, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return PRB_OK;
 }

@@ -39,6 +39,35 @@ float prh_sun_radiance(float wavelength, float theta, float turbidity) { return 
 
 const char* prh_last_error() { return g_err.c_str(); }
 void prh_set_verbosity(int level) { logVerbosity() = level; }
+// sizeof() of the POD structs of include/prb200_abi.h as this library was compiled, for checking FFI mirrors (ctypes, cgo ...)
+uint32_t prh_abi_sizeof(const char* name)
+{
+	const std::string n = name ? name : "";
+#define PRH_SIZE_OF(T) \
+	if (n == #T)       \
+		return (uint32_t)sizeof(T);
+	PRH_SIZE_OF(prb_ray_soa)
+	PRH_SIZE_OF(prb_hit_soa)
+	PRH_SIZE_OF(prb_node)
+	PRH_SIZE_OF(prb_material)
+	PRH_SIZE_OF(prb_emission)
+	PRH_SIZE_OF(prb_mesh)
+	PRH_SIZE_OF(prb_entity)
+	PRH_SIZE_OF(prb_bvh8_node)
+	PRH_SIZE_OF(prb_bvh_tri)
+	PRH_SIZE_OF(prb_light)
+	PRH_SIZE_OF(prb_sampler)
+	PRH_SIZE_OF(prb_spectral_mapper)
+	PRH_SIZE_OF(prb_camera)
+	PRH_SIZE_OF(prb_settings)
+	PRH_SIZE_OF(prb_scene_desc)
+	PRH_SIZE_OF(prb_tile)
+	PRH_SIZE_OF(prb_stats)
+	PRH_SIZE_OF(prb_material_query)
+	PRH_SIZE_OF(prb_material_result)
+#undef PRH_SIZE_OF
+	return 0;
+}
 
 // Load a .prc file (or source string) and compile it; returns NULL on error.
 void* prh_load_scene_file(const char* path)

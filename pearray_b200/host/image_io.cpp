@@ -36,7 +36,7 @@ const VarName k1D[]		  = { { "entity_id", OV_EntityID, "entity_id" }, { "entity"
 							  { "displace_id", OV_Unsupported, "displace_id" }, { "displace", OV_Unsupported, "displace_id" },
 							  { "depth", OV_Depth, "depth" }, { "d", OV_Depth, "depth" } };
 const VarName kCounter[]  = { { "sample_count", OV_SampleCount, "sample_count" }, { "samples", OV_SampleCount, "sample_count" }, { "s", OV_SampleCount, "sample_count" },
-							  { "feedback", OV_Unsupported, "feedback" }, { "f", OV_Unsupported, "feedback" }, { "error", OV_Unsupported, "feedback" } };
+							  { "feedback", OV_Feedback, "feedback" }, { "f", OV_Feedback, "feedback" }, { "error", OV_Feedback, "feedback" } };
 const VarName k3D[]		  = { { "position", OV_Position, "position" }, { "pos", OV_Position, "position" }, { "p", OV_Position, "position" },
 							  { "normal", OV_Normal, "normal" }, { "norm", OV_Normal, "normal" }, { "n", OV_Normal, "normal" },
 							  { "normal_geometric", OV_Unsupported, "normal_geometric" }, { "ng", OV_Unsupported, "normal_geometric" },
@@ -308,6 +308,9 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 		if (c.variable == OV_SampleCount && film.sampleCount)
 			for (size_t i = 0; i < n; ++i)
 				p[i] = static_cast<float>(film.sampleCount[i]);
+		if (c.variable == OV_Feedback && film.feedback) // AOV_Feedback: OR of the OutputFeedback bits of rejected fragments
+			for (size_t i = 0; i < n; ++i)
+				p[i] = static_cast<float>(film.feedback[i]);
 	}
 	if (data.empty())
 		return false;

@@ -404,11 +404,6 @@ std::shared_ptr<Environment> SceneLoader::createEnvironment(const std::vector<DL
 	}
 	if (spectralHeroD.type() == DL::DT_Bool)
 		rs.spectralHero = spectralHeroD.getBool();
-	if (rs.spectralMono) // known deviation, DESIGN.md section 6: the reference's monotonic film stores the hero weight in all three channels
-		PR_LOG(L_WARNING) << "single-wavelength spectral_domain: the film holds the CIE-weighted XYZ of the hero sample, the reference writes the "
-							 "unweighted hero sample to all three channels (LocalFrameOutputDevice.cpp:76-85)"
-						  << std::endl;
-
 	std::vector<DL::DataGroup> inner;
 	for (size_t i = 0; i < top.anonymousCount(); ++i)
 		if (top.at(i).type() == DL::DT_Group)

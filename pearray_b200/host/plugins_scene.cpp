@@ -253,11 +253,64 @@ public:
 		}
 		out.near_t = mNearT;
 		out.far_t  = mFarT;
+		out.type   = PRB_CAMERA_PERSPECTIVE;
 	}
 
 private:
 	float mWidth, mHeight, mNearT, mFarT;
 	Vector3f mLD, mLR, mLU;
+};
+class OrthoCamera : public ICamera { // plugins/main/cameras/ortho.cpp:15-84
+public:
+	OrthoCamera(const std::string& name, const Transformf& t, float w, float h, float nearT, float farT, const Vector3f& ld, const Vector3f& lr, const Vector3f& lu)
+		: ICamera(name, t)
+		, mWidth(w)
+		, mHeight(h)
+		, mNearT(nearT)
+		, mFarT(farT)
+		, mLD(ld)
+		, mLR(lr)
+		, mLU(lu)
+	{
+	}
+	std::string type() const override { return "orthographic"; }
+	void describe(prb_camera& out) const override
+	{ // the cached members of the constructor, ortho.cpp:29-31: the direction is normalised, right / up carry half the extent
+		const Vector3f dir	 = (transform().linear() * mLD).normalized();
+		const Vector3f right = (transform().linear() * mLR) * 0.5f * mWidth;
+		const Vector3f up	 = (transform().linear() * mLU) * 0.5f * mHeight;
+		const Vector3f o	 = transform().translation();
+		for (int i = 0; i < 3; ++i) {
+			out.origin[i] = o[i];
+			out.right[i]  = right[i];
+			out.up[i]	  = up[i];
+			out.dir[i]	  = dir[i];
+		}
+		out.near_t = mNearT;
+		out.far_t  = mFarT;
+		out.type   = PRB_CAMERA_ORTHOGRAPHIC;
+	}
+
+private:
+	float mWidth, mHeight, mNearT, mFarT;
+	Vector3f mLD, mLR, mLU;
+};
+class OrthoCameraPlugin : public ICameraPlugin {
+public:
+	std::shared_ptr<ICamera> create(const std::string&, const SceneLoadContext& ctx) override
+	{
+		const ParameterGroup& params = ctx.parameters();
+		return std::make_shared<OrthoCamera>(params.getString("name", "__unnamed__"), ctx.transform(), params.getNumber("width", 1), params.getNumber("height", 1),
+											 params.getNumber("near", 0.000001f), params.getNumber("far", PR_INF),
+											 params.getVector3f("local_direction", Vector3f(0, 1, 0)), params.getVector3f("local_right", Vector3f(1, 0, 0)),
+											 params.getVector3f("local_up", Vector3f(0, 0, 1)));
+	}
+	const std::vector<std::string>& getNames() const override
+	{
+		static std::vector<std::string> names({ "ortho", "orthographic" });
+		return names;
+	}
+	std::string specification(const std::string&) const override { return "Orthogonal Camera: width, height, near, far, local_direction, local_right, local_up"; }
 };
 class PerspectiveCameraPlugin : public ICameraPlugin {
 public:
@@ -1114,6 +1167,7 @@ void registerScenePlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 	out.push_back(std::make_shared<SphereEntityPlugin>());
 	out.push_back(std::make_shared<PlaneEntityPlugin>());
 	out.push_back(std::make_shared<PerspectiveCameraPlugin>());
+	out.push_back(std::make_shared<OrthoCameraPlugin>());
 	out.push_back(std::make_shared<DiffuseEmissionPlugin>());
 	out.push_back(std::make_shared<EnvironmentLightFactory>());
 	out.push_back(std::make_shared<SamplerPlugin>(SamplerKind::Sobol));

@@ -637,7 +637,7 @@ struct RenderSettings { // reference src/core/renderer/RenderSettings.cpp:11-33
 
 // ------------------------------------------------------------------ output specification + image writer (image_io.cpp)
 enum class ToneColorMode { SRGB, XYZ, XYZNorm, Luminance }; // reference src/core/spectral/ToneMapper.h
-enum OutputVariable { OV_Unsupported = -1, OV_Output = 0, OV_Position, OV_Normal, OV_UVW, OV_Depth, OV_EntityID, OV_SampleCount };
+enum OutputVariable { OV_Unsupported = -1, OV_Output = 0, OV_Position, OV_Normal, OV_UVW, OV_Depth, OV_EntityID, OV_SampleCount, OV_Feedback };
 struct OutputChannel { // reference IM_ChannelSetting{Spec,3D,1D,Counter}, src/loader/output/io/ImageWriter.h
 	enum Kind { Spectral, ThreeD, OneD, Counter } kind = Spectral;
 	int variable	  = OV_Output;
@@ -654,6 +654,7 @@ struct FilmView { // what prb_film_download / prb_film_aov return for one contex
 	uint32 fullWidth = 0, fullHeight = 0; // film size
 	const float* xyz		  = nullptr;  // 3 per pixel
 	const uint32* sampleCount = nullptr;  // 1 per pixel
+	const uint32* feedback	  = nullptr;  // 1 per pixel: OR of PRB_FEEDBACK_* bits; may be null
 	const float* aov		  = nullptr;  // 10 per pixel (N, P, u, v, depth, entity id), sums over the samples; may be null
 };
 class OutputSpecification { // reference src/loader/output/io/OutputSpecification.h

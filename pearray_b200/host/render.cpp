@@ -88,7 +88,7 @@ int RenderContext::saveOutputs(const std::string& workingDir)
 	const prb_settings& st = mScene->desc.settings;
 	const size_t n		   = (size_t)st.film_width * st.film_height;
 	std::vector<float> xyz(n * 3), aov;
-	std::vector<uint32> count(n);
+	std::vector<uint32> count(n), feedback(n);
 	if (!mCtx || prb_film_download(mCtx, xyz.data(), count.data()) != PRB_OK) {
 		PR_LOG(L_ERROR) << "prb_film_download failed: " << prb_last_error() << std::endl;
 		return -1;
@@ -101,6 +101,8 @@ int RenderContext::saveOutputs(const std::string& workingDir)
 	aov.resize(n * 10);
 	if (prb_film_download_aov(mCtx, aov.data()) == PRB_OK) // AOVs are optional (prb_settings.enable_aov)
 		film.aov = aov.data();
+	if (prb_film_download_feedback(mCtx, feedback.data()) == PRB_OK)
+		film.feedback = feedback.data();
 	return mEnv->outputSpecification().save(workingDir, film, mRank);
 }
 prb_stats RenderContext::statistics() const

@@ -26,7 +26,9 @@ def lib():
         l.orc_scene_create.argtypes = [C.POINTER(prb.SceneDesc)]
         l.orc_scene_destroy.argtypes = [C.c_void_p]
         l.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(prb.Tile), C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_int]
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        l.orc_log_fragments.restype = C.c_size_t
+        l.orc_log_fragments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         l.orc_apply_filter.argtypes = [C.POINTER(prb.SceneDesc), C.c_void_p, C.c_void_p]
         l.orc_trace_closest.argtypes = [C.c_void_p, C.POINTER(prb.RaySoA), C.c_size_t, C.POINTER(prb.HitSoA), C.c_int]
         l.orc_trace_any.argtypes = [C.c_void_p, C.POINTER(prb.RaySoA), C.c_size_t, C.c_void_p, C.c_int]
@@ -81,23 +83,42 @@ class OracleScene:
         self.scene = scene
         self._h = lib().orc_scene_create(scene.desc)
 
-    def render(self, tiles, first_iteration, iteration_count, rng=None, threads=None, film=None, count=None, aov=True):
-        """returns dict(film (unfiltered mean), filtered, count, aov, stats, rng)"""
+    def render(self, tiles, first_iteration, iteration_count, rng=None, threads=None, film=None, count=None, aov=True, feedback=None):
+        """returns dict(film (unfiltered mean), filtered, count, aov, stats, rng, feedback)"""
         w, h = self.scene.width, self.scene.height
         rng = self.scene.rng_map() if rng is None else np.array(rng, dtype=np.uint64, copy=True)
         film = np.zeros((h, w, 3), np.float32) if film is None else film
         count = np.zeros((h, w), np.uint32) if count is None else count
         aovb = np.zeros((h, w, 10), np.float32) if aov else None
         stats = np.zeros(11, np.uint64)
+        feedback = np.zeros((h, w), np.uint32) if feedback is None else feedback
         threads = threads or os.cpu_count() or 1
         arr = prb.make_tiles(tiles)
         lib().orc_render(self._h, _p(rng), arr, len(tiles), first_iteration, iteration_count, _p(film), _p(count),
-                         _p(aovb) if aov else None, _p(stats), threads)
+                         _p(aovb) if aov else None, _p(stats), threads, _p(feedback))
         filtered = np.empty_like(film)
         lib().orc_apply_filter(self.scene.desc, _p(film), _p(filtered))
         names = ["camera_ray_count", "light_ray_count", "primary_ray_count", "bounce_ray_count", "shadow_ray_count", "monochrome_ray_count",
                  "pixel_sample_count", "entity_hit_count", "background_hit_count", "camera_depth_count", "light_depth_count"]
-        return dict(film=film, filtered=filtered, count=count, aov=aovb, stats=dict(zip(names, (int(x) for x in stats))), rng=rng)
+        return dict(film=film, filtered=filtered, count=count, aov=aovb, stats=dict(zip(names, (int(x) for x in stats))), rng=rng, feedback=feedback)
+
+    FRAG_FIELDS = [("kind", 1), ("flags", 1), ("depth", 1), ("pixel", 1), ("mis", 4), ("importance", 4), ("radiance", 4), ("pathPDF", 4),
+                   ("prevPathPDF", 4), ("wvlPDF", 4), ("bsdfPDF", 4), ("lightPdfS", 1), ("roulette", 1), ("extra", 1), ("accepted", 1),
+                   ("infPdfS", 4), ("wvl", 4), ("groupImportance", 4)]
+
+    def log_fragments(self, pixels, first_iteration, iteration_count, rng=None, capacity=1 << 20):
+        """every fragment the integrator pushes for the listed pixels (struct FragLog of oracle.cpp) as a dict of arrays"""
+        rng = self.scene.rng_map() if rng is None else np.ascontiguousarray(rng, dtype=np.uint64)
+        pixels = np.ascontiguousarray(pixels, dtype=np.uint32)
+        buf = np.zeros((capacity, 48), np.float32)
+        n = lib().orc_log_fragments(self._h, _p(rng), _p(pixels), pixels.size, first_iteration, iteration_count, _p(buf), capacity)
+        assert n <= capacity, "fragment log overflow"
+        buf = buf[:n]
+        out, o = {}, 0
+        for name, w in self.FRAG_FIELDS:
+            out[name] = buf[:, o] if w == 1 else buf[:, o:o + w]
+            o += w
+        return out
 
     @staticmethod
     def _soa(o, d, tmin, tmax, keep):

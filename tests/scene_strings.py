@@ -128,3 +128,134 @@ MATERIAL_ZOO3 = """
  (light :type 'env' :radiance (illuminant "D65"))
 )
 """
+
+# The two scenes of the reference's end-to-end furnace test, src/tests/python/whitefurnance.py:10-140, verbatim (test
+# fixtures: unit sphere, albedo 1, constant environment; orthographic camera, hammersley 8 spp, block filter radius 0).
+# Use with .format(size=...) / .format(hero="true"|"false", size=...).
+WHITEFURNACE_SPEC = """
+(scene
+    :name 'spectral_test'
+    :render_width {size}
+    :render_height {size}
+    :spectral_domain 520
+
+    ; Settings
+    (integrator
+        :type 'DIRECT'
+        :max_ray_depth 4
+        :light_sampe_count 1
+    )
+    (sampler
+        :slot 'aa'
+        :type 'hammersley'
+        :sample_count 8
+    )
+    (filter
+        :slot 'pixel'
+        :type 'BLOCK'
+        :radius 0
+    )
+    ; Outputs
+    (output
+        :name 'image'
+        (channel :type 'color' :color 'srgb' )
+    )
+    ; Camera
+    (camera
+        :name 'Camera'
+        :type 'orthographic'
+        :width 2
+        :height 2
+        :local_direction [0,0,1]
+        :local_up [0,1,0]
+        :local_right [1,0,0]
+        :position [0,0,-1.0005]
+    )
+    ; Background
+    (light
+        :name 'background'
+        :type 'env'
+        :radiance 1
+    )
+    ; Materials
+    (material
+        :name 'Diffuse'
+        :type 'diffuse'
+        :albedo 1
+    )
+    ; Primitives
+    (entity
+        :type "sphere"
+        :name "Unit Sphere"
+        :radius 1
+        :material "Diffuse"
+    )
+)
+"""
+
+WHITEFURNACE_FULL = """
+(scene
+    :name 'illum_test'
+    :render_width {size}
+    :render_height {size}
+    :camera 'Camera'
+    :spectral_hero {hero}
+
+    ; Settings
+    (integrator
+        :type 'DIRECT'
+        :max_ray_depth 4
+        :light_sampe_count 1
+    )
+    (sampler
+        :slot 'aa'
+        :type 'hammersley'
+        :sample_count 8
+    )
+    (sampler
+        :slot 'spectral'
+        :type 'random'
+        :sample_count 1
+    )
+    (filter
+        :slot 'pixel'
+        :type 'BLOCK'
+        :radius 0
+    )
+    ; Outputs
+    (output
+        :name 'image'
+        (channel :type 'color' :color 'srgb' )
+    )
+    ; Camera
+    (camera
+        :name 'Camera'
+        :type 'orthographic'
+        :width 2
+        :height 2
+        :local_direction [0,0,1]
+        :local_up [0,1,0]
+        :local_right [1,0,0]
+        :position [0,0,-1.00005]
+    )
+    ; Background
+    (light
+        :name 'background'
+        :type 'env'
+        :radiance (illuminant "D65")
+    )
+    ; Materials
+    (material
+        :name 'Diffuse'
+        :type 'diffuse'
+        :albedo "white"
+    )
+    ; Primitives
+    (entity
+        :type "sphere"
+        :name "Unit Sphere"
+        :radius 1
+        :material "Diffuse"
+    )
+)
+"""

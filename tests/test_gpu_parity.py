@@ -436,3 +436,196 @@ def test_gpu_vs_reference_golden_image():
     lum_err, ratio = cbox_reference_error(xyz)
     assert lum_err < CBOX_LUMINANCE_TOL, lum_err
     assert np.all(np.abs(ratio - 1) < CBOX_CHANNEL_TOL), ratio
+
+
+# ------------------------------------------------------------------ round 2: the reference's furnace test, monochrome modes, feedback
+@pytest.mark.parametrize("mode", ["spec", "non_hero", "full"])
+def test_whitefurnance_gpu(mode):
+    """literal port of src/tests/python/whitefurnance.py on the device (tests/test_whitefurnance.py holds the derivation of the
+    asserted values): 200x200, hammersley 8 spp, block filter radius 0, orthographic camera, ctx.start(8, 8); film, sample
+    counts, feedback bits, RNG states and counters bit-equal to the oracle, and the reference test's probes on the device film"""
+    import test_whitefurnance as wf
+    scene = prb.Scene.from_string(wf.MODES[mode])
+    ctx = make_ctx(scene)
+    ctx.reset_stats()
+    tiles = scene.tiles(8, 8)
+    ctx.render_tiles(tiles, 0, 8)
+    xyz, cnt = ctx.film()
+    fb = ctx.film_feedback()
+    ref = OracleScene(scene).render(tiles, 0, 8, rng=scene.rng_map())
+    assert np.array_equal(cnt, ref["count"])
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
+    assert np.array_equal(fb, ref["feedback"])
+    st = ctx.stats()
+    assert {k: int(getattr(st, k)) for k in STAT_NAMES} == ref["stats"]
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
+    if mode == "spec":
+        wf.check_spec(xyz, fb, cnt)
+    else:
+        other = "non_hero" if mode == "full" else "full"
+        s2 = prb.Scene.from_string(wf.MODES[other])
+        c2 = make_ctx(s2)
+        c2.render_tiles(s2.tiles(8, 8), 0, 8)
+        x2, _ = c2.film()
+        f2 = c2.film_feedback()
+        if mode == "full":
+            wf.check_cie_modes(xyz, x2, fb, f2, cnt)
+        else:
+            wf.check_cie_modes(x2, xyz, f2, fb, cnt)
+
+
+@pytest.mark.parametrize("variant", ["non_hero", "single_wavelength", "single_wavelength_zoo", "non_hero_zoo"])
+def test_monochrome_modes_vs_oracle(variant):
+    """`:spectral_hero false` (forced-monochrome rays, ordinary film) and `:spectral_domain <nm>` (monotonic film) against the
+    oracle: film, feedback bits, RNG states; on the furnace and on the material zoo (NEE fragments of monochrome rays are NaN
+    as direct.cpp is written, delta materials and area lights included)"""
+    if variant == "non_hero":
+        src, tile, it = FURNACE % dict(hero="false"), (0, 0, 48, 48), 16
+    elif variant == "single_wavelength":
+        src, tile, it = (FURNACE % dict(hero="true")).replace(":spectral_hero true", ":spectral_hero true :spectral_domain 520"), (0, 0, 48, 48), 16
+    elif variant == "single_wavelength_zoo":
+        src, tile, it = MATERIAL_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_domain 610"), (0, 0, 32, 32), 8
+    else:
+        src, tile, it = MATERIAL_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_hero false"), (0, 0, 32, 32), 8
+    scene = prb.Scene.from_string(src)
+    assert bool(scene.settings.film_monotonic) == variant.startswith("single_wavelength")
+    ctx = make_ctx(scene)
+    ctx.render_tiles([tile], 0, it)
+    xyz, cnt = ctx.film()
+    ref = OracleScene(scene).render([tile], 0, it, rng=scene.rng_map())
+    assert np.array_equal(ctx.download_rng(), ref["rng"]) and np.array_equal(cnt, ref["count"])
+    assert np.array_equal(ctx.film_feedback(), ref["feedback"])
+    assert ref["feedback"].any()
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
+    if variant.startswith("single_wavelength"):
+        assert np.array_equal(xyz[..., 0], xyz[..., 1]) and np.array_equal(xyz[..., 0], xyz[..., 2])
+
+
+def test_feedback_is_zero_on_the_config_scenes():
+    for name in ("c2_cornellbox", "c3_cornellbox_glassy"):
+        g = load_golden(name)
+        scene = load_scene(name)
+        ctx = make_ctx(scene)
+        sx, sy, ex, ey = (int(x) for x in g["tile"])
+        ctx.render_tiles([(sx, sy, ex, ey)], 0, 4)
+        ref = OracleScene(scene).render([(sx, sy, ex, ey)], 0, 4, rng=scene.rng_map())
+        assert np.array_equal(ctx.film_feedback(), ref["feedback"])
+
+
+def test_render_tiles_validation_and_rerender():
+    """overlapping tiles and a missing RNG map are rejected; a second render from iteration 0 starts the
+    counters from scratch; the cached CUDA graph serves calls with different iteration ranges"""
+    scene = load_scene("c2_cornellbox")
+    fresh = prb.Context(0)
+    fresh.upload_scene(scene)
+    with pytest.raises(prb.PrbError):
+        fresh.render_tiles([(0, 0, 8, 8)], 0, 1)  # prb_upload_rng not called
+    ctx = make_ctx(scene)
+    with pytest.raises(prb.PrbError):
+        ctx.render_tiles([(0, 0, 16, 16), (8, 8, 24, 24)], 0, 1)  # overlap
+    tile = [(100, 100, 164, 164)]
+    ctx.render_tiles(tile, 0, 3)
+    a, ca = ctx.film()
+    rng_a = ctx.download_rng()
+    ctx.upload_rng(scene.rng_map())
+    ctx.render_tiles(tile, 0, 3)  # again from scratch: same film, counts not doubled
+    b, cb = ctx.film()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ca, cb) and ca.max() == 3
+    assert np.array_equal(rng_a, ctx.download_rng())
+    ctx.upload_rng(scene.rng_map())
+    ctx.render_tiles(tile, 0, 1)  # 1 + 2 iterations through the same cached graph == 3
+    ctx.render_tiles(tile, 1, 2)
+    c, cc = ctx.film()
+    assert np.array_equal(a.view(np.uint32), c.view(np.uint32)) and np.array_equal(ca, cc)
+
+
+# ------------------------------------------------------------------ round 2: parity at the benchmarked C5 size
+@pytest.fixture(scope="module")
+def soup10m():
+    scene = prb.Scene.soup(10000000, seed=1234, film=(2048, 2048))
+    ctx = make_ctx(scene)
+    return scene, ctx, OracleScene(scene)
+
+
+def test_soup_10m_hits_bit_exact_vs_oracle(soup10m):
+    """BASELINE config 5 at its named size (10 M triangles, the scene bench.py --scene c5 times): 64 k primary rays, their
+    shadow rays and 64 k incoherent bounce rays through prb_trace_*_device (persistent kernels with the lane-refill path,
+    ray streams resident in HBM) against the oracle's own BVH: (entity, prim, u, v, t) and occlusion bit for bit"""
+    import torch
+    scene, ctx, ora = soup10m
+    dev = torch.device("cuda", 0)
+    n = 65536
+    org, dr, wvl, pix = ctx.generate_camera_rays([(0, 0, 2048, 2048)], 3)
+    rs = np.random.RandomState(11)
+    sel = np.sort(rs.choice(len(org), n, replace=False))
+    org, dr = np.ascontiguousarray(org[sel]), np.ascontiguousarray(dr[sel])
+
+    def device_closest(o, d, tmin=None):
+        cols = [torch.from_numpy(np.ascontiguousarray(o[:, i])).to(dev) for i in range(3)] + [torch.from_numpy(np.ascontiguousarray(d[:, i])).to(dev) for i in range(3)]
+        tm = torch.from_numpy(tmin).to(dev) if tmin is not None else None
+        ent = torch.empty(len(o), dtype=torch.int32, device=dev); prim = torch.empty_like(ent)
+        u = torch.empty(len(o), dtype=torch.float32, device=dev); v = torch.empty_like(u); t = torch.empty_like(u)
+        ctx.trace_closest_device([c.data_ptr() for c in cols] + [tm.data_ptr() if tm is not None else None, None], len(o),
+                                 [ent.data_ptr(), prim.data_ptr(), u.data_ptr(), v.data_ptr(), t.data_ptr()])
+        torch.cuda.synchronize(dev)
+        return (ent.cpu().numpy().view(np.uint32), prim.cpu().numpy().view(np.uint32), u.cpu().numpy(), v.cpu().numpy(), t.cpu().numpy())
+
+    def device_any(o, d, tmin, tmax):
+        cols = [torch.from_numpy(np.ascontiguousarray(o[:, i])).to(dev) for i in range(3)] + [torch.from_numpy(np.ascontiguousarray(d[:, i])).to(dev) for i in range(3)]
+        tm, tx = torch.from_numpy(tmin).to(dev), torch.from_numpy(tmax).to(dev)
+        occ = torch.empty(len(o), dtype=torch.uint8, device=dev)
+        ctx.trace_any_device([c.data_ptr() for c in cols] + [tm.data_ptr(), tx.data_ptr()], len(o), occ.data_ptr())
+        torch.cuda.synchronize(dev)
+        return occ.cpu().numpy()
+
+    got = device_closest(org, dr)
+    ref = ora.trace_closest(org, dr)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), "primary hit ids"
+    hit = got[0] != prb.INVALID_ID
+    assert hit.mean() > 0.5
+    for a, b in zip(got[2:], ref[2:]):
+        assert np.array_equal(a[hit].view(np.uint32), b[hit].view(np.uint32))
+    # shadow rays towards the point light of the benchmark (Scene::traceShadowRay semantics)
+    P = (org[hit] + dr[hit] * got[4][hit, None]).astype(np.float32)
+    L = np.array([0, 3, 0], np.float32) - P
+    dist = np.linalg.norm(L, axis=1).astype(np.float32)
+    L = (L / dist[:, None]).astype(np.float32)
+    tmin = np.full(len(P), 1e-4, np.float32)
+    tmax = (dist - 1e-3).astype(np.float32)
+    occ = device_any(P, L, tmin, tmax)
+    assert np.array_equal(occ, ora.trace_any(P, L, tmin, tmax)), "shadow occlusion"
+    assert 0.05 < occ.mean() < 1.0
+    # incoherent bounce rays
+    b = rs.normal(size=P.shape)
+    b = (b / np.linalg.norm(b, axis=1, keepdims=True)).astype(np.float32)
+    g2 = device_closest(P, b, tmin)
+    o2 = ora.trace_closest(P, b, tmin)
+    assert np.array_equal(g2[0], o2[0]) and np.array_equal(g2[1], o2[1]), "incoherent hit ids"
+    h2 = g2[0] != prb.INVALID_ID
+    for a, c in zip(g2[2:], o2[2:]):
+        assert np.array_equal(a[h2].view(np.uint32), c[h2].view(np.uint32))
+
+
+def test_bvh_deeper_than_the_traversal_stack_is_rejected():
+    """a BVH whose traversal could overflow the 48-entry stack must not be accepted silently"""
+    scene = load_scene("c2_cornellbox")
+    d = scene.desc.contents
+    n0 = int(d.n_bvh_nodes)
+    nodes = np.zeros((n0 + 40, 80), np.uint8)
+    nodes[:n0] = np.ctypeslib.as_array(C.cast(d.bvh_nodes, C.POINTER(C.c_uint8)), shape=(n0, 80))
+    for k in range(40):  # a chain: every node has one internal child in slot 0 (meta 0x80), the last one is empty
+        node = nodes[n0 + k]
+        node[:] = 0
+        node[24:32] = 0xFF
+        if k < 39:
+            node[16:20] = np.frombuffer(np.uint32(n0 + k + 1).tobytes(), np.uint8)
+            node[24] = 0x80
+            node[15] = 1
+    saved = (d.bvh_nodes, d.n_bvh_nodes, d.tlas_root)
+    try:
+        d.bvh_nodes, d.n_bvh_nodes, d.tlas_root = nodes.ctypes.data, n0 + 40, n0
+        ctx = prb.Context(0)
+        with pytest.raises(prb.PrbError, match="BVH too deep"):
+            ctx.upload_scene(scene)
+    finally:
+        d.bvh_nodes, d.n_bvh_nodes, d.tlas_root = saved
