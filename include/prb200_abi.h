@@ -454,6 +454,33 @@ prb_status prb_film_export_device(prb_ctx* ctx, float* device_dst);
 /* load an (already reduced) unfiltered film back and apply the pixel filter */
 prb_status prb_film_import_device(prb_ctx* ctx, const float* device_src);
 
+/* -- multi-GPU film combine (replaces the image-tile contexts of RenderFactory::create,
+ * src/core/renderer/RenderFactory.cpp:16-42, whose per-context outputs the reference client merges on the host,
+ * src/client/main.cpp:172-173).  The scene is replicated; every context renders its share and ONE reduction of the
+ * UNFILTERED film (xyz running mean + sample count + the ten AOV sums + feedback bits) lands in the root context, which
+ * then serves prb_film_download (pixel filter applied after the reduce).
+ *   PRB_PARTITION_TILES    every film pixel was rendered by exactly one context (interleaved tiles): plain sum, the
+ *                          root film is bit-identical to a single-context render of the same tiles
+ *   PRB_PARTITION_SAMPLES  every context rendered the whole film for its own iteration range [first, end) starting from
+ *                          an empty film (so its mean is sum / end): contexts are weighted end_r / total_iterations with
+ *                          total_iterations = the sum of the range lengths, counts / AOV sums / feedback bits add up */
+#define PRB_PARTITION_TILES 0
+#define PRB_PARTITION_SAMPLES 1
+/* one process driving several GPUs: ctxs[0] is the root.  With peer access the root reads the other films directly over
+ * NVLink inside ONE kernel (sum + import, no staging copy); without it the films are staged with cudaMemcpyPeer. */
+prb_status prb_film_reduce(prb_ctx** ctxs, int n_ctx, int partition);
+/* one process per GPU (torchrun / MPI): NCCL.  Rank 0 calls prb_comm_unique_id and ships the 128 bytes to the other ranks
+ * out of band (torch.distributed store, MPI_Bcast, a file ...); every rank calls prb_comm_init, then prb_film_reduce_comm
+ * once per render (collective: ncclReduce over NVLink on the context stream, root imports).  libnccl.so.2 is loaded at run
+ * time (the copy already in the process, e.g. torch's, else the system one): PRB_ERR_UNSUPPORTED when there is none. */
+#define PRB_COMM_UNIQUE_ID_BYTES 128
+prb_status prb_comm_unique_id(uint8_t id[PRB_COMM_UNIQUE_ID_BYTES]);
+prb_status prb_comm_init(prb_ctx* ctx, const uint8_t id[PRB_COMM_UNIQUE_ID_BYTES], int rank, int world);
+prb_status prb_comm_destroy(prb_ctx* ctx);
+prb_status prb_film_reduce_comm(prb_ctx* ctx, int partition, uint32_t total_iterations, int root);
+/* device ms (CUDA events on the context stream) of the last prb_film_reduce / prb_film_reduce_comm of this context */
+prb_status prb_last_reduce_ms(prb_ctx* ctx, float* ms);
+
 /* -- stream tracing.  Replace Scene::traceRays (Scene.cpp:138-218, rtcIntersect16) and
  * Scene::traceShadowRay (Scene.cpp:266-280, rtcOccluded1; occluded[i] = 1 if anything was hit in
  * [tmin, tmax]).  Host-pointer variants copy in/out; *_device variants take device pointers. */

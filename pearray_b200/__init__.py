@@ -147,7 +147,8 @@ ABI_SYMBOLS = ["prb_create", "prb_destroy", "prb_last_error", "prb_device_count"
                "prb_film_download_aov", "prb_film_download_feedback", "prb_film_export_device", "prb_film_import_device", "prb_trace_closest",
                "prb_trace_any", "prb_trace_closest_device", "prb_trace_any_device", "prb_generate_camera_rays",
                "prb_material_eval", "prb_material_sample", "prb_get_stats", "prb_reset_stats", "prb_last_device_ms",
-               "prb_set_profiling", "prb_get_stage_times"]
+               "prb_set_profiling", "prb_get_stage_times", "prb_film_reduce", "prb_comm_unique_id", "prb_comm_init",
+               "prb_comm_destroy", "prb_film_reduce_comm", "prb_last_reduce_ms"]
 
 
 def device_lib():
@@ -181,6 +182,12 @@ def device_lib():
                                                  C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         for n in ("prb_material_eval", "prb_material_sample"):
             getattr(lib, n).argtypes = [C.c_void_p, C.POINTER(MaterialQuery), C.c_size_t, C.POINTER(MaterialResult)]
+        lib.prb_film_reduce.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+        lib.prb_comm_unique_id.argtypes = [C.c_void_p]
+        lib.prb_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.prb_comm_destroy.argtypes = [C.c_void_p]
+        lib.prb_film_reduce_comm.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int]
+        lib.prb_last_reduce_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         lib.prb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         lib.prb_reset_stats.argtypes = [C.c_void_p]
         lib.prb_last_device_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -235,6 +242,8 @@ def host_lib():
         lib.prh_render_context_device.restype = C.c_void_p
         lib.prh_render_context_device.argtypes = [C.c_void_p]
         lib.prh_render_context_destroy.argtypes = [C.c_void_p]
+        lib.prh_render_context_join_communicator.argtypes = [C.c_void_p, C.c_void_p]
+        lib.prh_render_contexts_combine.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         lib.prh_render_context_save_outputs.restype = C.c_int
         lib.prh_render_context_save_outputs.argtypes = [C.c_void_p, C.c_char_p]
         _host = lib
@@ -320,6 +329,9 @@ class Scene:
             pass
 
 
+PARTITION = {"tiles": 0, "samples": 1}  # PRB_PARTITION_*
+
+
 def make_tiles(tiles):
     arr = (Tile * len(tiles))()
     for i, t in enumerate(tiles):
@@ -391,6 +403,41 @@ class Context:
 
     def film_import_device(self, device_ptr):
         self._chk(self._lib.prb_film_import_device(self._h, C.c_void_p(device_ptr)), "prb_film_import_device")
+
+    # ---- multi-GPU film combine (include/prb200_abi.h: prb_comm_*, prb_film_reduce*)
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes created by rank 0 (ncclGetUniqueId); ship them to the other ranks out of band"""
+        lib = device_lib()
+        buf = np.zeros(128, np.uint8)
+        if lib.prb_comm_unique_id(_ptr(buf)) != 0:
+            raise PrbError("prb_comm_unique_id: " + lib.prb_last_error().decode())
+        return buf
+
+    def comm_init(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        self._chk(self._lib.prb_comm_init(self._h, _ptr(uid), rank, world), "prb_comm_init")
+
+    def comm_destroy(self):
+        self._chk(self._lib.prb_comm_destroy(self._h), "prb_comm_destroy")
+
+    def film_reduce_comm(self, partition, total_iterations, root=0):
+        """collective over the communicator: the root context ends up with the combined film"""
+        self._chk(self._lib.prb_film_reduce_comm(self._h, PARTITION[partition], total_iterations, root), "prb_film_reduce_comm")
+
+    @staticmethod
+    def film_reduce(contexts, partition):
+        """single process, several contexts: contexts[0] ends up with the combined film (prb_film_reduce)"""
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        lib = device_lib()
+        if lib.prb_film_reduce(arr, len(contexts), PARTITION[partition]) != 0:
+            raise PrbError("prb_film_reduce: " + lib.prb_last_error().decode())
+
+    def last_reduce_ms(self):
+        ms = C.c_float()
+        self._chk(self._lib.prb_last_reduce_ms(self._h, C.byref(ms)), "prb_last_reduce_ms")
+        return float(ms.value)
 
     @staticmethod
     def _ray_soa(o, d, tmin, tmax, keep):

@@ -2,6 +2,8 @@
 // entry point fails with PRB_ERR_NO_DEVICE / PRB_ERR_CUDA when no B200-class device is usable.
 #include "dev_wavefront.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -84,6 +86,13 @@ struct prb_ctx {
 	DBuf<uint32_t> sampleCount, feedback;
 	DBuf<unsigned long long> stats;
 	bool rngUploaded = false;
+	uint32_t lastFirstIter = 0, lastEndIter = 0; // iteration range of the last prb_render_tiles call (sample-range film weights)
+	// multi-GPU film combine
+	void* ncclComm = nullptr;
+	int commRank = 0, commWorld = 1;
+	DBuf<float> reduceF;	 // FILM_PACK floats per pixel
+	DBuf<uint32_t> reduceU;	 // spread feedback bits
+	float lastReduceMs = 0;
 	// wavefront
 	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters, regenList;
 	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ, prevAcc;
@@ -180,6 +189,9 @@ void prb_destroy(prb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	if (c->graphExec)
 		cudaGraphExecDestroy(c->graphExec);
+	prb_comm_destroy(c);
+	c->reduceF.release();
+	c->reduceU.release();
 	DBuf<uint32_t>* ub[] = { &c->entityMaterials, &c->faceIndices, &c->faceSlots, &c->tlasRefs, &c->sampleCount, &c->feedback, &c->pixel, &c->iter, &c->flagsDepth,
 							 &c->slotState, &c->counters, &c->regenList, &c->scratchU };
 	for (auto* b : ub)
@@ -545,6 +557,8 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 	cudaStream_t s = c->stream;
 	const WFState W	 = makeWF(c, first_iteration, iteration_count);
 	const int blocks = (int)((c->nSlots + 127) / 128);
+	c->lastFirstIter = first_iteration;
+	c->lastEndIter	 = first_iteration + iteration_count;
 	CU(cudaEventRecord(c->evA, s));
 	CU(cudaMemsetAsync(c->counters.p, 0, CNT__COUNT * sizeof(uint32_t), s));
 	k_init_slots<<<blocks, 128, 0, s>>>(c->S, W);
@@ -736,6 +750,224 @@ prb_status prb_film_import_device(prb_ctx* c, const float* device_src)
 	c->kernelLaunches++;
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU film combine
+namespace {
+// the handful of NCCL entry points used, resolved at run time from libnccl.so.2 (no link-time dependency: a single-GPU
+// client never needs the library)
+struct NcclUniqueId {
+	char internal[128];
+};
+struct NcclApi {
+	void* lib = nullptr;
+	int (*GetUniqueId)(NcclUniqueId*)														   = nullptr;
+	int (*CommInitRank)(void**, int, NcclUniqueId, int)										   = nullptr;
+	int (*CommDestroy)(void*)																   = nullptr;
+	int (*Reduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, int, void*, cudaStream_t) = nullptr;
+	int (*GroupStart)()																		   = nullptr;
+	int (*GroupEnd)()																		   = nullptr;
+	const char* (*GetErrorString)(int)														   = nullptr;
+	bool ok() const { return GetUniqueId && CommInitRank && CommDestroy && Reduce && GroupStart && GroupEnd && GetErrorString; }
+};
+constexpr int NCCL_FLOAT32 = 7, NCCL_UINT32 = 3, NCCL_SUM = 0; // ncclDataType_t / ncclRedOp_t values (stable since NCCL 2.0)
+NcclApi& nccl()
+{
+	static NcclApi api = [] {
+		NcclApi a;
+		// RTLD_NOLOAD first: reuse the copy the process already holds (torch ships its own), else the system library
+		a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+		if (!a.lib)
+			a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!a.lib)
+			a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (a.lib) {
+			a.GetUniqueId	 = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.lib, "ncclGetUniqueId"));
+			a.CommInitRank	 = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.lib, "ncclCommInitRank"));
+			a.CommDestroy	 = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.lib, "ncclCommDestroy"));
+			a.Reduce		 = reinterpret_cast<decltype(a.Reduce)>(dlsym(a.lib, "ncclReduce"));
+			a.GroupStart	 = reinterpret_cast<decltype(a.GroupStart)>(dlsym(a.lib, "ncclGroupStart"));
+			a.GroupEnd		 = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(a.lib, "ncclGroupEnd"));
+			a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.lib, "ncclGetErrorString"));
+		}
+		return a;
+	}();
+	return api;
+}
+#define NC(x)                                                                                                 \
+	do {                                                                                                      \
+		int r_ = (x);                                                                                         \
+		if (r_ != 0)                                                                                          \
+			return fail(PRB_ERR_CUDA, std::string(#x) + ": " + nccl().GetErrorString(r_));                    \
+	} while (0)
+
+float partitionWeight(const prb_ctx* c, int partition, uint32_t totalIterations)
+{ // PRB_PARTITION_SAMPLES: the context's film is sum / lastEndIter (it started from an empty film at lastFirstIter)
+	if (partition != PRB_PARTITION_SAMPLES || totalIterations == 0)
+		return 1.0f;
+	return (float)c->lastEndIter / (float)totalIterations;
+}
+} // namespace
+
+prb_status prb_comm_unique_id(uint8_t id[PRB_COMM_UNIQUE_ID_BYTES])
+{
+	if (!id)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	if (!nccl().ok())
+		return fail(PRB_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+	NcclUniqueId u;
+	NC(nccl().GetUniqueId(&u));
+	static_assert(sizeof(u) == PRB_COMM_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+	std::memcpy(id, &u, sizeof(u));
+	return PRB_OK;
+}
+prb_status prb_comm_init(prb_ctx* c, const uint8_t id[PRB_COMM_UNIQUE_ID_BYTES], int rank, int world)
+{
+	if (!c || !id || world < 1 || rank < 0 || rank >= world)
+		return fail(PRB_ERR_INVALID_ARG, "invalid communicator arguments");
+	if (!nccl().ok())
+		return fail(PRB_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+	CU(cudaSetDevice(c->device));
+	prb_comm_destroy(c);
+	NcclUniqueId u;
+	std::memcpy(&u, id, sizeof(u));
+	NC(nccl().CommInitRank(&c->ncclComm, world, u, rank));
+	c->commRank	 = rank;
+	c->commWorld = world;
+	return PRB_OK;
+}
+prb_status prb_comm_destroy(prb_ctx* c)
+{
+	if (!c)
+		return fail(PRB_ERR_INVALID_ARG, "null context");
+	if (c->ncclComm) {
+		cudaSetDevice(c->device);
+		cudaStreamSynchronize(c->stream);
+		nccl().CommDestroy(c->ncclComm);
+		c->ncclComm = nullptr;
+	}
+	c->commRank	 = 0;
+	c->commWorld = 1;
+	return PRB_OK;
+}
+prb_status prb_film_reduce_comm(prb_ctx* c, int partition, uint32_t total_iterations, int root)
+{
+	if (!c || !c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (partition != PRB_PARTITION_TILES && partition != PRB_PARTITION_SAMPLES)
+		return fail(PRB_ERR_INVALID_ARG, "partition must be PRB_PARTITION_TILES or PRB_PARTITION_SAMPLES");
+	if (!c->ncclComm)
+		return fail(PRB_ERR_INVALID_ARG, "prb_comm_init has not been called");
+	if (root < 0 || root >= c->commWorld)
+		return fail(PRB_ERR_INVALID_ARG, "root out of range");
+	CU(cudaSetDevice(c->device));
+	const uint32_t npix = c->S.settings.film_width * c->S.settings.film_height;
+	CU(c->reduceF.alloc((size_t)npix * FILM_PACK));
+	CU(c->reduceU.alloc(npix));
+	cudaStream_t s = c->stream;
+	CU(cudaEventRecord(c->evA, s));
+	k_film_pack<<<c->smCount * 4, 256, 0, s>>>(c->filmMean.p, c->sampleCount.p, c->aov.p, c->feedback.p, partitionWeight(c, partition, total_iterations), c->reduceF.p,
+												c->reduceU.p, npix);
+	CU(cudaGetLastError());
+	NC(nccl().GroupStart());
+	NC(nccl().Reduce(c->reduceF.p, c->reduceF.p, (size_t)npix * FILM_PACK, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
+	NC(nccl().Reduce(c->reduceU.p, c->reduceU.p, npix, NCCL_UINT32, NCCL_SUM, root, c->ncclComm, s));
+	NC(nccl().GroupEnd());
+	c->kernelLaunches += 1;
+	if (c->commRank == root) {
+		k_film_unpack<<<c->smCount * 4, 256, 0, s>>>(c->reduceF.p, c->reduceU.p, c->filmMean.p, c->sampleCount.p, c->aov.p, c->feedback.p, npix);
+		CU(cudaGetLastError());
+		c->kernelLaunches += 1;
+	}
+	CU(cudaEventRecord(c->evB, s));
+	CU(cudaEventSynchronize(c->evB));
+	CU(cudaEventElapsedTime(&c->lastReduceMs, c->evA, c->evB));
+	return PRB_OK;
+}
+prb_status prb_film_reduce(prb_ctx** ctxs, int n, int partition)
+{
+	if (!ctxs || n < 1 || n > PEER_MAX + 1)
+		return fail(PRB_ERR_INVALID_ARG, "1 .. 16 contexts expected");
+	if (partition != PRB_PARTITION_TILES && partition != PRB_PARTITION_SAMPLES)
+		return fail(PRB_ERR_INVALID_ARG, "partition must be PRB_PARTITION_TILES or PRB_PARTITION_SAMPLES");
+	prb_ctx* root = ctxs[0];
+	uint32_t total = 0;
+	for (int i = 0; i < n; ++i) {
+		if (!ctxs[i] || !ctxs[i]->haveScene)
+			return fail(PRB_ERR_NO_SCENE, "a context has no scene");
+		if (ctxs[i]->S.settings.film_width != root->S.settings.film_width || ctxs[i]->S.settings.film_height != root->S.settings.film_height)
+			return fail(PRB_ERR_INVALID_ARG, "contexts render films of different sizes");
+		for (int j = 0; j < i; ++j)
+			if (ctxs[j] == ctxs[i])
+				return fail(PRB_ERR_INVALID_ARG, "a context is listed twice");
+		total += ctxs[i]->lastEndIter - ctxs[i]->lastFirstIter;
+	}
+	if (n == 1)
+		return PRB_OK;
+	const uint32_t npix = root->S.settings.film_width * root->S.settings.film_height;
+	PeerFilms P{};
+	P.n			 = n - 1;
+	P.rootWeight = partitionWeight(root, partition, total);
+	// every contributing film must be complete before the root reads it
+	for (int i = 1; i < n; ++i) {
+		CU(cudaSetDevice(ctxs[i]->device));
+		CU(cudaStreamSynchronize(ctxs[i]->stream));
+	}
+	CU(cudaSetDevice(root->device));
+	std::vector<DBuf<float>> stageF(n);
+	std::vector<DBuf<uint32_t>> stageU(n);
+	for (int i = 1; i < n; ++i) {
+		prb_ctx* p	 = ctxs[i];
+		bool direct = p->device == root->device;
+		if (!direct) {
+			int can = 0;
+			CU(cudaDeviceCanAccessPeer(&can, root->device, p->device));
+			if (can) {
+				const cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+				if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) {
+					cudaGetLastError();
+					direct = true;
+				}
+			}
+		}
+		if (direct) { // the gather kernel loads the peer's film through NVLink
+			P.mean[i - 1]	  = p->filmMean.p;
+			P.count[i - 1]	  = p->sampleCount.p;
+			P.aov[i - 1]	  = p->aov.p;
+			P.feedback[i - 1] = p->feedback.p;
+		} else { // no peer access: stage the film on the root device
+			CU(stageF[i].alloc((size_t)npix * 13));
+			CU(stageU[i].alloc((size_t)npix * 2));
+			CU(cudaMemcpyPeerAsync(stageF[i].p, root->device, p->filmMean.p, p->device, (size_t)npix * 3 * sizeof(float), root->stream));
+			CU(cudaMemcpyPeerAsync(stageF[i].p + (size_t)npix * 3, root->device, p->aov.p, p->device, (size_t)npix * 10 * sizeof(float), root->stream));
+			CU(cudaMemcpyPeerAsync(stageU[i].p, root->device, p->sampleCount.p, p->device, (size_t)npix * sizeof(uint32_t), root->stream));
+			CU(cudaMemcpyPeerAsync(stageU[i].p + npix, root->device, p->feedback.p, p->device, (size_t)npix * sizeof(uint32_t), root->stream));
+			P.mean[i - 1]	  = stageF[i].p;
+			P.aov[i - 1]	  = stageF[i].p + (size_t)npix * 3;
+			P.count[i - 1]	  = stageU[i].p;
+			P.feedback[i - 1] = stageU[i].p + npix;
+		}
+		P.weight[i - 1] = partitionWeight(p, partition, total);
+	}
+	CU(cudaEventRecord(root->evA, root->stream));
+	k_film_gather<<<root->smCount * 4, 256, 0, root->stream>>>(P, root->filmMean.p, root->sampleCount.p, root->aov.p, root->feedback.p, npix);
+	root->kernelLaunches += 1;
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(root->evB, root->stream));
+	CU(cudaEventSynchronize(root->evB));
+	CU(cudaEventElapsedTime(&root->lastReduceMs, root->evA, root->evB));
+	for (int i = 1; i < n; ++i) {
+		stageF[i].release();
+		stageU[i].release();
+	}
+	return PRB_OK;
+}
+prb_status prb_last_reduce_ms(prb_ctx* c, float* ms)
+{
+	if (!c || !ms)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	*ms = c->lastReduceMs;
 	return PRB_OK;
 }
 

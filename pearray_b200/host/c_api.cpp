@@ -242,4 +242,12 @@ int prh_render_context_save_outputs(void* rc, const char* dir) { return static_c
 void prh_render_context_wait(void* rc) { static_cast<RenderContext*>(rc)->waitForFinish(); }
 prb_ctx* prh_render_context_device(void* rc) { return static_cast<RenderContext*>(rc)->deviceContext(); }
 void prh_render_context_destroy(void* rc) { delete static_cast<RenderContext*>(rc); }
+int prh_render_context_join_communicator(void* rc, const uint8_t* id128) { return static_cast<RenderContext*>(rc)->joinCommunicator(id128) ? 0 : -1; }
+int prh_render_contexts_combine(void** rcs, int n)
+{
+	std::vector<RenderContext*> v;
+	for (int i = 0; i < n; ++i)
+		v.push_back(static_cast<RenderContext*>(rcs[i]));
+	return RenderContext::combineFilms(v) ? 0 : -1;
+}
 }

@@ -910,6 +910,12 @@ public:
 	prb_stats statistics() const;
 	const RenderSettings& settings() const { return mEnv->renderSettings(); }
 	const std::vector<RenderTile>& ownedTiles() const { return mOwnedTiles; }
+	// One process per GPU: joins the NCCL communicator of the job (id from prb_comm_unique_id of rank 0, shipped out of
+	// band); start() then ends with prb_film_reduce_comm, after which rank 0 holds the combined film.
+	bool joinCommunicator(const uint8_t id[PRB_COMM_UNIQUE_ID_BYTES]);
+	// One process driving several GPUs: combines the films of contexts[1..] into contexts[0] (prb_film_reduce).  The
+	// counterpart of the reference client merging its image-tile contexts (RenderFactory.cpp:16-42, client/main.cpp:172-173).
+	static bool combineFilms(const std::vector<RenderContext*>& contexts);
 
 private:
 	std::shared_ptr<Environment> mEnv;
@@ -917,6 +923,7 @@ private:
 	std::shared_ptr<IIntegrator> mIntegrator;
 	prb_ctx* mCtx = nullptr;
 	uint32 mRank, mWorldSize;
+	bool mHasCommunicator = false;
 	std::vector<RenderTile> mOwnedTiles;
 };
 } // namespace PR

@@ -68,7 +68,38 @@ bool RenderContext::start(uint32 rtx, uint32 rty, uint32 iterations)
 	}
 	instance->onEnd();
 	mIntegrator->onEnd();
+	// interleaved tiles: every pixel was rendered by exactly one rank, the reduced film on rank 0 is bit-identical to a
+	// single-GPU render (collective: every rank of the communicator gets here, also one that owns no tile)
+	if (ok && mHasCommunicator && prb_film_reduce_comm(mCtx, PRB_PARTITION_TILES, iterations, 0) != PRB_OK) {
+		PR_LOG(L_ERROR) << "prb_film_reduce_comm failed: " << prb_last_error() << std::endl;
+		ok = false;
+	}
 	return ok;
+}
+bool RenderContext::joinCommunicator(const uint8_t id[PRB_COMM_UNIQUE_ID_BYTES])
+{
+	if (!mCtx)
+		return false;
+	if (prb_comm_init(mCtx, id, (int)mRank, (int)mWorldSize) != PRB_OK) {
+		PR_LOG(L_ERROR) << "prb_comm_init failed: " << prb_last_error() << std::endl;
+		return false;
+	}
+	mHasCommunicator = true;
+	return true;
+}
+bool RenderContext::combineFilms(const std::vector<RenderContext*>& contexts)
+{
+	std::vector<prb_ctx*> ctxs;
+	for (RenderContext* rc : contexts) {
+		if (!rc || !rc->mCtx)
+			return false;
+		ctxs.push_back(rc->mCtx);
+	}
+	if (prb_film_reduce(ctxs.data(), (int)ctxs.size(), PRB_PARTITION_TILES) != PRB_OK) {
+		PR_LOG(L_ERROR) << "prb_film_reduce failed: " << prb_last_error() << std::endl;
+		return false;
+	}
+	return true;
 }
 void RenderContext::waitForFinish()
 {

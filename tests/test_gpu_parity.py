@@ -629,3 +629,65 @@ def test_bvh_deeper_than_the_traversal_stack_is_rejected():
             ctx.upload_scene(scene)
     finally:
         d.bvh_nodes, d.n_bvh_nodes, d.tlas_root = saved
+
+
+# ------------------------------------------------------------------ round 2: the film combine of the C ABI
+def test_film_reduce_single_process_tiles_bit_identical():
+    """prb_film_reduce(ctxs, n, PRB_PARTITION_TILES): three contexts own interleaved tiles, the root's film, sample counts,
+    AOV sums and feedback bits after the reduce are bit-identical to one context rendering every tile (here the contexts
+    share one device; with several GPUs the same kernel reads the peers over NVLink)"""
+    from pearray_b200 import multigpu
+    src = MATERIAL_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_hero false")  # leaves feedback bits behind
+    scene = prb.Scene.from_string(src)
+    tiles = scene.tiles(4, 4)
+    spp = 3
+    single = make_ctx(scene)
+    single.render_tiles(tiles, 0, spp)
+    parts = []
+    for rank in range(3):
+        c = make_ctx(scene)
+        c.render_tiles(multigpu.partition_tiles(tiles, rank, 3), 0, spp)
+        parts.append(c)
+    prb.Context.film_reduce(parts, "tiles")
+    a, ca = parts[0].film()
+    b, cb = single.film()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ca, cb)
+    assert np.array_equal(parts[0].film_aov().view(np.uint32), single.film_aov().view(np.uint32))
+    fb = single.film_feedback()
+    assert fb.any() and np.array_equal(parts[0].film_feedback(), fb)
+    assert parts[0].last_reduce_ms() > 0
+
+
+def test_film_reduce_single_process_sample_ranges():
+    """PRB_PARTITION_SAMPLES: two contexts render the iteration ranges [0, 3) and [3, 8) of ONE 8-iteration sequence from
+    decorrelated RNG maps; the combined film is the mean over all 8 iterations (weights end_r / total)"""
+    from pearray_b200 import multigpu
+    scene = load_scene("c0_evaluation")  # block filter radius 0: the download is the unfiltered film
+    assert int(scene.settings.filter_radius) == 0
+    tile = [(64, 64, 192, 192)]
+    a = make_ctx(scene)
+    a.render_tiles(tile, 0, 3)
+    fa, ca = a.film()
+    scene_b = load_scene("c0_evaluation")
+    scene_b.settings.seed = multigpu.rank_seed(scene_b.settings.seed, 1)
+    b = make_ctx(scene_b)
+    b.render_tiles(tile, 3, 5)
+    fb, cb = b.film()
+    prb.Context.film_reduce([a, b], "samples")
+    f, cnt = a.film()
+    expect = fa.astype(np.float64) * (3 / 8) + fb.astype(np.float64) * (8 / 8)  # film_r = sum_r / end_r
+    assert np.allclose(f, expect, rtol=1e-6, atol=1e-9)
+    assert np.array_equal(cnt, ca + cb)
+    assert not np.array_equal(fa, fb)
+
+
+def test_film_reduce_argument_checks():
+    scene = load_scene("c2_cornellbox")
+    a = make_ctx(scene)
+    with pytest.raises(prb.PrbError):
+        prb.Context.film_reduce([a, a], "tiles")  # the same context twice
+    with pytest.raises(prb.PrbError):
+        a.film_reduce_comm("tiles", 4)  # no communicator
+    other = make_ctx(load_scene("c3_cornellbox_glassy"))
+    with pytest.raises(prb.PrbError):
+        prb.Context.film_reduce([a, other], "tiles")  # different film sizes
