@@ -2,29 +2,37 @@
 """bench.py -- spectral path samples/s of the 'direct' (unidirectional PT) hot path on B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scene c2|c1|c3|c4|c4b|c4c|c0|c5] [--spp S]
-                  [--partition samples|tiles]
+                  [--partition samples|tiles] [--no-extras]
 
-Workload (BASELINE.json configs[1]): cornellbox.prc, 500x500, 'direct' integrator depth 6, mjitt sampler,
-1024 spp, diffuse materials + one area light.  One "step" = one complete render of that configuration
+Headline workload (BASELINE.json configs[1]): cornellbox.prc, 500x500, 'direct' integrator depth 6, mjitt
+sampler, 1024 spp, diffuse materials + one area light.  One "step" = one complete render of that configuration
 (500*500*1024 = 262 144 000 spectral path samples, 4 wavelengths each) through prb_render_tiles.
 
-Our arm prints one JSON line:
+Our arm prints ONE JSON line:
   value   samples/s with the scene, RNG map and film resident in HBM (CUDA events via the C ABI, max over ranks)
   e2e     samples/s through the C ABI with HOST buffers: per step the RNG map is uploaded, the tiles rendered and the
           film (xyz + sample counts) downloaded inside the timed region
-  roofline / cpu_baseline / clocks / gpu_launches as the contract asks (see DESIGN.md section "Measurement").
-Multi-GPU (torchrun, one rank per GPU): scene replicated, work partitioned by sample ranges (default; every rank
-renders the full film for its own 1024-iteration range with a decorrelated RNG map -> weak scaling) or by interleaved
-tiles (--partition tiles; bit-identical to 1 GPU, strong scaling); films combined by one NCCL reduce to rank 0
-inside the timed region.
+  roofline / cpu_baseline / clocks / gpu_launches as the contract asks (DESIGN.md section "Measurement")
+  workloads   (default run only) the same kind of numbers for the two other workloads BASELINE.json names:
+      complex   complex.prc as shipped (1920x1080, sky + sun, sobol; a bounded number of its 4096 spp per step)
+      c5        synthetic 10 M-triangle soup: primary / shadow / incoherent ray streams (Mrays/s), hit ids checked against
+                the oracle on a sample, e2e with host ray buffers in and hit buffers out
+  strong_scaling   (N > 1) complex.prc partitioned by INTERLEAVED TILES (fixed total work, time-to-image falls with N);
+                   the reduced film is checked bit-identical against a 1-GPU render outside the timed region
+  embree      whether Embree 3 is on the box (the "vs CPU Embree" half of the metric needs it; absent in this image)
+Multi-GPU (torchrun, one rank per GPU): scene replicated, films combined by prb_film_reduce_comm (NCCL over NVLink, inside
+the C ABI) in the timed region.  Headline partition: sample ranges (rank r renders iterations [r spp, (r+1) spp) of ONE
+N*spp-sample sequence from a decorrelated RNG map -> weak scaling); --partition tiles: interleaved tiles (strong scaling).
 
---impl reference: the reference's own CPU implementation cannot be built here (Eigen/Embree/TBB/OIIO absent, SURVEY
-F4), so the arm times oracle/ (the CPU restatement, std::thread x all host cores) on a bounded sample of the same
-workload.  This file and tests/ are the only places that execute oracle/.
+--impl reference: the reference's own CPU implementation cannot be built here (Eigen/Embree/TBB/OIIO absent), so
+the arm times oracle/ (the CPU restatement, std::thread x all host cores) on a bounded sample of the same workload.  This
+file and tests/ are the only places that execute oracle/.
 """
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -104,7 +112,7 @@ def measured_peak_gbs():
 
 def ncu_traffic(scene_key, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture of this
-    workload (profiles/traffic.json, written by hand from profiles/r01_ncu_*.txt); None when no capture is on file"""
+    workload (profiles/traffic.json, copied from the profiles/*_ncu_*.txt summaries); None when no capture is on file"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)[scene_key][kernel]["dram_bytes_per_launch"]
@@ -117,6 +125,32 @@ def bvh_depth_bytes(n_tris):
     import math
     levels = max(1, math.ceil(math.log(max(n_tris / 4.0, 1.0001), 8)))
     return 32 + 24 + 80 * levels + 4 * 48, 32 + 4 + 80 * levels + 4 * 48
+
+
+def embree_probe():
+    """SURVEY 8(d) CPU-baseline option 2: is Embree 3 on this box?  (header for the optional oracle stage + the library)"""
+    hdr = [p for pat in ("/usr/include/embree3/rtcore.h", "/usr/local/include/embree3/rtcore.h", "/opt/*/include/embree3/rtcore.h") for p in glob.glob(pat)]
+    lib = [p for pat in ("/usr/lib/x86_64-linux-gnu/libembree3.so*", "/usr/lib/libembree3.so*", "/usr/local/lib/libembree3.so*", "/opt/*/lib/libembree3.so*")
+           for p in glob.glob(pat)]
+    if hdr and lib:
+        return {"status": "present", "header": hdr[0], "library": lib[0],
+                "note": "oracle/Makefile builds oracle/_ref/liboracle_embree.so when the header is found; hit-id cross-check in tests/test_embree_crosscheck.py"}
+    return {"status": "absent", "note": "no embree3/rtcore.h or libembree3.so on this box: hit ids are pinned to the oracle's restatement of Embree's "
+                                         "documented robust semantics, the 'vs CPU Embree' half of the metric is unmeasured (cpu_baseline.kind = port)"}
+
+
+def load_scene(prb, key, aa_samples=None):
+    """the .prc scene of a config; aa_samples overrides the sample count of the 'aa' sampler (sample-range partition: ONE
+    sequence of world * spp samples whose index ranges are dealt to the ranks)"""
+    fname, label = SCENES[key]
+    path = os.path.join(ROOT, "scenes", fname)
+    if aa_samples is None:
+        return prb.Scene.from_file(path), fname, label
+    src = open(path).read()
+    pat = re.compile(r"(\(sampler\s+:slot\s+'aa'[^)]*?:sample_count\s+)(\d+)", re.S)
+    assert pat.search(src), "no aa sampler with a sample_count in " + fname
+    src = pat.sub(lambda m: m.group(1) + str(aa_samples), src, count=1)
+    return prb.Scene.from_string(src, path), fname, label
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -149,78 +183,123 @@ def run_reference(args, rank, world):
         rays += r["stats"]["primary_ray_count"] + r["stats"]["bounce_ray_count"] + r["stats"]["shadow_ray_count"]
     dt = time.perf_counter() - t0
     value = npix * spp * args.steps / dt
-    sample = "%d spp per step over the full %dx%d film (of %d spp), %d threads" % (spp, scene.width, scene.height, scene.settings.max_sample_count, cores)
+    sample = "%d spp per step over the full %dx%d film (of %d spp; rate-normalised), %d threads" % (spp, scene.width, scene.height, scene.settings.max_sample_count, cores)
     line = {"impl": "reference", "metric": "spectral path samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "mrays_per_s": rays / dt / 1e6,
-            "config": {"workload": label, "scene": fname, "note": "reference not buildable here (Eigen/Embree/TBB/OIIO absent): CPU oracle port, bounded sample"},
+            "config": {"workload": label, "scene": fname, "note": "reference not buildable here (Eigen/Embree/TBB/OIIO absent): CPU oracle port (scalar C++17, own "
+                                                                  "median-split BVH, no SIMD -- NOT Embree, NOT PearRay), bounded sample"},
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "embree": embree_probe(),
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-# ----------------------------------------------------------------------------------------------- our arm
-def run_ours(args, rank, world, local_rank):
-    import numpy as np
-    import torch
-    import pearray_b200 as prb
+# ----------------------------------------------------------------------------------------------- distributed plumbing
+class Job:
+    """rank / world, the torch.distributed process group (rendezvous, barrier, max over ranks) and the NCCL communicator of the
+    C ABI (prb_comm_init) that carries the film reduce"""
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    fname, label = SCENES[args.scene]
-    scene = prb.Scene.from_file(os.path.join(ROOT, "scenes", fname))
-    W, H = scene.width, scene.height
-    spp = int(scene.settings.max_sample_count) if args.spp is None else args.spp
-    all_tiles = scene.tiles(8, 8)
+    def __init__(self, rank, world, local_rank):
+        import torch
+        self.torch = torch
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        self.dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(self.dev)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather_rows(self, row):
+        if not self.dist:
+            return [row]
+        t = self.torch.tensor(row, dtype=self.torch.float64, device=self.dev)
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [[float(v) for v in x] for x in out]
+
+    def join_communicator(self, ctx):
+        """rank 0 creates the NCCL unique id through the C ABI, the 128 bytes travel over torch.distributed (out of band)"""
+        if not self.dist:
+            return
+        import pearray_b200 as prb
+        uid = self.torch.zeros(128, dtype=self.torch.uint8, device=self.dev)
+        if self.rank == 0:
+            uid.copy_(self.torch.from_numpy(prb.Context.comm_unique_id()))
+        self.dist.broadcast(uid, src=0)
+        ctx.comm_init(uid.cpu().numpy(), self.rank, self.world)
+
+    def finish(self):
+        if self.dist:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def render_workload(job, prb, key, spp, steps, warmup, partition, want_e2e=True, want_profile=True, cpu_seconds=0.0, clock_sampler=None):
+    """times `steps` renders of `spp` iterations of scene `key` on job.world GPUs; returns the dict of numbers of this workload
+    (rank 0; None on the other ranks).  partition: 'samples' (weak) | 'tiles' (strong) | 'single'."""
+    import numpy as np
+    torch = job.torch
     from pearray_b200 import multigpu
-    if args.partition == "tiles" and world > 1:
-        tiles = multigpu.partition_tiles(all_tiles, rank, world)  # interleaved tiles, bit-identical for any G
-        first_iter = 0
-        scaling = "strong"
-        seed_rank = 0
+    rank, world = job.rank, job.world
+    if world == 1:
+        partition = "single"
+    scene, fname, label = load_scene(prb, key, aa_samples=spp * world if partition == "samples" else None)
+    W, H = scene.width, scene.height
+    all_tiles = scene.tiles(8, 8)
+    if partition == "tiles":
+        tiles, first_iter, scaling, seed_rank = multigpu.partition_tiles(all_tiles, rank, world), 0, "strong", 0
+    elif partition == "samples":
+        tiles, first_iter, scaling, seed_rank = all_tiles, rank * spp, "weak", rank
     else:
-        tiles = all_tiles
-        first_iter = 0  # sample-range partition: every rank renders its own spp iterations of the full film, decorrelated RNG map
-        scaling = "weak"
-        seed_rank = rank
+        tiles, first_iter, scaling, seed_rank = all_tiles, 0, "weak", 0
     npix_rank = sum((t[2] - t[0]) * (t[3] - t[1]) for t in tiles)
-    samples_rank = npix_rank * spp
     scene.settings.seed = multigpu.rank_seed(scene.settings.seed, seed_rank)  # decorrelated per-rank RNG map in sample-range mode
-    ctx = prb.Context(local_rank)
+    ctx = prb.Context(job.local_rank)
     ctx.upload_scene(scene)
+    job.join_communicator(ctx)
     rng_host = scene.rng_map()
-    # pinned host buffers for the e2e leg
     rng_pinned = torch.empty(W * H, dtype=torch.int64).pin_memory()
     rng_pinned.numpy().view(np.uint64)[:] = rng_host
     film_pinned = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
     cnt_pinned = torch.empty((H, W), dtype=torch.int32).pin_memory()
-    film_dev = torch.zeros((H * W * 4,), dtype=torch.float32, device=dev)  # export buffer handed to the NCCL reduce
-
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-
-    def reduce_films():
-        """film export (own kernel) + one NCCL reduce to rank 0; returns device ms (CUDA events on torch's stream)"""
-        if world == 1:
-            return 0.0
-        ev0.record()
-        ctx.film_export_device(film_dev.data_ptr())
-        multigpu.reduce_film(film_dev.view(-1, 4), "samples" if scaling == "weak" else "tiles", world)
-        ev1.record()
-        ev1.synchronize()
-        return ev0.elapsed_time(ev1)
-
+    total_iters = spp * world if partition == "samples" else spp
     split_ms = [0.0, 0.0]  # render, film reduce (the reduce of a rank that finished early includes waiting for the slowest rank)
 
+    def reduce_films():
+        if world == 1:
+            return 0.0
+        ctx.film_reduce_comm("samples" if partition == "samples" else "tiles", total_iters, 0)  # export + ncclReduce + import on rank 0
+        return ctx.last_reduce_ms()
+
     def step_resident():
-        ctx.render_tiles(tiles, first_iter, spp)  # returns when the wavefront retired every sample
-        r = ctx.last_device_ms()
+        if world > 1:
+            ctx.upload_rng(rng_host)  # the film of rank 0 was overwritten by the last reduce: every step is a render from scratch
+        if tiles:
+            ctx.render_tiles(tiles, first_iter, spp)  # returns when the wavefront retired every sample
+        r = ctx.last_device_ms() if tiles else 0.0
         f = reduce_films()
         split_ms[0] += r
         split_ms[1] += f
@@ -229,72 +308,54 @@ def run_ours(args, rank, world, local_rank):
     def step_e2e():
         t0 = time.perf_counter()
         ctx.upload_rng(rng_pinned.numpy().view(np.uint64))
-        ctx.render_tiles(tiles, first_iter, spp)
+        if tiles:
+            ctx.render_tiles(tiles, first_iter, spp)
         reduce_films()
-        if world > 1 and rank == 0:
-            ctx.film_import_device(film_dev.data_ptr())
-        if rank == 0 or world == 1:
+        if rank == 0:
             ctx.film(out=film_pinned.numpy(), count_out=cnt_pinned.numpy().view(np.uint32))
         return 1e3 * (time.perf_counter() - t0)
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     ctx.upload_rng(rng_host)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
     ctx.reset_stats()
     split_ms[0] = split_ms[1] = 0.0
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    # ---- timed: K steps, device time (CUDA events on the context stream inside prb_render_tiles), max over ranks
-    barrier()
+    if clock_sampler is not None and rank == 0:
+        clock_sampler.start()
+    # ---- timed: K steps, device time (CUDA events on the context stream inside the C ABI), max over ranks
+    job.barrier()
     wall0 = time.perf_counter()
     dev_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         dev_ms += step_resident()
-    barrier()
+    job.barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
-    dev_ms = max_over_ranks(dev_ms)
+    dev_ms = job.max_over_ranks(dev_ms)
     rank_ms = None
-    if world > 1:  # per-rank split of the timed region, for the scaling analysis
-        t = torch.tensor(split_ms, dtype=torch.float64, device=dev)
-        allt = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allt, t)
-        rank_ms = [{"render": float(x[0]) / args.steps, "film_reduce": float(x[1]) / args.steps} for x in allt]
+    if world > 1:
+        rank_ms = [{"render": x[0] / steps, "film_reduce": x[1] / steps} for x in job.gather_rows(split_ms)]
     st = ctx.stats()
     launches = int(st.kernel_launches)
-    rays_rank = st.ray_count
+    rays_all = job.sum_over_ranks(float(st.ray_count))
     # ---- e2e leg: host buffers through the C ABI
-    for _ in range(min(args.warmup, 1)):
+    e2e_ms = None
+    if want_e2e:
         step_e2e()
-    barrier()
-    e2e_ms = 0.0
-    for _ in range(args.steps):
-        e2e_ms += step_e2e()
-    barrier()
-    e2e_ms = max_over_ranks(e2e_ms)
-    if rank == 0:
-        sampler.stop()
-    # ---- per-stage profile pass (rank 0): event pair around every kernel launch of one more identical step
-    roofline = None
-    stage = None
-    if rank == 0:
+        job.barrier()
+        e2e_ms = 0.0
+        for _ in range(steps):
+            e2e_ms += step_e2e()
+        job.barrier()
+        e2e_ms = job.max_over_ranks(e2e_ms)
+    if clock_sampler is not None and rank == 0:
+        clock_sampler.stop()
+    # ---- per-stage profile pass (rank 0): event pair around every kernel launch of one more render
+    roofline = stage = None
+    if want_profile and rank == 0 and tiles:
+        ctx.upload_rng(rng_host)
         ctx.set_profiling(True)
         ctx.reset_stats()
-        prof_spp = min(spp, 64)
-        ctx.render_tiles(tiles, first_iter, prof_spp)
+        ctx.render_tiles(tiles, first_iter, min(spp, 64))
         stage = ctx.stage_times()
         pst = ctx.stats()
         ctx.set_profiling(False)
@@ -302,88 +363,102 @@ def run_ours(args, rank, world, local_rank):
         dom = max(stage, key=lambda k: stage[k][0])
         n_tris = int(scene.desc.contents.n_bvh_tris)
         b_closest, b_any = bvh_depth_bytes(n_tris)
-        # algorithmic bytes per launch (DESIGN.md "Measurement"): trace = B_ray per closest-hit ray + B_any per any-hit ray
-        # (SURVEY 8(d)); shade = wavefront state read + written per path vertex (ray 2x32, hit 20, path state 5x16 r+w,
-        # RNG 16, film/accumulator 32, shadow ray out 48)
+        # algorithmic bytes per launch (DESIGN.md "Rooflines"): trace = B_ray per closest-hit ray + B_any per any-hit ray (SURVEY
+        # 8(d)); shade = wavefront state read + written per path vertex (ray 2x32, hit 20, path state 5x16 r+w, RNG 16,
+        # film/accumulator 32, shadow ray out 48)
         n_closest = int(pst.primary_ray_count + pst.bounce_ray_count)
         n_any = int(pst.shadow_ray_count)
         units = {"trace": n_closest + n_any, "shade": n_closest}
         bytes_total = {"trace": n_closest * b_closest + n_any * b_any, "shade": n_closest * (64 + 20 + 160 + 16 + 32 + 48)}
-        per_unit = {k: bytes_total[k] / max(units[k], 1) for k in units}
         ms_dom, n_dom = stage[dom]
         peak, peak_src = measured_peak_gbs()
         achieved = bytes_total[dom] / (ms_dom * 1e-3) / 1e9 if ms_dom > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": ncu_traffic(args.scene, "k_" + dom), "peak_source": peak_src, "avg_launch_us": 1e3 * ms_dom / max(n_dom, 1), "launches": n_dom,
-                    "bytes_per_unit": per_unit[dom], "units_per_launch": units[dom] / max(n_dom, 1),
-                    "stage_share": {k: v[0] / total for k, v in stage.items()},
+                    "traffic": ncu_traffic(key, "k_" + dom), "peak_source": peak_src, "avg_launch_us": 1e3 * ms_dom / max(n_dom, 1), "launches": n_dom,
+                    "bytes_per_unit": bytes_total[dom] / max(units[dom], 1), "units_per_launch": units[dom] / max(n_dom, 1),
+                    "slots": npix_rank, "stage_share": {k: v[0] / total for k, v in stage.items()},
                     "note": "scene is L2-resident (%d triangles): HBM is not the binding resource, see DESIGN.md" % n_tris}
     # ---- cpu baseline (rank 0, N=1 only): the oracle port on all host cores, bounded sample
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and cpu_seconds > 0:
         from oracle_binding import OracleScene
         ora = OracleScene(scene)
         cores = os.cpu_count() or 1
         t0 = time.perf_counter()
         ora.render(all_tiles, 0, 1, rng=rng_host, threads=cores, aov=False)
         t1 = time.perf_counter() - t0
-        n = max(1, min(spp, int(round(12.0 / max(t1, 1e-3)))))
+        n = max(1, min(spp, int(round(cpu_seconds / max(t1, 1e-3)))))
         t0 = time.perf_counter()
         ora.render(all_tiles, 0, n, rng=rng_host, threads=cores, aov=False)
         dt = time.perf_counter() - t0
         cpu = {"value": W * H * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": "%d of %d spp over the full %dx%d film, oracle (C++17 restatement, std::thread x %d)" % (n, spp, W, H, cores)}
+               "sample": "%d of %d spp over the full %dx%d film (rate-normalised), oracle (scalar C++17 restatement, own BVH, std::thread x %d; not Embree)" % (n, spp, W, H, cores)}
+    out = None
     if rank == 0:
-        total_samples = samples_rank * world * args.steps if scaling == "weak" else W * H * spp * args.steps
-        value = total_samples / (dev_ms * 1e-3)
-        e2e = total_samples / (e2e_ms * 1e-3)
-        h2d = W * H * 8 + len(tiles) * 16
-        d2h = W * H * 3 * 4 + W * H * 4
-        line = {"metric": "spectral path samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "mrays_per_s": rays_rank * world / (dev_ms * 1e-3) / 1e6 if scaling == "weak" else None,
-                "wall_ms_per_step": wall_ms / args.steps,
-                "config": {"workload": label, "scene": fname, "spp_per_step": spp, "film": [W, H], "partition": args.partition if world > 1 else "single",
-                           "l2": "wavefront state (%d paths x ~250 B) and film are re-written every wavefront iteration; scene is L2-resident by nature" % npix_rank},
-                "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-                "stage_ms": {k: v[0] for k, v in stage.items()} if stage else None, "rank_ms_per_step": rank_ms}
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        total_samples = npix_rank * spp * world * steps if scaling == "weak" else W * H * spp * steps
+        out = {"value": total_samples / (dev_ms * 1e-3), "unit": "samples/s", "ms_per_step": dev_ms / steps, "wall_ms_per_step": wall_ms / steps, "scaling": scaling,
+               "mrays_per_s": rays_all / (dev_ms * 1e-3) / 1e6,
+               "config": {"workload": label, "scene": fname, "spp_per_step": spp, "spp_of_scene": int(scene.settings.max_sample_count) // (world if partition == "samples" else 1),
+                          "film": [W, H], "partition": partition, "paths_in_flight_per_gpu": npix_rank,
+                          "l2": "wavefront state (%d paths x ~250 B) and film are re-written every wavefront iteration; scene is L2-resident by nature" % npix_rank},
+               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "stage_ms": {k: v[0] for k, v in stage.items()} if stage else None,
+               "rank_ms_per_step": rank_ms}
+        if e2e_ms is not None:
+            out["e2e"] = {"value": total_samples / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": W * H * 8 + len(tiles) * 16,
+                          "d2h_bytes_per_step": W * H * 3 * 4 + W * H * 4, "ms_per_step": e2e_ms / steps}
+    ctx.close()
+    return out
+
+
+def verify_tile_partition(job, prb, key, iters):
+    """outside every timed region: the film reduced over job.world GPUs in tile mode must be bit-identical to a 1-GPU render"""
+    import numpy as np
+    from pearray_b200 import multigpu
+    scene, _, _ = load_scene(prb, key)
+    tiles = scene.tiles(8, 8)
+    ctx = prb.Context(job.local_rank)
+    ctx.upload_scene(scene)
+    job.join_communicator(ctx)
+    ctx.upload_rng(scene.rng_map())
+    mine = multigpu.partition_tiles(tiles, job.rank, job.world)
+    if mine:
+        ctx.render_tiles(mine, 0, iters)
+    ctx.film_reduce_comm("tiles", iters, 0)
+    ok = None
+    if job.rank == 0:
+        xyz, cnt = ctx.film()
+        single = prb.Context(job.local_rank)
+        single.upload_scene(scene)
+        single.upload_rng(scene.rng_map())
+        single.render_tiles(tiles, 0, iters)
+        sx, sc = single.film()
+        ok = bool(np.array_equal(xyz.view(np.uint32), sx.view(np.uint32)) and np.array_equal(cnt, sc))
+        single.close()
+    ctx.close()
+    job.barrier()
+    return ok
 
 
 # ----------------------------------------------------------------------------------------------- C5: triangle soup
-def run_soup(args, rank, world, local_rank):
-    """synthetic N-triangle soup (default 10 M), 2048x2048 pinhole, 16 jittered passes; three ray classes
-    timed separately through prb_trace_closest_device / prb_trace_any_device with the ray streams resident in HBM:
-    primary (coherent closest hit), shadow (any hit towards a point light at (0,3,0), tfar = dist - 1e-3) and incoherent
-    (cosine-hemisphere bounce from every primary hit, closest hit).  The only configuration that streams the BVH from HBM."""
+def soup_workload(job, prb, args, steps, passes, want_cpu, clock_sampler=None):
+    """synthetic N-triangle soup (default 10 M), 2048x2048 pinhole, jittered passes; three ray classes timed
+    separately through prb_trace_closest_device / prb_trace_any_device with the ray streams resident in HBM: primary (coherent
+    closest hit), shadow (any hit towards a point light at (0,3,0), tfar = dist - 1e-3) and incoherent (cosine-hemisphere bounce
+    from every primary hit, closest hit).  The only configuration that streams the BVH from HBM.  Weak scaling over ranks (every
+    rank traces its own passes against the replicated scene)."""
     import numpy as np
-    import torch
-    import pearray_b200 as prb
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
+    torch = job.torch
+    rank, world, dev = job.rank, job.world, job.dev
     res = args.soup_film
     t0 = time.perf_counter()
     scene = prb.Scene.soup(args.triangles, seed=1234, film=(res, res))
     build_s = time.perf_counter() - t0
     d = scene.desc.contents
-    ctx = prb.Context(local_rank)
+    ctx = prb.Context(job.local_rank)
     ctx.upload_scene(scene)
     ctx.upload_rng(scene.rng_map())
     verts = torch.from_numpy(np.ctypeslib.as_array(d.vertices, shape=(d.n_vertices, 3)).copy()).to(dev).view(-1, 3, 3)
     n = res * res
-    passes = args.passes
-    # weak scaling over ranks: every rank traces its own passes (pass index offset by rank) against the replicated scene
     f32 = dict(dtype=torch.float32, device=dev)
     ent = torch.empty(n, dtype=torch.int32, device=dev); prim = torch.empty_like(ent)
     u = torch.empty(n, **f32); v = torch.empty(n, **f32); t = torch.empty(n, **f32)
@@ -402,7 +477,7 @@ def run_soup(args, rank, world, local_rank):
     ms = {"primary": 0.0, "shadow": 0.0, "incoherent": 0.0}
     rays = {"primary": 0, "shadow": 0, "incoherent": 0}
     hits = {"primary": 0, "shadow": 0, "incoherent": 0}
-    sampler = ClockSampler(local_rank)
+    keep = {}
 
     def one_pass(p, timed):
         org, dr, _, _ = ctx.generate_camera_rays([(0, 0, res, res)], p)
@@ -437,40 +512,36 @@ def run_soup(args, rank, world, local_rank):
         ct = r1.sqrt(); st_ = (1 - r1).clamp_min(0).sqrt(); ph = 2 * np.pi * r2
         a = torch.where(N[:, 0:1].abs() > 0.9, torch.tensor([0.0, 1.0, 0.0], **f32), torch.tensor([1.0, 0.0, 0.0], **f32)).expand(m, 3)
         T = torch.linalg.cross(N, a); T = T / T.norm(dim=1, keepdim=True); B = torch.linalg.cross(N, T)
-        W = T * (st_ * ph.cos())[:, None] + B * (st_ * ph.sin())[:, None] + N * ct[:, None]
-        bo = soa(P); bd = soa(W)
+        Wd = T * (st_ * ph.cos())[:, None] + B * (st_ * ph.sin())[:, None] + N * ct[:, None]
+        bo = soa(P); bd = soa(Wd)
         torch.cuda.synchronize(dev)
         ctx.trace_closest_device(ptrs(bo, bd, tmin, None), m, hitp)
         if timed:
             ms["incoherent"] += ctx.last_device_ms(); rays["incoherent"] += m; hits["incoherent"] += int((ent[:m] != -1).sum())
+        if not keep:  # one sample of every class, with the device results, for the oracle cross-check and the e2e / cpu legs
+            sel = torch.randperm(m, generator=torch.Generator().manual_seed(5))[:65536].to(dev)
+            keep.update(org=org[:65536].copy(), dr=dr[:65536].copy(), P=P[sel].cpu().numpy(), L=L[sel].cpu().numpy(), tmax=tmax[sel].cpu().numpy(),
+                        W=Wd[sel].cpu().numpy(), occ=occ[:m][sel].cpu().numpy(), ent2=ent[:m][sel].cpu().numpy().view(np.uint32),
+                        prim2=prim[:m][sel].cpu().numpy().view(np.uint32), t2=t[:m][sel].cpu().numpy())
 
     for w in range(max(args.warmup, 1)):
         one_pass(1000 + w, False)
+    keep.clear()
     ctx.reset_stats()
-    if rank == 0:
-        sampler.start()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
+    if clock_sampler is not None and rank == 0:
+        clock_sampler.start()
+    job.barrier()
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         for p in range(passes):
             one_pass(rank * passes + p, True)
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - wall0
-    if rank == 0:
-        sampler.stop()
-    tot_ms = sum(ms.values())
-    tot_rays = sum(rays.values())
-    if world > 1:
-        tt = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tot_ms_max = float(tt.item())
-        rr = torch.tensor([float(tot_rays)], dtype=torch.float64, device=dev)
-        dist.all_reduce(rr, op=dist.ReduceOp.SUM)
-        all_rays = float(rr.item())
-    else:
-        tot_ms_max, all_rays = tot_ms, float(tot_rays)
+    if clock_sampler is not None and rank == 0:
+        clock_sampler.stop()
+    tot_ms_max = job.max_over_ranks(sum(ms.values()))
+    all_rays = job.sum_over_ranks(float(sum(rays.values())))
+    out = None
     if rank == 0:
         n_tris = int(d.n_bvh_tris)
         b_closest, b_any = bvh_depth_bytes(n_tris)
@@ -481,22 +552,109 @@ def run_soup(args, rank, world, local_rank):
             per_class[k] = {"mrays_per_s": rays[k] / (ms[k] * 1e-3) / 1e6, "hit_fraction": hits[k] / max(rays[k], 1), "ms": ms[k],
                             "achieved_gbs": rays[k] * bpr / (ms[k] * 1e-3) / 1e9, "frac": rays[k] * bpr / (ms[k] * 1e-3) / 1e9 / peak, "bytes_per_ray": bpr}
         dom = max(ms, key=lambda k: ms[k])
-        launches = args.steps * passes
+        launches = steps * passes
         roofline = {"bound": "hbm", "kernel": "k_trace_any" if dom == "shadow" else "k_trace_closest (%s rays)" % dom, "achieved": per_class[dom]["achieved_gbs"],
-                    "peak": peak, "unit": "GB/s", "frac": per_class[dom]["frac"], "traffic": ncu_traffic("c5", "k_trace_any" if dom == "shadow" else "k_trace_closest"), "peak_source": peak_src,
-                    "avg_launch_us": 1e3 * ms[dom] / launches, "launches": launches, "bytes_per_unit": per_class[dom]["bytes_per_ray"],
+                    "peak": peak, "unit": "GB/s", "frac": per_class[dom]["frac"], "traffic": ncu_traffic("c5", "k_trace_any" if dom == "shadow" else "k_trace_closest"),
+                    "peak_source": peak_src, "avg_launch_us": 1e3 * ms[dom] / launches, "launches": launches, "bytes_per_unit": per_class[dom]["bytes_per_ray"],
                     "units_per_launch": rays[dom] / launches}
-        line = {"metric": "rays/s (primary+shadow+incoherent)", "value": all_rays / (tot_ms_max * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": "synthetic %d-triangle soup, %dx%d pinhole, %d passes/step, primary+shadow+1-bounce incoherent" % (n_tris, res, res, passes),
-                                                "bvh_nodes": int(d.n_bvh_nodes), "bvh_mbytes": (int(d.n_bvh_nodes) * 80 + n_tris * 48) / 1e6, "host_build_s": build_s,
-                                                "l2": "BVH + triangles (%.0f MB) exceed the 126 MB L2 for >= 2.4 M triangles" % ((int(d.n_bvh_nodes) * 80 + n_tris * 48) / 1e6)},
-                "classes": per_class, "roofline": roofline, "gpu_launches": int(ctx.stats().kernel_launches), "clocks": sampler.summary(),
-                "e2e": None, "cpu_baseline": None, "wall_s": wall}
+        # ---- e2e: HOST ray buffers in, hit buffers out through prb_trace_closest / prb_trace_any (copies inside the timed region)
+        k = keep
+        ne = len(k["org"])
+        tmin_h = np.full(len(k["P"]), 1e-4, np.float32)
+        ctx.trace_closest(k["org"], k["dr"])  # warm the scratch buffers
+        t0 = time.perf_counter()
+        reps = 4
+        for _ in range(reps):
+            got1 = ctx.trace_closest(k["org"], k["dr"])
+            got_occ = ctx.trace_any(k["P"], k["L"], tmin_h, k["tmax"])
+            got2 = ctx.trace_closest(k["P"], k["W"], tmin_h)
+        e2e_dt = time.perf_counter() - t0
+        e2e_rays = reps * (ne + 2 * len(k["P"]))
+        e2e = {"value": e2e_rays / e2e_dt, "unit": "rays/s", "h2d_bytes_per_step": (ne * 24 + len(k["P"]) * (32 + 28)), "d2h_bytes_per_step": ne * 20 + len(k["P"]) * 21,
+               "sample": "%d primary + %d shadow + %d incoherent rays per step in host arrays (64 k-ray calls: launch + copy latency bound)" % (ne, len(k["P"]), len(k["P"]))}
+        # the HBM-resident timed launches returned the same answers as the host-buffer calls
+        consistent = bool(np.array_equal(got_occ, k["occ"]) and np.array_equal(got2[0], k["ent2"]) and np.array_equal(got2[1], k["prim2"]))
+        cpu = parity = None
+        if want_cpu:
+            from oracle_binding import OracleScene
+            t0 = time.perf_counter()
+            ora = OracleScene(scene)
+            accel_s = time.perf_counter() - t0
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            ref1 = ora.trace_closest(k["org"], k["dr"], threads=cores)
+            ref_occ = ora.trace_any(k["P"], k["L"], tmin_h, k["tmax"], threads=cores)
+            ref2 = ora.trace_closest(k["P"], k["W"], tmin_h, threads=cores)
+            dt = time.perf_counter() - t0
+            cpu = {"value": (ne + 2 * len(k["P"])) / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+                   "sample": "%d primary + %d shadow + %d incoherent rays, oracle BVH (median split, scalar), std::thread x %d; accel build %.1f s" % (ne, len(k["P"]), len(k["P"]), cores, accel_s)}
+            h1 = ref1[0] != 0xFFFFFFFF
+            parity = {"rays_checked": int(ne + 2 * len(k["P"])),
+                      "primary_id_mismatches": int((got1[0] != ref1[0]).sum() + (got1[1] != ref1[1]).sum()),
+                      "primary_t_mismatches": int((got1[4][h1].view(np.uint32) != ref1[4][h1].view(np.uint32)).sum()),
+                      "shadow_mismatches": int((got_occ != ref_occ).sum()),
+                      "incoherent_id_mismatches": int((got2[0] != ref2[0]).sum() + (got2[1] != ref2[1]).sum())}
+        out = {"metric": "rays/s (primary+shadow+incoherent)", "value": all_rays / (tot_ms_max * 1e-3), "unit": "rays/s", "ms_per_step": tot_ms_max / steps,
+               "scaling": "weak", "n_gpus": world,
+               "config": {"workload": "synthetic %d-triangle soup, %dx%d pinhole, %d passes/step, primary+shadow+1-bounce incoherent" % (n_tris, res, res, passes),
+                          "bvh_nodes": int(d.n_bvh_nodes), "bvh_mbytes": (int(d.n_bvh_nodes) * 80 + n_tris * 48) / 1e6, "host_build_s": build_s,
+                          "l2": "BVH + triangles (%.0f MB) exceed the 126 MB L2 for >= 2.4 M triangles" % ((int(d.n_bvh_nodes) * 80 + n_tris * 48) / 1e6)},
+               "classes": per_class, "roofline": roofline, "gpu_launches": int(ctx.stats().kernel_launches), "e2e": e2e, "cpu_baseline": cpu,
+               "parity_vs_oracle": parity, "resident_equals_host_path": consistent, "wall_s": wall}
+    ctx.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import pearray_b200 as prb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
+    job = Job(rank, world, local_rank)
+    sampler = ClockSampler(local_rank)
+    line = None
+    if args.scene == "c5":
+        r = soup_workload(job, prb, args, args.steps, args.passes, want_cpu=(world == 1 and not args.no_cpu), clock_sampler=sampler)
+        if rank == 0:
+            line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": r["config"], "classes": r["classes"],
+                    "roofline": r["roofline"], "gpu_launches": r["gpu_launches"], "clocks": sampler.summary(), "e2e": r["e2e"], "cpu_baseline": r["cpu_baseline"],
+                    "parity_vs_oracle": r["parity_vs_oracle"], "resident_equals_host_path": r["resident_equals_host_path"], "embree": embree_probe()}
+    else:
+        key = args.scene
+        scene_spp = {"c1": 64, "c2": 1024, "c3": 128, "c4": 256, "c4b": 4096, "c4c": 4096, "c0": 128}[key]
+        spp = scene_spp if args.spp is None else args.spp
+        r = render_workload(job, prb, key, spp, args.steps, args.warmup, args.partition, cpu_seconds=0.0 if args.no_cpu else 12.0, clock_sampler=sampler)
+        extras = {}
+        if not args.no_extras and key == "c2" and args.spp is None:
+            if world == 1:
+                # the two other workloads BASELINE.json names, bounded so that the default run stays within a few minutes
+                c = render_workload(job, prb, "c4c", 64, 2, 1, "single", cpu_seconds=0.0 if args.no_cpu else 8.0)
+                extras["workloads"] = {"complex": c}
+                s = soup_workload(job, prb, args, 1, 4, want_cpu=not args.no_cpu)
+                extras["workloads"]["c5"] = s
+            else:
+                # strong scaling on the north star's target: complex.prc by interleaved tiles, fixed total work
+                ss = render_workload(job, prb, "c4c", 64, 2, 1, "tiles", want_e2e=True, want_profile=False)
+                ok = verify_tile_partition(job, prb, "c4c", 2)
+                if rank == 0:
+                    ss["tile_film_bit_identical_to_1gpu"] = ok
+                    ss["note"] = "fixed total work: 64 spp of the 1920x1080 film per step over %d GPUs (interleaved 8x8 tile map), one prb_film_reduce_comm per step" % world
+                    extras["strong_scaling"] = ss
+                s = soup_workload(job, prb, args, 1, 4, want_cpu=False)
+                if rank == 0:
+                    extras["workloads"] = {"c5": s}
+        if rank == 0:
+            line = {"metric": "spectral path samples/s", "value": r["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": r["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "mrays_per_s": r["mrays_per_s"], "wall_ms_per_step": r["wall_ms_per_step"], "config": r["config"], "e2e": r.get("e2e"),
+                    "gpu_launches": r["gpu_launches"], "clocks": sampler.summary(), "roofline": r["roofline"], "cpu_baseline": r["cpu_baseline"],
+                    "stage_ms": r["stage_ms"], "rank_ms_per_step": r["rank_ms_per_step"], "embree": embree_probe()}
+            line.update(extras)
+    if rank == 0:
         emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    job.finish()
 
 
 _JSON_FD = None
@@ -528,7 +686,8 @@ def main():
     ap.add_argument("--passes", type=int, default=16, help="c5: jittered passes per step")
     ap.add_argument("--spp", type=int, default=None, help="iterations per step (default: the scene's sample count)")
     ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="default run: skip the complex.prc / C5 / strong-scaling legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -536,15 +695,57 @@ def main():
     import __graft_entry__ as g
     if rank == 0 and not os.path.exists(os.path.join(ROOT, "pearray_b200", "libprb200.so")):
         g.build()
-    if args.scene == "c5":
-        if args.impl == "reference":
-            emit({"impl": "reference", "unavailable": "c5 is a GPU ray-stream workload; the CPU arm is defined for the path-tracing configs c1-c4"})
-            return
-        run_soup(args, rank, world, local_rank)
-    elif args.impl == "reference":
-        run_reference(args, rank, world)
+    if args.impl == "reference":
+        if args.scene == "c5":
+            run_reference_soup(args, rank)
+        else:
+            run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
+
+
+def run_reference_soup(args, rank):
+    """CPU arm of C5: the oracle's own BVH traced on all host cores over a bounded sample of the same three ray classes"""
+    if rank != 0:
+        return
+    import numpy as np
+    import pearray_b200 as prb
+    from oracle_binding import OracleScene
+    res = args.soup_film
+    scene = prb.Scene.soup(args.triangles, seed=1234, film=(res, res))
+    ora = OracleScene(scene)
+    cores = os.cpu_count() or 1
+    n = 262144
+    rs = np.random.RandomState(3)
+    # pinhole at (0,0,-3) looking +z, fov 40 degrees, jittered pixel positions
+    px = rs.rand(n, 2).astype(np.float32) * 2 - 1
+    half = np.float32(np.tan(np.radians(20.0)))
+    dr = np.stack([px[:, 0] * half, px[:, 1] * half, np.ones(n, np.float32)], 1).astype(np.float32)
+    dr /= np.linalg.norm(dr, axis=1, keepdims=True)
+    org = np.tile(np.array([0, 0, -3], np.float32), (n, 1))
+    ora.trace_closest(org[:4096], dr[:4096], threads=cores)
+    t0 = time.perf_counter()
+    rays = 0
+    for _ in range(args.steps):
+        ent, prim, u, v, t = ora.trace_closest(org, dr, threads=cores)
+        hit = ent != 0xFFFFFFFF
+        P = (org[hit] + dr[hit] * t[hit, None]).astype(np.float32)
+        L = np.array([0, 3, 0], np.float32) - P
+        dist = np.linalg.norm(L, axis=1).astype(np.float32)
+        L = (L / dist[:, None]).astype(np.float32)
+        tmin = np.full(len(P), 1e-4, np.float32)
+        ora.trace_any(P, L, tmin, (dist - 1e-3).astype(np.float32), threads=cores)
+        b = rs.normal(size=P.shape).astype(np.float32)
+        b /= np.linalg.norm(b, axis=1, keepdims=True)
+        ora.trace_closest(P, b, tmin, threads=cores)
+        rays += n + 2 * len(P)
+    dt = time.perf_counter() - t0
+    value = rays / dt
+    emit({"impl": "reference", "metric": "rays/s (primary+shadow+incoherent)", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+          "data": "synthetic", "config": {"workload": "synthetic %d-triangle soup, %d primary rays per step + their shadow and bounce rays" % (args.triangles, n)},
+          "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": "%d primary rays per step, oracle BVH (scalar, median split), std::thread x %d" % (n, cores)},
+          "embree": embree_probe(), "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 if __name__ == "__main__":

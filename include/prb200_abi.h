@@ -320,7 +320,10 @@ typedef struct prb_settings { /* RenderSettings.cpp:11-33 + DiParameters direct.
 	/* monotonic film: FrameOutputDevice(filter, size, 3, spectralMono) (loader/Environment.cpp:194-198) -> every fragment
 	 * stores its unweighted hero sample in all three channels (mapSpectral<true>, LocalFrameOutputDevice.cpp:76-85) */
 	uint32_t film_monotonic;
-	uint32_t _pad;
+	/* accumulate AOV_OnlineMean / AOV_OnlineVariance (src/core/buffer/VarianceEstimator.inl:16-28, driven per merged tile and
+	 * iteration from FrameOutputDevice::mergeLocal, loader/output/FrameOutputDevice.cpp:104-109): set by the host when an
+	 * (output ...) block asks for a `variance` / `online_mean` channel */
+	uint32_t want_variance;
 } prb_settings;
 
 /* ---------------------------------------------------------------- the scene */
@@ -448,6 +451,12 @@ prb_status prb_film_download_aov(prb_ctx* ctx, float* aov10);
 #define PRB_FEEDBACK_INFINITE 0x2u	/* OutputFeedback::Infinite */
 #define PRB_FEEDBACK_NEGATIVE 0x4u	/* OutputFeedback::Negative */
 prb_status prb_film_download_feedback(prb_ctx* ctx, uint32_t* feedback);
+/* AOV_OnlineMean and AOV_OnlineVariance of the unfiltered per-iteration pixel value (W*H*3 floats each; either may be NULL):
+ * Welford's update exactly as VarianceEstimator::addValue writes it.  Identical to the reference for a radius-0 pixel filter
+ * (the reference feeds the estimator the FILTERED tile image of every iteration, and pixels under the filter footprint of
+ * two tiles twice per iteration in thread order -- not reproducible even by the reference itself).  PRB_ERR_UNSUPPORTED unless
+ * prb_settings.want_variance was set at upload. */
+prb_status prb_film_download_variance(prb_ctx* ctx, float* online_mean, float* online_variance);
 /* copy the UNFILTERED film (xyz mean, 3 floats/pixel, then sample counts as float) into a caller
  * provided DEVICE buffer of W*H*4 floats -- the buffer handed to the NCCL reduce in multi-GPU runs. */
 prb_status prb_film_export_device(prb_ctx* ctx, float* device_dst);

@@ -1481,6 +1481,8 @@ struct Film {
 	uint32_t* sampleCount;
 	float* aov; // 10 floats/pixel or null
 	uint32_t* feedback = nullptr; // AOV_Feedback, W*H words or null
+	float* varMean	   = nullptr; // AOV_OnlineMean / AOV_OnlineVariance, W*H*3 each or null
+	float* varVar	   = nullptr;
 };
 struct Stats {
 	uint64_t c[11] = {};
@@ -2315,9 +2317,10 @@ void orc_scene_destroy(orc_scene* s) { delete s; }
 
 // Render iterations [first, first+count) of the given tiles.  rng: W*H states (updated in place).
 // film_mean: W*H*3 running mean (unfiltered; updated), sample_count: W*H, aov: W*H*10 or NULL, stats: 11 counters,
-// feedback: W*H words (OR of PRB_FEEDBACK_* bits, updated) or NULL.
+// feedback: W*H words (OR of PRB_FEEDBACK_* bits, updated) or NULL; online_mean / online_variance: W*H*3 each or NULL.
 void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count,
-				float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback)
+				float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback, float* online_mean,
+				float* online_variance)
 {
 	const prb_settings& st = s->sc.d->settings;
 	const uint32_t W	   = st.film_width;
@@ -2327,6 +2330,8 @@ void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_til
 	film.sampleCount = sample_count;
 	film.aov		 = aov;
 	film.feedback	 = feedback;
+	film.varMean	 = online_mean;
+	film.varVar		 = online_variance;
 	// pixel list (pixels are independent: own RNG stream, own film cell)
 	std::vector<uint32_t> pixels;
 	for (size_t t = 0; t < n_tiles; ++t)
@@ -2358,6 +2363,16 @@ void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_til
 						float& a = film.mean[3 * (size_t)p + c];
 						a		 = (a * (float)it + film.iterXYZ[3 * (size_t)p + c]) / iter;
 					}
+					if (film.varMean && film.varVar) // VarianceEstimator::addValue, src/core/buffer/VarianceEstimator.inl:16-28
+						for (int c = 0; c < 3; ++c) {
+							const float value = film.iterXYZ[3 * (size_t)p + c];
+							float& mean		  = film.varMean[3 * (size_t)p + c];
+							float& var		  = film.varVar[3 * (size_t)p + c];
+							const float delta = value - mean;
+							mean += delta / iter;
+							const float delta2 = value - mean;
+							var				   = (var * (float)it + delta * delta2) / iter;
+						}
 				}
 				rng[p] = rnd.s;
 			}

@@ -40,7 +40,7 @@ class Settings(C.Structure):
                 ("spectral_start", C.c_float), ("spectral_end", C.c_float),
                 ("light_range_start", C.c_float), ("light_range_end", C.c_float),
                 ("time_alpha", C.c_float), ("time_beta", C.c_float),
-                ("filter_radius", C.c_int32), ("filter_offset", C.c_uint32), ("film_monotonic", C.c_uint32), ("_pad", C.c_uint32)]
+                ("filter_radius", C.c_int32), ("filter_offset", C.c_uint32), ("film_monotonic", C.c_uint32), ("want_variance", C.c_uint32)]
 
 
 class Camera(C.Structure):
@@ -144,7 +144,7 @@ _host = None
 # every symbol include/prb200_abi.h declares
 ABI_SYMBOLS = ["prb_create", "prb_destroy", "prb_last_error", "prb_device_count", "prb_upload_scene", "prb_upload_rng",
                "prb_download_rng", "prb_render_tiles", "prb_sync", "prb_film_clear", "prb_film_download",
-               "prb_film_download_aov", "prb_film_download_feedback", "prb_film_export_device", "prb_film_import_device", "prb_trace_closest",
+               "prb_film_download_aov", "prb_film_download_feedback", "prb_film_download_variance", "prb_film_export_device", "prb_film_import_device", "prb_trace_closest",
                "prb_trace_any", "prb_trace_closest_device", "prb_trace_any_device", "prb_generate_camera_rays",
                "prb_material_eval", "prb_material_sample", "prb_get_stats", "prb_reset_stats", "prb_last_device_ms",
                "prb_set_profiling", "prb_get_stage_times", "prb_film_reduce", "prb_comm_unique_id", "prb_comm_init",
@@ -172,6 +172,7 @@ def device_lib():
         lib.prb_film_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.prb_film_download_aov.argtypes = [C.c_void_p, C.c_void_p]
         lib.prb_film_download_feedback.argtypes = [C.c_void_p, C.c_void_p]
+        lib.prb_film_download_variance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.prb_film_export_device.argtypes = [C.c_void_p, C.c_void_p]
         lib.prb_film_import_device.argtypes = [C.c_void_p, C.c_void_p]
         for n in ("prb_trace_closest", "prb_trace_closest_device"):
@@ -397,6 +398,13 @@ class Context:
         fb = np.empty((self.scene.height, self.scene.width), dtype=np.uint32)
         self._chk(self._lib.prb_film_download_feedback(self._h, _ptr(fb)), "prb_film_download_feedback")
         return fb
+
+    def film_variance(self):
+        """(online_mean, online_variance), each (H, W, 3): AOV_OnlineMean / AOV_OnlineVariance"""
+        shape = (self.scene.height, self.scene.width, 3)
+        mean, var = np.empty(shape, np.float32), np.empty(shape, np.float32)
+        self._chk(self._lib.prb_film_download_variance(self._h, _ptr(mean), _ptr(var)), "prb_film_download_variance")
+        return mean, var
 
     def film_export_device(self, device_ptr):
         self._chk(self._lib.prb_film_export_device(self._h, C.c_void_p(device_ptr)), "prb_film_export_device")

@@ -41,7 +41,12 @@ struct DScene { // device pointers + by-value small structs; passed to kernels b
 	uint32_t nMaterials, nEmissions, nEntities, nLights, nMeshes, tlasRoot, cieOffset, rrCount;
 	uint32_t hasInfLight;
 	uint32_t hasCombined; // any blend / add material in the scene (keeps the check off the path of scenes without them)
+	// tiny scenes (<= SMALL_MAX_TRIS triangles in <= SMALL_MAX_ENTS entities: the Cornell boxes and the sphere scene of the
+	// reference's examples): a flat list of entity headers + their local-space triangles for the BVH-free trace kernel
+	const uint4* small; // nSmallEnts x 4 uint4 headers, then the triangles (3 x float4 each)
+	uint32_t nSmallEnts, nSmallU4;
 };
+constexpr uint32_t SMALL_MAX_TRIS = 64, SMALL_MAX_ENTS = 16;
 
 struct HitRec {
 	uint32_t entity, prim;
@@ -512,6 +517,65 @@ PRB_DEV bool traverseScene(const DScene& S, bool live, bool anyHit, V3 wO, V3 wD
 	}
 	best = tr.best;
 	return tr.hit();
+}
+
+// BVH-free closest / any hit for tiny scenes: every lane tests its ray against EVERY entity and triangle of the scene, read
+// from shared memory at warp-uniform addresses (broadcast loads, no divergence, no stack, no node tests).  For the
+// 32-triangle Cornell box a BVH traversal spends ~4900 warp instructions per warp of rays at 20 of 32 lanes, almost all of it
+// TLAS -> BLAS entries and exits of eight tiny instances; the exhaustive loop needs ~3000 at full lanes.  Same triangle
+// test in the same (instance-local) space and the same (t, entity, prim) order as the traversal: bit-identical results.
+PRB_DEV bool traverseSmall(const uint4* __restrict__ sm, uint32_t nEnts, bool live, bool anyHit, V3 O, V3 D, float tmin, float tmax, HitRec& best)
+{
+	best.entity = PRB_INVALID_ID;
+	best.prim	= 0;
+	best.u = best.v = 0;
+	best.t			= tmax;
+	bool done		= !live;
+	for (uint32_t e = 0; e < nEnts; ++e) { // warp-uniform
+		const uint4 h = sm[4 * e];		   // type, entity id, first triangle (uint4 index), triangle count
+		const float4 r0 = *reinterpret_cast<const float4*>(sm + 4 * e + 1), r1 = *reinterpret_cast<const float4*>(sm + 4 * e + 2),
+					 r2 = *reinterpret_cast<const float4*>(sm + 4 * e + 3);
+		if (h.x == PRB_ENTITY_SPHERE) {
+			float t;
+			if (!done && sphereTest(O, D, tmin, best.t, mk(r0.x, r0.y, r0.z), r0.w, t) && betterHit(t, h.y, 0, best)) {
+				best.entity = h.y;
+				best.prim	= 0;
+				best.t		= t;
+				best.u = best.v = 0;
+				done			= anyHit;
+			}
+		} else {
+			V3 lo = O, ld = D;
+			if (h.x == PRB_ENTITY_MESH) { // planes are stored in world space
+				const float m[12] = { r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w };
+				lo				  = xfPoint(m, O);
+				ld				  = xfVec(m, D);
+			}
+			const float4* tp = reinterpret_cast<const float4*>(sm + h.z);
+			for (uint32_t k = 0; k < h.w; ++k, tp += 3) {
+				const float4 a = tp[0], b = tp[1], c = tp[2];
+				float t, u, v;
+				if (!done && triTest(lo, ld, tmin, best.t, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v)) {
+					const uint32_t prim = __float_as_uint(a.w);
+					if (betterHit(t, h.y, prim, best)) {
+						if (__float_as_uint(b.w) & 1u) {
+							u = 1 - u;
+							v = 1 - v;
+						}
+						best.entity = h.y;
+						best.prim	= prim;
+						best.t		= t;
+						best.u		= u;
+						best.v		= v;
+						done		= anyHit;
+					}
+				}
+			}
+		}
+		if (anyHit && __all_sync(0xFFFFFFFFu, done))
+			break;
+	}
+	return best.entity != PRB_INVALID_ID;
 }
 
 // warp-aggregated fetch of the next work item from a global counter; every lane of the warp must call it.

@@ -14,6 +14,24 @@ namespace prb {
 // wavelengths); inlining every copy made k_shade ~1 MB of SASS and instruction-fetch bound (ncu: stall_no_instruction
 // 63 warps per issue).  One copy each keeps the hot code inside the instruction cache.
 #define PRB_DEV_NI __device__ __noinline__
+// Code-size diet of k_shade (round 2): ncu shows the shading kernel INSTRUCTION-FETCH bound (sm__icc_request_hit_rate 76 %,
+// gcc instruction requests at 55 % of peak, stall_no_instruction 2.6 warps per issue; more resident warps change nothing) --
+// 219 KB of SASS for the all-Lambert instantiation, 22 % of it seven inlined copies of the double-precision sincos.  Level 1
+// takes the correctly rounded transcendental wrappers out of line, level 2 also the medium-sized helpers that are inlined
+// at many call sites (normalized, tableLookup, evalLeafNode, fragmentXYZ); results are bit-identical by construction.
+#ifndef PRB_SMALL_CODE
+#define PRB_SMALL_CODE 0
+#endif
+#if PRB_SMALL_CODE >= 1
+#define PRB_DEV_TRANS __device__ __noinline__
+#else
+#define PRB_DEV_TRANS __device__ __forceinline__
+#endif
+#if PRB_SMALL_CODE >= 2
+#define PRB_DEV_MED __device__ __noinline__
+#else
+#define PRB_DEV_MED __device__ __forceinline__
+#endif
 
 constexpr float PR_EPSILON	= 1.1920928955078125e-07f; // std::numeric_limits<float>::epsilon()
 constexpr float PR_PI		= 3.14159265358979323846f;
@@ -34,7 +52,7 @@ PRB_DEV V3 operator/(V3 a, float f) { return { a.x / f, a.y / f, a.z / f }; }
 PRB_DEV float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 PRB_DEV V3 cross(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
 PRB_DEV float norm2(V3 a) { return dot(a, a); }
-PRB_DEV V3 normalized(V3 a)
+PRB_DEV_MED V3 normalized(V3 a)
 {
 	const float z = norm2(a);
 	return z > 0 ? a / sqrtf(z) : a;
@@ -104,21 +122,21 @@ PRB_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 // so the last bit is libm-version dependent.  Device and oracle both use the CORRECTLY ROUNDED fp32 result instead
 // (evaluate in fp64, round once): libm-independent, and the two sides agree bit for bit, which keeps long specular
 // chains from diverging chaotically.
-PRB_DEV void cr_sincos(float x, float* s, float* c)
+PRB_DEV_TRANS void cr_sincos(float x, float* s, float* c)
 {
 	double ds, dc;
 	sincos((double)x, &ds, &dc);
 	*s = (float)ds;
 	*c = (float)dc;
 }
-PRB_DEV float cr_sin(float x) { return (float)sin((double)x); }
-PRB_DEV float cr_cos(float x) { return (float)cos((double)x); }
-PRB_DEV float cr_tan(float x) { return (float)tan((double)x); }
-PRB_DEV float cr_atanh(float x) { return (float)atanh((double)x); }
-PRB_DEV float cr_cosh(float x) { return (float)cosh((double)x); }
-PRB_DEV float cr_atan(float x) { return (float)atan((double)x); }
-PRB_DEV float cr_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
-PRB_DEV float cr_acos(float x) { return (float)acos((double)x); }
+PRB_DEV_TRANS float cr_sin(float x) { return (float)sin((double)x); }
+PRB_DEV_TRANS float cr_cos(float x) { return (float)cos((double)x); }
+PRB_DEV_TRANS float cr_tan(float x) { return (float)tan((double)x); }
+PRB_DEV_TRANS float cr_atanh(float x) { return (float)atanh((double)x); }
+PRB_DEV_TRANS float cr_cosh(float x) { return (float)cosh((double)x); }
+PRB_DEV_TRANS float cr_atan(float x) { return (float)atan((double)x); }
+PRB_DEV_TRANS float cr_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+PRB_DEV_TRANS float cr_acos(float x) { return (float)acos((double)x); }
 
 // ---------------------------------------------------------------- Sampling (src/base/math/Sampling.h:38-57)
 PRB_DEV V3 cos_hemi(float u1, float u2)

@@ -6,7 +6,7 @@
 
 namespace prb {
 // ------------------------------------------------------------------ spectra / nodes
-PRB_DEV float tableLookup(const float* data, uint32_t count, float start, float end, float w)
+PRB_DEV_MED float tableLookup(const float* data, uint32_t count, float start, float end, float w)
 { // EquidistantSpectrumView::lookup, src/core/spectral/EquidistantSpectrum.inl:34-41
 	const float delta = (end - start) / (count - 1);
 	const float af	  = fmaxf(0.0f, (w - start) / delta);
@@ -234,7 +234,13 @@ struct MatCtx {
 	Blob wvl;
 	float u, v;
 	uint32_t rayFlags;
+	// One-entry cache of a shading-node value: NEE (IMaterial::eval) and scattering (IMaterial::sample) of a path vertex
+	// evaluate the same albedo node at the same wavelengths and surface parameters; the second evaluation (an IEEE sqrt and
+	// division per wavelength for an upsampled RGB colour) is a copy of the first.  Valid for one vertex (wvl, u, v fixed).
+	mutable uint32_t cachedNode = PRB_INVALID_ID;
+	mutable Blob cachedValue;
 };
+PRB_DEV Blob evalNodeCached(const DScene& S, const MatCtx& c, uint32_t node);
 PRB_DEV uint32_t contribFlags(const prb_material& m) { return (m.flags & PRB_MATF_SPECTRAL_VARYING) ? MSF_SpectralVarying : 0; }
 PRB_DEV void rejectSample(MatSample& s, uint32_t type, uint32_t flags)
 {
@@ -572,11 +578,19 @@ struct RoughDielectric {
 
 // LambertMaterial::eval / ::sample (lambert.cpp:33-43, :53-73); inline so that k_shade's all-Lambert instantiation can use
 // them without the out-of-line material dispatch
+PRB_DEV Blob evalNodeCached(const DScene& S, const MatCtx& c, uint32_t node)
+{
+	if (c.cachedNode != node) {
+		c.cachedValue = evalNode(S, node, c.wvl, c.u, c.v);
+		c.cachedNode  = node;
+	}
+	return c.cachedValue;
+}
 PRB_DEV void lambertEval(const DScene& S, const prb_material& m, const MatCtx& c, MatEval& out)
 {
 	const bool two = m.flags & PRB_MATF_TWO_SIDED;
 	const float d  = sameHemisphere(c.V, c.L) ? (two ? fabsf(c.L.z) : fmaxf(0.0f, c.L.z)) : 0;
-	out.weight	   = evalNode(S, m.node[0], c.wvl, c.u, c.v) * d * PR_INV_PI;
+	out.weight	   = evalNodeCached(S, c, m.node[0]) * d * PR_INV_PI;
 	out.pdf		   = blob(cos_hemi_pdf(d));
 }
 PRB_DEV void lambertSample(const DScene& S, const prb_material& m, const MatCtx& c, Rng& rnd, MatSample& out)
@@ -588,7 +602,7 @@ PRB_DEV void lambertSample(const DScene& S, const prb_material& m, const MatCtx&
 	const float u2 = rnd.getFloat(); // cos_hemi(RND.getFloat(), RND.getFloat()): second argument drawn first
 	const float u1 = rnd.getFloat();
 	out.L		   = cos_hemi(u1, u2);
-	out.weight	   = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+	out.weight	   = evalNodeCached(S, c, m.node[0]);
 	out.pdf		   = blob(cos_hemi_pdf(out.L.z));
 	out.L		   = makeSameHemisphere(c.V, out.L);
 }
@@ -597,7 +611,7 @@ PRB_DEV Blob orenNayarCalc(const DScene& S, const prb_material& m, const MatCtx&
 {
 	float roughness = m.f[0];
 	roughness *= roughness;
-	Blob weight = evalNode(S, m.node[0], c.wvl, c.u, c.v);
+	Blob weight = evalNodeCached(S, c, m.node[0]);
 	if (roughness > PR_EPSILON) {
 		const float s = -NdotL * c.V.z + dot(c.V, L);
 		const float t = s < PR_EPSILON ? 1.0f : fmaxf(NdotL, c.V.z);

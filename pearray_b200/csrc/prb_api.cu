@@ -82,7 +82,7 @@ struct prb_ctx {
 	DBuf<float4> bvhTris;
 	// film
 	DBuf<uint64_t> rng;
-	DBuf<float> filmMean, filmTmp, aov;
+	DBuf<float> filmMean, filmTmp, aov, varMean, varVar; // varMean / varVar only with prb_settings.want_variance
 	DBuf<uint32_t> sampleCount, feedback;
 	DBuf<unsigned long long> stats;
 	bool rngUploaded = false;
@@ -116,6 +116,8 @@ struct prb_ctx {
 	uint64_t graphKey = 0, stateVersion = 1; // stateVersion: bumped whenever the scene or the slot buffers change
 	bool wantAOV = true;
 	bool persistentTrace = true; // k_trace (persistent threads) vs k_trace_static, chosen per scene in prb_upload_scene
+	bool smallScene = false;	 // k_trace_static<true>: exhaustive test of a tiny scene from shared memory, no BVH
+	DBuf<uint4> small;
 	// per-stage profiling (prb_set_profiling)
 	bool profiling = false;
 	std::vector<cudaEvent_t> profEvents; // pairs
@@ -196,7 +198,7 @@ void prb_destroy(prb_ctx* c)
 							 &c->slotState, &c->counters, &c->regenList, &c->scratchU };
 	for (auto* b : ub)
 		b->release();
-	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->hitT, &c->scratchF };
+	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->varMean, &c->varVar, &c->hitT, &c->scratchF };
 	for (auto* b : fb)
 		b->release();
 	DBuf<float4>* f4[] = { &c->bvhTris, &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc };
@@ -213,6 +215,7 @@ void prb_destroy(prb_ctx* c)
 	c->stats.release();
 	c->hit.release();
 	c->scratchB.release();
+	c->small.release();
 	c->scratchQ.release();
 	c->scratchR.release();
 	if (c->hostCounters)
@@ -316,6 +319,15 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	CU(c->aov.alloc(npix * 10));
 	CU(c->feedback.alloc(npix));
 	CU(cudaMemsetAsync(c->feedback.p, 0, npix * sizeof(uint32_t), s));
+	if (d->settings.want_variance) {
+		CU(c->varMean.alloc(npix * 3));
+		CU(c->varVar.alloc(npix * 3));
+		CU(cudaMemsetAsync(c->varMean.p, 0, npix * 3 * sizeof(float), s));
+		CU(cudaMemsetAsync(c->varVar.p, 0, npix * 3 * sizeof(float), s));
+	} else {
+		c->varMean.release();
+		c->varVar.release();
+	}
 	CU(cudaMemsetAsync(c->filmMean.p, 0, npix * 3 * sizeof(float), s));
 	CU(cudaMemsetAsync(c->sampleCount.p, 0, npix * sizeof(uint32_t), s));
 	CU(cudaMemsetAsync(c->aov.p, 0, npix * 10 * sizeof(float), s));
@@ -376,6 +388,67 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 		else if (std::strcmp(m, "persistent") == 0)
 			c->persistentTrace = true;
 	}
+	// tiny scenes: flat entity / triangle list for the BVH-free trace kernel (traverseSmall)
+	c->smallScene	= false;
+	c->S.small		= nullptr;
+	c->S.nSmallEnts = c->S.nSmallU4 = 0;
+	if (!c->persistentTrace && d->n_bvh_tris <= SMALL_MAX_TRIS && d->n_entities <= SMALL_MAX_ENTS && d->n_entities > 0) {
+		std::vector<uint4> blob(4 * (size_t)d->n_entities);
+		bool ok = true;
+		for (uint32_t e = 0; e < d->n_entities && ok; ++e) {
+			const prb_entity& en = d->entities[e];
+			uint4 h				 = make_uint4(en.type, e, 0, 0);
+			float rows[12]		 = {};
+			if (en.type == PRB_ENTITY_SPHERE) {
+				rows[0] = en.geo[0], rows[1] = en.geo[1], rows[2] = en.geo[2], rows[3] = en.geo[3];
+			} else {
+				std::memcpy(rows, en.world_to_local, sizeof(rows));
+				h.z = (uint32_t)blob.size();
+				// every triangle below the BLAS root, in leaf order
+				std::vector<uint32_t> todo{ en.blas_root };
+				while (!todo.empty() && ok) {
+					const uint32_t ni = todo.back();
+					todo.pop_back();
+					if (ni >= d->n_bvh_nodes) {
+						ok = false;
+						break;
+					}
+					const prb_bvh8_node& n = d->bvh_nodes[ni];
+					for (int i = 0; i < 8; ++i) {
+						if (n.meta[i] == 0xFF)
+							continue;
+						if (n.meta[i] & 0x80) {
+							todo.push_back(n.child_base + (n.meta[i] & 0x7Fu));
+						} else {
+							const uint32_t count = ((n.meta[i] >> 5) & 3u) + 1, first = n.prim_base + (n.meta[i] & 0x1Fu);
+							for (uint32_t k = 0; k < count; ++k) {
+								if (first + k >= d->n_bvh_tris) {
+									ok = false;
+									break;
+								}
+								const uint4* t = reinterpret_cast<const uint4*>(d->bvh_tris + first + k);
+								blob.insert(blob.end(), t, t + 3);
+								++h.w;
+							}
+						}
+					}
+				}
+			}
+			blob[4 * e] = h;
+			std::memcpy(&blob[4 * e + 1], rows, sizeof(rows));
+		}
+		if (ok && blob.size() <= SMALL_MAX_ENTS * 4 + SMALL_MAX_TRIS * 3) {
+			CU(c->small.upload(blob.data(), blob.size(), s));
+			CU(cudaStreamSynchronize(s));
+			c->S.small		= c->small.p;
+			c->S.nSmallEnts = d->n_entities;
+			c->S.nSmallU4	= (uint32_t)blob.size();
+			c->smallScene	= true;
+		}
+	}
+	if (const char* m = std::getenv("PRB_TRACE_MODE"))
+		if (std::strcmp(m, "bvh") == 0)
+			c->smallScene = false;
 	c->haveScene   = true;
 	c->rngUploaded = false; // the RNG map was zeroed above: state 0 of the pcg32_fast MCG stays 0 forever
 	c->cachedTiles.clear();
@@ -422,6 +495,10 @@ prb_status prb_film_clear(prb_ctx* c)
 	CU(cudaMemsetAsync(c->sampleCount.p, 0, npix * sizeof(uint32_t), c->stream));
 	CU(cudaMemsetAsync(c->aov.p, 0, npix * 10 * sizeof(float), c->stream));
 	CU(cudaMemsetAsync(c->feedback.p, 0, npix * sizeof(uint32_t), c->stream));
+	if (c->varMean.p) {
+		CU(cudaMemsetAsync(c->varMean.p, 0, npix * 3 * sizeof(float), c->stream));
+		CU(cudaMemsetAsync(c->varVar.p, 0, npix * 3 * sizeof(float), c->stream));
+	}
 	return PRB_OK;
 }
 
@@ -500,8 +577,10 @@ static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s
 {
 	if (c->persistentTrace)
 		k_trace<<<c->gridTrace, 128, 0, s>>>(c->S, W);
+	else if (c->smallScene)
+		k_trace_static<true><<<blocks, 128, 0, s>>>(c->S, W);
 	else
-		k_trace_static<<<blocks, 128, 0, s>>>(c->S, W);
+		k_trace_static<false><<<blocks, 128, 0, s>>>(c->S, W);
 }
 
 static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
@@ -533,6 +612,8 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.sampleCount = c->sampleCount.p;
 	W.aov		  = c->wantAOV ? c->aov.p : nullptr;
 	W.feedback	  = c->feedback.p;
+	W.varMean	  = c->S.settings.want_variance ? c->varMean.p : nullptr;
+	W.varVar	  = c->S.settings.want_variance ? c->varVar.p : nullptr;
 	W.stats		  = c->stats.p;
 	W.nSlots	  = c->nSlots;
 	W.firstIter	  = first;
@@ -611,7 +692,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 	} else {
 		// the kernels of the graph read the iteration range from device memory (CNT_END_ITER, written by k_init_slots), so one
 		// instantiated graph serves every call until the scene, the slot buffers or the kernel variant change
-		const uint64_t key = (c->stateVersion << 2) | (c->persistentTrace ? 1u : 0u) | (c->wantAOV ? 2u : 0u);
+		const uint64_t key = (c->stateVersion << 3) | (c->persistentTrace ? 1u : 0u) | (c->wantAOV ? 2u : 0u) | (c->smallScene ? 4u : 0u);
 		if (!c->graphExec || c->graphKey != key) {
 			if (c->graphExec) {
 				cudaGraphExecDestroy(c->graphExec);
@@ -725,6 +806,21 @@ prb_status prb_film_download_feedback(prb_ctx* c, uint32_t* feedback)
 	CU(cudaSetDevice(c->device));
 	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
 	CU(cudaMemcpyAsync(feedback, c->feedback.p, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_film_download_variance(prb_ctx* c, float* online_mean, float* online_variance)
+{
+	if (!c || !c->haveScene)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded");
+	if (!c->S.settings.want_variance || !c->varMean.p)
+		return fail(PRB_ERR_UNSUPPORTED, "the scene was uploaded without prb_settings.want_variance");
+	CU(cudaSetDevice(c->device));
+	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
+	if (online_mean)
+		CU(cudaMemcpyAsync(online_mean, c->varMean.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	if (online_variance)
+		CU(cudaMemcpyAsync(online_variance, c->varVar.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return PRB_OK;
 }
@@ -873,6 +969,10 @@ prb_status prb_film_reduce_comm(prb_ctx* c, int partition, uint32_t total_iterat
 	NC(nccl().GroupStart());
 	NC(nccl().Reduce(c->reduceF.p, c->reduceF.p, (size_t)npix * FILM_PACK, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
 	NC(nccl().Reduce(c->reduceU.p, c->reduceU.p, npix, NCCL_UINT32, NCCL_SUM, root, c->ncclComm, s));
+	if (c->varMean.p && partition == PRB_PARTITION_TILES) { // disjoint pixel ownership: the sum is the owner's value
+		NC(nccl().Reduce(c->varMean.p, c->varMean.p, (size_t)npix * 3, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
+		NC(nccl().Reduce(c->varVar.p, c->varVar.p, (size_t)npix * 3, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
+	}
 	NC(nccl().GroupEnd());
 	c->kernelLaunches += 1;
 	if (c->commRank == root) {
@@ -954,6 +1054,23 @@ prb_status prb_film_reduce(prb_ctx** ctxs, int n, int partition)
 	k_film_gather<<<root->smCount * 4, 256, 0, root->stream>>>(P, root->filmMean.p, root->sampleCount.p, root->aov.p, root->feedback.p, npix);
 	root->kernelLaunches += 1;
 	CU(cudaGetLastError());
+	if (root->varMean.p && partition == PRB_PARTITION_TILES) {
+		DBuf<float> stage;
+		CU(stage.alloc((size_t)npix * 3));
+		for (int i = 1; i < n; ++i) {
+			if (!ctxs[i]->varMean.p)
+				continue;
+			float* srcs[2] = { ctxs[i]->varMean.p, ctxs[i]->varVar.p };
+			float* dsts[2] = { root->varMean.p, root->varVar.p };
+			for (int k = 0; k < 2; ++k) {
+				CU(cudaMemcpyPeerAsync(stage.p, root->device, srcs[k], ctxs[i]->device, (size_t)npix * 3 * sizeof(float), root->stream));
+				k_add_buffer<<<root->smCount * 4, 256, 0, root->stream>>>(dsts[k], stage.p, (size_t)npix * 3);
+				root->kernelLaunches += 1;
+			}
+		}
+		CU(cudaStreamSynchronize(root->stream));
+		stage.release();
+	}
 	CU(cudaEventRecord(root->evB, root->stream));
 	CU(cudaEventSynchronize(root->evB));
 	CU(cudaEventElapsedTime(&root->lastReduceMs, root->evA, root->evB));

@@ -28,8 +28,8 @@ struct VarName {
 	const char* canonical; // variableToString(): the first spelling of the variable, used as the channel name
 };
 const VarName kSpectral[] = { { "color", OV_Output, "color" }, { "spectral", OV_Output, "color" }, { "output", OV_Output, "color" }, { "rgb", OV_Output, "color" },
-							  { "online_mean", OV_Unsupported, "online_mean" }, { "variance", OV_Unsupported, "variance" },
-							  { "online_variance", OV_Unsupported, "variance" }, { "var", OV_Unsupported, "variance" } };
+							  { "online_mean", OV_OnlineMean, "online_mean" }, { "variance", OV_OnlineVariance, "variance" },
+							  { "online_variance", OV_OnlineVariance, "variance" }, { "var", OV_OnlineVariance, "variance" } };
 const VarName k1D[]		  = { { "entity_id", OV_EntityID, "entity_id" }, { "entity", OV_EntityID, "entity_id" }, { "id", OV_EntityID, "entity_id" },
 							  { "material_id", OV_Unsupported, "material_id" }, { "material", OV_Unsupported, "material_id" }, { "mat", OV_Unsupported, "material_id" },
 							  { "emission_id", OV_Unsupported, "emission_id" }, { "emission", OV_Unsupported, "emission_id" },
@@ -258,11 +258,12 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 		addPlane(c.name.empty() ? "R" : c.name + ".R");
 		addPlane(c.name.empty() ? "G" : c.name + ".G");
 		addPlane(c.name.empty() ? "B" : c.name + ".B");
-		if (c.variable != OV_Output || !film.xyz)
+		const float* src = c.variable == OV_Output ? film.xyz : c.variable == OV_OnlineMean ? film.onlineMean : c.variable == OV_OnlineVariance ? film.onlineVariance : nullptr;
+		if (!src)
 			continue;
 		for (size_t i = 0; i < n; ++i) {
 			float rgb[3];
-			toneMap(c.tcm, film.xyz + 3 * i, rgb);
+			toneMap(c.tcm, src + 3 * i, rgb);
 			data[base][i] = rgb[0], data[base + 1][i] = rgb[1], data[base + 2][i] = rgb[2];
 		}
 	}

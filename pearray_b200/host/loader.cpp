@@ -2,6 +2,9 @@
 // (reference src/loader/{Environment,SceneLoadContext,SceneLoader}.cpp, plugin/PluginManager.cpp).
 #include "prh.h"
 
+#include <dirent.h>
+#include <sys/stat.h>
+
 #include <dlfcn.h>
 #include <fstream>
 #include <map>
@@ -26,8 +29,9 @@ void registerEmbeddedPlugins(std::vector<std::shared_ptr<IPlugin>>& out)
 PluginManager::PluginManager(const std::string& pluginPath)
 {
 	loadEmbeddedPlugins();
-	// external plugins: <pluginPath>/(lib)?pr_pl_*.so given explicitly as a ':' separated list of files
-	// or through PR_PLUGIN_PATH (PluginManager.cpp:7,14-29); each must export `_pr_exports`.
+	// external plugins (PluginManager::initPlugins / loadFromDirectory, PluginManager.cpp:14-66): every entry of the ':' separated
+	// plugin path and of the environment variable PR_PLUGIN_PATH is a DIRECTORY searched for (lib)?pr_pl_<name>.so, or -- an
+	// extension -- one such file given explicitly; each object must export `_pr_exports` (Plugin.h:52-66).
 	std::string paths = pluginPath;
 	if (const char* e = std::getenv("PR_PLUGIN_PATH")) {
 		if (!paths.empty())
@@ -40,9 +44,36 @@ PluginManager::PluginManager(const std::string& pluginPath)
 		if (end == std::string::npos)
 			end = paths.size();
 		const std::string f = paths.substr(pos, end - pos);
-		if (f.size() > 3 && f.substr(f.size() - 3) == ".so")
+		pos					= end + 1;
+		if (f.empty())
+			continue;
+		struct stat sb;
+		if (stat(f.c_str(), &sb) != 0)
+			continue;
+		if (S_ISDIR(sb.st_mode)) {
+			std::vector<std::string> found;
+			if (DIR* dir = opendir(f.c_str())) {
+				while (const dirent* de = readdir(dir)) {
+					std::string n = de->d_name;
+					if (n.size() <= 3 || n.substr(n.size() - 3) != ".so")
+						continue;
+					std::string stem = n.substr(0, n.size() - 3);
+					if (stem.rfind("lib", 0) == 0)
+						stem = stem.substr(3);
+					if (stem.rfind("pr_pl_", 0) != 0 || stem.size() <= 6)
+						continue;
+					if (stem.size() > 2 && stem.substr(stem.size() - 2) == "_d") // debug builds are ignored, PluginManager.cpp:52-56
+						continue;
+					found.push_back(f + "/" + n);
+				}
+				closedir(dir);
+			}
+			std::sort(found.begin(), found.end());
+			for (const std::string& so : found)
+				tryLoad(so);
+		} else if (f.size() > 3 && f.substr(f.size() - 3) == ".so") {
 			tryLoad(f);
-		pos = end + 1;
+		}
 	}
 }
 PluginManager::~PluginManager()

@@ -637,7 +637,7 @@ struct RenderSettings { // reference src/core/renderer/RenderSettings.cpp:11-33
 
 // ------------------------------------------------------------------ output specification + image writer (image_io.cpp)
 enum class ToneColorMode { SRGB, XYZ, XYZNorm, Luminance }; // reference src/core/spectral/ToneMapper.h
-enum OutputVariable { OV_Unsupported = -1, OV_Output = 0, OV_Position, OV_Normal, OV_UVW, OV_Depth, OV_EntityID, OV_SampleCount, OV_Feedback };
+enum OutputVariable { OV_Unsupported = -1, OV_Output = 0, OV_Position, OV_Normal, OV_UVW, OV_Depth, OV_EntityID, OV_SampleCount, OV_Feedback, OV_OnlineMean, OV_OnlineVariance };
 struct OutputChannel { // reference IM_ChannelSetting{Spec,3D,1D,Counter}, src/loader/output/io/ImageWriter.h
 	enum Kind { Spectral, ThreeD, OneD, Counter } kind = Spectral;
 	int variable	  = OV_Output;
@@ -655,12 +655,23 @@ struct FilmView { // what prb_film_download / prb_film_aov return for one contex
 	const float* xyz		  = nullptr;  // 3 per pixel
 	const uint32* sampleCount = nullptr;  // 1 per pixel
 	const uint32* feedback	  = nullptr;  // 1 per pixel: OR of PRB_FEEDBACK_* bits; may be null
+	const float* onlineMean		= nullptr; // 3 per pixel (AOV_OnlineMean); may be null
+	const float* onlineVariance = nullptr; // 3 per pixel (AOV_OnlineVariance); may be null
 	const float* aov		  = nullptr;  // 10 per pixel (N, P, u, v, depth, entity id), sums over the samples; may be null
 };
 class OutputSpecification { // reference src/loader/output/io/OutputSpecification.h
 public:
 	void parse(const DL::DataGroup& entry);
 	const std::vector<OutputFile>& files() const { return mFiles; }
+	// does any channel ask for the online mean / variance AOVs (FrameOutputData::hasVarianceEstimator)?
+	bool wantsVariance() const
+	{
+		for (const OutputFile& f : mFiles)
+			for (const OutputChannel& c : f.channels)
+				if (c.variable == OV_OnlineMean || c.variable == OV_OnlineVariance)
+					return true;
+		return false;
+	}
 	// writes <workingDir>/results[_<contextIndex>]/<name>.exr for every (output ...) block; returns the number written
 	int save(const std::string& workingDir, const FilmView& film, uint32 contextIndex = 0) const;
 
@@ -682,6 +693,13 @@ public:
 	OutputSpecification& outputSpecification() { return mOutputSpecification; }
 	const OutputSpecification& outputSpecification() const { return mOutputSpecification; }
 
+private:
+	// Declared FIRST so that it is destroyed LAST: the factories below and every object they created (materials, nodes ...
+	// held by the scene database) may live in an external plugin library, which ~PluginManager unloads (the reference keeps
+	// the same order: "library unloaded after plugin reset", loader/plugin/PluginManager.h:38-50).
+	PluginManager mPluginManager;
+
+public:
 	AbstractManager<ICameraPlugin> cameraManager;
 	AbstractManager<IEmissionPlugin> emissionManager;
 	AbstractManager<IEntityPlugin> entityManager;
@@ -702,7 +720,6 @@ public:
 	bool createDefaultsIfNecessary();
 
 private:
-	PluginManager mPluginManager;
 	RenderSettings mRenderSettings;
 	SceneDatabase mDatabase;
 	std::shared_ptr<SpectralUpsampler> mUpsampler;

@@ -134,6 +134,15 @@ int RenderContext::saveOutputs(const std::string& workingDir)
 		film.aov = aov.data();
 	if (prb_film_download_feedback(mCtx, feedback.data()) == PRB_OK)
 		film.feedback = feedback.data();
+	std::vector<float> onlineMean, onlineVariance;
+	if (st.want_variance) {
+		onlineMean.resize(n * 3);
+		onlineVariance.resize(n * 3);
+		if (prb_film_download_variance(mCtx, onlineMean.data(), onlineVariance.data()) == PRB_OK) {
+			film.onlineMean		= onlineMean.data();
+			film.onlineVariance = onlineVariance.data();
+		}
+	}
 	return mEnv->outputSpecification().save(workingDir, film, mRank);
 }
 prb_stats RenderContext::statistics() const

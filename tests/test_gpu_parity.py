@@ -12,7 +12,7 @@ import pytest
 import pearray_b200 as prb
 from conftest import scene_path
 from oracle_binding import OracleScene
-from scene_strings import FURNACE, MATERIAL_ZOO, MATERIAL_ZOO2
+from scene_strings import FURNACE, MATERIAL_ZOO, MATERIAL_ZOO2, SKYSUN_ZOO
 from test_golden_oracle import CBOX_CHANNEL_TOL, CBOX_LUMINANCE_TOL, GOLDEN, STAT_NAMES, cbox_reference_error, load_golden, load_scene
 
 pytestmark = pytest.mark.gpu
@@ -484,9 +484,9 @@ def test_monochrome_modes_vs_oracle(variant):
     elif variant == "single_wavelength":
         src, tile, it = (FURNACE % dict(hero="true")).replace(":spectral_hero true", ":spectral_hero true :spectral_domain 520"), (0, 0, 48, 48), 16
     elif variant == "single_wavelength_zoo":
-        src, tile, it = MATERIAL_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_domain 610"), (0, 0, 32, 32), 8
+        src, tile, it = SKYSUN_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_domain 610"), (0, 0, 48, 48), 8
     else:
-        src, tile, it = MATERIAL_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_hero false"), (0, 0, 32, 32), 8
+        src, tile, it = SKYSUN_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_hero false"), (0, 0, 48, 48), 8
     scene = prb.Scene.from_string(src)
     assert bool(scene.settings.film_monotonic) == variant.startswith("single_wavelength")
     ctx = make_ctx(scene)
@@ -637,7 +637,7 @@ def test_film_reduce_single_process_tiles_bit_identical():
     AOV sums and feedback bits after the reduce are bit-identical to one context rendering every tile (here the contexts
     share one device; with several GPUs the same kernel reads the peers over NVLink)"""
     from pearray_b200 import multigpu
-    src = MATERIAL_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_hero false")  # leaves feedback bits behind
+    src = SKYSUN_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_hero false")  # leaves feedback bits behind
     scene = prb.Scene.from_string(src)
     tiles = scene.tiles(4, 4)
     spp = 3
