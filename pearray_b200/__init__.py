@@ -234,6 +234,8 @@ def host_lib():
         lib.prh_random_advance.argtypes = [C.c_uint64, C.c_uint64]
         lib.prh_list_plugins.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
         lib.prh_set_verbosity.argtypes = [C.c_int]
+        lib.prh_lpe_match.restype = C.c_int
+        lib.prh_lpe_match.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32]
         lib.prh_abi_sizeof.restype = C.c_uint32
         lib.prh_abi_sizeof.argtypes = [C.c_char_p]
         lib.prh_render_context_create.restype = C.c_void_p

@@ -578,8 +578,13 @@ struct RoughDielectric {
 
 // LambertMaterial::eval / ::sample (lambert.cpp:33-43, :53-73); inline so that k_shade's all-Lambert instantiation can use
 // them without the out-of-line material dispatch
+#ifndef PRB_NODE_CACHE
+#define PRB_NODE_CACHE 1
+#endif
 PRB_DEV Blob evalNodeCached(const DScene& S, const MatCtx& c, uint32_t node)
 {
+	if (!PRB_NODE_CACHE)
+		return evalNode(S, node, c.wvl, c.u, c.v);
 	if (c.cachedNode != node) {
 		c.cachedValue = evalNode(S, node, c.wvl, c.u, c.v);
 		c.cachedNode  = node;

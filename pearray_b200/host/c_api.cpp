@@ -39,6 +39,17 @@ float prh_sun_radiance(float wavelength, float theta, float turbidity) { return 
 
 const char* prh_last_error() { return g_err.c_str(); }
 void prh_set_verbosity(int level) { logVerbosity() = level; }
+// LightPathExpression(expr).isValid() / .match(path): tokens = n (type, event) pairs; returns -1 invalid, 0 no match, 1 match
+int prh_lpe_match(const char* expr, const int32_t* tokens, uint32_t n)
+{
+	const LPEAutomaton a = compileLPE(expr ? expr : "");
+	if (!a.valid)
+		return -1;
+	std::vector<std::pair<int, int>> t;
+	for (uint32_t i = 0; i < n; ++i)
+		t.emplace_back(tokens[2 * i], tokens[2 * i + 1]);
+	return a.match(t) ? 1 : 0;
+}
 // sizeof() of the POD structs of include/prb200_abi.h as this library was compiled, for checking FFI mirrors (ctypes, cgo ...)
 uint32_t prh_abi_sizeof(const char* name)
 {

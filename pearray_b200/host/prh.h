@@ -635,6 +635,18 @@ struct RenderSettings { // reference src/core/renderer/RenderSettings.cpp:11-33
 	uint32 cropOffsetY() const { return (uint32)(cropMinY * filmHeight); }
 };
 
+// ------------------------------------------------------------------ light path expressions (lpe.cpp)
+// reference src/core/path/LightPathExpression.h; dense DFA over the 15 (ScatteringType, ScatteringEvent) symbols
+constexpr uint8_t LPE_REJECT = 0xFF;
+struct LPEAutomaton {
+	bool valid		  = false;
+	uint32 stateCount = 0;	   // state 0 is the start state
+	std::vector<uint8_t> next; // [state * 15 + type * 3 + event] -> state or LPE_REJECT
+	std::vector<uint8_t> final;
+	bool match(const std::vector<std::pair<int, int>>& tokens) const; // (type, event) pairs, LightPathToken.h:6-20
+};
+LPEAutomaton compileLPE(const std::string& expression);
+
 // ------------------------------------------------------------------ output specification + image writer (image_io.cpp)
 enum class ToneColorMode { SRGB, XYZ, XYZNorm, Luminance }; // reference src/core/spectral/ToneMapper.h
 enum OutputVariable { OV_Unsupported = -1, OV_Output = 0, OV_Position, OV_Normal, OV_UVW, OV_Depth, OV_EntityID, OV_SampleCount, OV_Feedback, OV_OnlineMean, OV_OnlineVariance };
