@@ -404,7 +404,8 @@ def render_workload(job, prb, key, spp, steps, warmup, partition, want_e2e=True,
                           "film": [W, H], "partition": partition, "paths_in_flight_per_gpu": npix_rank,
                           "l2": "wavefront state (%d paths x ~250 B) and film are re-written every wavefront iteration; scene is L2-resident by nature" % npix_rank},
                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "stage_ms": {k: v[0] for k, v in stage.items()} if stage else None,
-               "rank_ms_per_step": rank_ms}
+               "rank_ms_per_step": rank_ms,
+               "shading": {0: "single k_shade", 1: "staged (k_shade_geom + nee/scatter per material type)", -1: "undecided"}[ctx.shading_mode()]}
         if e2e_ms is not None:
             out["e2e"] = {"value": total_samples / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": W * H * 8 + len(tiles) * 16,
                           "d2h_bytes_per_step": W * H * 3 * 4 + W * H * 4, "ms_per_step": e2e_ms / steps}

@@ -522,6 +522,15 @@ enum { PRB_STAGE_TRACE = 0, PRB_STAGE_SHADE = 1, PRB_STAGE__COUNT = 2 };
 prb_status prb_set_profiling(prb_ctx* ctx, int enabled);
 prb_status prb_get_stage_times(prb_ctx* ctx, float* ms, uint64_t* launches);
 
+/* -- shading path.  The shading stage exists in two bit-identical forms: ONE kernel (k_shade, slots sorted by material per
+ * block) or STAGED (k_shade_geom, then k_shade_nee / k_shade_scatter once per material type over compact queues).  Which is
+ * faster depends on the scene, so by default (PRB_SHADING_AUTO) a context times both during the first poll intervals of the
+ * first render after prb_upload_scene and keeps the faster one.  prb_set_shading_mode pins it (also: environment variable
+ * PRB_STAGED=0|1); prb_get_shading_mode reports the current choice, PRB_SHADING_AUTO while still undecided. */
+enum { PRB_SHADING_AUTO = -1, PRB_SHADING_SINGLE = 0, PRB_SHADING_STAGED = 1 };
+prb_status prb_set_shading_mode(prb_ctx* ctx, int mode);
+prb_status prb_get_shading_mode(prb_ctx* ctx, int* mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,7 +148,7 @@ ABI_SYMBOLS = ["prb_create", "prb_destroy", "prb_last_error", "prb_device_count"
                "prb_trace_any", "prb_trace_closest_device", "prb_trace_any_device", "prb_generate_camera_rays",
                "prb_material_eval", "prb_material_sample", "prb_get_stats", "prb_reset_stats", "prb_last_device_ms",
                "prb_set_profiling", "prb_get_stage_times", "prb_film_reduce", "prb_comm_unique_id", "prb_comm_init",
-               "prb_comm_destroy", "prb_film_reduce_comm", "prb_last_reduce_ms"]
+               "prb_comm_destroy", "prb_film_reduce_comm", "prb_last_reduce_ms", "prb_set_shading_mode", "prb_get_shading_mode"]
 
 
 def device_lib():
@@ -194,6 +194,8 @@ def device_lib():
         lib.prb_last_device_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         lib.prb_set_profiling.argtypes = [C.c_void_p, C.c_int]
         lib.prb_get_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+        lib.prb_set_shading_mode.argtypes = [C.c_void_p, C.c_int]
+        lib.prb_get_shading_mode.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         _dev = lib
     return _dev
 
@@ -518,6 +520,15 @@ class Context:
         ms = C.c_float()
         self._chk(self._lib.prb_last_device_ms(self._h, C.byref(ms)), "prb_last_device_ms")
         return float(ms.value)
+
+    def set_shading_mode(self, mode):
+        """-1 measure and pick (default), 0 single k_shade, 1 staged per-material-type kernels (bit-identical films)"""
+        self._chk(self._lib.prb_set_shading_mode(self._h, int(mode)), "prb_set_shading_mode")
+
+    def shading_mode(self):
+        m = C.c_int()
+        self._chk(self._lib.prb_get_shading_mode(self._h, C.byref(m)), "prb_get_shading_mode")
+        return int(m.value)
 
     def set_profiling(self, enabled):
         self._chk(self._lib.prb_set_profiling(self._h, 1 if enabled else 0), "prb_set_profiling")

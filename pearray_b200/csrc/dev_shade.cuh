@@ -627,12 +627,14 @@ PRB_DEV Blob orenNayarCalc(const DScene& S, const prb_material& m, const MatCtx&
 	return weight;
 }
 
-__device__ __noinline__ void materialEvalLeaf(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
+// FIXED >= 0: the caller knows the material type at compile time (the per-type stage kernels): the switch folds to one case
+template <int FIXED>
+__device__ __noinline__ void materialEvalLeafT(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
 {
 	const prb_material m = S.materials[matID];
 	out.flags			 = 0;
 	out.type			 = 0;
-	switch (m.type) {
+	switch (FIXED >= 0 ? (uint32_t)FIXED : m.type) {
 	case PRB_MAT_DIFFUSE: lambertEval(S, m, c, out); break;
 	case PRB_MAT_DIELECTRIC:
 		out.pdf	   = blob(0);
@@ -719,12 +721,13 @@ __device__ __noinline__ void materialEvalLeaf(const DScene& S, uint32_t matID, c
 	}
 }
 
-__device__ __noinline__ void materialSampleLeaf(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
+template <int FIXED>
+__device__ __noinline__ void materialSampleLeafT(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
 {
 	const prb_material m = S.materials[matID];
 	out.flags			 = 0;
 	out.type			 = 0;
-	switch (m.type) {
+	switch (FIXED >= 0 ? (uint32_t)FIXED : m.type) {
 	case PRB_MAT_DIFFUSE: lambertSample(S, m, c, rnd, out); break;
 	case PRB_MAT_DIELECTRIC: { // dielectric.cpp:60-114
 		out.pdf		  = blob(1);
@@ -870,6 +873,8 @@ __device__ __noinline__ void materialSampleLeaf(const DScene& S, uint32_t matID,
 // blend.cpp:20-148 / add.cpp:20-122 over two LEAF materials (node[0], node[1] hold their ids); everything else is a leaf.
 // No recursion: the host rejects nested combinations, so the device stack stays statically sized.
 PRB_DEV bool isCombination(uint32_t type) { return type == PRB_MAT_BLEND || type == PRB_MAT_ADD; }
+PRB_DEV void materialEvalLeaf(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out) { materialEvalLeafT<-1>(S, matID, c, out); }
+PRB_DEV void materialSampleLeaf(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out) { materialSampleLeafT<-1>(S, matID, c, rnd, out); }
 __device__ __noinline__ void materialEvalCombined(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
 { // out of line: its two child results only occupy stack while a combination is evaluated
 	const prb_material& m = S.materials[matID];
@@ -906,11 +911,14 @@ __device__ __noinline__ void materialEvalCombined(const DScene& S, uint32_t matI
 }
 // k_shade is instantiated per KIND: without the combination path for scenes that have no blend / add material (merely having
 // the call in the kernel cost 4-5 % of k_shade on C2 / C4), and with the Lambert code inline for all-Lambert scenes.
-enum { SHADE_MATERIALS_LEAF = 0, SHADE_MATERIALS_COMBINED = 1, SHADE_MATERIALS_LAMBERT = 2 };
+// SHADE_MATERIALS_TYPE + t: every slot the kernel sees has a material of type t (the per-type queues of the staged path)
+enum { SHADE_MATERIALS_LEAF = 0, SHADE_MATERIALS_COMBINED = 1, SHADE_MATERIALS_LAMBERT = 2, SHADE_MATERIALS_TYPE = 16 };
 template <int KIND>
 PRB_DEV void materialEval(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
 {
-	if (KIND == SHADE_MATERIALS_LAMBERT) { // every material of the scene is a Lambert material (Cornell box)
+	if (KIND >= SHADE_MATERIALS_TYPE) {
+		materialEvalLeafT<KIND - SHADE_MATERIALS_TYPE>(S, matID, c, out);
+	} else if (KIND == SHADE_MATERIALS_LAMBERT) { // every material of the scene is a Lambert material (Cornell box)
 		out.flags = 0;
 		out.type  = 0;
 		lambertEval(S, S.materials[matID], c, out);
@@ -937,7 +945,9 @@ __device__ __noinline__ void materialSampleCombined(const DScene& S, uint32_t ma
 template <int KIND>
 PRB_DEV void materialSample(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
 {
-	if (KIND == SHADE_MATERIALS_LAMBERT) {
+	if (KIND >= SHADE_MATERIALS_TYPE) {
+		materialSampleLeafT<KIND - SHADE_MATERIALS_TYPE>(S, matID, c, rnd, out);
+	} else if (KIND == SHADE_MATERIALS_LAMBERT) {
 		out.flags = 0;
 		out.type  = 0;
 		lambertSample(S, S.materials[matID], c, rnd, out);

@@ -14,6 +14,10 @@
 
 using namespace prb;
 
+// Staged shading (k_shade_geom / _nee / _scatter per material type) against the single k_shade: films are bit-identical, which
+// one is faster depends on the scene (boltsandgears 164 -> 233 Msamples/s staged, cornellbox_glassy 51 -> 39), so a context
+// MEASURES both on the first poll intervals of a render and keeps the faster (PRB_STAGED=0|1 pins the choice).
+
 namespace {
 thread_local std::string g_err;
 prb_status fail(prb_status code, const std::string& msg)
@@ -62,7 +66,7 @@ struct DBuf {
 struct prb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t evA = nullptr, evB = nullptr;
+	cudaEvent_t evA = nullptr, evB = nullptr, evT0 = nullptr, evT1 = nullptr;
 	int smCount = 148;
 	bool allLambert = false;	 // every material is PRB_MAT_DIFFUSE: k_shade with the Lambert code inline
 	bool mixedMaterials = false; // the scene mixes material types: k_shade sorts larger windows (launchShade)
@@ -94,8 +98,16 @@ struct prb_ctx {
 	DBuf<uint32_t> reduceU;	 // spread feedback bits
 	float lastReduceMs = 0;
 	// wavefront
-	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters, regenList;
-	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ, prevAcc;
+	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters, regenList, neeList, scatterList;
+	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ, prevAcc, vxP, vxN, vxNx, vxNy, vxD;
+	bool staged = false;	   // k_shade_geom -> k_shade_nee / k_shade_scatter per material type instead of k_shade
+	bool stagedAuto = false;   // not pinned: decided by measurement (tuneStep / tuneMs) during the first render of the scene
+	int tuneStep = 0;		   // poll intervals measured so far (modes 0,1,1,0: cancels the drift of the falling path count)
+	float tuneMs[2] = { 0, 0 };
+	uint8_t queueOfType[SHADE_QUEUES];	   // material type -> queue index, 0xFF when the scene has no material of the type
+	bool queueWantsNEE[SHADE_QUEUES] = {}; // some material of the queue's type has a non-delta lobe
+	uint32_t nQueues = 0, nNeeQueues = 0;
+	uint32_t launchesPerIteration(bool stagedMode) const { return stagedMode ? 3 + nQueues + nNeeQueues : 3; }
 	DBuf<uint4> hit;
 	DBuf<float> hitT;
 	std::vector<prb_tile> cachedTiles;
@@ -112,8 +124,8 @@ struct prb_ctx {
 	float lastMs = 0;
 	// the wavefront graph (ITERS_PER_GRAPH x k_trace, k_shade, k_regen) is instantiated once and replayed by every
 	// prb_render_tiles call until something baked into its kernel parameters changes (scene, slot buffers, variant)
-	cudaGraphExec_t graphExec = nullptr;
-	uint64_t graphKey = 0, stateVersion = 1; // stateVersion: bumped whenever the scene or the slot buffers change
+	cudaGraphExec_t graphExec[2] = { nullptr, nullptr }; // [staged]
+	uint64_t graphKey[2] = { 0, 0 }, stateVersion = 1; // stateVersion: bumped whenever the scene or the slot buffers change
 	bool wantAOV = true;
 	bool persistentTrace = true; // k_trace (persistent threads) vs k_trace_static, chosen per scene in prb_upload_scene
 	bool smallScene = false;	 // k_trace_static<true>: exhaustive test of a tiny scene from shared memory, no BVH
@@ -124,6 +136,15 @@ struct prb_ctx {
 	float stageMs[PRB_STAGE__COUNT] = {};
 	uint64_t stageLaunches[PRB_STAGE__COUNT] = {};
 };
+
+template <int KIND>
+static void launchStageKernels(prb_ctx* c, const WFState& W, uint32_t queue, cudaStream_t s)
+{
+	const int grid = (int)((c->nSlots + 127) / 128);
+	if (c->queueWantsNEE[queue]) // (a queue of delta-only materials never does NEE)
+		k_shade_nee<KIND><<<grid, 128, 0, s>>>(c->S, W, queue);
+	k_shade_scatter<KIND><<<grid, 128, 0, s>>>(c->S, W, queue);
+}
 
 extern "C" {
 const char* prb_last_error(void) { return g_err.c_str(); }
@@ -160,6 +181,10 @@ prb_status prb_create(int device, prb_ctx** out)
 	if (e == cudaSuccess)
 		e = cudaEventCreate(&c->evB);
 	if (e == cudaSuccess)
+		e = cudaEventCreate(&c->evT0);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&c->evT1);
+	if (e == cudaSuccess)
 		e = cudaMallocHost(&c->hostCounters, CNT__COUNT * sizeof(uint32_t));
 	if (e == cudaSuccess)
 		e = c->stats.alloc(ST__COUNT);
@@ -189,19 +214,20 @@ void prb_destroy(prb_ctx* c)
 		return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
-	if (c->graphExec)
-		cudaGraphExecDestroy(c->graphExec);
+	for (cudaGraphExec_t& g : c->graphExec)
+		if (g)
+			cudaGraphExecDestroy(g);
 	prb_comm_destroy(c);
 	c->reduceF.release();
 	c->reduceU.release();
 	DBuf<uint32_t>* ub[] = { &c->entityMaterials, &c->faceIndices, &c->faceSlots, &c->tlasRefs, &c->sampleCount, &c->feedback, &c->pixel, &c->iter, &c->flagsDepth,
-							 &c->slotState, &c->counters, &c->regenList, &c->scratchU };
+							 &c->slotState, &c->counters, &c->regenList, &c->neeList, &c->scatterList, &c->scratchU };
 	for (auto* b : ub)
 		b->release();
 	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->varMean, &c->varVar, &c->hitT, &c->scratchF };
 	for (auto* b : fb)
 		b->release();
-	DBuf<float4>* f4[] = { &c->bvhTris, &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc };
+	DBuf<float4>* f4[] = { &c->bvhTris, &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc, &c->vxP, &c->vxN, &c->vxNx, &c->vxNy, &c->vxD };
 	for (auto* b : f4)
 		b->release();
 	c->nodes.release();
@@ -224,6 +250,8 @@ void prb_destroy(prb_ctx* c)
 		cudaEventDestroy(ev);
 	cudaEventDestroy(c->evA);
 	cudaEventDestroy(c->evB);
+	cudaEventDestroy(c->evT0);
+	cudaEventDestroy(c->evT1);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -449,6 +477,29 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	if (const char* m = std::getenv("PRB_TRACE_MODE"))
 		if (std::strcmp(m, "bvh") == 0)
 			c->smallScene = false;
+	// staged shading pays off where material types mix (one compact kernel per type instead of one 400 KB kernel that is
+	// instruction-fetch bound); an all-Lambert scene is served best by the single inlined k_shade (measured: C2 272 vs 226 M)
+	c->staged	  = false;
+	c->stagedAuto = !c->allLambert;
+	c->tuneStep	  = 0;
+	c->tuneMs[0] = c->tuneMs[1] = 0;
+	if (const char* m = std::getenv("PRB_STAGED")) {
+		c->staged	  = std::atoi(m) != 0;
+		c->stagedAuto = false;
+	}
+	std::memset(c->queueOfType, 0xFF, sizeof(c->queueOfType));
+	std::memset(c->queueWantsNEE, 0, sizeof(c->queueWantsNEE));
+	c->nQueues = 0;
+	for (uint32_t i = 0; i < d->n_materials; ++i) {
+		const uint32_t t = std::min<uint32_t>(d->materials[i].type, SHADE_QUEUES - 1);
+		if (c->queueOfType[t] == 0xFF)
+			c->queueOfType[t] = (uint8_t)c->nQueues++;
+		if (!(d->materials[i].flags & PRB_MATF_ONLY_DELTA))
+			c->queueWantsNEE[c->queueOfType[t]] = true;
+	}
+	c->nNeeQueues = 0;
+	for (uint32_t q = 0; q < c->nQueues; ++q)
+		c->nNeeQueues += c->queueWantsNEE[q] ? 1u : 0u;
 	c->haveScene   = true;
 	c->rngUploaded = false; // the RNG map was zeroed above: state 0 of the pcg32_fast MCG stays 0 forever
 	c->cachedTiles.clear();
@@ -527,8 +578,13 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 	CU(c->flagsDepth.alloc(n));
 	CU(c->slotState.alloc(n));
 	CU(c->regenList.alloc(n));
+	if (c->staged || c->stagedAuto) { // one queue per material type of the scene
+		CU(c->neeList.alloc(n * std::max<size_t>(c->nQueues, 1)));
+		CU(c->scatterList.alloc(n * std::max<size_t>(c->nQueues, 1)));
+	}
 	CU(c->counters.alloc(CNT__COUNT));
-	DBuf<float4>* f4[] = { &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc };
+	DBuf<float4>* f4[] = { &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc,
+						   &c->vxP, &c->vxN, &c->vxNx, &c->vxNy, &c->vxD };
 	for (auto* b : f4)
 		CU(b->alloc(n));
 	CU(c->hit.alloc(n));
@@ -537,6 +593,10 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 	c->cachedTiles.assign(tiles, tiles + n_tiles);
 	c->nSlots = (uint32_t)n;
 	c->stateVersion++;
+	if (c->stagedAuto) { // another wave size: measure again
+		c->tuneStep = 0;
+		c->tuneMs[0] = c->tuneMs[1] = 0;
+	}
 	return PRB_OK;
 }
 
@@ -550,8 +610,34 @@ static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
 	launchShadeOnly(c, W, s);
 	k_regen<<<(int)((c->nSlots + 127) / 128), 128, 0, s>>>(c->S, W);
 }
+// staged shading: k_shade_geom, then one k_shade_nee / k_shade_scatter launch per material TYPE present in the scene over that
+// type's queue (grids sized for the worst case; blocks past the end of a queue return at once)
+static void launchShadeStaged(prb_ctx* c, const WFState& W, cudaStream_t s)
+{
+	k_shade_geom<<<(int)((c->nSlots + 127) / 128), 128, 0, s>>>(c->S, W);
+	for (uint32_t t = 0; t < (uint32_t)SHADE_QUEUES; ++t) {
+		const uint32_t q = W.queueOfType[t];
+		if (q == 0xFF)
+			continue;
+		switch (t) {
+		case PRB_MAT_DIFFUSE: launchStageKernels<SHADE_MATERIALS_LAMBERT>(c, W, q, s); break;
+		case PRB_MAT_DIELECTRIC: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_DIELECTRIC>(c, W, q, s); break;
+		case PRB_MAT_CONDUCTOR: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_CONDUCTOR>(c, W, q, s); break;
+		case PRB_MAT_ROUGHCONDUCTOR: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_ROUGHCONDUCTOR>(c, W, q, s); break;
+		case PRB_MAT_ROUGHDIELECTRIC: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_ROUGHDIELECTRIC>(c, W, q, s); break;
+		case PRB_MAT_PRINCIPLED: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_PRINCIPLED>(c, W, q, s); break;
+		case PRB_MAT_MIRROR: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_MIRROR>(c, W, q, s); break;
+		case PRB_MAT_ORENNAYAR: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_ORENNAYAR>(c, W, q, s); break;
+		default: launchStageKernels<SHADE_MATERIALS_COMBINED>(c, W, q, s); break; // blend / add: children of any leaf type
+		}
+	}
+}
 static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s)
 {
+	if (c->staged) {
+		launchShadeStaged(c, W, s);
+		return;
+	}
 	const bool combined = c->S.hasCombined != 0; // a scene with blend / add materials always mixes material types
 	if (!c->mixedMaterials && !combined) {
 		const int grid = (int)((c->nSlots + SHADE_BLOCK_UNIFORM - 1) / SHADE_BLOCK_UNIFORM);
@@ -607,6 +693,14 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.state		  = c->slotState.p;
 	W.counters	  = c->counters.p;
 	W.regenList	  = c->regenList.p;
+	W.neeList	  = c->neeList.p;
+	W.scatterList = c->scatterList.p;
+	W.vxP		  = c->vxP.p;
+	W.vxN		  = c->vxN.p;
+	W.vxNx		  = c->vxNx.p;
+	W.vxNy		  = c->vxNy.p;
+	W.vxD		  = c->vxD.p;
+	std::memcpy(W.queueOfType, c->queueOfType, sizeof(W.queueOfType));
 	W.rng		  = c->rng.p;
 	W.filmMean	  = c->filmMean.p;
 	W.sampleCount = c->sampleCount.p;
@@ -679,7 +773,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 				CU(cudaGetLastError());
 			}
 			done += ITERS_PER_GRAPH * GRAPHS_PER_POLL;
-			c->kernelLaunches += 3 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
+			c->kernelLaunches += c->launchesPerIteration(c->staged) * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
 			CU(poll());
 			for (size_t i = 0; i + 1 < ne; i += 2) {
 				float ms = 0;
@@ -692,43 +786,73 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 	} else {
 		// the kernels of the graph read the iteration range from device memory (CNT_END_ITER, written by k_init_slots), so one
 		// instantiated graph serves every call until the scene, the slot buffers or the kernel variant change
-		const uint64_t key = (c->stateVersion << 3) | (c->persistentTrace ? 1u : 0u) | (c->wantAOV ? 2u : 0u) | (c->smallScene ? 4u : 0u);
-		if (!c->graphExec || c->graphKey != key) {
-			if (c->graphExec) {
-				cudaGraphExecDestroy(c->graphExec);
-				c->graphExec = nullptr;
+		auto ensureGraph = [&](bool stagedMode) -> prb_status {
+			const uint64_t key = (c->stateVersion << 4) | (c->persistentTrace ? 1u : 0u) | (c->wantAOV ? 2u : 0u) | (c->smallScene ? 4u : 0u) | (stagedMode ? 8u : 0u);
+			cudaGraphExec_t& exec = c->graphExec[stagedMode ? 1 : 0];
+			if (exec && c->graphKey[stagedMode ? 1 : 0] == key)
+				return PRB_OK;
+			if (exec) {
+				cudaGraphExecDestroy(exec);
+				exec = nullptr;
 			}
+			const bool keep = c->staged;
+			c->staged		= stagedMode;
 			cudaGraph_t graph = nullptr;
-			CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-			for (int r = 0; r < ITERS_PER_GRAPH; ++r) {
-				launchTrace(c, W, blocks, s);
-				launchShade(c, W, s);
-			}
-			const cudaError_t ce = cudaGetLastError();
-			const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+			cudaError_t be	  = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+			if (be == cudaSuccess)
+				for (int r = 0; r < ITERS_PER_GRAPH; ++r) {
+					launchTrace(c, W, blocks, s);
+					launchShade(c, W, s);
+				}
+			c->staged = keep;
+			const cudaError_t ce = be == cudaSuccess ? cudaGetLastError() : be;
+			const cudaError_t ee = be == cudaSuccess ? cudaStreamEndCapture(s, &graph) : be;
 			if (ce != cudaSuccess || ee != cudaSuccess) {
 				if (graph)
 					cudaGraphDestroy(graph);
 				return fail(PRB_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
 			}
-			const cudaError_t ie = cudaGraphInstantiate(&c->graphExec, graph, 0);
+			const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
 			cudaGraphDestroy(graph);
 			if (ie != cudaSuccess) {
-				c->graphExec = nullptr;
+				exec = nullptr;
 				return fail(PRB_ERR_CUDA, std::string("graph instantiation failed: ") + cudaGetErrorString(ie));
 			}
-			c->graphKey = key;
-		}
+			c->graphKey[stagedMode ? 1 : 0] = key;
+			return PRB_OK;
+		};
+		// Undecided contexts time poll intervals in the order single, staged, staged, single (the number of live paths falls
+		// slowly over a render; the symmetric order cancels that drift) and keep the faster path from then on.  Both leave the
+		// same wavefront state behind every iteration, so they can alternate freely.
+		static const bool tuneOrder[4] = { false, true, true, false };
 		while (!finished && done < maxIters + ITERS_PER_GRAPH * GRAPHS_PER_POLL) {
+			const bool tuning = c->stagedAuto && c->tuneStep < 4;
+			const bool mode	  = tuning ? tuneOrder[c->tuneStep] : c->staged;
+			prb_status gs	  = ensureGraph(mode);
+			if (gs != PRB_OK)
+				return gs;
 			cudaError_t e = cudaSuccess;
+			if (tuning)
+				e = cudaEventRecord(c->evT0, s);
 			for (int r = 0; r < GRAPHS_PER_POLL && e == cudaSuccess; ++r)
-				e = cudaGraphLaunch(c->graphExec, s);
+				e = cudaGraphLaunch(c->graphExec[mode ? 1 : 0], s);
+			if (tuning && e == cudaSuccess)
+				e = cudaEventRecord(c->evT1, s);
 			done += ITERS_PER_GRAPH * GRAPHS_PER_POLL;
-			c->kernelLaunches += 3 * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
+			c->kernelLaunches += c->launchesPerIteration(mode) * ITERS_PER_GRAPH * GRAPHS_PER_POLL;
 			if (e == cudaSuccess)
 				e = poll();
 			if (e != cudaSuccess)
 				return fail(PRB_ERR_CUDA, std::string("wavefront loop failed: ") + cudaGetErrorString(e));
+			if (tuning) {
+				float ms = 0;
+				CU(cudaEventElapsedTime(&ms, c->evT0, c->evT1));
+				c->tuneMs[mode ? 1 : 0] += ms;
+				if (++c->tuneStep == 4) {
+					c->staged	  = c->tuneMs[1] < c->tuneMs[0];
+					c->stagedAuto = false;
+				}
+			}
 		}
 	}
 	// flush: samples that ended with their last shadow ray in flight are folded into the film by k_trace
@@ -1312,6 +1436,27 @@ prb_status prb_get_stage_times(prb_ctx* c, float* ms4, uint64_t* launches4)
 		ms4[i]		 = c->stageMs[i];
 		launches4[i] = c->stageLaunches[i];
 	}
+	return PRB_OK;
+}
+prb_status prb_set_shading_mode(prb_ctx* c, int mode)
+{
+	if (!c || mode < PRB_SHADING_AUTO || mode > PRB_SHADING_STAGED)
+		return fail(PRB_ERR_INVALID_ARG, "invalid shading mode");
+	c->stagedAuto = mode == PRB_SHADING_AUTO && !c->allLambert;
+	c->staged	  = mode == PRB_SHADING_STAGED;
+	c->tuneStep	  = 0;
+	c->tuneMs[0] = c->tuneMs[1] = 0;
+	if (c->nSlots) { // the queues of the staged path are sized with the slots
+		c->cachedTiles.clear();
+		c->nSlots = 0;
+	}
+	return PRB_OK;
+}
+prb_status prb_get_shading_mode(prb_ctx* c, int* mode)
+{
+	if (!c || !mode)
+		return fail(PRB_ERR_INVALID_ARG, "null argument");
+	*mode = c->stagedAuto ? PRB_SHADING_AUTO : (c->staged ? PRB_SHADING_STAGED : PRB_SHADING_SINGLE);
 	return PRB_OK;
 }
 prb_status prb_last_device_ms(prb_ctx* c, float* ms)

@@ -28,9 +28,11 @@ FILM_TOL = 0.0
 RNG_EQUAL_MIN = 1.0
 
 
-def make_ctx(scene):
+def make_ctx(scene, shading=None):
     ctx = prb.Context(0)
     ctx.upload_scene(scene)
+    if shading is not None:
+        ctx.set_shading_mode(shading)
     ctx.upload_rng(scene.rng_map())
     return ctx
 
@@ -56,11 +58,14 @@ def test_hits_bit_exact_vs_golden(name):
     assert np.array_equal(occ, g["inc_occ"])
 
 
+# shading: -1 = the context times the single k_shade against the staged per-material-type kernels and alternates between them
+# while it does (the default), 0 / 1 = pinned to one of them; the film must not depend on it
+@pytest.mark.parametrize("shading", [-1, 0, 1])
 @pytest.mark.parametrize("name", GOLDEN)
-def test_film_vs_golden(name):
+def test_film_vs_golden(name, shading):
     g = load_golden(name)
     scene = load_scene(name)
-    ctx = make_ctx(scene)
+    ctx = make_ctx(scene, shading)
     ctx.reset_stats()
     sx, sy, ex, ey = (int(x) for x in g["tile"])
     ctx.render_tiles([(sx, sy, ex, ey)], 0, 4)
@@ -317,6 +322,26 @@ def test_full_frame_large_films_vs_oracle(name, iters):
     st = ctx.stats()
     assert {k: int(getattr(st, k)) for k in STAT_NAMES} == ref["stats"]
     assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
+
+
+def test_shading_mode_is_measured_and_does_not_change_the_film():
+    """a mixed-material scene starts undecided, decides within the first 4 poll intervals (128 wavefront iterations) and
+    renders the same bits as either pinned mode"""
+    scene = load_scene("c4_boltsandgears")
+    tiles = [(200, 200, 456, 328)]
+    films = {}
+    for mode in (-1, 0, 1):
+        ctx = make_ctx(scene, mode)
+        assert ctx.shading_mode() == mode
+        ctx.render_tiles(tiles, 0, 48)
+        films[mode] = (ctx.film()[0], ctx.download_rng(), ctx.shading_mode())
+        ctx.close()
+    assert films[-1][2] in (0, 1), "still undecided after a 48-spp render"
+    for mode in (0, 1):
+        assert np.array_equal(films[mode][0].view(np.uint32), films[-1][0].view(np.uint32))
+        assert np.array_equal(films[mode][1], films[-1][1])
+    lam = make_ctx(load_scene("c2_cornellbox"))
+    assert lam.shading_mode() == 0, "an all-Lambert scene always takes the inlined single kernel"
 
 
 def test_uniform_non_lambert_scene_uses_the_generic_single_pass_kernel():
