@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 2u
+#define PRB_ABI_VERSION 3u
 #define PRB_INVALID_ID 0xFFFFFFFFu /* reference PR_INVALID_ID, src/base/config/Constants.inl */
 #define PRB_SPECTRAL_BLOB_SIZE 4	/* reference SpectralBlob, src/core/spectral/SpectralBlob.h:7-20 */
 
@@ -326,6 +326,23 @@ typedef struct prb_settings { /* RenderSettings.cpp:11-33 + DiParameters direct.
 	uint32_t want_variance;
 } prb_settings;
 
+/* ---------------------------------------------------------------- light path expressions
+ * One compiled `:lpe` expression of an (output (channel ...)) block (reference src/core/path/LightPathExpression.cpp,
+ * LPE_Automaton.cpp): a dense DFA over the 15 path-token symbols  symbol = ScatteringType * 3 + ScatteringEvent
+ * (LightPathToken.h:6-20: Camera, Emissive, Refraction, Reflection, Background x Diffuse, Specular, None).
+ * next[state * 15 + symbol] is the next state or PRB_LPE_REJECT; final[state] != 0 marks accepting states.  A fragment is
+ * added to the channel when the automaton, started in start_state, accepts the fragment's token string
+ * (LocalFrameOutputDevice.cpp:100-111). */
+#define PRB_MAX_LPE 8u
+#define PRB_LPE_SYMBOLS 15u
+#define PRB_LPE_REJECT 0xFFu
+typedef struct prb_lpe {
+	uint32_t next_offset;  /* into prb_scene_desc::lpe_tables: n_states * 15 bytes */
+	uint32_t final_offset; /* into lpe_tables: n_states bytes */
+	uint32_t n_states;	   /* <= 255 */
+	uint32_t start_state;
+} prb_lpe;
+
 /* ---------------------------------------------------------------- the scene */
 typedef struct prb_scene_desc {
 	uint32_t abi_version;
@@ -371,6 +388,12 @@ typedef struct prb_scene_desc {
 	const float* pool; /* CIE tables, illuminants, CDFs, Sobol tables, filter table */
 	uint32_t cie_offset; /* 3 x 441 floats: x, y, z (CIE 2006, 390..830 nm) */
 	uint32_t _pad;
+
+	/* spectral output channels restricted by a light path expression (at most PRB_MAX_LPE) */
+	uint32_t n_lpe;
+	uint32_t n_lpe_bytes;
+	const uint8_t* lpe_tables;
+	prb_lpe lpe[PRB_MAX_LPE];
 } prb_scene_desc;
 
 /* One render tile (reference RenderTile start/end, src/core/renderer/RenderTile.h).  Pixels are film
@@ -457,6 +480,10 @@ prb_status prb_film_download_feedback(prb_ctx* ctx, uint32_t* feedback);
  * two tiles twice per iteration in thread order -- not reproducible even by the reference itself).  PRB_ERR_UNSUPPORTED unless
  * prb_settings.want_variance was set at upload. */
 prb_status prb_film_download_variance(prb_ctx* ctx, float* online_mean, float* online_variance);
+/* the spectral channel of light path expression `index` (prb_scene_desc::lpe): XYZ running mean of the fragments whose path the
+ * expression accepts, 3 floats per film pixel, pixel filter applied like prb_film_download
+ * (LocalFrameOutputDevice.cpp:100-111, FrameOutputDevice.cpp:216-218) */
+prb_status prb_film_download_lpe(prb_ctx* ctx, uint32_t index, float* xyz);
 /* copy the UNFILTERED film (xyz mean, 3 floats/pixel, then sample counts as float) into a caller
  * provided DEVICE buffer of W*H*4 floats -- the buffer handed to the NCCL reduce in multi-GPU runs. */
 prb_status prb_film_export_device(prb_ctx* ctx, float* device_dst);

@@ -1483,6 +1483,10 @@ struct Film {
 	uint32_t* feedback = nullptr; // AOV_Feedback, W*H words or null
 	float* varMean	   = nullptr; // AOV_OnlineMean / AOV_OnlineVariance, W*H*3 each or null
 	float* varVar	   = nullptr;
+	// spectral channels restricted by a light path expression (prb_scene_desc::lpe): per expression a W*H*3 running mean at
+	// lpeMean + k * W*H*3 and the sums of the running iteration, or null
+	float* lpeMean = nullptr;
+	std::vector<float> lpeIter;
 };
 struct Stats {
 	uint64_t c[11] = {};
@@ -1541,6 +1545,32 @@ struct Integrator {
 	Group grp;
 	std::vector<FragLog>* log = nullptr;
 	FragLog pending{}; // filled by the handlers before pushSpectralFragment
+	// LightPath mCameraPath (direct.cpp:67,472): the token string of the path so far, symbol = ScatteringType * 3 + ScatteringEvent
+	// (LightPathToken.h:6-20)
+	std::vector<uint8_t> path{};
+	enum { TOK_CAMERA = 0 * 3 + 2, TOK_EMISSIVE = 1 * 3 + 2, TOK_BACKGROUND = 4 * 3 + 2 };
+	static uint8_t scatterToken(uint32_t materialScatteringType)
+	{ // LightPathToken(MaterialScatteringType), LightPathToken.h:40-60
+		switch (materialScatteringType) {
+		case 0: return 3 * 3 + 0; // DiffuseReflection  -> Reflection, Diffuse
+		case 1: return 3 * 3 + 1; // SpecularReflection -> Reflection, Specular
+		case 2: return 2 * 3 + 0; // DiffuseTransmission -> Refraction, Diffuse
+		default: return 2 * 3 + 1; // SpecularTransmission -> Refraction, Specular
+		}
+	}
+	// LightPathExpression::match (LPE_Automaton.h:17-33): the whole token string is walked from the start state
+	bool lpeMatches(uint32_t k) const
+	{
+		const prb_scene_desc& d = *sc.d;
+		const prb_lpe& l		= d.lpe[k];
+		uint32_t state			= l.start_state;
+		for (uint8_t sym : path) {
+			state = d.lpe_tables[l.next_offset + state * PRB_LPE_SYMBOLS + sym];
+			if (state == PRB_LPE_REJECT)
+				return false;
+		}
+		return d.lpe_tables[l.final_offset + state] != 0;
+	}
 
 	// LocalFrameOutputDevice::commitSpectrals2, src/loader/output/LocalFrameOutputDevice.cpp:88-164 (filter applied later)
 	void pushSpectralFragment(const Blob& mis, const Blob& importance, const Blob& radiance, uint32_t rayFlags)
@@ -1593,6 +1623,13 @@ struct Integrator {
 		}
 		for (int c = 0; c < 3; ++c)
 			film.iterXYZ[3 * (size_t)pixelIndex + c] += grp.blendWeight * xyz[c];
+		if (film.lpeMean) { // LocalFrameOutputDevice.cpp:100-111: every expression that matches the fragment's path takes the triplet too
+			const size_t stride = (size_t)sc.d->settings.film_width * sc.d->settings.film_height * 3;
+			for (uint32_t k = 0; k < sc.d->n_lpe; ++k)
+				if (lpeMatches(k))
+					for (int c = 0; c < 3; ++c)
+						film.lpeIter[k * stride + 3 * (size_t)pixelIndex + c] += grp.blendWeight * xyz[c];
+		}
 	}
 	void logState(int kind, uint32_t flags, uint32_t depth, const PathState& cur)
 	{
@@ -1629,7 +1666,9 @@ struct Integrator {
 		const Blob heroFactor	 = mono ? heroOnly() : blob(1);
 		logState(FK_DIRECT_HIT, hitFromBehind ? FF_FROM_BEHIND : 0, ip.ray.depth, cur);
 		if (!d.settings.do_nee || hitFromBehind || cur.LastWasDelta) {
+			path.push_back(TOK_EMISSIVE); // direct.cpp:387-389
 			pushSpectralFragment(heroFactor / (cur.WavelengthPDF * bsum(heroFactor)), cur.Throughput, radiance, ip.ray.flags);
+			path.pop_back();
 			return;
 		}
 		const prb_entity& en = d.entities[ip.g.entity];
@@ -1647,7 +1686,9 @@ struct Integrator {
 		const float denom	 = bsum(misTerm(power, cur.PrevPathPDF * posPDF_S)) + bsum(misTerm(power, cur.PathPDF));
 		const Blob mis		 = (heroFactor * misTerm(power, cur.PathPDF[0])) / (misTerm(power, cur.WavelengthPDF) * denom);
 		pending.lightPdfS	 = posPDF_S;
+		path.push_back(TOK_EMISSIVE); // direct.cpp:409-411
 		pushSpectralFragment(mis, cur.Throughput, radiance, ip.ray.flags);
+		path.pop_back();
 	}
 
 	// IEntity::sampleParameterPointPDF(p, info): mesh default 1/worldArea; sphere 2*pdfCache; plane spherical rectangle
@@ -2051,7 +2092,11 @@ struct Integrator {
 			for (int i = 0; i < 4; ++i)
 				pending.bsdfPDF[i] = mout.pdf[i];
 		}
+		path.push_back(scatterToken(mout.type)); // direct.cpp:337-351
+		path.push_back(ls.infinite ? TOK_BACKGROUND : TOK_EMISSIVE);
 		pushSpectralFragment(mis, cur.Throughput, contrib, shadow.flags);
+		path.pop_back();
+		path.pop_back();
 	}
 
 	bool handleScattering(const IP& ip, uint32_t matID, PathState& cur, Rng& rnd, RayS& next)
@@ -2078,6 +2123,7 @@ struct Integrator {
 		mc.rayFlags = ip.ray.flags;
 		MatSample sout;
 		materialSample(sc, matID, mc, rnd, sout);
+		path.push_back(scatterToken(sout.type)); // mCameraPath.addToken(sout.Type), direct.cpp:197
 		const V3 L			= normalized(fromTangentSpace(ip.N, ip.Nx, ip.Ny, sout.L)); // MaterialSampleOutput::globalL
 		cur.LastWasDelta	= sout.isDelta();
 		cur.PrevPathPDF		= cur.PathPDF;
@@ -2206,6 +2252,7 @@ struct Integrator {
 	{
 		const prb_scene_desc& d = *sc.d;
 		stats.c[S_PIXEL_SAMPLE]++;
+		path.assign(1, (uint8_t)TOK_CAMERA); // mCameraPath = [Camera] (direct.cpp:67; popTokenUntil(1) after every camera path, :137)
 		CameraSampleOut cs;
 		constructCameraRay(sc, px + d.settings.view_x * 0, py, iteration, rnd, cs);
 		grp.importance	= cs.importance;
@@ -2228,6 +2275,7 @@ struct Integrator {
 		if (!hit) { // IntegratorUtils::handleBackgroundGroup, IntegratorUtils.h:16-53
 			stats.c[S_CAMERA_DEPTH]++;
 			stats.c[S_BG_HIT]++;
+			path.push_back(TOK_BACKGROUND); // LightPath::createCB(), IntegratorUtils.h:19
 			bool illuminated = false;
 			for (uint32_t i = 0; i < d.n_lights; ++i) {
 				const prb_light& l = d.lights[i];
@@ -2260,7 +2308,9 @@ struct Integrator {
 				stats.c[S_MONO]++;
 			Hit bh;
 			if (!traceScene(sc, A, ray.O, ray.D, ray.tmin, ray.tmax, false, bh)) {
+				path.push_back(TOK_BACKGROUND); // direct.cpp:124-134
 				handleMiss(ray, cur);
+				path.pop_back();
 				break;
 			}
 			makeIP(ray, bh, ip);
@@ -2318,9 +2368,20 @@ void orc_scene_destroy(orc_scene* s) { delete s; }
 // Render iterations [first, first+count) of the given tiles.  rng: W*H states (updated in place).
 // film_mean: W*H*3 running mean (unfiltered; updated), sample_count: W*H, aov: W*H*10 or NULL, stats: 11 counters,
 // feedback: W*H words (OR of PRB_FEEDBACK_* bits, updated) or NULL; online_mean / online_variance: W*H*3 each or NULL.
+// lpe_mean: n_lpe films of W*H*3 floats (running means of the light path expression channels, updated) or NULL.
+void orc_render_lpe(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count,
+					float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback, float* online_mean,
+					float* online_variance, float* lpe_mean);
 void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count,
 				float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback, float* online_mean,
 				float* online_variance)
+{
+	orc_render_lpe(s, rng, tiles, n_tiles, first_iteration, iteration_count, film_mean, sample_count, aov, stats11, threads, feedback, online_mean, online_variance,
+				   nullptr);
+}
+void orc_render_lpe(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count,
+					float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback, float* online_mean,
+					float* online_variance, float* lpe_mean)
 {
 	const prb_settings& st = s->sc.d->settings;
 	const uint32_t W	   = st.film_width;
@@ -2332,6 +2393,12 @@ void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_til
 	film.feedback	 = feedback;
 	film.varMean	 = online_mean;
 	film.varVar		 = online_variance;
+	const size_t lpeStride = (size_t)W * st.film_height * 3;
+	const uint32_t nLPE	   = lpe_mean ? s->sc.d->n_lpe : 0;
+	if (nLPE) {
+		film.lpeMean = lpe_mean;
+		film.lpeIter.assign(lpeStride * nLPE, 0.0f);
+	}
 	// pixel list (pixels are independent: own RNG stream, own film cell)
 	std::vector<uint32_t> pixels;
 	for (size_t t = 0; t < n_tiles; ++t)
@@ -2356,6 +2423,9 @@ void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_til
 					I.pixelIndex = p;
 					for (int c = 0; c < 3; ++c)
 						film.iterXYZ[3 * (size_t)p + c] = 0.0f;
+					for (uint32_t k = 0; k < nLPE; ++k)
+						for (int c = 0; c < 3; ++c)
+							film.lpeIter[k * lpeStride + 3 * (size_t)p + c] = 0.0f;
 					I.renderSample(p % W, p / W, it, rnd);
 					// FrameOutputDevice::onEndOfIteration: (a * (iteration - 1) + b) / iteration, 1-based
 					const float iter = (float)(it + 1);
@@ -2363,6 +2433,11 @@ void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_til
 						float& a = film.mean[3 * (size_t)p + c];
 						a		 = (a * (float)it + film.iterXYZ[3 * (size_t)p + c]) / iter;
 					}
+					for (uint32_t k = 0; k < nLPE; ++k) // the expression channels merge like the main one, FrameOutputDevice.cpp:216-218
+						for (int c = 0; c < 3; ++c) {
+							float& a = film.lpeMean[k * lpeStride + 3 * (size_t)p + c];
+							a		 = (a * (float)it + film.lpeIter[k * lpeStride + 3 * (size_t)p + c]) / iter;
+						}
 					if (film.varMean && film.varVar) // VarianceEstimator::addValue, src/core/buffer/VarianceEstimator.inl:16-28
 						for (int c = 0; c < 3; ++c) {
 							const float value = film.iterXYZ[3 * (size_t)p + c];

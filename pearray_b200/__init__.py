@@ -92,6 +92,13 @@ class Light(C.Structure):
                 ("sun_dy", C.c_float * 3), ("sun_cos_theta", C.c_float), ("sun_pdf", C.c_float)]
 
 
+MAX_LPE = 8
+
+
+class LPE(C.Structure):
+    _fields_ = [("next_offset", C.c_uint32), ("final_offset", C.c_uint32), ("n_states", C.c_uint32), ("start_state", C.c_uint32)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("settings", Settings), ("camera", Camera),
                 ("aa_sampler", Sampler), ("lens_sampler", Sampler), ("time_sampler", Sampler), ("pixel_mapper", SpectralMapper),
@@ -110,7 +117,8 @@ class SceneDesc(C.Structure):
                 ("n_bvh_tris", C.c_uint32), ("bvh_tris", C.c_void_p),
                 ("n_tlas_refs", C.c_uint32), ("tlas_refs", C.POINTER(C.c_uint32)),
                 ("n_pool", C.c_uint32), ("pool", C.POINTER(C.c_float)),
-                ("cie_offset", C.c_uint32), ("_pad", C.c_uint32)]
+                ("cie_offset", C.c_uint32), ("_pad", C.c_uint32),
+                ("n_lpe", C.c_uint32), ("n_lpe_bytes", C.c_uint32), ("lpe_tables", C.POINTER(C.c_uint8)), ("lpe", LPE * MAX_LPE)]
 
 
 class Stats(C.Structure):
@@ -148,7 +156,7 @@ ABI_SYMBOLS = ["prb_create", "prb_destroy", "prb_last_error", "prb_device_count"
                "prb_trace_any", "prb_trace_closest_device", "prb_trace_any_device", "prb_generate_camera_rays",
                "prb_material_eval", "prb_material_sample", "prb_get_stats", "prb_reset_stats", "prb_last_device_ms",
                "prb_set_profiling", "prb_get_stage_times", "prb_film_reduce", "prb_comm_unique_id", "prb_comm_init",
-               "prb_comm_destroy", "prb_film_reduce_comm", "prb_last_reduce_ms", "prb_set_shading_mode", "prb_get_shading_mode"]
+               "prb_comm_destroy", "prb_film_reduce_comm", "prb_last_reduce_ms", "prb_set_shading_mode", "prb_get_shading_mode", "prb_film_download_lpe"]
 
 
 def device_lib():
@@ -194,6 +202,7 @@ def device_lib():
         lib.prb_last_device_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         lib.prb_set_profiling.argtypes = [C.c_void_p, C.c_int]
         lib.prb_get_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+        lib.prb_film_download_lpe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         lib.prb_set_shading_mode.argtypes = [C.c_void_p, C.c_int]
         lib.prb_get_shading_mode.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         _dev = lib
@@ -409,6 +418,12 @@ class Context:
         mean, var = np.empty(shape, np.float32), np.empty(shape, np.float32)
         self._chk(self._lib.prb_film_download_variance(self._h, _ptr(mean), _ptr(var)), "prb_film_download_variance")
         return mean, var
+
+    def film_lpe(self, index):
+        """(H, W, 3) XYZ film of the fragments accepted by light path expression `index` of the scene's output channels"""
+        xyz = np.empty((self.scene.height, self.scene.width, 3), dtype=np.float32)
+        self._chk(self._lib.prb_film_download_lpe(self._h, int(index), _ptr(xyz)), "prb_film_download_lpe")
+        return xyz
 
     def film_export_device(self, device_ptr):
         self._chk(self._lib.prb_film_export_device(self._h, C.c_void_p(device_ptr)), "prb_film_export_device")

@@ -45,6 +45,10 @@ struct DScene { // device pointers + by-value small structs; passed to kernels b
 	// reference's examples): a flat list of entity headers + their local-space triangles for the BVH-free trace kernel
 	const uint4* small; // nSmallEnts x 4 uint4 headers, then the triangles (3 x float4 each)
 	uint32_t nSmallEnts, nSmallU4;
+	// light path expressions (prb_scene_desc::lpe): dense DFA tables, bytes
+	const uint8_t* lpeTables;
+	uint32_t nLPE;
+	prb_lpe lpe[PRB_MAX_LPE];
 };
 constexpr uint32_t SMALL_MAX_TRIS = 64, SMALL_MAX_ENTS = 16;
 

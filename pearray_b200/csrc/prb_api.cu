@@ -110,6 +110,11 @@ struct prb_ctx {
 	uint32_t launchesPerIteration(bool stagedMode) const { return stagedMode ? 3 + nQueues + nNeeQueues : 3; }
 	DBuf<uint4> hit;
 	DBuf<float> hitT;
+	// light path expression channels (scenes with prb_scene_desc::n_lpe > 0)
+	DBuf<uint8_t> lpeTables;
+	DBuf<uint2> lpeState;
+	DBuf<float4> lpeAcc, lpePrev;
+	DBuf<float> lpeFilm; // n_lpe films of npix * 3 floats
 	std::vector<prb_tile> cachedTiles;
 	uint32_t nSlots = 0;
 	uint32_t* hostCounters = nullptr; // pinned
@@ -240,6 +245,11 @@ void prb_destroy(prb_ctx* c)
 	c->rng.release();
 	c->stats.release();
 	c->hit.release();
+	c->lpeTables.release();
+	c->lpeState.release();
+	c->lpeAcc.release();
+	c->lpePrev.release();
+	c->lpeFilm.release();
 	c->scratchB.release();
 	c->small.release();
 	c->scratchQ.release();
@@ -328,6 +338,26 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	CU(c->bvhTris.upload(reinterpret_cast<const float4*>(d->bvh_tris), (size_t)d->n_bvh_tris * 3, s));
 	CU(c->tlasRefs.upload(d->tlas_refs, d->n_tlas_refs, s));
 	CU(c->pool.upload(d->pool, d->n_pool, s));
+	if (d->n_lpe > PRB_MAX_LPE)
+		return fail(PRB_ERR_INVALID_ARG, "more than PRB_MAX_LPE light path expressions");
+	for (uint32_t k = 0; k < d->n_lpe; ++k) {
+		const prb_lpe& l = d->lpe[k];
+		if (l.n_states == 0 || l.n_states > 255 || l.start_state >= l.n_states || !d->lpe_tables ||
+			(uint64_t)l.next_offset + (uint64_t)l.n_states * PRB_LPE_SYMBOLS > d->n_lpe_bytes || (uint64_t)l.final_offset + l.n_states > d->n_lpe_bytes)
+			return fail(PRB_ERR_INVALID_ARG, "light path expression " + std::to_string(k) + ": table out of range");
+		for (uint32_t i = 0; i < l.n_states * PRB_LPE_SYMBOLS; ++i) {
+			const uint8_t n = d->lpe_tables[l.next_offset + i];
+			if (n != PRB_LPE_REJECT && n >= l.n_states)
+				return fail(PRB_ERR_INVALID_ARG, "light path expression " + std::to_string(k) + ": transition to a state that does not exist");
+		}
+	}
+	c->S.nLPE	   = d->n_lpe;
+	c->S.lpeTables = nullptr;
+	std::memcpy(c->S.lpe, d->lpe, sizeof(c->S.lpe));
+	if (d->n_lpe) {
+		CU(c->lpeTables.upload(d->lpe_tables, d->n_lpe_bytes, s));
+		c->S.lpeTables = c->lpeTables.p;
+	}
 	// RussianRoulette::probability table (vcm/RussianRoulette.h:22-34): min(1, pow(0.9f, len - soft)) evaluated in
 	// double and rounded to float exactly like std::pow(float, size_t) does on the host
 	const uint32_t soft = d->settings.soft_max_ray_depth;
@@ -347,6 +377,12 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	CU(c->aov.alloc(npix * 10));
 	CU(c->feedback.alloc(npix));
 	CU(cudaMemsetAsync(c->feedback.p, 0, npix * sizeof(uint32_t), s));
+	if (d->n_lpe) {
+		CU(c->lpeFilm.alloc(npix * 3 * d->n_lpe));
+		CU(cudaMemsetAsync(c->lpeFilm.p, 0, npix * 3 * d->n_lpe * sizeof(float), s));
+	} else {
+		c->lpeFilm.release();
+	}
 	if (d->settings.want_variance) {
 		CU(c->varMean.alloc(npix * 3));
 		CU(c->varVar.alloc(npix * 3));
@@ -487,6 +523,10 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 		c->staged	  = std::atoi(m) != 0;
 		c->stagedAuto = false;
 	}
+	if (d->n_lpe) { // the light path expression channels are accumulated by the staged kernels only
+		c->staged	  = true;
+		c->stagedAuto = false;
+	}
 	std::memset(c->queueOfType, 0xFF, sizeof(c->queueOfType));
 	std::memset(c->queueWantsNEE, 0, sizeof(c->queueWantsNEE));
 	c->nQueues = 0;
@@ -550,6 +590,8 @@ prb_status prb_film_clear(prb_ctx* c)
 		CU(cudaMemsetAsync(c->varMean.p, 0, npix * 3 * sizeof(float), c->stream));
 		CU(cudaMemsetAsync(c->varVar.p, 0, npix * 3 * sizeof(float), c->stream));
 	}
+	if (c->lpeFilm.p)
+		CU(cudaMemsetAsync(c->lpeFilm.p, 0, npix * 3 * c->S.nLPE * sizeof(float), c->stream));
 	return PRB_OK;
 }
 
@@ -589,6 +631,11 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 		CU(b->alloc(n));
 	CU(c->hit.alloc(n));
 	CU(c->hitT.alloc(n));
+	if (c->S.nLPE) {
+		CU(c->lpeState.alloc(n));
+		CU(c->lpeAcc.alloc(n * c->S.nLPE));
+		CU(c->lpePrev.alloc(n * c->S.nLPE));
+	}
 	CU(cudaStreamSynchronize(c->stream));
 	c->cachedTiles.assign(tiles, tiles + n_tiles);
 	c->nSlots = (uint32_t)n;
@@ -701,6 +748,11 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.vxNy		  = c->vxNy.p;
 	W.vxD		  = c->vxD.p;
 	std::memcpy(W.queueOfType, c->queueOfType, sizeof(W.queueOfType));
+	W.lpeState		= c->lpeState.p;
+	W.lpeAcc		= c->lpeAcc.p;
+	W.lpePrev		= c->lpePrev.p;
+	W.lpeFilm		= c->lpeFilm.p;
+	W.lpeFilmStride = (size_t)c->S.settings.film_width * c->S.settings.film_height * 3;
 	W.rng		  = c->rng.p;
 	W.filmMean	  = c->filmMean.p;
 	W.sampleCount = c->sampleCount.p;
@@ -877,18 +929,20 @@ prb_status prb_sync(prb_ctx* c)
 	return PRB_OK;
 }
 
-static prb_status filteredFilm(prb_ctx* c, float** out)
+static prb_status filteredFilm(prb_ctx* c, float** out, float* film = nullptr)
 {
+	if (!film)
+		film = c->filmMean.p;
 	const prb_settings& st = c->S.settings;
 	const int r			   = st.filter_radius;
 	bool identity		   = true; // centre weight 1, everything else <= eps (e.g. mitchell radius 1)
 	if (r > 0)
 		identity = false;
 	if (identity) {
-		*out = c->filmMean.p;
+		*out = film;
 		return PRB_OK;
 	}
-	k_filter<<<c->smCount * 4, 256, 0, c->stream>>>(c->filmMean.p, c->filmTmp.p, (int)st.film_width, (int)st.film_height, r, c->pool.p + st.filter_offset);
+	k_filter<<<c->smCount * 4, 256, 0, c->stream>>>(film, c->filmTmp.p, (int)st.film_width, (int)st.film_height, r, c->pool.p + st.filter_offset);
 	c->kernelLaunches++;
 	CU(cudaGetLastError());
 	*out = c->filmTmp.p;
@@ -945,6 +999,22 @@ prb_status prb_film_download_variance(prb_ctx* c, float* online_mean, float* onl
 		CU(cudaMemcpyAsync(online_mean, c->varMean.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	if (online_variance)
 		CU(cudaMemcpyAsync(online_variance, c->varVar.p, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
+prb_status prb_film_download_lpe(prb_ctx* c, uint32_t index, float* xyz)
+{
+	if (!c || !c->haveScene || !xyz)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded / null buffer");
+	if (index >= c->S.nLPE || !c->lpeFilm.p)
+		return fail(PRB_ERR_INVALID_ARG, "the scene has no light path expression " + std::to_string(index));
+	CU(cudaSetDevice(c->device));
+	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
+	float* src		  = nullptr;
+	prb_status st	  = filteredFilm(c, &src, c->lpeFilm.p + (size_t)index * npix * 3);
+	if (st != PRB_OK)
+		return st;
+	CU(cudaMemcpyAsync(xyz, src, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return PRB_OK;
 }
@@ -1442,6 +1512,8 @@ prb_status prb_set_shading_mode(prb_ctx* c, int mode)
 {
 	if (!c || mode < PRB_SHADING_AUTO || mode > PRB_SHADING_STAGED)
 		return fail(PRB_ERR_INVALID_ARG, "invalid shading mode");
+	if (c->S.nLPE && mode != PRB_SHADING_STAGED)
+		return fail(PRB_ERR_UNSUPPORTED, "scenes with light path expression channels shade staged");
 	c->stagedAuto = mode == PRB_SHADING_AUTO && !c->allLambert;
 	c->staged	  = mode == PRB_SHADING_STAGED;
 	c->tuneStep	  = 0;

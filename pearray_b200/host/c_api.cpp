@@ -72,6 +72,7 @@ uint32_t prh_abi_sizeof(const char* name)
 	PRH_SIZE_OF(prb_camera)
 	PRH_SIZE_OF(prb_settings)
 	PRH_SIZE_OF(prb_scene_desc)
+	PRH_SIZE_OF(prb_lpe)
 	PRH_SIZE_OF(prb_tile)
 	PRH_SIZE_OF(prb_stats)
 	PRH_SIZE_OF(prb_material_query)

@@ -115,13 +115,32 @@ void OutputSpecification::parse(const DL::DataGroup& entry)
 			PR_LOG(L_ERROR) << "Unknown channel type " << type << std::endl;
 			continue;
 		}
-		if (!lpe.empty()) {
-			ch.name += "[" + lpe + "]";
-			ch.variable = OV_Unsupported; // light path expressions are not evaluated on the device path
+		if (!lpe.empty()) { // OutputSpecification.cpp:296-331: an invalid expression is dropped with an error, the channel stays
+			if (!compileLPE(lpe).valid) {
+				PR_LOG(L_ERROR) << "Invalid LPE '" << lpe << "'. Skipping entry" << std::endl;
+			} else {
+				ch.name += "[" + lpe + "]";
+				ch.lpe = lpe;
+				if (ch.kind == OutputChannel::Spectral && ch.variable == OV_Output) {
+					size_t k = 0;
+					while (k < mLPEs.size() && mLPEs[k] != lpe)
+						++k;
+					if (k == mLPEs.size() && k < PRB_MAX_LPE)
+						mLPEs.push_back(lpe);
+					if (k < PRB_MAX_LPE) {
+						ch.lpeIndex = (int)k;
+					} else {
+						PR_LOG(L_WARNING) << "Output '" << file.name << "': more than " << PRB_MAX_LPE << " distinct light path expressions; '" << lpe
+										  << "' is written as zeros" << std::endl;
+						ch.variable = OV_Unsupported;
+					}
+				}
+				// shading-point channels (position, normal, ...) with an expression: the only path a shading-point fragment
+				// carries is the camera token (direct.cpp:86-87), matched when the file is written (saveImage)
+			}
 		}
 		if (ch.variable == OV_Unsupported)
-			PR_LOG(L_WARNING) << "Output '" << file.name << "': channel '" << type << (lpe.empty() ? "" : "' with lpe '" + lpe)
-							  << "' is not accumulated by the device path; written as zeros" << std::endl;
+			PR_LOG(L_WARNING) << "Output '" << file.name << "': channel '" << type << "' is not accumulated by the device path; written as zeros" << std::endl;
 		file.channels.push_back(ch);
 	}
 	mFiles.push_back(file);
@@ -259,6 +278,8 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 		addPlane(c.name.empty() ? "G" : c.name + ".G");
 		addPlane(c.name.empty() ? "B" : c.name + ".B");
 		const float* src = c.variable == OV_Output ? film.xyz : c.variable == OV_OnlineMean ? film.onlineMean : c.variable == OV_OnlineVariance ? film.onlineVariance : nullptr;
+		if (!c.lpe.empty()) // the expression's own film (prb_film_download_lpe); the variance estimators have no per-expression copy
+			src = c.lpeIndex >= 0 && (size_t)c.lpeIndex < film.lpe.size() ? film.lpe[c.lpeIndex] : nullptr;
 		if (!src)
 			continue;
 		for (size_t i = 0; i < n; ++i) {
@@ -267,6 +288,10 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 			data[base][i] = rgb[0], data[base + 1][i] = rgb[1], data[base + 2][i] = rgb[2];
 		}
 	}
+	// a shading-point fragment (position, normal, ..., sample count) carries the path of the first camera vertex, i.e. the
+	// camera token alone (direct.cpp:86-87), so a channel with an expression holds the AOV when the expression accepts "C"
+	// and stays empty otherwise (LocalFrameOutputDevice.cpp:177-187, 289-302)
+	auto passesLPE = [](const OutputChannel& c) { return c.lpe.empty() || compileLPE(c.lpe).match({ { 0, 2 } }); };
 	auto sampleFactor = [&](size_t i) { // technical AOVs are sums over the samples: scaled by 1 / sample count
 		const uint32 s = film.sampleCount ? film.sampleCount[i] : 0;
 		return s == 0 ? 1.0f : 1.0f / s;
@@ -278,7 +303,7 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 		addPlane(c.name + ".x");
 		addPlane(c.name + ".y");
 		addPlane(c.name + ".z");
-		if (!film.aov || c.variable == OV_Unsupported)
+		if (!film.aov || c.variable == OV_Unsupported || !passesLPE(c))
 			continue;
 		for (size_t i = 0; i < n; ++i) {
 			const float* a = film.aov + 10 * i; // prb_film_aov layout: N(3) P(3) u v depth entity
@@ -297,7 +322,7 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 		if (c.kind != OutputChannel::OneD)
 			continue;
 		std::vector<float>& p = addPlane(c.name);
-		if (!film.aov || c.variable == OV_Unsupported)
+		if (!film.aov || c.variable == OV_Unsupported || !passesLPE(c))
 			continue;
 		for (size_t i = 0; i < n; ++i)
 			p[i] = sampleFactor(i) * film.aov[10 * i + (c.variable == OV_Depth ? 8 : 9)];
@@ -306,6 +331,8 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 		if (c.kind != OutputChannel::Counter)
 			continue;
 		std::vector<float>& p = addPlane(c.name);
+		if (!passesLPE(c))
+			continue;
 		if (c.variable == OV_SampleCount && film.sampleCount)
 			for (size_t i = 0; i < n; ++i)
 				p[i] = static_cast<float>(film.sampleCount[i]);

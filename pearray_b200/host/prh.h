@@ -655,6 +655,8 @@ struct OutputChannel { // reference IM_ChannelSetting{Spec,3D,1D,Counter}, src/l
 	int variable	  = OV_Output;
 	ToneColorMode tcm = ToneColorMode::SRGB;
 	std::string name; // empty for the plain colour channel ("R", "G", "B")
+	std::string lpe;  // light path expression restricting the channel ("" = none)
+	int lpeIndex = -1; // spectral channels: index into the scene's LPE list (OutputSpecification::lpeExpressions)
 };
 struct OutputFile {
 	std::string name;
@@ -670,6 +672,7 @@ struct FilmView { // what prb_film_download / prb_film_aov return for one contex
 	const float* onlineMean		= nullptr; // 3 per pixel (AOV_OnlineMean); may be null
 	const float* onlineVariance = nullptr; // 3 per pixel (AOV_OnlineVariance); may be null
 	const float* aov		  = nullptr;  // 10 per pixel (N, P, u, v, depth, entity id), sums over the samples; may be null
+	std::vector<const float*> lpe;		  // per light path expression of the scene: 3 per pixel (XYZ), may be empty / null entries
 };
 class OutputSpecification { // reference src/loader/output/io/OutputSpecification.h
 public:
@@ -684,11 +687,14 @@ public:
 					return true;
 		return false;
 	}
+	// the distinct light path expressions of the spectral channels, in registration order (prb_scene_desc::lpe)
+	const std::vector<std::string>& lpeExpressions() const { return mLPEs; }
 	// writes <workingDir>/results[_<contextIndex>]/<name>.exr for every (output ...) block; returns the number written
 	int save(const std::string& workingDir, const FilmView& film, uint32 contextIndex = 0) const;
 
 private:
 	std::vector<OutputFile> mFiles;
+	std::vector<std::string> mLPEs;
 };
 bool saveImage(const std::string& path, const OutputFile& file, const FilmView& film);
 bool writeEXR(const std::string& path, const std::vector<std::string>& channelNames, const std::vector<const float*>& planes, uint32 width, uint32 height,
@@ -870,6 +876,7 @@ public:
 	std::vector<prb_bvh_tri> bvhTris;
 	std::vector<uint32> tlasRefs;
 	std::vector<float> pool;
+	std::vector<uint8_t> lpeTables;
 	BoundingBox sceneBounds;
 	float sceneRadius = 0;
 	double bvhBuildSeconds = 0;

@@ -143,6 +143,9 @@ int RenderContext::saveOutputs(const std::string& workingDir)
 			film.onlineVariance = onlineVariance.data();
 		}
 	}
+	std::vector<std::vector<float>> lpe(mScene->desc.n_lpe, std::vector<float>(n * 3));
+	for (uint32 k = 0; k < mScene->desc.n_lpe; ++k)
+		film.lpe.push_back(prb_film_download_lpe(mCtx, k, lpe[k].data()) == PRB_OK ? lpe[k].data() : nullptr);
 	return mEnv->outputSpecification().save(workingDir, film, mRank);
 }
 prb_stats RenderContext::statistics() const

@@ -39,6 +39,8 @@ void CompiledScene::finalize()
 	desc.tlas_refs			= tlasRefs.data();
 	desc.n_pool				= (uint32)pool.size();
 	desc.pool				= pool.data();
+	desc.n_lpe_bytes		= (uint32)lpeTables.size();
+	desc.lpe_tables			= lpeTables.data();
 }
 
 static BoundingBox padBox(BoundingBox b)
@@ -309,6 +311,21 @@ std::shared_ptr<CompiledScene> SceneCompiler::compile()
 		for (int y = -r; y <= r; ++y) // FilterCache, src/core/filter/FilterCache.h:6-31
 			for (int x = -r; x <= r; ++x)
 				s.pool.push_back(filter->evalWeight((float)x, (float)y));
+	}
+	// light path expressions of the spectral output channels: dense DFA tables (lpe.cpp)
+	for (const std::string& expr : mEnv->outputSpecification().lpeExpressions()) {
+		const LPEAutomaton a = compileLPE(expr);
+		if (!a.valid || a.stateCount > 255 || s.desc.n_lpe >= PRB_MAX_LPE) {
+			PR_LOG(L_ERROR) << "Light path expression '" << expr << "' cannot be compiled for the device (" << a.stateCount << " states)" << std::endl;
+			return nullptr;
+		}
+		prb_lpe& l	  = s.desc.lpe[s.desc.n_lpe++];
+		l.n_states	  = a.stateCount;
+		l.start_state = 0;
+		l.next_offset = (uint32)s.lpeTables.size();
+		s.lpeTables.insert(s.lpeTables.end(), a.next.begin(), a.next.end());
+		l.final_offset = (uint32)s.lpeTables.size();
+		s.lpeTables.insert(s.lpeTables.end(), a.final.begin(), a.final.end());
 	}
 	s.nodes = emitter.nodes;
 	s.finalize();

@@ -259,3 +259,12 @@ WHITEFURNACE_FULL = """
     )
 )
 """
+
+
+# light path expression channels (SURVEY 8(f)-4): the material zoo (every scattering type; area light + environment) with one
+# spectral channel per expression.  'C.*L' accepts every path, so its channel must equal the colour channel bit for bit.
+LPE_EXPRESSIONS = ["C.*L", "CL", "C.+L", "C.*B", "C.*E", "CDL", "C<T,S>+.*L", "C<R,S>[DS]*E"]
+# (the lamp is moved out of the camera's view so that the spheres and the floor are seen and lit by it)
+LPE_ZOO = MATERIAL_ZOO.replace(":transform [1,0,0,0, 0,-1,0,0, 0,0,-1,3, 0,0,0,1])", ":transform [1,0,0,1.2, 0,-1,0,1.2, 0,0,-1,3, 0,0,0,1])").replace("(light :type 'env'", "(output :name 'image' (channel :type 'color' :color 'xyz')\n"
+                               + "".join("   (channel :type 'color' :color 'xyz' :lpe '%s')\n" % e for e in LPE_EXPRESSIONS)
+                               + "   (channel :type 'depth' :lpe 'C') (channel :type 'n' :lpe 'CD'))\n (light :type 'env'")

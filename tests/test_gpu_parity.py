@@ -12,7 +12,7 @@ import pytest
 import pearray_b200 as prb
 from conftest import scene_path
 from oracle_binding import OracleScene
-from scene_strings import FURNACE, MATERIAL_ZOO, MATERIAL_ZOO2, SKYSUN_ZOO
+from scene_strings import FURNACE, LPE_EXPRESSIONS, LPE_ZOO, MATERIAL_ZOO, MATERIAL_ZOO2, SKYSUN_ZOO
 from test_golden_oracle import CBOX_CHANNEL_TOL, CBOX_LUMINANCE_TOL, GOLDEN, STAT_NAMES, cbox_reference_error, load_golden, load_scene
 
 pytestmark = pytest.mark.gpu
@@ -344,6 +344,34 @@ def test_shading_mode_is_measured_and_does_not_change_the_film():
     assert lam.shading_mode() == 0, "an all-Lambert scene always takes the inlined single kernel"
 
 
+def test_lpe_channels_bit_exact_vs_oracle(tmp_path):
+    """one spectral channel per light path expression; the device carries the DFA state of every expression per
+    slot, the oracle re-walks the token string of every fragment from the start (LightPathExpression::match)"""
+    scene = prb.Scene.from_string(LPE_ZOO)
+    ctx = make_ctx(scene)
+    assert ctx.shading_mode() == 1, "scenes with LPE channels shade staged"
+    tiles = [(0, 0, scene.width, scene.height)]
+    ref = OracleScene(scene).render(tiles, 0, 6)
+    ctx.render_tiles(tiles, 0, 4)
+    ctx.render_tiles(tiles, 4, 2)  # the channels resume like the main film
+    xyz, cnt = ctx.film()
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
+    for k, expr in enumerate(LPE_EXPRESSIONS):
+        ch = ctx.film_lpe(k)
+        assert np.array_equal(ch.view(np.uint32), ref["lpe_filtered"][k].view(np.uint32)), expr
+        assert ch.max() > 0, expr
+    assert np.array_equal(ctx.film_lpe(LPE_EXPRESSIONS.index("C.*L")).view(np.uint32), xyz.view(np.uint32))
+    with pytest.raises(prb.PrbError):
+        ctx.film_lpe(len(LPE_EXPRESSIONS))
+    with pytest.raises(prb.PrbError):
+        ctx.set_shading_mode(0)
+    # a re-render from iteration 0 starts the channels from zero again
+    ctx.upload_rng(scene.rng_map())
+    ctx.render_tiles(tiles, 0, 6)
+    assert np.array_equal(ctx.film_lpe(1).view(np.uint32), ref["lpe_filtered"][1].view(np.uint32))
+
+
 def test_uniform_non_lambert_scene_uses_the_generic_single_pass_kernel():
     """all materials of one non-Lambert type: k_shade<128, 1, leaf dispatch> (the Cornell box takes the all-Lambert
     instantiation, mixed scenes the 512-thread one)"""
@@ -430,6 +458,7 @@ def test_host_render_context_writes_the_output_files(tmp_path):
     _, _, pl = read_exr(str(tmp_path / "results" / "aovs.exr"))
     for k, c in enumerate("RGB"):  # :color 'xyz'
         assert np.array_equal(pl[c], xyz[..., k])
+        assert np.array_equal(pl["[C.*L]." + c], xyz[..., 1])  # :color 'lum' of an expression that accepts every path: Y of the same film
     assert np.array_equal(pl["sample_count"], cnt.astype(np.float32))
     assert cnt.max() == 4 and xyz.max() > 0
     _, chans, _ = read_exr(str(tmp_path / "results" / "image.exr"))

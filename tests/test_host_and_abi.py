@@ -38,12 +38,12 @@ def test_abi_struct_sizes_match_header():
     assert C.sizeof(prb.Stats) == 13 * 8
     scene = prb.Scene.from_file(scene_path("c2_cornellbox.prc"))
     d = scene.desc.contents
-    assert d.abi_version == 2
+    assert d.abi_version == 3
     # every mirrored struct has the size the C compiler gave it
     mirrors = {"prb_tile": prb.Tile, "prb_ray_soa": prb.RaySoA, "prb_hit_soa": prb.HitSoA, "prb_settings": prb.Settings, "prb_camera": prb.Camera,
                "prb_sampler": prb.Sampler, "prb_spectral_mapper": prb.SpectralMapper, "prb_node": prb.Node, "prb_material": prb.Material,
                "prb_emission": prb.Emission, "prb_mesh": prb.Mesh, "prb_entity": prb.Entity, "prb_light": prb.Light, "prb_scene_desc": prb.SceneDesc,
-               "prb_stats": prb.Stats, "prb_material_query": prb.MaterialQuery, "prb_material_result": prb.MaterialResult}
+               "prb_stats": prb.Stats, "prb_lpe": prb.LPE, "prb_material_query": prb.MaterialQuery, "prb_material_result": prb.MaterialResult}
     for name, cls in mirrors.items():
         assert prb.host_lib().prh_abi_sizeof(name.encode()) == C.sizeof(cls), name
     assert prb.host_lib().prh_abi_sizeof(b"prb_bvh8_node") == 80 and prb.host_lib().prh_abi_sizeof(b"prb_bvh_tri") == 48
