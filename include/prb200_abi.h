@@ -324,6 +324,9 @@ typedef struct prb_settings { /* RenderSettings.cpp:11-33 + DiParameters direct.
 	 * iteration from FrameOutputDevice::mergeLocal, loader/output/FrameOutputDevice.cpp:104-109): set by the host when an
 	 * (output ...) block asks for a `variance` / `online_mean` channel */
 	uint32_t want_variance;
+	/* accumulate the extended shading-point AOVs of prb_film_download_aov_ext (tangent, bitangent, view, material / emission id):
+	 * set by the host when an (output ...) block asks for one of them */
+	uint32_t want_aov_ext;
 } prb_settings;
 
 /* ---------------------------------------------------------------- light path expressions
@@ -468,6 +471,12 @@ prb_status prb_film_download(prb_ctx* ctx, float* xyz, uint32_t* sample_count);
 /* optional first-hit AOVs (sums over samples as commitShadingPoints, LocalFrameOutputDevice.cpp:252-302):
  * normal (3), position (3), uv (2), depth (1), entity id (1) -> 10 floats per pixel, may be NULL */
 prb_status prb_film_download_aov(prb_ctx* ctx, float* aov10);
+/* the remaining shading-point AOVs of commitShadingPoints (LocalFrameOutputDevice.cpp:268-284), sums over the samples,
+ * PRB_AOV_EXT floats per pixel: tangent Nx (3), bitangent Ny (3), view direction (3), material id, emission id.
+ * (AOV_NormalG equals AOV_Normal on this path -- IntersectionPoint::setForSurface copies Geometry.N -- and AOV_DisplaceID is
+ * PR_INVALID_ID for every entity type of the path; both are produced by the host writer.) */
+#define PRB_AOV_EXT 11u
+prb_status prb_film_download_aov_ext(prb_ctx* ctx, float* aov11);
 /* AOV_Feedback (LocalFrameOutputDevice.cpp:125-143, FrameOutputDevice.cpp:150-153): per pixel the OR of the PRB_FEEDBACK_*
  * bits of every fragment that was rejected there; W*H words */
 #define PRB_FEEDBACK_NAN 0x1u		/* OutputFeedback::NaN, src/core/output/Feedback.h:6-12 */

@@ -1480,6 +1480,7 @@ struct Film {
 	float* mean;				// running mean, W*H*3 (FrameOutputDevice::onEndOfIteration)
 	uint32_t* sampleCount;
 	float* aov; // 10 floats/pixel or null
+	float* aovExt = nullptr; // PRB_AOV_EXT floats/pixel (tangent, bitangent, view, material id, emission id) or null
 	uint32_t* feedback = nullptr; // AOV_Feedback, W*H words or null
 	float* varMean	   = nullptr; // AOV_OnlineMean / AOV_OnlineVariance, W*H*3 each or null
 	float* varVar	   = nullptr;
@@ -2165,6 +2166,20 @@ struct Integrator {
 				a[8] += std::sqrt(ip.depth2);
 				a[9] += (float)ip.g.entity;
 			}
+			if (film.aovExt) { // BLEND_3D(AOV_Tangent / AOV_Bitangent / AOV_View), BLEND_1D(AOV_MaterialID / AOV_EmissionID), LocalFrameOutputDevice.cpp:268-284
+				float* b = film.aovExt + PRB_AOV_EXT * (size_t)pixelIndex;
+				b[0] += ip.Nx.x;
+				b[1] += ip.Nx.y;
+				b[2] += ip.Nx.z;
+				b[3] += ip.Ny.x;
+				b[4] += ip.Ny.y;
+				b[5] += ip.Ny.z;
+				b[6] += ip.ray.D.x;
+				b[7] += ip.ray.D.y;
+				b[8] += ip.ray.D.z;
+				b[9] += (float)ip.g.material;
+				b[10] += (float)ip.g.emission;
+			}
 		}
 		const bool hasEmission = ip.g.emission != PRB_INVALID_ID;
 		if (d.settings.do_direct && hasEmission) {
@@ -2368,20 +2383,21 @@ void orc_scene_destroy(orc_scene* s) { delete s; }
 // Render iterations [first, first+count) of the given tiles.  rng: W*H states (updated in place).
 // film_mean: W*H*3 running mean (unfiltered; updated), sample_count: W*H, aov: W*H*10 or NULL, stats: 11 counters,
 // feedback: W*H words (OR of PRB_FEEDBACK_* bits, updated) or NULL; online_mean / online_variance: W*H*3 each or NULL.
-// lpe_mean: n_lpe films of W*H*3 floats (running means of the light path expression channels, updated) or NULL.
+// lpe_mean: n_lpe films of W*H*3 floats (running means of the light path expression channels, updated) or NULL;
+// aov_ext: W*H*PRB_AOV_EXT floats (sums, updated) or NULL.
 void orc_render_lpe(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count,
 					float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback, float* online_mean,
-					float* online_variance, float* lpe_mean);
+					float* online_variance, float* lpe_mean, float* aov_ext);
 void orc_render(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count,
 				float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback, float* online_mean,
 				float* online_variance)
 {
 	orc_render_lpe(s, rng, tiles, n_tiles, first_iteration, iteration_count, film_mean, sample_count, aov, stats11, threads, feedback, online_mean, online_variance,
-				   nullptr);
+				   nullptr, nullptr);
 }
 void orc_render_lpe(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n_tiles, uint32_t first_iteration, uint32_t iteration_count,
 					float* film_mean, uint32_t* sample_count, float* aov, uint64_t* stats11, int threads, uint32_t* feedback, float* online_mean,
-					float* online_variance, float* lpe_mean)
+					float* online_variance, float* lpe_mean, float* aov_ext)
 {
 	const prb_settings& st = s->sc.d->settings;
 	const uint32_t W	   = st.film_width;
@@ -2390,6 +2406,7 @@ void orc_render_lpe(orc_scene* s, uint64_t* rng, const prb_tile* tiles, size_t n
 	film.mean		 = film_mean;
 	film.sampleCount = sample_count;
 	film.aov		 = aov;
+	film.aovExt		 = aov_ext;
 	film.feedback	 = feedback;
 	film.varMean	 = online_mean;
 	film.varVar		 = online_variance;

@@ -40,7 +40,7 @@ class Settings(C.Structure):
                 ("spectral_start", C.c_float), ("spectral_end", C.c_float),
                 ("light_range_start", C.c_float), ("light_range_end", C.c_float),
                 ("time_alpha", C.c_float), ("time_beta", C.c_float),
-                ("filter_radius", C.c_int32), ("filter_offset", C.c_uint32), ("film_monotonic", C.c_uint32), ("want_variance", C.c_uint32)]
+                ("filter_radius", C.c_int32), ("filter_offset", C.c_uint32), ("film_monotonic", C.c_uint32), ("want_variance", C.c_uint32), ("want_aov_ext", C.c_uint32)]
 
 
 class Camera(C.Structure):
@@ -156,7 +156,7 @@ ABI_SYMBOLS = ["prb_create", "prb_destroy", "prb_last_error", "prb_device_count"
                "prb_trace_any", "prb_trace_closest_device", "prb_trace_any_device", "prb_generate_camera_rays",
                "prb_material_eval", "prb_material_sample", "prb_get_stats", "prb_reset_stats", "prb_last_device_ms",
                "prb_set_profiling", "prb_get_stage_times", "prb_film_reduce", "prb_comm_unique_id", "prb_comm_init",
-               "prb_comm_destroy", "prb_film_reduce_comm", "prb_last_reduce_ms", "prb_set_shading_mode", "prb_get_shading_mode", "prb_film_download_lpe"]
+               "prb_comm_destroy", "prb_film_reduce_comm", "prb_last_reduce_ms", "prb_set_shading_mode", "prb_get_shading_mode", "prb_film_download_lpe", "prb_film_download_aov_ext"]
 
 
 def device_lib():
@@ -203,6 +203,7 @@ def device_lib():
         lib.prb_set_profiling.argtypes = [C.c_void_p, C.c_int]
         lib.prb_get_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
         lib.prb_film_download_lpe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.prb_film_download_aov_ext.argtypes = [C.c_void_p, C.c_void_p]
         lib.prb_set_shading_mode.argtypes = [C.c_void_p, C.c_int]
         lib.prb_get_shading_mode.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         _dev = lib
@@ -404,6 +405,12 @@ class Context:
         w, h = self.scene.width, self.scene.height
         aov = np.empty((h, w, 10), dtype=np.float32)
         self._chk(self._lib.prb_film_download_aov(self._h, _ptr(aov)), "prb_film_download_aov")
+        return aov
+
+    def film_aov_ext(self):
+        """(H, W, 11) sums over the samples: tangent (3), bitangent (3), view direction (3), material id, emission id"""
+        aov = np.empty((self.scene.height, self.scene.width, 11), dtype=np.float32)
+        self._chk(self._lib.prb_film_download_aov_ext(self._h, _ptr(aov)), "prb_film_download_aov_ext")
         return aov
 
     def film_feedback(self):

@@ -86,7 +86,7 @@ struct prb_ctx {
 	DBuf<float4> bvhTris;
 	// film
 	DBuf<uint64_t> rng;
-	DBuf<float> filmMean, filmTmp, aov, varMean, varVar; // varMean / varVar only with prb_settings.want_variance
+	DBuf<float> filmMean, filmTmp, aov, aovExt, varMean, varVar; // varMean / varVar only with prb_settings.want_variance
 	DBuf<uint32_t> sampleCount, feedback;
 	DBuf<unsigned long long> stats;
 	bool rngUploaded = false;
@@ -229,7 +229,7 @@ void prb_destroy(prb_ctx* c)
 							 &c->slotState, &c->counters, &c->regenList, &c->neeList, &c->scatterList, &c->scratchU };
 	for (auto* b : ub)
 		b->release();
-	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->varMean, &c->varVar, &c->hitT, &c->scratchF };
+	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->aovExt, &c->varMean, &c->varVar, &c->hitT, &c->scratchF };
 	for (auto* b : fb)
 		b->release();
 	DBuf<float4>* f4[] = { &c->bvhTris, &c->rayO, &c->rayD, &c->wvl, &c->thr, &c->pathPDF, &c->prevPDF, &c->wvlPDF, &c->lastPos, &c->shO, &c->shD, &c->shXYZ, &c->iterXYZ, &c->prevAcc, &c->vxP, &c->vxN, &c->vxNx, &c->vxNy, &c->vxD };
@@ -375,6 +375,12 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	CU(c->filmTmp.alloc(npix * 4));
 	CU(c->sampleCount.alloc(npix));
 	CU(c->aov.alloc(npix * 10));
+	if (d->settings.want_aov_ext) {
+		CU(c->aovExt.alloc(npix * PRB_AOV_EXT));
+		CU(cudaMemsetAsync(c->aovExt.p, 0, npix * PRB_AOV_EXT * sizeof(float), s));
+	} else {
+		c->aovExt.release();
+	}
 	CU(c->feedback.alloc(npix));
 	CU(cudaMemsetAsync(c->feedback.p, 0, npix * sizeof(uint32_t), s));
 	if (d->n_lpe) {
@@ -585,6 +591,8 @@ prb_status prb_film_clear(prb_ctx* c)
 	CU(cudaMemsetAsync(c->filmMean.p, 0, npix * 3 * sizeof(float), c->stream));
 	CU(cudaMemsetAsync(c->sampleCount.p, 0, npix * sizeof(uint32_t), c->stream));
 	CU(cudaMemsetAsync(c->aov.p, 0, npix * 10 * sizeof(float), c->stream));
+	if (c->aovExt.p)
+		CU(cudaMemsetAsync(c->aovExt.p, 0, npix * PRB_AOV_EXT * sizeof(float), c->stream));
 	CU(cudaMemsetAsync(c->feedback.p, 0, npix * sizeof(uint32_t), c->stream));
 	if (c->varMean.p) {
 		CU(cudaMemsetAsync(c->varMean.p, 0, npix * 3 * sizeof(float), c->stream));
@@ -757,6 +765,7 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.filmMean	  = c->filmMean.p;
 	W.sampleCount = c->sampleCount.p;
 	W.aov		  = c->wantAOV ? c->aov.p : nullptr;
+	W.aovExt	  = c->aovExt.p;
 	W.feedback	  = c->feedback.p;
 	W.varMean	  = c->S.settings.want_variance ? c->varMean.p : nullptr;
 	W.varVar	  = c->S.settings.want_variance ? c->varVar.p : nullptr;
@@ -1002,6 +1011,18 @@ prb_status prb_film_download_variance(prb_ctx* c, float* online_mean, float* onl
 	CU(cudaStreamSynchronize(c->stream));
 	return PRB_OK;
 }
+prb_status prb_film_download_aov_ext(prb_ctx* c, float* aov11)
+{
+	if (!c || !c->haveScene || !aov11)
+		return fail(PRB_ERR_NO_SCENE, "no scene uploaded / null buffer");
+	if (!c->aovExt.p)
+		return fail(PRB_ERR_UNSUPPORTED, "the scene was uploaded without prb_settings.want_aov_ext");
+	CU(cudaSetDevice(c->device));
+	const size_t npix = (size_t)c->S.settings.film_width * c->S.settings.film_height;
+	CU(cudaMemcpyAsync(aov11, c->aovExt.p, npix * PRB_AOV_EXT * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return PRB_OK;
+}
 prb_status prb_film_download_lpe(prb_ctx* c, uint32_t index, float* xyz)
 {
 	if (!c || !c->haveScene || !xyz)
@@ -1160,6 +1181,13 @@ prb_status prb_film_reduce_comm(prb_ctx* c, int partition, uint32_t total_iterat
 	k_film_pack<<<c->smCount * 4, 256, 0, s>>>(c->filmMean.p, c->sampleCount.p, c->aov.p, c->feedback.p, partitionWeight(c, partition, total_iterations), c->reduceF.p,
 												c->reduceU.p, npix);
 	CU(cudaGetLastError());
+	if (c->lpeFilm.p) {
+		const float w = partitionWeight(c, partition, total_iterations);
+		if (w != 1.0f) {
+			k_scale_add<<<c->smCount * 4, 256, 0, s>>>(c->lpeFilm.p, nullptr, w, 0.0f, (size_t)npix * 3 * c->S.nLPE);
+			c->kernelLaunches += 1;
+		}
+	}
 	NC(nccl().GroupStart());
 	NC(nccl().Reduce(c->reduceF.p, c->reduceF.p, (size_t)npix * FILM_PACK, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
 	NC(nccl().Reduce(c->reduceU.p, c->reduceU.p, npix, NCCL_UINT32, NCCL_SUM, root, c->ncclComm, s));
@@ -1167,6 +1195,11 @@ prb_status prb_film_reduce_comm(prb_ctx* c, int partition, uint32_t total_iterat
 		NC(nccl().Reduce(c->varMean.p, c->varMean.p, (size_t)npix * 3, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
 		NC(nccl().Reduce(c->varVar.p, c->varVar.p, (size_t)npix * 3, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
 	}
+	// the extended AOV sums add up like the ten packed ones; the expression channels are films: weighted like the main one
+	if (c->aovExt.p)
+		NC(nccl().Reduce(c->aovExt.p, c->aovExt.p, (size_t)npix * PRB_AOV_EXT, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
+	if (c->lpeFilm.p)
+		NC(nccl().Reduce(c->lpeFilm.p, c->lpeFilm.p, (size_t)npix * 3 * c->S.nLPE, NCCL_FLOAT32, NCCL_SUM, root, c->ncclComm, s));
 	NC(nccl().GroupEnd());
 	c->kernelLaunches += 1;
 	if (c->commRank == root) {
@@ -1248,6 +1281,29 @@ prb_status prb_film_reduce(prb_ctx** ctxs, int n, int partition)
 	k_film_gather<<<root->smCount * 4, 256, 0, root->stream>>>(P, root->filmMean.p, root->sampleCount.p, root->aov.p, root->feedback.p, npix);
 	root->kernelLaunches += 1;
 	CU(cudaGetLastError());
+	{ // extended AOV sums and expression channels: one staged pass per peer and buffer
+		const size_t nExt = root->aovExt.p ? (size_t)npix * PRB_AOV_EXT : 0, nLpe = root->lpeFilm.p ? (size_t)npix * 3 * root->S.nLPE : 0;
+		DBuf<float> stage;
+		CU(stage.alloc(std::max<size_t>(std::max(nExt, nLpe), 1)));
+		if (nLpe && P.rootWeight != 1.0f) {
+			k_scale_add<<<root->smCount * 4, 256, 0, root->stream>>>(root->lpeFilm.p, nullptr, P.rootWeight, 0.0f, nLpe);
+			root->kernelLaunches += 1;
+		}
+		for (int i = 1; i < n; ++i) {
+			if (nExt && ctxs[i]->aovExt.p) {
+				CU(cudaMemcpyPeerAsync(stage.p, root->device, ctxs[i]->aovExt.p, ctxs[i]->device, nExt * sizeof(float), root->stream));
+				k_add_buffer<<<root->smCount * 4, 256, 0, root->stream>>>(root->aovExt.p, stage.p, nExt);
+				root->kernelLaunches += 1;
+			}
+			if (nLpe && ctxs[i]->lpeFilm.p && ctxs[i]->S.nLPE == root->S.nLPE) {
+				CU(cudaMemcpyPeerAsync(stage.p, root->device, ctxs[i]->lpeFilm.p, ctxs[i]->device, nLpe * sizeof(float), root->stream));
+				k_scale_add<<<root->smCount * 4, 256, 0, root->stream>>>(root->lpeFilm.p, stage.p, 1.0f, P.weight[i - 1], nLpe);
+				root->kernelLaunches += 1;
+			}
+		}
+		CU(cudaStreamSynchronize(root->stream));
+		stage.release();
+	}
 	if (root->varMean.p && partition == PRB_PARTITION_TILES) {
 		DBuf<float> stage;
 		CU(stage.alloc((size_t)npix * 3));

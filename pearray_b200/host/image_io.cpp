@@ -31,18 +31,18 @@ const VarName kSpectral[] = { { "color", OV_Output, "color" }, { "spectral", OV_
 							  { "online_mean", OV_OnlineMean, "online_mean" }, { "variance", OV_OnlineVariance, "variance" },
 							  { "online_variance", OV_OnlineVariance, "variance" }, { "var", OV_OnlineVariance, "variance" } };
 const VarName k1D[]		  = { { "entity_id", OV_EntityID, "entity_id" }, { "entity", OV_EntityID, "entity_id" }, { "id", OV_EntityID, "entity_id" },
-							  { "material_id", OV_Unsupported, "material_id" }, { "material", OV_Unsupported, "material_id" }, { "mat", OV_Unsupported, "material_id" },
-							  { "emission_id", OV_Unsupported, "emission_id" }, { "emission", OV_Unsupported, "emission_id" },
-							  { "displace_id", OV_Unsupported, "displace_id" }, { "displace", OV_Unsupported, "displace_id" },
+							  { "material_id", OV_MaterialID, "material_id" }, { "material", OV_MaterialID, "material_id" }, { "mat", OV_MaterialID, "material_id" },
+							  { "emission_id", OV_EmissionID, "emission_id" }, { "emission", OV_EmissionID, "emission_id" },
+							  { "displace_id", OV_DisplaceID, "displace_id" }, { "displace", OV_DisplaceID, "displace_id" },
 							  { "depth", OV_Depth, "depth" }, { "d", OV_Depth, "depth" } };
 const VarName kCounter[]  = { { "sample_count", OV_SampleCount, "sample_count" }, { "samples", OV_SampleCount, "sample_count" }, { "s", OV_SampleCount, "sample_count" },
 							  { "feedback", OV_Feedback, "feedback" }, { "f", OV_Feedback, "feedback" }, { "error", OV_Feedback, "feedback" } };
 const VarName k3D[]		  = { { "position", OV_Position, "position" }, { "pos", OV_Position, "position" }, { "p", OV_Position, "position" },
 							  { "normal", OV_Normal, "normal" }, { "norm", OV_Normal, "normal" }, { "n", OV_Normal, "normal" },
-							  { "normal_geometric", OV_Unsupported, "normal_geometric" }, { "ng", OV_Unsupported, "normal_geometric" },
-							  { "tangent", OV_Unsupported, "tangent" }, { "tan", OV_Unsupported, "tangent" }, { "nx", OV_Unsupported, "tangent" },
-							  { "bitangent", OV_Unsupported, "bitangent" }, { "binormal", OV_Unsupported, "bitangent" }, { "bi", OV_Unsupported, "bitangent" },
-							  { "ny", OV_Unsupported, "bitangent" }, { "view", OV_Unsupported, "view" }, { "v", OV_Unsupported, "view" },
+							  { "normal_geometric", OV_NormalG, "normal_geometric" }, { "ng", OV_NormalG, "normal_geometric" },
+							  { "tangent", OV_Tangent, "tangent" }, { "tan", OV_Tangent, "tangent" }, { "nx", OV_Tangent, "tangent" },
+							  { "bitangent", OV_Bitangent, "bitangent" }, { "binormal", OV_Bitangent, "bitangent" }, { "bi", OV_Bitangent, "bitangent" },
+							  { "ny", OV_Bitangent, "bitangent" }, { "view", OV_View, "view" }, { "v", OV_View, "view" },
 							  { "texture", OV_UVW, "texture" }, { "uvw", OV_UVW, "texture" }, { "uv", OV_UVW, "texture" }, { "tex", OV_UVW, "texture" } };
 template <size_t N>
 bool lookup(const VarName (&table)[N], const std::string& type, int& var, std::string& name)
@@ -309,8 +309,15 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 			const float* a = film.aov + 10 * i; // prb_film_aov layout: N(3) P(3) u v depth entity
 			const float sf = sampleFactor(i);
 			float v[3]	   = { 0, 0, 0 };
-			if (c.variable == OV_Normal)
+			const float* b = film.aovExt ? film.aovExt + PRB_AOV_EXT * i : nullptr; // prb_film_download_aov_ext layout
+			if (c.variable == OV_Normal || c.variable == OV_NormalG) // Surface.N is a copy of Geometry.N (IntersectionPoint::setForSurface)
 				v[0] = a[0], v[1] = a[1], v[2] = a[2];
+			else if (b && c.variable == OV_Tangent)
+				v[0] = b[0], v[1] = b[1], v[2] = b[2];
+			else if (b && c.variable == OV_Bitangent)
+				v[0] = b[3], v[1] = b[4], v[2] = b[5];
+			else if (b && c.variable == OV_View)
+				v[0] = b[6], v[1] = b[7], v[2] = b[8];
 			else if (c.variable == OV_Position)
 				v[0] = a[3], v[1] = a[4], v[2] = a[5];
 			else if (c.variable == OV_UVW)
@@ -324,8 +331,20 @@ bool saveImage(const std::string& path, const OutputFile& file, const FilmView& 
 		std::vector<float>& p = addPlane(c.name);
 		if (!film.aov || c.variable == OV_Unsupported || !passesLPE(c))
 			continue;
-		for (size_t i = 0; i < n; ++i)
-			p[i] = sampleFactor(i) * film.aov[10 * i + (c.variable == OV_Depth ? 8 : 9)];
+		for (size_t i = 0; i < n; ++i) {
+			float sum = 0;
+			if (c.variable == OV_Depth)
+				sum = film.aov[10 * i + 8];
+			else if (c.variable == OV_EntityID)
+				sum = film.aov[10 * i + 9];
+			else if (c.variable == OV_MaterialID && film.aovExt)
+				sum = film.aovExt[PRB_AOV_EXT * i + 9];
+			else if (c.variable == OV_EmissionID && film.aovExt)
+				sum = film.aovExt[PRB_AOV_EXT * i + 10];
+			else if (c.variable == OV_DisplaceID) // GeometryPoint::DisplaceID stays PR_INVALID_ID for meshes, spheres and planes (GeometryPoint.h:24)
+				sum = (film.sampleCount ? (float)film.sampleCount[i] : 0.0f) * 4294967296.0f;
+			p[i] = sampleFactor(i) * sum;
+		}
 	}
 	for (const OutputChannel& c : file.channels) {
 		if (c.kind != OutputChannel::Counter)

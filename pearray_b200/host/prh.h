@@ -649,7 +649,26 @@ LPEAutomaton compileLPE(const std::string& expression);
 
 // ------------------------------------------------------------------ output specification + image writer (image_io.cpp)
 enum class ToneColorMode { SRGB, XYZ, XYZNorm, Luminance }; // reference src/core/spectral/ToneMapper.h
-enum OutputVariable { OV_Unsupported = -1, OV_Output = 0, OV_Position, OV_Normal, OV_UVW, OV_Depth, OV_EntityID, OV_SampleCount, OV_Feedback, OV_OnlineMean, OV_OnlineVariance };
+enum OutputVariable {
+	OV_Unsupported = -1,
+	OV_Output	   = 0,
+	OV_Position,
+	OV_Normal,
+	OV_UVW,
+	OV_Depth,
+	OV_EntityID,
+	OV_SampleCount,
+	OV_Feedback,
+	OV_OnlineMean,
+	OV_OnlineVariance,
+	OV_NormalG,
+	OV_Tangent,
+	OV_Bitangent,
+	OV_View,
+	OV_MaterialID,
+	OV_EmissionID,
+	OV_DisplaceID
+};
 struct OutputChannel { // reference IM_ChannelSetting{Spec,3D,1D,Counter}, src/loader/output/io/ImageWriter.h
 	enum Kind { Spectral, ThreeD, OneD, Counter } kind = Spectral;
 	int variable	  = OV_Output;
@@ -672,6 +691,7 @@ struct FilmView { // what prb_film_download / prb_film_aov return for one contex
 	const float* onlineMean		= nullptr; // 3 per pixel (AOV_OnlineMean); may be null
 	const float* onlineVariance = nullptr; // 3 per pixel (AOV_OnlineVariance); may be null
 	const float* aov		  = nullptr;  // 10 per pixel (N, P, u, v, depth, entity id), sums over the samples; may be null
+	const float* aovExt		  = nullptr;  // PRB_AOV_EXT per pixel (tangent, bitangent, view, material id, emission id), sums; may be null
 	std::vector<const float*> lpe;		  // per light path expression of the scene: 3 per pixel (XYZ), may be empty / null entries
 };
 class OutputSpecification { // reference src/loader/output/io/OutputSpecification.h
@@ -684,6 +704,15 @@ public:
 		for (const OutputFile& f : mFiles)
 			for (const OutputChannel& c : f.channels)
 				if (c.variable == OV_OnlineMean || c.variable == OV_OnlineVariance)
+					return true;
+		return false;
+	}
+	// does any channel ask for an AOV of prb_film_download_aov_ext (tangent, bitangent, view, material / emission id)?
+	bool wantsExtendedAOVs() const
+	{
+		for (const OutputFile& f : mFiles)
+			for (const OutputChannel& c : f.channels)
+				if (c.variable == OV_Tangent || c.variable == OV_Bitangent || c.variable == OV_View || c.variable == OV_MaterialID || c.variable == OV_EmissionID)
 					return true;
 		return false;
 	}

@@ -132,6 +132,12 @@ int RenderContext::saveOutputs(const std::string& workingDir)
 	aov.resize(n * 10);
 	if (prb_film_download_aov(mCtx, aov.data()) == PRB_OK) // AOVs are optional (prb_settings.enable_aov)
 		film.aov = aov.data();
+	std::vector<float> aovExt;
+	if (st.want_aov_ext) {
+		aovExt.resize(n * PRB_AOV_EXT);
+		if (prb_film_download_aov_ext(mCtx, aovExt.data()) == PRB_OK)
+			film.aovExt = aovExt.data();
+	}
 	if (prb_film_download_feedback(mCtx, feedback.data()) == PRB_OK)
 		film.feedback = feedback.data();
 	std::vector<float> onlineMean, onlineVariance;

@@ -191,6 +191,7 @@ std::shared_ptr<CompiledScene> SceneCompiler::compile()
 	st.spectral_mono		 = rs.spectralMono;
 	st.film_monotonic		 = rs.spectralMono; // FrameOutputDevice(filter, viewSize, 3, spectralMono), loader/Environment.cpp:194-198
 	st.want_variance		 = mEnv->outputSpecification().wantsVariance();
+	st.want_aov_ext			 = mEnv->outputSpecification().wantsExtendedAOVs();
 	st.spectral_hero		 = rs.spectralHero;
 	st.spectral_start		 = rs.spectralStart;
 	st.spectral_end			 = rs.spectralEnd;

@@ -27,7 +27,7 @@ def lib():
         l.orc_scene_destroy.argtypes = [C.c_void_p]
         l.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(prb.Tile), C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        l.orc_render_lpe.argtypes = l.orc_render.argtypes + [C.c_void_p]
+        l.orc_render_lpe.argtypes = l.orc_render.argtypes + [C.c_void_p, C.c_void_p]
         l.orc_log_fragments.restype = C.c_size_t
         l.orc_log_fragments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         l.orc_apply_filter.argtypes = [C.POINTER(prb.SceneDesc), C.c_void_p, C.c_void_p]
@@ -92,6 +92,7 @@ class OracleScene:
         film = np.zeros((h, w, 3), np.float32) if film is None else film
         count = np.zeros((h, w), np.uint32) if count is None else count
         aovb = np.zeros((h, w, 10), np.float32) if aov else None
+        aove = np.zeros((h, w, 11), np.float32) if aov else None
         stats = np.zeros(11, np.uint64)
         feedback = np.zeros((h, w), np.uint32) if feedback is None else feedback
         threads = threads or os.cpu_count() or 1
@@ -105,7 +106,7 @@ class OracleScene:
         lpe = np.zeros((n_lpe, h, w, 3), np.float32) if n_lpe and lpe is None else lpe
         lib().orc_render_lpe(self._h, _p(rng), arr, len(tiles), first_iteration, iteration_count, _p(film), _p(count),
                              _p(aovb) if aov else None, _p(stats), threads, _p(feedback), _p(vmean) if vmean is not None else None,
-                             _p(vvar) if vvar is not None else None, _p(lpe) if n_lpe else None)
+                             _p(vvar) if vvar is not None else None, _p(lpe) if n_lpe else None, _p(aove) if aov else None)
         filtered = np.empty_like(film)
         lib().orc_apply_filter(self.scene.desc, _p(film), _p(filtered))
         lpe_filtered = None
@@ -116,7 +117,7 @@ class OracleScene:
         names = ["camera_ray_count", "light_ray_count", "primary_ray_count", "bounce_ray_count", "shadow_ray_count", "monochrome_ray_count",
                  "pixel_sample_count", "entity_hit_count", "background_hit_count", "camera_depth_count", "light_depth_count"]
         return dict(film=film, filtered=filtered, count=count, aov=aovb, stats=dict(zip(names, (int(x) for x in stats))), rng=rng, feedback=feedback,
-                    online_mean=vmean, online_variance=vvar, lpe=lpe, lpe_filtered=lpe_filtered)
+                    online_mean=vmean, online_variance=vvar, lpe=lpe, lpe_filtered=lpe_filtered, aov_ext=aove)
 
     FRAG_FIELDS = [("kind", 1), ("flags", 1), ("depth", 1), ("pixel", 1), ("mis", 4), ("importance", 4), ("radiance", 4), ("pathPDF", 4),
                    ("prevPathPDF", 4), ("wvlPDF", 4), ("bsdfPDF", 4), ("lightPdfS", 1), ("roulette", 1), ("extra", 1), ("accepted", 1),

@@ -303,6 +303,14 @@ def test_full_frame_c2_vs_oracle_and_stats():
     assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32))
     aov = ctx.film_aov()
     assert np.array_equal(aov.view(np.uint32), ref["aov"].view(np.uint32))
+    with pytest.raises(prb.PrbError):  # opt in: prb_settings.want_aov_ext (the host sets it from the scene's output channels)
+        ctx.film_aov_ext()
+    scene.settings.want_aov_ext = 1
+    ctx2 = make_ctx(scene)
+    ctx2.render_tiles(tiles, 0, 2)
+    ext = ctx2.film_aov_ext()  # tangent, bitangent, view, material id, emission id (LocalFrameOutputDevice.cpp:268-284)
+    assert np.array_equal(ext.view(np.uint32), ref["aov_ext"].view(np.uint32)) and np.abs(ext[..., :9]).max() > 0
+    assert np.array_equal(ctx2.film()[0].view(np.uint32), xyz.view(np.uint32))
 
 
 @pytest.mark.parametrize("name,iters", [("c4_boltsandgears", 2), ("c4c_complex", 1)])
@@ -693,6 +701,7 @@ def test_film_reduce_single_process_tiles_bit_identical():
     from pearray_b200 import multigpu
     src = SKYSUN_ZOO.replace(":camera 'Camera'", ":camera 'Camera' :spectral_hero false")  # leaves feedback bits behind
     scene = prb.Scene.from_string(src)
+    scene.settings.want_aov_ext = 1
     tiles = scene.tiles(4, 4)
     spp = 3
     single = make_ctx(scene)
@@ -707,9 +716,35 @@ def test_film_reduce_single_process_tiles_bit_identical():
     b, cb = single.film()
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ca, cb)
     assert np.array_equal(parts[0].film_aov().view(np.uint32), single.film_aov().view(np.uint32))
+    assert np.array_equal(parts[0].film_aov_ext().view(np.uint32), single.film_aov_ext().view(np.uint32))
     fb = single.film_feedback()
     assert fb.any() and np.array_equal(parts[0].film_feedback(), fb)
     assert parts[0].last_reduce_ms() > 0
+
+
+def test_film_reduce_carries_the_lpe_channels():
+    """the expression channels are films of their own: tiles -> the owner's value, sample ranges -> weighted like the main film"""
+    from pearray_b200 import multigpu
+    scene = prb.Scene.from_string(LPE_ZOO)
+    tiles = scene.tiles(4, 4)
+    single = make_ctx(scene)
+    single.render_tiles(tiles, 0, 4)
+    parts = []
+    for rank in range(2):
+        c = make_ctx(scene)
+        c.render_tiles(multigpu.partition_tiles(tiles, rank, 2), 0, 4)
+        parts.append(c)
+    prb.Context.film_reduce(parts, "tiles")
+    for k in range(len(LPE_EXPRESSIONS)):
+        assert np.array_equal(parts[0].film_lpe(k).view(np.uint32), single.film_lpe(k).view(np.uint32)), LPE_EXPRESSIONS[k]
+    # sample ranges: 'C.*L' keeps tracking the main film through the weighted combine
+    a, b = make_ctx(scene), make_ctx(scene)
+    a.render_tiles(tiles, 0, 3)
+    b.upload_rng(scene.rng_map(1))
+    b.render_tiles(tiles, 3, 5)
+    prb.Context.film_reduce([a, b], "samples")
+    k = LPE_EXPRESSIONS.index("C.*L")
+    np.testing.assert_allclose(a.film_lpe(k), a.film()[0], rtol=1e-5, atol=1e-6)
 
 
 def test_film_reduce_single_process_sample_ranges():

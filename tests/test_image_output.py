@@ -108,8 +108,9 @@ def test_output_files_follow_the_reference_layout(tmp_path):
     np.testing.assert_allclose(pl["depth"], sf * aov[..., 8], rtol=1e-6)
     np.testing.assert_allclose(pl["entity_id"], sf * aov[..., 9], rtol=1e-6)
     assert np.array_equal(pl["sample_count"], cnt.astype(np.float32))  # counters are not weighted
-    for c in ("normal_geometric.x", "[C.*L].R"):  # not accumulated on the device path: zeros, like a missing channel
-        assert not pl[c].any()
+    for k, c in enumerate("xyz"):  # Surface.N is a copy of Geometry.N on this path (IntersectionPoint::setForSurface)
+        np.testing.assert_allclose(pl["normal_geometric." + c], sf * aov[..., k], rtol=1e-6)
+    assert not pl["[C.*L].R"].any()  # no expression film handed to the writer here: zeros, like a missing channel
 
 
 def test_an_independent_reader_decodes_the_file(tmp_path):
