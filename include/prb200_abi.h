@@ -70,8 +70,17 @@ enum {
 	PRB_NODE_TABLE		  = 3, /* a=pool offset,b=count,p[0]=start nm,p[1]=end nm   EquidistantSpectrumView::lookup */
 	PRB_NODE_SELLMEIER	  = 4, /* a=pool offset (B[n],C[n]), b=n   SellmeierIndexNode, node/ReflectiveNode.cpp:104-140 */
 	PRB_NODE_MUL		  = 5, /* a,b = node ids             MulSpectralMath ('smul') */
-	PRB_NODE_CHECKER	  = 6  /* a,b = node ids, p[0]=su,p[1]=sv,p[2]=mode(0 none,1 iso,2 aniso)  CheckerboardNode.cpp:26-48 */
+	PRB_NODE_CHECKER	  = 6, /* a,b = node ids, p[0]=su,p[1]=sv,p[2]=mode(0 none,1 iso,2 aniso)  CheckerboardNode.cpp:26-48 */
+	/* NonParametricImageNode (loader/shader/ImageNode.cpp:93-162): a = pool offset of width*height RGB texels (rows top to
+	 * bottom as stored in the file), b = width | height << 16, p[0] = interpolation (PRB_TEX_*), p[1] / p[2] = wrap mode of
+	 * s / t (PRB_WRAP_*), p[3] != 0: the file is sRGB encoded -> RGBConverter::linearize after the lookup.  The texel fetch
+	 * restates OpenImageIO's TextureSystem::texture() without MIP levels and derivatives (an un-vendored dependency of the
+	 * reference: texel centres at (i + 0.5) / size, t = 1 - v), then SpectralUpsampler::prepare + ::compute per lookup
+	 * against the coefficient cube at prb_scene_desc::upsampler_offset. */
+	PRB_NODE_IMAGE = 7
 };
+enum { PRB_TEX_CLOSEST = 0, PRB_TEX_BILINEAR = 1, PRB_TEX_BICUBIC = 2 };
+enum { PRB_WRAP_BLACK = 0, PRB_WRAP_CLAMP = 1, PRB_WRAP_PERIODIC = 2, PRB_WRAP_MIRROR = 3 };
 #define PRB_NODE_FLAG_SPECTRAL_VARYING 0x1u /* NodeFlag::SpectralVarying */
 #define PRB_NODE_FLAG_TEXTURE_VARYING 0x2u
 
@@ -215,7 +224,7 @@ typedef struct prb_bvh_tri {
 /* ---------------------------------------------------------------- lights */
 enum {
 	PRB_LIGHT_AREA		= 0,
-	PRB_LIGHT_ENV		= 1, /* plugins/main/infinitelights/environment.cpp (no-distribution branches) */
+	PRB_LIGHT_ENV		= 1, /* plugins/main/infinitelights/environment.cpp; dist_w > 0: the Distribution2D branches (image based radiance) */
 	PRB_LIGHT_SKY		= 2, /* plugins/main/infinitelights/sky.cpp:27-173 (Hosek-Wilkie table + Distribution2D) */
 	PRB_LIGHT_SUN		= 3, /* plugins/main/infinitelights/sun.cpp:27-140 (cone) */
 	PRB_LIGHT_SUN_DELTA = 4	 /* plugins/main/infinitelights/sun.cpp:142-240 (radius <= eps: delta direction) */
@@ -392,6 +401,10 @@ typedef struct prb_scene_desc {
 	uint32_t cie_offset; /* 3 x 441 floats: x, y, z (CIE 2006, 390..830 nm) */
 	uint32_t _pad;
 
+	/* RGB -> spectrum coefficient cube of the SpectralUpsampler (src/core/spectral/SpectralUpsampler.cpp; Jakob & Hanika 2019)
+	 * for image textures, in the pool: upsampler_res scale values, then 3 * res^3 * 3 coefficients; 0 / 0 when the scene has
+	 * no image node */
+	uint32_t upsampler_offset, upsampler_res;
 	/* spectral output channels restricted by a light path expression (at most PRB_MAX_LPE) */
 	uint32_t n_lpe;
 	uint32_t n_lpe_bytes;

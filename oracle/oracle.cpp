@@ -75,11 +75,160 @@ inline float cieEval(const Scene& sc, int c, float w)
 	return tableLookup(sc.d->pool + sc.d->cie_offset + c * CIE_N, CIE_N, CIE_START, CIE_END, w) / CIE_Y_NORM * CIE_RANGE;
 }
 
+// ---- image textures: NonParametricImageNode::eval, loader/shader/ImageNode.cpp:131-162.  OpenImageIO's texture system is an
+// un-vendored dependency of the reference; the lookup restates its documented behaviour without MIP levels and derivatives
+// (texel centres at (i + 0.5) / size, wrap modes black / clamp / periodic / mirror, closest / bilinear / B-spline bicubic).
+bool wrapTexel(int& i, int size, int mode)
+{
+	if (i >= 0 && i < size)
+		return true;
+	switch (mode) {
+	default: return false; // black
+	case PRB_WRAP_CLAMP: i = i < 0 ? 0 : size - 1; return true;
+	case PRB_WRAP_PERIODIC:
+		i %= size;
+		if (i < 0)
+			i += size;
+		return true;
+	case PRB_WRAP_MIRROR: {
+		const int period = 2 * size;
+		i %= period;
+		if (i < 0)
+			i += period;
+		if (i >= size)
+			i = period - 1 - i;
+		return true;
+	}
+	}
+}
+void fetchTexel(const float* img, int w, int h, int x, int y, int wrapS, int wrapT, float rgb[3])
+{
+	rgb[0] = rgb[1] = rgb[2] = 0;
+	if (!wrapTexel(x, w, wrapS) || !wrapTexel(y, h, wrapT))
+		return;
+	const float* t = img + 3 * ((size_t)y * w + x);
+	rgb[0] = t[0], rgb[1] = t[1], rgb[2] = t[2];
+}
+void bsplineWeights(float f, float w[4])
+{
+	const float one_f = 1.0f - f;
+	w[0]			  = (one_f * one_f * one_f) / 6.0f;
+	w[1]			  = 2.0f / 3.0f - 0.5f * f * f * (2.0f - f);
+	w[2]			  = 2.0f / 3.0f - 0.5f * one_f * one_f * (2.0f - one_f);
+	w[3]			  = (f * f * f) / 6.0f;
+}
+void upsamplerPrepare(const Scene& sc, const float rgb[3], float coeffs[3])
+{ // SpectralUpsampler::prepare for one triple, src/core/spectral/SpectralUpsampler.cpp
+	constexpr float EPS = 0.0001f;
+	if (rgb[0] <= EPS && rgb[1] <= EPS && rgb[2] <= EPS) {
+		coeffs[0] = 0, coeffs[1] = 0, coeffs[2] = -500.0f;
+		return;
+	}
+	if (1 - rgb[0] <= EPS && 1 - rgb[1] <= EPS && 1 - rgb[2] <= EPS) {
+		coeffs[0] = 0, coeffs[1] = 0, coeffs[2] = 5000000.0f;
+		return;
+	}
+	const uint32_t res = sc.d->upsampler_res;
+	const float* scale = sc.d->pool + sc.d->upsampler_offset;
+	const float* d	   = scale + res;
+	const uint32_t dx = 3, dy = 3 * res, dz = 3 * res * res;
+	int largest = 0;
+	for (int j = 1; j < 3; ++j)
+		if (rgb[largest] <= rgb[j])
+			largest = j;
+	const float z	  = rgb[largest];
+	const float scl	  = (float)(res - 1) / z;
+	const float x	  = rgb[(largest + 1) % 3] * scl;
+	const float y	  = rgb[(largest + 2) % 3] * scl;
+	const uint32_t xi = std::min((uint32_t)x, res - 2);
+	const uint32_t yi = std::min((uint32_t)y, res - 2);
+	int left = 0, size = (int)res - 2;
+	const int lastInterval = (int)res - 2;
+	while (size > 0) {
+		const int half = size >> 1, middle = left + half + 1;
+		if (scale[middle] < z) {
+			left = middle;
+			size -= half + 1;
+		} else {
+			size = half;
+		}
+	}
+	const uint32_t zi = (uint32_t)std::min(left, lastInterval);
+	uint32_t off	  = (((largest * res + zi) * res + yi) * res + xi) * 3;
+	const float x1 = x - (float)xi, x0 = 1.0f - x1, y1 = y - (float)yi, y0 = 1.0f - y1;
+	const float z1 = (z - scale[zi]) / (scale[zi + 1] - scale[zi]), z0 = 1.0f - z1;
+	for (int j = 0; j < 3; ++j) {
+		coeffs[j] = ((d[off] * x0 + d[off + dx] * x1) * y0 + (d[off + dy] * x0 + d[off + dy + dx] * x1) * y1) * z0
+					+ ((d[off + dz] * x0 + d[off + dz + dx] * x1) * y0 + (d[off + dz + dy] * x0 + d[off + dz + dy + dx] * x1) * y1) * z1;
+		++off;
+	}
+}
+float srgbLinearize(float x)
+{ // RGBConverter::linearize, src/core/spectral/RGBConverter.cpp:53-58 -- as written there, `x / 12.92 * x` on the linear segment
+	if (x <= 0.04045f)
+		return x / 12.92f * x;
+	return (float)std::pow((double)((x + 0.055f) / 1.055f), (double)2.4f);
+}
+Blob evalImageNode(const Scene& sc, const prb_node& n, const Blob& wvl, float u, float v)
+{
+	const int w = (int)(n.b & 0xFFFFu), h = (int)(n.b >> 16);
+	const float* img = sc.d->pool + n.a;
+	const int interp = (int)n.p[0], wrapS = (int)n.p[1], wrapT = (int)n.p[2];
+	const float x = u * (float)w - 0.5f, y = (1 - v) * (float)h - 0.5f; // texture(s = u, t = 1 - v), ImageNode.cpp:141-145
+	const float flx = std::floor(x), fly = std::floor(y);
+	int ix = (int)flx, iy = (int)fly;
+	const float fx = x - flx, fy = y - fly;
+	float rgb[3];
+	if (interp == PRB_TEX_CLOSEST) {
+		if (fx > 0.5f)
+			++ix;
+		if (fy > 0.5f)
+			++iy;
+		fetchTexel(img, w, h, ix, iy, wrapS, wrapT, rgb);
+	} else if (interp == PRB_TEX_BILINEAR) {
+		float c00[3], c10[3], c01[3], c11[3];
+		fetchTexel(img, w, h, ix, iy, wrapS, wrapT, c00);
+		fetchTexel(img, w, h, ix + 1, iy, wrapS, wrapT, c10);
+		fetchTexel(img, w, h, ix, iy + 1, wrapS, wrapT, c01);
+		fetchTexel(img, w, h, ix + 1, iy + 1, wrapS, wrapT, c11);
+		for (int c = 0; c < 3; ++c)
+			rgb[c] = (c00[c] * (1 - fx) + c10[c] * fx) * (1 - fy) + (c01[c] * (1 - fx) + c11[c] * fx) * fy;
+	} else {
+		float wx[4], wy[4];
+		bsplineWeights(fx, wx);
+		bsplineWeights(fy, wy);
+		rgb[0] = rgb[1] = rgb[2] = 0;
+		for (int j = 0; j < 4; ++j) {
+			float row[3] = { 0, 0, 0 };
+			for (int i = 0; i < 4; ++i) {
+				float t[3];
+				fetchTexel(img, w, h, ix - 1 + i, iy - 1 + j, wrapS, wrapT, t);
+				for (int c = 0; c < 3; ++c)
+					row[c] += wx[i] * t[c];
+			}
+			for (int c = 0; c < 3; ++c)
+				rgb[c] += wy[j] * row[c];
+		}
+	}
+	if (n.p[3] != 0.0f)
+		for (int c = 0; c < 3; ++c)
+			rgb[c] = srgbLinearize(rgb[c]);
+	float k[3];
+	upsamplerPrepare(sc, rgb, k);
+	Blob r;
+	for (int i = 0; i < 4; ++i) { // SpectralUpsampler::compute, SpectralUpsampler.h:45-49
+		const float q = (k[0] * wvl[i] + k[1]) * wvl[i] + k[2];
+		r[i]		  = 0.5f * q * (1.0f / std::sqrt(q * q + 1.0f)) + 0.5f;
+	}
+	return r;
+}
+
 Blob evalNode(const Scene& sc, uint32_t id, const Blob& w, float u, float v)
 {
 	const prb_node& n = sc.d->nodes[id];
 	Blob r;
 	switch (n.type) {
+	case PRB_NODE_IMAGE: return evalImageNode(sc, n, w, u, v);
 	default:
 	case PRB_NODE_CONST: return blob(n.p[0]);
 	case PRB_NODE_PARAM:
@@ -1907,8 +2056,20 @@ struct Integrator {
 			float dx, dy, px, py;
 			rnd.get2D(dx, dy);
 			rnd.get2D(px, py);
-			const V3 local = cos_hemi(dx, dy);
-			o.dirPDF_S	   = cos_hemi_pdf(local.z);
+			V3 local;
+			if (l.dist_w) { // EnvironmentLight<UseDistribution = true>::sampleDir, environment.cpp:83-104
+				float u0, u1, pdf;
+				dist2DSampleContinuous(l, dx, dy, u0, u1, pdf);
+				local				 = cartesian_from_uv(u0, u1);
+				const float sinTheta = cr_sin(u1 * PR_PI);
+				const float denom	 = 2 * PR_PI * PR_PI * sinTheta;
+				o.dirPDF_S			 = pdf * ((denom <= PR_EPSILON) ? 0.0f : 1.0f / denom);
+				dx					 = u0; // coord.UV = uv
+				dy					 = u1;
+			} else {
+				local	   = cos_hemi(dx, dy);
+				o.dirPDF_S = cos_hemi_pdf(local.z);
+			}
 			o.outgoing	   = m3mul(l.normal_matrix, local);
 			o.radiance	   = evalNode(sc, l.radiance_node, ip.ray.wvl, dx, dy);
 			o.lightPos	   = ip.P + l.scene_radius * o.outgoing;
@@ -2247,7 +2408,14 @@ struct Integrator {
 		uv_from_normal(ld, u, v);
 		const uint32_t node = (l.env_split && ray.depth == 0) ? l.background_node : l.radiance_node;
 		rad					= evalNode(sc, node, ray.wvl, u, v);
-		pdfS				= cos_hemi_pdf(std::abs(ld.z));
+		if (l.dist_w) { // UseDistribution, environment.cpp:68-72
+			pdfS				 = dist2DContinuousPdf(l, u, v);
+			const float sinTheta = cr_sin(v * PR_PI);
+			const float denom	 = 2 * PR_PI * PR_PI * sinTheta;
+			pdfS *= (denom <= PR_EPSILON) ? 0.0f : 1.0f / denom;
+		} else {
+			pdfS = cos_hemi_pdf(std::abs(ld.z));
+		}
 	}
 
 	void makeIP(const RayS& ray, const Hit& h, IP& ip)

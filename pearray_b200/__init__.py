@@ -118,6 +118,7 @@ class SceneDesc(C.Structure):
                 ("n_tlas_refs", C.c_uint32), ("tlas_refs", C.POINTER(C.c_uint32)),
                 ("n_pool", C.c_uint32), ("pool", C.POINTER(C.c_float)),
                 ("cie_offset", C.c_uint32), ("_pad", C.c_uint32),
+                ("upsampler_offset", C.c_uint32), ("upsampler_res", C.c_uint32),
                 ("n_lpe", C.c_uint32), ("n_lpe_bytes", C.c_uint32), ("lpe_tables", C.POINTER(C.c_uint8)), ("lpe", LPE * MAX_LPE)]
 
 

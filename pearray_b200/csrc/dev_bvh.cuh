@@ -40,6 +40,7 @@ struct DScene { // device pointers + by-value small structs; passed to kernels b
 	const float* rrProb; // RussianRoulette::probability(len) table
 	uint32_t nMaterials, nEmissions, nEntities, nLights, nMeshes, tlasRoot, cieOffset, rrCount;
 	uint32_t hasInfLight;
+	uint32_t upsamplerOffset, upsamplerRes; // RGB -> spectrum coefficient cube in the pool (image textures)
 	uint32_t hasCombined; // any blend / add material in the scene (keeps the check off the path of scenes without them)
 	// tiny scenes (<= SMALL_MAX_TRIS triangles in <= SMALL_MAX_ENTS entities: the Cornell boxes and the sphere scene of the
 	// reference's examples): a flat list of entity headers + their local-space triangles for the BVH-free trace kernel

@@ -338,6 +338,16 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	CU(c->bvhTris.upload(reinterpret_cast<const float4*>(d->bvh_tris), (size_t)d->n_bvh_tris * 3, s));
 	CU(c->tlasRefs.upload(d->tlas_refs, d->n_tlas_refs, s));
 	CU(c->pool.upload(d->pool, d->n_pool, s));
+	for (uint32_t i = 0; i < d->n_nodes; ++i) {
+		const prb_node& n = d->nodes[i];
+		if (n.type != PRB_NODE_IMAGE)
+			continue;
+		const uint64_t w = n.b & 0xFFFFu, h = n.b >> 16, res = d->upsampler_res;
+		if (w == 0 || h == 0 || (uint64_t)n.a + w * h * 3 > d->n_pool)
+			return fail(PRB_ERR_INVALID_ARG, "image node " + std::to_string(i) + ": texels outside the pool");
+		if (res < 2 || (uint64_t)d->upsampler_offset + res + 9 * res * res * res > d->n_pool)
+			return fail(PRB_ERR_INVALID_ARG, "image node " + std::to_string(i) + ": the scene carries no spectral upsampler table");
+	}
 	if (d->n_lpe > PRB_MAX_LPE)
 		return fail(PRB_ERR_INVALID_ARG, "more than PRB_MAX_LPE light path expressions");
 	for (uint32_t k = 0; k < d->n_lpe; ++k) {
@@ -435,6 +445,8 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	S.nMeshes		  = d->n_meshes;
 	S.tlasRoot		  = d->tlas_root;
 	S.cieOffset		  = d->cie_offset;
+	S.upsamplerOffset = d->upsampler_offset;
+	S.upsamplerRes	  = d->upsampler_res;
 	c->mixedMaterials = false;
 	c->allLambert	  = d->n_materials > 0 && d->materials[0].type == PRB_MAT_DIFFUSE;
 	for (uint32_t i = 1; i < d->n_materials; ++i)

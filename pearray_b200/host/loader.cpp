@@ -458,7 +458,9 @@ void SceneLoader::setupEnvironment(const std::vector<DL::DataGroup>& groups, Sce
 			addFilter(entry, ctx);
 		else if (id == "integrator")
 			addIntegrator(entry, ctx);
-		else if (id == "node" || id == "texture")
+		else if (id == "texture") // "just a sophisticated node", SceneLoader.cpp:167-168
+			addTexture(entry, ctx);
+		else if (id == "node")
 			addNode(entry, ctx);
 		else if (id == "mesh")
 			addMesh(entry, ctx);
@@ -802,6 +804,64 @@ void SceneLoader::addNode(const DL::DataGroup& group, SceneLoadContext& ctx)
 	auto node		 = fac->create(type, ctx);
 	if (node)
 		ctx.environment()->namedNodes[nameD.getString()] = node;
+}
+void SceneLoader::addTexture(const DL::DataGroup& group, SceneLoadContext& ctx)
+{ // SceneLoader.cpp:656-670 + parser/TextureParser.cpp:64-211
+	const DL::Data nameD = group.getFromKey("name");
+	if (nameD.type() != DL::DT_String) {
+		PR_LOG(L_ERROR) << "[Loader] No texture name set" << std::endl;
+		return;
+	}
+	const std::string name = nameD.getString();
+	DL::Data fileD		   = group.getFromKey("file");
+	if (!fileD.isValid())
+		fileD = group.getFromKey("filename");
+	if (fileD.type() != DL::DT_String) {
+		PR_LOG(L_ERROR) << "No valid filename given for texture " << name << std::endl;
+		return;
+	}
+	auto parseWrap = [](std::string w) { // TextureParser.cpp:20-32; WrapDefault of a file without a wrap attribute is black
+		w = lower(w);
+		return w == "clamp" ? PRB_WRAP_CLAMP : w == "periodic" ? PRB_WRAP_PERIODIC : w == "mirror" ? PRB_WRAP_MIRROR : PRB_WRAP_BLACK;
+	};
+	int wrapS = PRB_WRAP_BLACK, wrapT = PRB_WRAP_BLACK;
+	const DL::Data wrapD = group.getFromKey("wrap");
+	if (wrapD.type() == DL::DT_String) {
+		wrapS = wrapT = parseWrap(wrapD.getString());
+	} else if (wrapD.type() == DL::DT_Group) {
+		const DL::DataGroup arr = wrapD.getGroup();
+		if (arr.anonymousCount() > 0 && arr.at(0).type() == DL::DT_String)
+			wrapS = parseWrap(arr.at(0).getString());
+		if (arr.anonymousCount() > 1 && arr.at(1).type() == DL::DT_String)
+			wrapT = parseWrap(arr.at(1).getString());
+	}
+	int interp			   = PRB_TEX_BICUBIC; // InterpSmartBicubic without derivatives magnifies: bicubic (TextureParser.cpp:50-60)
+	const DL::Data interpD = group.getFromKey("interpolation");
+	if (interpD.type() == DL::DT_String) {
+		const std::string i = lower(interpD.getString());
+		interp				= i == "closest" ? PRB_TEX_CLOSEST : (i == "bi" || i == "bilinear") ? PRB_TEX_BILINEAR : PRB_TEX_BICUBIC;
+	}
+	const DL::Data mipD = group.getFromKey("mip");
+	if (mipD.type() == DL::DT_String && lower(mipD.getString()) != "none")
+		PR_LOG(L_WARNING) << "Texture " << name << ": MIP levels are not used on this path (lookups carry no derivatives, ImageNode.cpp:143-145)" << std::endl;
+	std::string type	 = "color";
+	const DL::Data typeD = group.getFromKey("type");
+	if (typeD.type() == DL::DT_String)
+		type = lower(typeD.getString());
+	else
+		PR_LOG(L_WARNING) << "No valid type given for texture " << name << ": Assuming color" << std::endl;
+	if (ctx.environment()->namedNodes.count(name)) {
+		PR_LOG(L_ERROR) << "Texture " << name << " already exists" << std::endl;
+		return;
+	}
+	if (type != "grayscale" && type != "color" && type != "spectral") {
+		PR_LOG(L_ERROR) << (type == "scalar" ? "Scalar textures are not supported on this path: texture " : "No known type given for texture ") << name << std::endl;
+		return;
+	}
+	const std::string file = ctx.setupParametricPath(fileD.getString());
+	auto node			   = makeImageNode(file, interp, wrapS, wrapT, ctx.environment()->defaultSpectralUpsampler());
+	if (node)
+		ctx.environment()->namedNodes[name] = node;
 }
 uint32 SceneLoader::addNodeInline(const DL::DataGroup& group, SceneLoadContext& ctx)
 { // SceneLoader.cpp: inline shading network, node type == group id

@@ -310,6 +310,172 @@ SpectralBlob average(const SpectralBlob& wvls, const FloatSpectralNode* node)
 }
 } // namespace NodeUtils
 
+namespace {
+// ------------------------------------------------------------------ image textures
+// NonParametricImageNode (reference src/loader/shader/ImageNode.cpp:93-182; the parametric variant is compiled out there by
+// PARAMETRIC_FILE_WORKAROUND, TextureParser.cpp:17): an RGB lookup, RGBConverter::linearize for sRGB encoded files, then
+// SpectralUpsampler::prepare + ::compute per lookup.  The lookup itself is OpenImageIO's TextureSystem::texture() in the
+// reference; restated here (and on the device, csrc/dev_shade.cuh evalImageNode) without MIP levels and derivatives.
+class ImageSpectralNode : public FloatSpectralNode {
+public:
+	ImageSpectralNode(ImageData img, int interp, int wrapS, int wrapT, const std::shared_ptr<SpectralUpsampler>& upsampler, const std::string& file)
+		: FloatSpectralNode(NF_TextureVarying | NF_SpectralVarying)
+		, mImg(std::move(img))
+		, mInterp(interp)
+		, mWrapS(wrapS)
+		, mWrapT(wrapT)
+		, mUpsampler(upsampler)
+		, mFile(file)
+	{
+		if (mImg.channels == 1) { // grayscale: the same value in every channel
+			std::vector<float> rgb(mImg.data.size() * 3);
+			for (size_t i = 0; i < mImg.data.size(); ++i)
+				rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = mImg.data[i];
+			mImg.data.swap(rgb);
+			mImg.channels = 3;
+		}
+	}
+	static bool wrapTexel(int& i, int size, int mode)
+	{
+		if (i >= 0 && i < size)
+			return true;
+		switch (mode) {
+		default: return false;
+		case PRB_WRAP_CLAMP: i = i < 0 ? 0 : size - 1; return true;
+		case PRB_WRAP_PERIODIC:
+			i %= size;
+			if (i < 0)
+				i += size;
+			return true;
+		case PRB_WRAP_MIRROR: {
+			const int period = 2 * size;
+			i %= period;
+			if (i < 0)
+				i += period;
+			if (i >= size)
+				i = period - 1 - i;
+			return true;
+		}
+		}
+	}
+	void fetch(int x, int y, float rgb[3]) const
+	{
+		rgb[0] = rgb[1] = rgb[2] = 0;
+		if (!wrapTexel(x, (int)mImg.width, mWrapS) || !wrapTexel(y, (int)mImg.height, mWrapT))
+			return;
+		const float* t = mImg.data.data() + 3 * ((size_t)y * mImg.width + x);
+		rgb[0] = t[0], rgb[1] = t[1], rgb[2] = t[2];
+	}
+	static void bspline(float f, float w[4])
+	{
+		const float one_f = 1.0f - f;
+		w[0]			  = (one_f * one_f * one_f) / 6.0f;
+		w[1]			  = 2.0f / 3.0f - 0.5f * f * f * (2.0f - f);
+		w[2]			  = 2.0f / 3.0f - 0.5f * one_f * one_f * (2.0f - one_f);
+		w[3]			  = (f * f * f) / 6.0f;
+	}
+	void lookup(float u, float v, float rgb[3]) const
+	{
+		const int w = (int)mImg.width, h = (int)mImg.height;
+		const float x = u * (float)w - 0.5f, y = (1 - v) * (float)h - 0.5f; // texture(s = u, t = 1 - v), ImageNode.cpp:141-145
+		const float flx = std::floor(x), fly = std::floor(y);
+		int ix = (int)flx, iy = (int)fly;
+		const float fx = x - flx, fy = y - fly;
+		if (mInterp == PRB_TEX_CLOSEST) {
+			if (fx > 0.5f)
+				++ix;
+			if (fy > 0.5f)
+				++iy;
+			fetch(ix, iy, rgb);
+		} else if (mInterp == PRB_TEX_BILINEAR) {
+			float c00[3], c10[3], c01[3], c11[3];
+			fetch(ix, iy, c00);
+			fetch(ix + 1, iy, c10);
+			fetch(ix, iy + 1, c01);
+			fetch(ix + 1, iy + 1, c11);
+			for (int c = 0; c < 3; ++c)
+				rgb[c] = (c00[c] * (1 - fx) + c10[c] * fx) * (1 - fy) + (c01[c] * (1 - fx) + c11[c] * fx) * fy;
+		} else {
+			float wx[4], wy[4];
+			bspline(fx, wx);
+			bspline(fy, wy);
+			rgb[0] = rgb[1] = rgb[2] = 0;
+			for (int j = 0; j < 4; ++j) {
+				float row[3] = { 0, 0, 0 };
+				for (int i = 0; i < 4; ++i) {
+					float t[3];
+					fetch(ix - 1 + i, iy - 1 + j, t);
+					for (int c = 0; c < 3; ++c)
+						row[c] += wx[i] * t[c];
+				}
+				for (int c = 0; c < 3; ++c)
+					rgb[c] += wy[j] * row[c];
+			}
+		}
+		if (!mImg.linear) // RGBConverter::linearize as written (RGBConverter.cpp:53-58)
+			for (int c = 0; c < 3; ++c)
+				rgb[c] = rgb[c] <= 0.04045f ? rgb[c] / 12.92f * rgb[c] : (float)std::pow((double)((rgb[c] + 0.055f) / 1.055f), (double)2.4f);
+	}
+	SpectralBlob eval(const ShadingContext& ctx) const override
+	{
+		float rgb[3], k[3];
+		lookup(ctx.UV.x, ctx.UV.y, rgb);
+		mUpsampler->prepare(&rgb[0], &rgb[1], &rgb[2], &k[0], &k[1], &k[2], 1);
+		SpectralBlob r;
+		for (int i = 0; i < 4; ++i) { // SpectralUpsampler::compute, SpectralUpsampler.h:45-49
+			const float q = (k[0] * ctx.WavelengthNM[i] + k[1]) * ctx.WavelengthNM[i] + k[2];
+			r[i]		  = 0.5f * q * (1.0f / std::sqrt(q * q + 1.0f)) + 0.5f;
+		}
+		return r;
+	}
+	void queryRecommendedSize(int& w, int& h) const override
+	{
+		w = (int)mImg.width;
+		h = (int)mImg.height;
+	}
+	uint32 emit(NodeEmitter& e) const override
+	{
+		uint32 id;
+		if (e.find(this, id))
+			return id;
+		prb_node n{};
+		n.type	= PRB_NODE_IMAGE;
+		n.flags = devFlags(flags());
+		n.a		= (uint32)e.pool->size();
+		n.b		= mImg.width | (mImg.height << 16);
+		n.p[0]	= (float)mInterp;
+		n.p[1]	= (float)mWrapS;
+		n.p[2]	= (float)mWrapT;
+		n.p[3]	= mImg.linear ? 0.0f : 1.0f;
+		e.pool->insert(e.pool->end(), mImg.data.begin(), mImg.data.end());
+		e.upsampler = mUpsampler.get();
+		return e.add(this, n);
+	}
+	std::string dumpInformation() const override { return mFile + " [NonParam]"; }
+
+private:
+	ImageData mImg;
+	int mInterp, mWrapS, mWrapT;
+	std::shared_ptr<SpectralUpsampler> mUpsampler;
+	std::string mFile;
+};
+} // namespace
+std::shared_ptr<FloatSpectralNode> makeImageNode(const std::string& file, int interp, int wrapS, int wrapT, const std::shared_ptr<SpectralUpsampler>& upsampler)
+{
+	ImageData img;
+	if (!loadImage(file, img)) {
+		PR_LOG(L_ERROR) << "Could not read image " << file << " (supported: EXR scanline half/float with no / ZIPS / ZIP compression, PFM, binary PPM / PGM)" << std::endl;
+		return nullptr;
+	}
+	if (img.width == 0 || img.height == 0 || img.width > 65535 || img.height > 65535) {
+		PR_LOG(L_ERROR) << "Image " << file << ": unsupported size " << img.width << "x" << img.height << std::endl;
+		return nullptr;
+	}
+	return std::make_shared<ImageSpectralNode>(std::move(img), interp, wrapS, wrapT, upsampler, file);
+}
+namespace {
+} // namespace
+
 // ------------------------------------------------------------------ plugins
 namespace {
 class SpectralValuePlugin : public INodePlugin { // SpectralValueNode.cpp:12-70

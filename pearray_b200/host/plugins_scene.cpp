@@ -367,13 +367,39 @@ public:
 };
 
 // ------------------------------------------------------------------ environment light
-class EnvironmentLight : public IInfiniteLight { // plugins/main/infinitelights/environment.cpp (no-distribution branches)
+class EnvironmentLight : public IInfiniteLight { // plugins/main/infinitelights/environment.cpp:24-146
 public:
-	EnvironmentLight(const std::string& name, const Transformf& t, const std::shared_ptr<FloatSpectralNode>& rad, const std::shared_ptr<FloatSpectralNode>& bg)
+	EnvironmentLight(const std::string& name, const Transformf& t, const std::shared_ptr<FloatSpectralNode>& rad, const std::shared_ptr<FloatSpectralNode>& bg,
+					 bool allowDistribution)
 		: IInfiniteLight(name, t)
 		, mRadiance(rad)
 		, mBackground(bg)
 	{
+		// EnvironmentLightFactory::create, environment.cpp:172-198: an image based radiance gets a Distribution2D of its size
+		int w = 1, h = 1;
+		mRadiance->queryRecommendedSize(w, h);
+		if (allowDistribution && w > 1 && h > 1) {
+			mW = w;
+			mH = h;
+			std::vector<float> integrals(mH, 0.0f);
+			mConditional.assign(mH, Distribution1D(mW));
+			for (int y = 0; y < mH; ++y)
+				mConditional[y].generate(
+					[&](size_t x) {
+						const float u		 = (x + 0.5f) / (float)mW;
+						const float v		 = (y + 0.5f) / (float)mH;
+						const float sinTheta = std::sin(PR_PI * v);
+						ShadingContext coord;
+						coord.UV		   = Vector2f(u, v);
+						coord.WavelengthNM = SpectralBlob(560.0f, 540.0f, 400.0f, 600.0f); // preset of wavelengths to test
+						const SpectralBlob r = mRadiance->eval(coord);
+						const float val		 = sinTheta * std::max(std::max(r[0], r[1]), std::max(r[2], r[3]));
+						return (val <= PR_EPSILON) ? 0.0f : val;
+					},
+					&integrals[y]);
+			mMarginal = Distribution1D(mH);
+			mMarginal.generate([&](size_t y) { return integrals[y]; });
+		}
 	}
 	SpectralBlob power(const SpectralBlob& wvl) const override { return NodeUtils::average(wvl, mRadiance.get()); }
 	SpectralRange spectralRange() const override { return mRadiance->spectralRange(); }
@@ -387,10 +413,22 @@ public:
 			out.normal_matrix[i]	 = normalMatrix().m[i];
 			out.inv_normal_matrix[i] = invNormalMatrix().m[i];
 		}
+		if (mW > 0) { // marginal CDF, then one conditional CDF per row (the layout of the sky light's Distribution2D)
+			std::vector<float>& pool = *e.pool;
+			out.dist_offset			 = (uint32)pool.size();
+			out.dist_w				 = (uint32)mW;
+			out.dist_h				 = (uint32)mH;
+			pool.insert(pool.end(), mMarginal.cdf().begin(), mMarginal.cdf().end());
+			for (int y = 0; y < mH; ++y)
+				pool.insert(pool.end(), mConditional[y].cdf().begin(), mConditional[y].cdf().end());
+		}
 	}
 
 private:
 	std::shared_ptr<FloatSpectralNode> mRadiance, mBackground;
+	int mW = 0, mH = 0;
+	std::vector<Distribution1D> mConditional;
+	Distribution1D mMarginal;
 };
 class EnvironmentLightFactory : public IInfiniteLightPlugin {
 public:
@@ -410,8 +448,9 @@ public:
 			background = ctx.lookupSpectralNode(backgroundP, 1);
 			radiance   = background;
 		}
-		// image based radiance (queryRecommendedSize() > 1) would need the Distribution2D branch: SURVEY 8(f)-1
-		return std::make_shared<EnvironmentLight>(params.getString("name", "__unknown"), ctx.transform(), radiance, background);
+		if (params.getBool("compensation", false))
+			throw std::runtime_error("env: ':compensation true' (MIS compensation, off by default in the reference) is not supported");
+		return std::make_shared<EnvironmentLight>(params.getString("name", "__unknown"), ctx.transform(), radiance, background, params.getBool("distribution", true));
 	}
 	const std::vector<std::string>& getNames() const override
 	{

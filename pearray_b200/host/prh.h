@@ -155,6 +155,9 @@ class SpectralUpsampler {
 public:
 	explicit SpectralUpsampler(const std::string& file); // pearray_b200/data/rgb2spec_srgb.bin
 	void prepare(const float* r, const float* g, const float* b, float* out_a, float* out_b, float* out_c, size_t elems) const;
+	uint32 resolution() const { return mRes; }
+	const std::vector<float>& scale() const { return mScale; }
+	const std::vector<float>& data() const { return mData; }
 	static void computeSingle(float a, float b, float c, const float* wavelengths, float* out_weights, size_t elems);
 
 private:
@@ -257,6 +260,8 @@ public:
 	}
 	virtual SpectralBlob eval(const ShadingContext&) const = 0;
 	virtual SpectralRange spectralRange() const { return SpectralRange(); }
+	// INode::queryRecommendedSize (image nodes: the image size; everything else 1 x 1)
+	virtual void queryRecommendedSize(int& w, int& h) const { w = h = 1; }
 	// flatten into the device node table, returns node id
 	virtual uint32 emit(NodeEmitter& e) const = 0;
 };
@@ -264,6 +269,8 @@ class NodeEmitter {
 public:
 	std::vector<prb_node> nodes;
 	std::vector<float>* pool = nullptr;
+	// set by the first image node that is emitted: the scene needs the RGB -> spectrum coefficient cube in its pool
+	const SpectralUpsampler* upsampler = nullptr;
 	uint32 add(const FloatSpectralNode* key, const prb_node& n);
 	bool find(const FloatSpectralNode* key, uint32& id) const;
 	uint32 emitNode(const std::shared_ptr<FloatSpectralNode>& n) { return n->emit(*this); }
@@ -275,6 +282,8 @@ namespace NodeUtils { // reference src/core/shader/NodeUtils.cpp (32x32 UV avera
 SpectralBlob average(const SpectralBlob& wvls, const FloatSpectralNode* node);
 }
 std::shared_ptr<FloatScalarNode> makeConstScalarNode(float f);
+// NonParametricImageNode over an image file (plugins_nodes.cpp); interp: PRB_TEX_*, wraps: PRB_WRAP_*; null when unreadable
+std::shared_ptr<FloatSpectralNode> makeImageNode(const std::string& file, int interp, int wrapS, int wrapT, const std::shared_ptr<SpectralUpsampler>& upsampler);
 std::shared_ptr<FloatSpectralNode> makeConstSpectralNode(float f);
 
 // ------------------------------------------------------------------ scene objects
@@ -726,6 +735,13 @@ private:
 	std::vector<std::string> mLPEs;
 };
 bool saveImage(const std::string& path, const OutputFile& file, const FilmView& film);
+// image files for texture nodes (image_read.cpp): EXR scanline (half / float; none, ZIPS, ZIP), PFM, binary PPM / PGM
+struct ImageData {
+	uint32 width = 0, height = 0, channels = 0; // 1 or 3 channels, rows top to bottom
+	bool linear = true;							// false: sRGB encoded (integer formats)
+	std::vector<float> data;
+};
+bool loadImage(const std::string& path, ImageData& img);
 bool writeEXR(const std::string& path, const std::vector<std::string>& channelNames, const std::vector<const float*>& planes, uint32 width, uint32 height,
 			  int32_t offX, int32_t offY, uint32 fullWidth, uint32 fullHeight);
 
@@ -837,6 +853,7 @@ private:
 	static void addEmission(const DL::DataGroup& g, SceneLoadContext& ctx);
 	static void addMaterial(const DL::DataGroup& g, SceneLoadContext& ctx);
 	static void addNode(const DL::DataGroup& g, SceneLoadContext& ctx);
+	static void addTexture(const DL::DataGroup& g, SceneLoadContext& ctx);
 	static void addMesh(const DL::DataGroup& g, SceneLoadContext& ctx);
 	static void addInclude(const DL::DataGroup& g, SceneLoadContext& ctx);
 	static void addSubGraph(const DL::DataGroup& g, SceneLoadContext& ctx); // (embed :loader 'obj' ...)

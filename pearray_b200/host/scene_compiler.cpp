@@ -313,6 +313,13 @@ std::shared_ptr<CompiledScene> SceneCompiler::compile()
 			for (int x = -r; x <= r; ++x)
 				s.pool.push_back(filter->evalWeight((float)x, (float)y));
 	}
+	// image textures evaluate SpectralUpsampler::prepare per lookup: the coefficient cube travels in the pool
+	if (emitter.upsampler) {
+		s.desc.upsampler_offset = (uint32)s.pool.size();
+		s.desc.upsampler_res	= emitter.upsampler->resolution();
+		s.pool.insert(s.pool.end(), emitter.upsampler->scale().begin(), emitter.upsampler->scale().end());
+		s.pool.insert(s.pool.end(), emitter.upsampler->data().begin(), emitter.upsampler->data().end());
+	}
 	// light path expressions of the spectral output channels: dense DFA tables (lpe.cpp)
 	for (const std::string& expr : mEnv->outputSpecification().lpeExpressions()) {
 		const LPEAutomaton a = compileLPE(expr);

@@ -186,6 +186,47 @@ def test_material_unit_calls_vs_oracle():
             assert same.all(), (mat, kind, "weight / pdf / direction bits", int((~same).sum()))
 
 
+@pytest.mark.parametrize("interp", ["closest", "bilinear", "bicubic"])
+def test_textured_scene_bit_exact_vs_oracle(tmp_path, interp):
+    """an image texture as albedo (NonParametricImageNode: texel fetch, sRGB linearisation, RGB ->
+    spectrum coefficient-cube lookup per shading point) under an image-based environment light (Distribution2D sampling)"""
+    from test_textures import SCENE, write_pfm, write_ppm
+    rs = np.random.RandomState(11)
+    write_ppm(str(tmp_path / "albedo.ppm"), rs.randint(0, 256, size=(9, 13, 3)).astype(np.uint8))  # sRGB encoded
+    env = np.full((8, 16, 3), 0.05, np.float32)
+    env[2:4, 5:7] = (0.9, 0.8, 0.7)
+    write_pfm(str(tmp_path / "env.pfm"), env)
+    src = SCENE.replace("(light :type 'env' :radiance %(env)s)", "(texture :name 'sky' :type 'color' :file '%s' :interpolation '%s' :wrap 'periodic')\n"
+                        " (light :type 'env' :radiance (texture 'sky'))" % (tmp_path / "env.pfm", interp))
+    scene = prb.Scene.from_string(src % dict(file=tmp_path / "albedo.ppm", options=":interpolation '%s' :wrap 'mirror'" % interp, env="1"))
+    d = scene.desc.contents
+    assert sum(d.nodes[i].type == 7 for i in range(d.n_nodes)) == 2 and d.lights[0].dist_w == 16
+    ctx = make_ctx(scene)
+    ora = OracleScene(scene)
+    tiles = [(0, 0, scene.width, scene.height)]
+    ctx.render_tiles(tiles, 0, 6)
+    xyz, cnt = ctx.film()
+    ref = ora.render(tiles, 0, 6)
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32)) and xyz.max() > 0
+    # IMaterial::eval at random surface parameters, also outside [0, 1] (wrap mode)
+    q = (prb.MaterialQuery * 256)()
+    for i in range(256):
+        v = rs.normal(size=3); v[2] = abs(v[2]); v /= np.linalg.norm(v)
+        l = rs.normal(size=3); l[2] = abs(l[2]); l /= np.linalg.norm(l)
+        q[i].V[:] = [float(x) for x in v]
+        q[i].L[:] = [float(x) for x in l]
+        q[i].wavelength_nm[:] = [float(x) for x in rs.uniform(400, 780, 4)]
+        q[i].uv[:] = [float(x) for x in rs.uniform(-0.5, 1.5, 2)]
+        q[i].ray_flags = 1
+        q[i].material_id = 0
+        q[i].rng_state = 3
+    g, o = ctx.material_eval(q), ora.material_eval(q)
+    ga = np.array([[*r.weight, *r.pdf_s] for r in g], dtype=np.float32)
+    oa = np.array([[*r.weight, *r.pdf_s] for r in o], dtype=np.float32)
+    assert np.array_equal(ga.view(np.uint32), oa.view(np.uint32)) and ga[:, :4].max() > 0
+
+
 def test_soup_hits_bit_exact_vs_oracle():
     """synthetic triangle soup (SURVEY 8(d) C5 at a size the oracle finishes in seconds): primary, shadow and incoherent
     bounce rays"""
