@@ -98,10 +98,10 @@ PRB_DEV void fetchTexel(const float* img, int w, int h, int x, int y, int wrapS,
 PRB_DEV void bsplineWeights(float f, float w[4])
 {
 	const float one_f = 1.0f - f;
-	w[0]			  = (one_f * one_f * one_f) / 6.0f;
+	w[0]			  = fdiv(one_f * one_f * one_f, 6.0f);
 	w[1]			  = 2.0f / 3.0f - 0.5f * f * f * (2.0f - f);
 	w[2]			  = 2.0f / 3.0f - 0.5f * one_f * one_f * (2.0f - one_f);
-	w[3]			  = (f * f * f) / 6.0f;
+	w[3]			  = fdiv(f * f * f, 6.0f);
 }
 // SpectralUpsampler::prepare for one RGB triple, src/core/spectral/SpectralUpsampler.cpp (trilinear lookup in the coefficient cube)
 PRB_DEV void upsamplerPrepare(const DScene& S, const float rgb[3], float coeffs[3])
