@@ -292,12 +292,18 @@ inline bool better(float t, uint32_t e, uint32_t p, const Hit& h)
 // Embree 3 PlueckerIntersector (kernels/geometry/triangle_intersector_pluecker.h), scalar restatement:
 // edge functions of the ray against the triangle edges relative to the ray origin, accepted when all have
 // the same sign within ulp*|U+V+W|; t = (v0.Ng)/(d.Ng) with the "stable" normal; two-sided.
+// Embree writes its vector algebra with msub / madd (common/math/vec3.h: cross = msub(a.y, b.z, a.z * b.y) ..., dot =
+// madd(a.x, b.x, madd(a.y, b.y, a.z * b.z))), which ARE fused multiply-adds in the AVX2 / AVX-512 kernels its ISA dispatch
+// selects on any current host, so the restatement uses explicit std::fma in exactly those places (the build adds -mfma).
+inline float msub(float a, float b, float c) { return std::fma(a, b, -c); }
+inline V3 crossE(V3 a, V3 b) { return mk(msub(a.y, b.z, a.z * b.y), msub(a.z, b.x, a.x * b.z), msub(a.x, b.y, a.y * b.x)); }
+inline float dotE(V3 a, V3 b) { return std::fma(a.x, b.x, std::fma(a.y, b.y, a.z * b.z)); }
 inline V3 stableTriangleNormal(V3 a, V3 b, V3 c)
 {
 	const float ab_x = a.z * b.y, ab_y = a.x * b.z, ab_z = a.y * b.x;
 	const float bc_x = b.z * c.y, bc_y = b.x * c.z, bc_z = b.y * c.x;
-	const V3 cross_ab = mk(a.y * b.z - ab_x, a.z * b.x - ab_y, a.x * b.y - ab_z);
-	const V3 cross_bc = mk(b.y * c.z - bc_x, b.z * c.x - bc_y, b.x * c.y - bc_z);
+	const V3 cross_ab = mk(msub(a.y, b.z, ab_x), msub(a.z, b.x, ab_y), msub(a.x, b.y, ab_z));
+	const V3 cross_bc = mk(msub(b.y, c.z, bc_x), msub(b.z, c.x, bc_y), msub(b.x, c.y, bc_z));
 	const bool sx = std::abs(ab_x) < std::abs(bc_x), sy = std::abs(ab_y) < std::abs(bc_y), sz = std::abs(ab_z) < std::abs(bc_z);
 	return mk(sx ? cross_ab.x : cross_bc.x, sy ? cross_ab.y : cross_bc.y, sz ? cross_ab.z : cross_bc.z);
 }
@@ -305,20 +311,20 @@ inline bool triTest(V3 O, V3 D, float tmin, float tmax, V3 p0, V3 p1, V3 p2, flo
 {
 	const V3 v0 = p0 - O, v1 = p1 - O, v2 = p2 - O;
 	const V3 e0 = v2 - v0, e1 = v0 - v1, e2 = v1 - v2;
-	const float U	= dot(cross(e0, v2 + v0), D);
-	const float V	= dot(cross(e1, v0 + v1), D);
-	const float W	= dot(cross(e2, v1 + v2), D);
+	const float U	= dotE(crossE(e0, v2 + v0), D);
+	const float V	= dotE(crossE(e1, v0 + v1), D);
+	const float W	= dotE(crossE(e2, v1 + v2), D);
 	const float UVW = (U + V) + W;
 	const float eps = PR_EPSILON * std::abs(UVW);
 	const float mn = std::min(U, std::min(V, W)), mx = std::max(U, std::max(V, W));
 	if (!(mn >= -eps || mx <= eps))
 		return false;
 	const V3 Ng		= stableTriangleNormal(e0, e1, e2);
-	const float den = 2 * dot(Ng, D);
+	const float den = 2 * dotE(Ng, D);
 	if (den == 0)
 		return false;
-	const float T = 2 * dot(v0, Ng);
-	t			  = T / den;
+	const float T = 2 * dotE(v0, Ng);
+	t			  = T / den; // (Embree multiplies by a Newton-refined reciprocal here: not reproducible bit for bit)
 	if (!(tmin <= t && t <= tmax))
 		return false;
 	if (UVW == 0) { // degenerate (edge-on / zero-area) configuration: Embree masks rcp(0) to 0
@@ -329,6 +335,16 @@ inline bool triTest(V3 O, V3 D, float tmin, float tmax, V3 p0, V3 p1, V3 p2, flo
 		v = std::min(V / UVW, 1.0f);
 	}
 	return true;
+}
+// instance transform of the ray (Embree xfmPoint / xfmVector, common/math/affinespace.h: madd chains)
+inline V3 xfPointE(const float* m, V3 p)
+{
+	return mk(std::fma(p.x, m[0], std::fma(p.y, m[1], std::fma(p.z, m[2], m[3]))), std::fma(p.x, m[4], std::fma(p.y, m[5], std::fma(p.z, m[6], m[7]))),
+			  std::fma(p.x, m[8], std::fma(p.y, m[9], std::fma(p.z, m[10], m[11]))));
+}
+inline V3 xfVecE(const float* m, V3 p)
+{
+	return mk(std::fma(p.x, m[0], std::fma(p.y, m[1], p.z * m[2])), std::fma(p.x, m[4], std::fma(p.y, m[5], p.z * m[6])), std::fma(p.x, m[8], std::fma(p.y, m[9], p.z * m[10])));
 }
 // Embree 3 SphereIntersector1 (kernels/geometry/sphere_intersector.h), front hit first then back hit
 inline bool sphereTest(V3 O, V3 D, float tmin, float tmax, V3 center, float radius, float& t)
@@ -520,7 +536,7 @@ bool traceScene(const Scene& sc, const Accel& A, V3 O, V3 D, float tmin, float t
 			if (triTest(O, D, tmin, found ? best.t : tmax, v2, v3, v1, t, u, v))
 				consider(e, 0, t, 1 - u, 1 - v);
 		} else { // mesh instance: ray into local space by the inverse transform, direction not re-normalised
-			const V3 lo = xfPoint(en.world_to_local, O), ld = xfVec(en.world_to_local, D);
+			const V3 lo = xfPointE(en.world_to_local, O), ld = xfVecE(en.world_to_local, D);
 			const auto& tris = A.meshTris[en.mesh_id];
 			const OMeshAccel& acc = A.meshAccel[en.mesh_id];
 			auto testTri = [&](const OTri& tr) {
@@ -1323,16 +1339,16 @@ void materialEval(const Scene& sc, uint32_t matID, const MatCtx& c, MatEval& out
 		out.weight = blob(0);
 		out.type   = 3;
 		out.flags  = 0;
-	} else if (d0 || d1) { // the non-delta child alone, scaled by its share
-		materialEvalLeaf(sc, m.node[d0 ? 1 : 0], c, out);
+	} else if (d0 || d1) { // the non-delta child alone, scaled by its share (children may be combinations themselves)
+		materialEval(sc, m.node[d0 ? 1 : 0], c, out);
 		const float share = add ? 0.5f : (d0 ? prob : 1 - prob);
 		out.pdf			  = out.pdf * share;
 		if (!add)
 			out.weight = out.weight * share;
 	} else {
 		MatEval o1, o2;
-		materialEvalLeaf(sc, m.node[0], c, o1);
-		materialEvalLeaf(sc, m.node[1], c, o2);
+		materialEval(sc, m.node[0], c, o1);
+		materialEval(sc, m.node[1], c, o2);
 		out.flags = 0;
 		if (add) {
 			out.pdf	   = (o1.pdf + o2.pdf) / 2.0f;
@@ -1355,7 +1371,7 @@ void materialSample(const Scene& sc, uint32_t matID, const MatCtx& c, Rng& rnd, 
 	const bool add	 = m.type == PRB_MAT_ADD;
 	const float prob = add ? 0.5f : std::min(1.0f, std::max(0.0f, m.f[0]));
 	const bool first = rnd.getFloat() < (add ? 0.5f : 1 - prob);
-	materialSampleLeaf(sc, m.node[first ? 0 : 1], c, rnd, out);
+	materialSample(sc, m.node[first ? 0 : 1], c, rnd, out);
 	const float share = add ? 0.5f : (first ? 1 - prob : prob);
 	if (!add)
 		out.weight = out.weight * share;

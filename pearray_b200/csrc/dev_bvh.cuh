@@ -71,12 +71,17 @@ PRB_DEV bool betterHit(float t, uint32_t e, uint32_t p, const HitRec& h)
 
 // Watertight ray/triangle test (restatement of Embree 3's robust "Pluecker" intersector):
 // edge functions relative to the ray origin, accepted when all share a sign within ulp*|U+V+W|, two sided.
+// Embree writes cross / dot with msub / madd (common/math/vec3.h), fused multiply-adds in the AVX2 / AVX-512 kernels its ISA
+// dispatch selects on current hosts: explicit fmaf in exactly those places, mirrored by std::fma in the oracle.
+PRB_DEV float msubE(float a, float b, float c) { return fmaf(a, b, -c); }
+PRB_DEV V3 crossE(V3 a, V3 b) { return mk(msubE(a.y, b.z, a.z * b.y), msubE(a.z, b.x, a.x * b.z), msubE(a.x, b.y, a.y * b.x)); }
+PRB_DEV float dotE(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 PRB_DEV V3 stableTriangleNormal(V3 a, V3 b, V3 c)
 {
 	const float ab_x = a.z * b.y, ab_y = a.x * b.z, ab_z = a.y * b.x;
 	const float bc_x = b.z * c.y, bc_y = b.x * c.z, bc_z = b.y * c.x;
-	const V3 cross_ab = mk(a.y * b.z - ab_x, a.z * b.x - ab_y, a.x * b.y - ab_z);
-	const V3 cross_bc = mk(b.y * c.z - bc_x, b.z * c.x - bc_y, b.x * c.y - bc_z);
+	const V3 cross_ab = mk(msubE(a.y, b.z, ab_x), msubE(a.z, b.x, ab_y), msubE(a.x, b.y, ab_z));
+	const V3 cross_bc = mk(msubE(b.y, c.z, bc_x), msubE(b.z, c.x, bc_y), msubE(b.x, c.y, bc_z));
 	const bool sx = fabsf(ab_x) < fabsf(bc_x), sy = fabsf(ab_y) < fabsf(bc_y), sz = fabsf(ab_z) < fabsf(bc_z);
 	return mk(sx ? cross_ab.x : cross_bc.x, sy ? cross_ab.y : cross_bc.y, sz ? cross_ab.z : cross_bc.z);
 }
@@ -84,19 +89,19 @@ PRB_DEV bool triTest(V3 O, V3 D, float tmin, float tmax, V3 p0, V3 p1, V3 p2, fl
 {
 	const V3 v0 = p0 - O, v1 = p1 - O, v2 = p2 - O;
 	const V3 e0 = v2 - v0, e1 = v0 - v1, e2 = v1 - v2;
-	const float U	= dot(cross(e0, v2 + v0), D);
-	const float V	= dot(cross(e1, v0 + v1), D);
-	const float W	= dot(cross(e2, v1 + v2), D);
+	const float U	= dotE(crossE(e0, v2 + v0), D);
+	const float V	= dotE(crossE(e1, v0 + v1), D);
+	const float W	= dotE(crossE(e2, v1 + v2), D);
 	const float UVW = (U + V) + W;
 	const float eps = PR_EPSILON * fabsf(UVW);
 	const float mn = fminf(U, fminf(V, W)), mx = fmaxf(U, fmaxf(V, W));
 	if (!(mn >= -eps || mx <= eps))
 		return false;
 	const V3 Ng		= stableTriangleNormal(e0, e1, e2);
-	const float den = 2 * dot(Ng, D);
+	const float den = 2 * dotE(Ng, D);
 	if (den == 0)
 		return false;
-	const float T = 2 * dot(v0, Ng);
+	const float T = 2 * dotE(v0, Ng);
 	t			  = T / den;
 	if (!(tmin <= t && t <= tmax))
 		return false;
@@ -140,6 +145,15 @@ PRB_DEV V3 xfPoint(const float* m, V3 p)
 PRB_DEV V3 xfVec(const float* m, V3 p)
 {
 	return mk((m[0] * p.x + m[1] * p.y) + m[2] * p.z, (m[4] * p.x + m[5] * p.y) + m[6] * p.z, (m[8] * p.x + m[9] * p.y) + m[10] * p.z);
+}
+// the ray into an instance's local space: Embree xfmPoint / xfmVector (common/math/affinespace.h), madd chains
+PRB_DEV V3 xfPointE(const float* m, V3 p)
+{
+	return mk(fmaf(p.x, m[0], fmaf(p.y, m[1], fmaf(p.z, m[2], m[3]))), fmaf(p.x, m[4], fmaf(p.y, m[5], fmaf(p.z, m[6], m[7]))), fmaf(p.x, m[8], fmaf(p.y, m[9], fmaf(p.z, m[10], m[11]))));
+}
+PRB_DEV V3 xfVecE(const float* m, V3 p)
+{
+	return mk(fmaf(p.x, m[0], fmaf(p.y, m[1], p.z * m[2])), fmaf(p.x, m[4], fmaf(p.y, m[5], p.z * m[6])), fmaf(p.x, m[8], fmaf(p.y, m[9], p.z * m[10])));
 }
 PRB_DEV V3 m3mul(const float* m, V3 p)
 {
@@ -383,8 +397,8 @@ struct Trav {
 						stack[sp++] = make_uint2(GRP_EXIT, 0);
 					curEnt = e;
 					if (type == PRB_ENTITY_MESH) { // planes are stored in world space: no transform (plane.cpp:71-94)
-						O	= xfPoint(en.world_to_local, O); // at TLAS level (O, D) is the world-space ray
-						D	= xfVec(en.world_to_local, D);
+						O	= xfPointE(en.world_to_local, O); // at TLAS level (O, D) is the world-space ray
+						D	= xfVecE(en.world_to_local, D);
 						inv = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
 						oct = rayOctant(inv);
 					}
@@ -553,8 +567,8 @@ PRB_DEV bool traverseSmall(const uint4* __restrict__ sm, uint32_t nEnts, bool li
 			V3 lo = O, ld = D;
 			if (h.x == PRB_ENTITY_MESH) { // planes are stored in world space
 				const float m[12] = { r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w };
-				lo				  = xfPoint(m, O);
-				ld				  = xfVec(m, D);
+				lo				  = xfPointE(m, O);
+				ld				  = xfVecE(m, D);
 			}
 			const float4* tp = reinterpret_cast<const float4*>(sm + h.z);
 			for (uint32_t k = 0; k < h.w; ++k, tp += 3) {

@@ -156,8 +156,19 @@ PRB_DEV float srgbLinearize(float x)
 		return fdiv(x, 12.92f) * x;
 	return (float)pow((double)fdiv(x + 0.055f, 1.055f), (double)2.4f);
 }
-__device__ __noinline__ Blob evalImageNode(const DScene& S, const prb_node& n, const Blob& wvl, float u, float v)
+PRB_DEV prb_node loadNode(const DScene& S, uint32_t id)
+{ // 32 bytes as two 128-bit loads
+	const uint4* p = reinterpret_cast<const uint4*>(S.nodes + id);
+	const uint4 a = __ldg(p), b = __ldg(p + 1);
+	prb_node n;
+	n.type = a.x, n.flags = a.y, n.a = a.z, n.b = a.w;
+	n.p[0] = __uint_as_float(b.x), n.p[1] = __uint_as_float(b.y), n.p[2] = __uint_as_float(b.z), n.p[3] = __uint_as_float(b.w);
+	return n;
+}
+// (takes the node id, not the node: a by-reference argument would force the caller's copy of the node into local memory)
+__device__ __noinline__ Blob evalImageNode(const DScene& S, uint32_t nodeID, const Blob& wvl, float u, float v)
 {
+	const prb_node n = loadNode(S, nodeID);
 	const int w = (int)(n.b & 0xFFFFu), h = (int)(n.b >> 16);
 	const float* img = S.pool + n.a;
 	const int interp = (int)n.p[0], wrapS = (int)n.p[1], wrapT = (int)n.p[2];
@@ -223,7 +234,12 @@ PRB_DEV bool checkerSelectsB(const prb_node& n, float u, float v)
 	}
 	return ((int)floorf(cu) + (int)floorf(cv)) % 2 == 0;
 }
-__device__ __noinline__ Blob evalNode(const DScene& S, uint32_t id, const Blob& w, float u, float v)
+// Two out-of-line forms: evalNodeBase knows no image nodes and makes no calls of its own (a leaf function: no register saves
+// around a call -- ncu on the Cornell box: the call to evalImageNode inside the loop doubled the local-memory stores of
+// k_shade and cost 5 % although it is never taken there), evalNodeTex also fetches image textures.  The kernels that inline
+// the Lambert code use evalNodeBase (MatCtx::noImageNodes; the host picks them only for scenes without image nodes).
+template <bool TEX>
+PRB_DEV Blob evalNodeBody(const DScene& S, uint32_t id, const Blob& w, float u, float v)
 {
 	// product of factors: MUL nodes push both operands, CHECKER picks one; leaves multiply into the result
 	uint32_t st[8];
@@ -232,7 +248,8 @@ __device__ __noinline__ Blob evalNode(const DScene& S, uint32_t id, const Blob& 
 	Blob acc = blob(1.0f);
 	bool first = true;
 	while (sp > 0) {
-		const prb_node n = S.nodes[st[--sp]];
+		const uint32_t nodeID = st[--sp];
+		const prb_node n	  = loadNode(S, nodeID);
 		if (n.type == PRB_NODE_MUL) {
 			if (sp + 2 <= 8) {
 				st[sp++] = n.b; // evaluated second: a * b with a first
@@ -242,13 +259,20 @@ __device__ __noinline__ Blob evalNode(const DScene& S, uint32_t id, const Blob& 
 			if (sp < 8)
 				st[sp++] = checkerSelectsB(n, u, v) ? n.b : n.a;
 		} else {
-			const Blob leaf = n.type == PRB_NODE_IMAGE ? evalImageNode(S, n, w, u, v) : evalLeafNode(S, n, w);
-			acc				= first ? leaf : acc * leaf;
-			first			= false;
+			Blob leaf;
+			if (TEX && n.type == PRB_NODE_IMAGE)
+				leaf = evalImageNode(S, nodeID, w, u, v);
+			else
+				leaf = evalLeafNode(S, n, w);
+			acc	  = first ? leaf : acc * leaf;
+			first = false;
 		}
 	}
 	return acc;
 }
+__device__ __noinline__ Blob evalNodeBase(const DScene& S, uint32_t id, const Blob& w, float u, float v) { return evalNodeBody<false>(S, id, w, u, v); }
+__device__ __noinline__ Blob evalNodeTex(const DScene& S, uint32_t id, const Blob& w, float u, float v) { return evalNodeBody<true>(S, id, w, u, v); }
+PRB_DEV Blob evalNode(const DScene& S, uint32_t id, const Blob& w, float u, float v) { return evalNodeTex(S, id, w, u, v); }
 
 // ------------------------------------------------------------------ geometry point (GeometryPoint.h:10-25)
 struct GeomPoint {
@@ -389,6 +413,9 @@ struct MatCtx {
 	// division per wavelength for an upsampled RGB colour) is a copy of the first.  Valid for one vertex (wvl, u, v fixed).
 	mutable uint32_t cachedNode = PRB_INVALID_ID;
 	mutable Blob cachedValue;
+	// set by the kernels that inline the Lambert code (the host only picks them for scenes without image nodes): node
+	// evaluation goes straight to the leaf-only evalNodeBase; a compile-time constant there, so the test folds away
+	bool noImageNodes = false;
 };
 PRB_DEV Blob evalNodeCached(const DScene& S, const MatCtx& c, uint32_t node);
 PRB_DEV uint32_t contribFlags(const prb_material& m) { return (m.flags & PRB_MATF_SPECTRAL_VARYING) ? MSF_SpectralVarying : 0; }
@@ -734,9 +761,9 @@ struct RoughDielectric {
 PRB_DEV Blob evalNodeCached(const DScene& S, const MatCtx& c, uint32_t node)
 {
 	if (!PRB_NODE_CACHE)
-		return evalNode(S, node, c.wvl, c.u, c.v);
+		return c.noImageNodes ? evalNodeBase(S, node, c.wvl, c.u, c.v) : evalNodeTex(S, node, c.wvl, c.u, c.v);
 	if (c.cachedNode != node) {
-		c.cachedValue = evalNode(S, node, c.wvl, c.u, c.v);
+		c.cachedValue = c.noImageNodes ? evalNodeBase(S, node, c.wvl, c.u, c.v) : evalNodeTex(S, node, c.wvl, c.u, c.v);
 		c.cachedNode  = node;
 	}
 	return c.cachedValue;
@@ -1025,7 +1052,25 @@ __device__ __noinline__ void materialSampleLeafT(const DScene& S, uint32_t matID
 PRB_DEV bool isCombination(uint32_t type) { return type == PRB_MAT_BLEND || type == PRB_MAT_ADD; }
 PRB_DEV void materialEvalLeaf(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out) { materialEvalLeafT<-1>(S, matID, c, out); }
 PRB_DEV void materialSampleLeaf(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out) { materialSampleLeafT<-1>(S, matID, c, rnd, out); }
-__device__ __noinline__ void materialEvalCombined(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
+// Children of a combination may be combinations themselves (blend.cpp / add.cpp take any IMaterial).  The device has no
+// recursion budget, so the nesting is unrolled at compile time: a combination at depth DEPTH evaluates combination children
+// with DEPTH - 1; the host refuses materials nested deeper than COMBINE_MAX_DEPTH levels.
+constexpr int COMBINE_MAX_DEPTH = 3;
+template <int DEPTH>
+__device__ __noinline__ void materialEvalCombinedT(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out);
+template <int DEPTH>
+PRB_DEV void materialEvalChild(const DScene& S, uint32_t id, const MatCtx& c, MatEval& out)
+{
+	if constexpr (DEPTH > 1) {
+		if (isCombination(S.materials[id].type)) {
+			materialEvalCombinedT<DEPTH - 1>(S, id, c, out);
+			return;
+		}
+	}
+	materialEvalLeaf(S, id, c, out);
+}
+template <int DEPTH>
+__device__ __noinline__ void materialEvalCombinedT(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out)
 { // out of line: its two child results only occupy stack while a combination is evaluated
 	const prb_material& m = S.materials[matID];
 	const uint32_t type	  = m.type;
@@ -1038,15 +1083,15 @@ __device__ __noinline__ void materialEvalCombined(const DScene& S, uint32_t matI
 		out.type   = 3;
 		out.flags  = 0;
 	} else if (d0 || d1) { // the non-delta child alone, scaled by its share
-		materialEvalLeaf(S, m.node[d0 ? 1 : 0], c, out);
+		materialEvalChild<DEPTH>(S, m.node[d0 ? 1 : 0], c, out);
 		const float share = add ? 0.5f : (d0 ? prob : 1 - prob);
 		out.pdf			  = out.pdf * share;
 		if (!add)
 			out.weight = out.weight * share;
 	} else {
 		MatEval o1, o2;
-		materialEvalLeaf(S, m.node[0], c, o1);
-		materialEvalLeaf(S, m.node[1], c, o2);
+		materialEvalChild<DEPTH>(S, m.node[0], c, o1);
+		materialEvalChild<DEPTH>(S, m.node[1], c, o2);
 		out.flags = 0;
 		if (add) {
 			out.pdf	   = (o1.pdf + o2.pdf) * 0.5f; // (a + b) / 2
@@ -1059,6 +1104,7 @@ __device__ __noinline__ void materialEvalCombined(const DScene& S, uint32_t matI
 		}
 	}
 }
+PRB_DEV void materialEvalCombined(const DScene& S, uint32_t matID, const MatCtx& c, MatEval& out) { materialEvalCombinedT<COMBINE_MAX_DEPTH>(S, matID, c, out); }
 // k_shade is instantiated per KIND: without the combination path for scenes that have no blend / add material (merely having
 // the call in the kernel cost 4-5 % of k_shade on C2 / C4), and with the Lambert code inline for all-Lambert scenes.
 // SHADE_MATERIALS_TYPE + t: every slot the kernel sees has a material of type t (the per-type queues of the staged path)
@@ -1079,17 +1125,28 @@ PRB_DEV void materialEval(const DScene& S, uint32_t matID, const MatCtx& c, MatE
 	}
 }
 __device__ __noinline__ void materialSampleCombined(const DScene& S, uint32_t matID, const MatCtx& c, Rng& rnd, MatSample& out)
-{
-	const prb_material& m = S.materials[matID];
-	const uint32_t type	  = m.type;
-	const bool add		  = type == PRB_MAT_ADD;
-	const float prob	  = add ? 0.5f : fminf(1.0f, fmaxf(0.0f, m.f[0]));
-	const bool first	  = rnd.getFloat() < (add ? 0.5f : 1 - prob);
-	materialSampleLeaf(S, m.node[first ? 0 : 1], c, rnd, out);
-	const float share = add ? 0.5f : (first ? 1 - prob : prob);
-	if (!add)
-		out.weight = out.weight * share;
-	out.pdf = out.pdf * share;
+{ // BlendMaterial / AddMaterial::sample (blend.cpp:112-130, add.cpp:97-113): one random number picks the child at every level;
+  // the shares are applied innermost first, like the nested calls of the reference return
+	float shares[COMBINE_MAX_DEPTH];
+	bool adds[COMBINE_MAX_DEPTH];
+	int depth	= 0;
+	uint32_t id = matID;
+	while (depth < COMBINE_MAX_DEPTH && isCombination(S.materials[id].type)) {
+		const prb_material& m = S.materials[id];
+		const bool add		  = m.type == PRB_MAT_ADD;
+		const float prob	  = add ? 0.5f : fminf(1.0f, fmaxf(0.0f, m.f[0]));
+		const bool first	  = rnd.getFloat() < (add ? 0.5f : 1 - prob);
+		shares[depth]		  = add ? 0.5f : (first ? 1 - prob : prob);
+		adds[depth]			  = add;
+		++depth;
+		id = m.node[first ? 0 : 1];
+	}
+	materialSampleLeaf(S, id, c, rnd, out);
+	for (int i = depth - 1; i >= 0; --i) {
+		if (!adds[i])
+			out.weight = out.weight * shares[i];
+		out.pdf = out.pdf * shares[i];
+	}
 }
 
 template <int KIND>
@@ -1456,7 +1513,33 @@ PRB_DEV bool isInfLight(const prb_light& l) { return l.type != PRB_LIGHT_AREA; }
 PRB_DEV bool isDeltaLight(const prb_light& l) { return l.type == PRB_LIGHT_SUN_DELTA; }
 
 // Light::sample with SamplingInfo + Point (NEE), src/core/light/Light.cpp:108-226
-PRB_DEV void sampleLightInline(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o)
+// EnvironmentLight<UseDistribution = true>::sampleDir / samplePosDir (environment.cpp:83-104): (u, v) from the Distribution2D of
+// the image, direction = Spherical::cartesian_from_uv.  Out of line: the inline light sampling below is part of the
+// all-Lambert k_shade, whose executed footprint bounds it (instruction fetch).
+__device__ __noinline__ void sampleEnvironmentMap(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o)
+{
+	float dx, dy, px, py;
+	rnd.get2D(dx, dy);
+	rnd.get2D(px, py);
+	float u0, u1, pdf;
+	dist2DSampleContinuous(S, l, dx, dy, u0, u1, pdf);
+	const V3 local		 = cartesian_from_uv(u0, u1);
+	const float sinTheta = cr_sin(u1 * PR_PI);
+	const float denom	 = 2 * PR_PI * PR_PI * sinTheta;
+	o.delta				 = false;
+	o.dirPDF_S			 = pdf * ((denom <= PR_EPSILON) ? 0.0f : 1.0f / denom);
+	o.outgoing			 = m3mul(l.normal_matrix, local);
+	o.radiance			 = evalNode(S, l.radiance_node, wvl, u0, u1); // coord.UV = uv
+	o.lightPos			 = P + l.scene_radius * o.outgoing;
+	o.posPDF			 = 1;
+	o.cosLight			 = 1;
+	o.infinite			 = true;
+}
+// ENVMAP: with the image-based environment light and image-capable node evaluation (the generic, out-of-line sampleLight);
+// without, the form the all-Lambert kernels inline -- the host only picks those for scenes without image nodes, and every
+// out-of-line call in their body costs registers there whether it is taken or not
+template <bool ENVMAP>
+PRB_DEV void sampleLightBody(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o)
 {
 	o.delta = false;
 	if (l.type == PRB_LIGHT_SKY) { // SkyLight::sampleDir / samplePosDir, sky.cpp:82-113
@@ -1509,25 +1592,17 @@ PRB_DEV void sampleLightInline(const DScene& S, const prb_light& l, V3 P, const 
 		return;
 	}
 	if (l.type == PRB_LIGHT_ENV) { // environment.cpp sampleDir / samplePosDir, :83-104
+		if (ENVMAP && l.dist_w) { // UseDistribution (image based radiance)
+			sampleEnvironmentMap(S, l, P, wvl, rnd, o);
+			return;
+		}
 		float dx, dy, px, py;
 		rnd.get2D(dx, dy);
 		rnd.get2D(px, py);
-		V3 local;
-		if (l.dist_w) { // UseDistribution: image based radiance
-			float u0, u1, pdf;
-			dist2DSampleContinuous(S, l, dx, dy, u0, u1, pdf);
-			local				 = cartesian_from_uv(u0, u1);
-			const float sinTheta = cr_sin(u1 * PR_PI);
-			const float denom	 = 2 * PR_PI * PR_PI * sinTheta;
-			o.dirPDF_S			 = pdf * ((denom <= PR_EPSILON) ? 0.0f : 1.0f / denom);
-			dx					 = u0;
-			dy					 = u1;
-		} else {
-			local	   = cos_hemi(dx, dy);
-			o.dirPDF_S = cos_hemi_pdf(local.z);
-		}
+		const V3 local = cos_hemi(dx, dy);
+		o.dirPDF_S	   = cos_hemi_pdf(local.z);
 		o.outgoing	   = m3mul(l.normal_matrix, local);
-		o.radiance	   = evalNode(S, l.radiance_node, wvl, dx, dy);
+		o.radiance	   = ENVMAP ? evalNodeTex(S, l.radiance_node, wvl, dx, dy) : evalNodeBase(S, l.radiance_node, wvl, dx, dy);
 		o.lightPos	   = P + l.scene_radius * o.outgoing;
 		o.posPDF	   = 1;
 		o.cosLight	   = 1;
@@ -1604,11 +1679,12 @@ PRB_DEV void sampleLightInline(const DScene& S, const prb_light& l, V3 P, const 
 	o.outgoing = normalized(pos - P);
 	o.dirPDF_S = 1;
 	o.cosLight = fminf(1.0f, fmaxf(-1.0f, -dot(o.outgoing, gp.N)));
-	o.radiance = evalNode(S, S.emissions[l.emission_id].radiance_node, wvl, gp.u, gp.v);
+	o.radiance = ENVMAP ? evalNodeTex(S, S.emissions[l.emission_id].radiance_node, wvl, gp.u, gp.v) : evalNodeBase(S, S.emissions[l.emission_id].radiance_node, wvl, gp.u, gp.v);
 	o.posPDF   = pdfA;
 	o.lightPos = pos;
 }
-__device__ __noinline__ void sampleLight(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o) { sampleLightInline(S, l, P, wvl, rnd, o); }
+PRB_DEV void sampleLightInline(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o) { sampleLightBody<false>(S, l, P, wvl, rnd, o); }
+__device__ __noinline__ void sampleLight(const DScene& S, const prb_light& l, V3 P, const Blob& wvl, Rng& rnd, LightSample& o) { sampleLightBody<true>(S, l, P, wvl, rnd, o); }
 PRB_DEV void envEval(const DScene& S, const prb_light& l, V3 dir, uint32_t depth, const Blob& wvl, Blob& rad, float& pdfS)
 { // EnvironmentLight::eval (no distribution), environment.cpp
 	const V3 ld = m3mul(l.inv_normal_matrix, dir);

@@ -69,6 +69,7 @@ struct prb_ctx {
 	cudaEvent_t evA = nullptr, evB = nullptr, evT0 = nullptr, evT1 = nullptr;
 	int smCount = 148;
 	bool allLambert = false;	 // every material is PRB_MAT_DIFFUSE: k_shade with the Lambert code inline
+	bool hasImageNodes = false;	 // some node is an image texture: no kernel with the Lambert code inline (leaf-only node evaluation)
 	bool mixedMaterials = false; // the scene mixes material types: k_shade sorts larger windows (launchShade)
 	int gridTrace = 148 * 4, gridTraceClosest = 148 * 4, gridTraceAny = 148 * 4; // persistent grids: SMs x resident blocks
 	bool haveScene = false;
@@ -449,6 +450,12 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	S.upsamplerRes	  = d->upsampler_res;
 	c->mixedMaterials = false;
 	c->allLambert	  = d->n_materials > 0 && d->materials[0].type == PRB_MAT_DIFFUSE;
+	c->hasImageNodes = false;
+	for (uint32_t i = 0; i < d->n_nodes; ++i) // the kernels with the Lambert code inline evaluate nodes without the image-texture path
+		if (d->nodes[i].type == PRB_NODE_IMAGE)
+			c->hasImageNodes = true;
+	if (c->hasImageNodes)
+		c->allLambert = false;
 	for (uint32_t i = 1; i < d->n_materials; ++i)
 		if (d->materials[i].type != d->materials[0].type)
 			c->mixedMaterials = true;
@@ -687,7 +694,12 @@ static void launchShadeStaged(prb_ctx* c, const WFState& W, cudaStream_t s)
 		if (q == 0xFF)
 			continue;
 		switch (t) {
-		case PRB_MAT_DIFFUSE: launchStageKernels<SHADE_MATERIALS_LAMBERT>(c, W, q, s); break;
+		case PRB_MAT_DIFFUSE:
+			if (c->hasImageNodes)
+				launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_DIFFUSE>(c, W, q, s);
+			else
+				launchStageKernels<SHADE_MATERIALS_LAMBERT>(c, W, q, s);
+			break;
 		case PRB_MAT_DIELECTRIC: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_DIELECTRIC>(c, W, q, s); break;
 		case PRB_MAT_CONDUCTOR: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_CONDUCTOR>(c, W, q, s); break;
 		case PRB_MAT_ROUGHCONDUCTOR: launchStageKernels<SHADE_MATERIALS_TYPE + PRB_MAT_ROUGHCONDUCTOR>(c, W, q, s); break;

@@ -433,6 +433,15 @@ public:
 	{
 	}
 	bool hasOnlyDeltaDistribution() const override { return mMaterials[0]->hasOnlyDeltaDistribution() && mMaterials[1]->hasOnlyDeltaDistribution(); }
+	// levels of combinations below and including this one
+	int depth() const
+	{
+		int d = 0;
+		for (const auto& m : mMaterials)
+			if (const auto c = std::dynamic_pointer_cast<CombineMaterial>(m))
+				d = std::max(d, c->depth());
+		return d + 1;
+	}
 	void describe(prb_material& out, NodeEmitter&) const override
 	{
 		out.type	= mAdd ? PRB_MAT_ADD : PRB_MAT_BLEND;
@@ -468,12 +477,13 @@ public:
 			PR_LOG(L_ERROR) << "Valid material1 or material2 parameters for blend material missing" << std::endl;
 			return nullptr;
 		}
-		if (std::dynamic_pointer_cast<CombineMaterial>(mat1) || std::dynamic_pointer_cast<CombineMaterial>(mat2)) {
-			PR_LOG(L_ERROR) << "blend / add of a blend / add material is not supported on the device path (no nested material evaluation)" << std::endl;
+		const float factor = mAdd ? 0.5f : constScalar(ctx.lookupScalarNode("factor", 0.5f), "factor");
+		auto mat		   = std::make_shared<CombineMaterial>(mAdd, mat1, mat2, factor);
+		if (mat->depth() > 3) { // COMBINE_MAX_DEPTH of csrc/dev_shade.cuh: the device unrolls the nesting at compile time
+			PR_LOG(L_ERROR) << "blend / add materials nested more than 3 levels deep are not supported on the device path" << std::endl;
 			return nullptr;
 		}
-		const float factor = mAdd ? 0.5f : constScalar(ctx.lookupScalarNode("factor", 0.5f), "factor");
-		return std::make_shared<CombineMaterial>(mAdd, mat1, mat2, factor);
+		return mat;
 	}
 	const std::vector<std::string>& getNames() const override
 	{

@@ -8,10 +8,10 @@ import pytest
 import pearray_b200 as prb
 from conftest import ROOT, scene_path
 from oracle_binding import OracleScene
-from scene_strings import FURNACE, MATERIAL_ZOO, MATERIAL_ZOO2, MATERIAL_ZOO3, SKYSUN_ZOO
+from scene_strings import FURNACE, LPE_ZOO, MATERIAL_ZOO, MATERIAL_ZOO2, MATERIAL_ZOO3, MATERIAL_ZOO4, SKYSUN_ZOO
 
 GOLDEN = ["c0_evaluation", "c1_sphere", "c2_cornellbox", "c3_cornellbox_glassy", "c4_boltsandgears", "c4b_complex_env", "c4c_complex", "material_zoo",
-          "skysun_zoo", "material_zoo2", "material_zoo3"]
+          "skysun_zoo", "material_zoo2", "material_zoo3", "material_zoo4", "lpe_zoo"]
 STAT_NAMES = ["camera_ray_count", "light_ray_count", "primary_ray_count", "bounce_ray_count", "shadow_ray_count", "monochrome_ray_count",
               "pixel_sample_count", "entity_hit_count", "background_hit_count", "camera_depth_count", "light_depth_count"]
 
@@ -21,6 +21,10 @@ def load_scene(name):
         return prb.Scene.from_string(MATERIAL_ZOO)
     if name == "material_zoo3":
         return prb.Scene.from_string(MATERIAL_ZOO3)
+    if name == "material_zoo4":
+        return prb.Scene.from_string(MATERIAL_ZOO4)
+    if name == "lpe_zoo":
+        return prb.Scene.from_string(LPE_ZOO)
     if name == "material_zoo2":
         return prb.Scene.from_string(MATERIAL_ZOO2)
     if name == "skysun_zoo":

@@ -501,3 +501,53 @@ def test_agh_mapper_follows_its_closed_form(cmis):
         span = 440.0
         for k in range(1, 4):
             assert np.allclose(wvl[:, k], 390.0 + np.mod(wvl[:, 0] - 390.0 + k * span / 4, span), atol=2e-3)
+
+
+def test_nested_blend_and_add():
+    """children of a blend / add may be blends / adds themselves: the nested result is the composition of the one-level rules"""
+    from scene_strings import MATERIAL_ZOO4
+    scene = prb.Scene.from_string(MATERIAL_ZOO4)
+    ora = ob.OracleScene(scene)
+    d = scene.desc.contents
+    V, L = nrm(0.3, 0.2, 0.9), nrm(-0.4, 0.1, 0.8)
+    ev = lambda m: ora.material_eval(_query(scene, m, V, L))[0]
+    arr = lambda x: np.array(list(x), np.float32)
+    combos = [i for i in range(d.n_materials) if d.materials[i].type in (8, 9)]
+    nested = [i for i in combos if d.materials[d.materials[i].node[0]].type in (8, 9) or d.materials[d.materials[i].node[1]].type in (8, 9)]
+    assert len(nested) == 4
+    n2, n3, n_delta_first, n_all = nested
+    half = np.float32(0.5)
+    # n2 = blend(b_none, m_oren, 0.5): (1 - f) * blend(...) + f * oren
+    m = d.materials[n2]
+    e, e0, e1 = ev(n2), ev(m.node[0]), ev(m.node[1])
+    assert d.materials[m.node[0]].type == 8
+    assert np.array_equal(arr(e.weight), (1 - half) * arr(e0.weight) + half * arr(e1.weight))
+    assert np.array_equal(arr(e.pdf_s), (1 - half) * arr(e0.pdf_s) + half * arr(e1.pdf_s))
+    # n3 = add(n2, a_first): three levels; weights add, pdfs average
+    m = d.materials[n3]
+    e, e0, e1 = ev(n3), ev(m.node[0]), ev(m.node[1])
+    assert np.array_equal(arr(e.weight), arr(e0.weight) + arr(e1.weight)) and np.array_equal(arr(e.pdf_s), (arr(e0.pdf_s) + arr(e1.pdf_s)) / 2)
+    # n_delta_first = blend(b_all [all delta], n2, 0.7): MaterialDelta::First -> the second (nested) child scaled by f
+    m = d.materials[n_delta_first]
+    assert m.flags & 0x100 and not m.flags & 0x200
+    f = np.float32(m.f[0])
+    e, e1 = ev(n_delta_first), ev(m.node[1])
+    assert np.array_equal(arr(e.weight), arr(e1.weight) * f) and np.array_equal(arr(e.pdf_s), arr(e1.pdf_s) * f)
+    # n_all: every leaf below is delta -> only-delta material, its samples are delta
+    assert d.materials[n_all].flags & 0x20
+    assert ora.material_sample(_query(scene, n_all, V))[0].flags & 0x2
+    # sampling n3 draws one number per level; whatever leaf is reached, the pdf carries the product of the shares: compare with the
+    # pdf the eval of the same direction reports for non-delta samples of a tree without delta leaves (n2)
+    for seed in [(0x9E3779B97F4A7C15 * k) & 0xFFFFFFFFFFFFFFFF for k in range(1, 21)]:
+        s = ora.material_sample(_query(scene, n2, V, seed=seed))[0]
+        if s.flags & 0x2 or not np.all(np.isfinite(arr(s.pdf_s))) or arr(s.pdf_s)[0] <= 0:
+            continue
+        shares = {np.float32(0.5) * np.float32(0.7), np.float32(0.5) * np.float32(0.3), np.float32(0.5)}  # b_none: 0.7 / 0.3, n2: 0.5
+        assert any(np.isclose(arr(s.pdf_s)[0] / sh, arr(ora.material_eval(_query(scene, leaf, V, arr(s.L)))[0].pdf_s)[0], rtol=1e-5)
+                   for sh in shares for leaf in range(d.n_materials) if d.materials[leaf].type not in (8, 9)), seed
+    # four levels are refused by the loader (the device unrolls three)
+    deep = MATERIAL_ZOO4.replace(" (entity :name 'floor'", " (material :name 'n4' :type 'blend' :material1 'n3' :material2 'm_diffuse')\n (entity :name 'floor'")
+    deep = deep.replace(":material 'a_none' :position", ":material 'n4' :position")
+    sc4 = prb.Scene.from_string(deep)
+    d4 = sc4.desc.contents
+    assert d4.n_materials == d.n_materials  # n4 was not created (logged as an error)

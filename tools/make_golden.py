@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pearray_b200 as prb  # noqa: E402
 from oracle_binding import OracleScene  # noqa: E402
-from scene_strings import MATERIAL_ZOO, MATERIAL_ZOO2, MATERIAL_ZOO3, SKYSUN_ZOO  # noqa: E402
+from scene_strings import LPE_ZOO, MATERIAL_ZOO, MATERIAL_ZOO2, MATERIAL_ZOO3, MATERIAL_ZOO4, SKYSUN_ZOO  # noqa: E402
 
 GOLDEN_ITER = 4
 GOLDEN_TILE = 48
@@ -99,10 +99,14 @@ def import_reference_image():
 
 
 if __name__ == "__main__":
-    import_reference_image()
+    only = set(sys.argv[1:])  # python tools/make_golden.py [name ...]: only the named fixtures
+    want = lambda n: not only or n in only
+    if want("cbox_reference_blocks"):
+        import_reference_image()
     for n in ("c0_evaluation", "c1_sphere", "c2_cornellbox", "c3_cornellbox_glassy", "c4_boltsandgears", "c4b_complex_env", "c4c_complex"):
-        make(n, prb.Scene.from_file(os.path.join(ROOT, "scenes", n + ".prc")))
-    make("material_zoo", prb.Scene.from_string(MATERIAL_ZOO))
-    make("skysun_zoo", prb.Scene.from_string(SKYSUN_ZOO))
-    make("material_zoo2", prb.Scene.from_string(MATERIAL_ZOO2))
-    make("material_zoo3", prb.Scene.from_string(MATERIAL_ZOO3))
+        if want(n):
+            make(n, prb.Scene.from_file(os.path.join(ROOT, "scenes", n + ".prc")))
+    for n, src in (("material_zoo", MATERIAL_ZOO), ("skysun_zoo", SKYSUN_ZOO), ("material_zoo2", MATERIAL_ZOO2), ("material_zoo3", MATERIAL_ZOO3),
+                   ("material_zoo4", MATERIAL_ZOO4), ("lpe_zoo", LPE_ZOO)):
+        if want(n):
+            make(n, prb.Scene.from_string(src))
