@@ -147,9 +147,15 @@ template <int KIND>
 static void launchStageKernels(prb_ctx* c, const WFState& W, uint32_t queue, cudaStream_t s)
 {
 	const int grid = (int)((c->nSlots + 127) / 128);
-	if (c->queueWantsNEE[queue]) // (a queue of delta-only materials never does NEE)
-		k_shade_nee<KIND><<<grid, 128, 0, s>>>(c->S, W, queue);
-	k_shade_scatter<KIND><<<grid, 128, 0, s>>>(c->S, W, queue);
+	if (c->S.nLPE) {
+		if (c->queueWantsNEE[queue]) // (a queue of delta-only materials never does NEE)
+			k_shade_nee<KIND, true><<<grid, 128, 0, s>>>(c->S, W, queue);
+		k_shade_scatter<KIND, true><<<grid, 128, 0, s>>>(c->S, W, queue);
+	} else {
+		if (c->queueWantsNEE[queue])
+			k_shade_nee<KIND, false><<<grid, 128, 0, s>>>(c->S, W, queue);
+		k_shade_scatter<KIND, false><<<grid, 128, 0, s>>>(c->S, W, queue);
+	}
 }
 
 extern "C" {
@@ -688,7 +694,10 @@ static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
 // type's queue (grids sized for the worst case; blocks past the end of a queue return at once)
 static void launchShadeStaged(prb_ctx* c, const WFState& W, cudaStream_t s)
 {
-	k_shade_geom<<<(int)((c->nSlots + 127) / 128), 128, 0, s>>>(c->S, W);
+	if (c->S.nLPE)
+		k_shade_geom<true><<<(int)((c->nSlots + 127) / 128), 128, 0, s>>>(c->S, W);
+	else
+		k_shade_geom<false><<<(int)((c->nSlots + 127) / 128), 128, 0, s>>>(c->S, W);
 	for (uint32_t t = 0; t < (uint32_t)SHADE_QUEUES; ++t) {
 		const uint32_t q = W.queueOfType[t];
 		if (q == 0xFF)
