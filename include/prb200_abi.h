@@ -308,7 +308,9 @@ typedef struct prb_camera {
 	float dir[3];	/* perspective: mFocalDistance_Cache; orthographic: mDirection_Cache (normalised) */
 	float near_t, far_t;
 	uint32_t type; /* PRB_CAMERA_* */
-	uint32_t _pad;
+	uint32_t has_dof; /* PerspectiveCamera<HasDOF = true> (perspective.cpp:66-75): the lens sample moves the origin inside the aperture */
+	float aperture_x[3]; /* mXApertureRadius_Cache */
+	float aperture_y[3]; /* mYApertureRadius_Cache */
 } prb_camera;
 
 typedef struct prb_settings { /* RenderSettings.cpp:11-33 + DiParameters direct.cpp:34-39 */

@@ -1627,9 +1627,16 @@ void constructCameraRay(const Scene& sc, uint32_t px, uint32_t py, uint32_t iter
 		o.origin = (ld3(d.camera.origin) + ld3(d.camera.right) * nx) + ld3(d.camera.up) * ny;
 		o.dir	 = ld3(d.camera.dir);
 	} else {
-		const V3 dir = (ld3(d.camera.right) * nx + ld3(d.camera.up) * ny) + ld3(d.camera.dir);
-		o.origin	 = ld3(d.camera.origin);
-		o.dir		 = normalized(dir);
+		V3 dir	 = (ld3(d.camera.right) * nx + ld3(d.camera.up) * ny) + ld3(d.camera.dir);
+		o.origin = ld3(d.camera.origin);
+		if (d.camera.has_dof) { // PerspectiveCamera<HasDOF = true>::constructRay, perspective.cpp:66-75
+			const float t = 2 * PR_PI * lx;
+			const float s = cr_sin(t), c = cr_cos(t);
+			const V3 e	  = (ld3(d.camera.aperture_x) * ly) * s + (ld3(d.camera.aperture_y) * ly) * c;
+			o.origin	  = o.origin + e;
+			dir			  = dir - e;
+		}
+		o.dir = normalized(dir);
 	}
 	o.tmin		   = d.camera.near_t;
 	o.tmax		   = d.camera.far_t;

@@ -45,7 +45,8 @@ class Settings(C.Structure):
 
 class Camera(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("right", C.c_float * 3), ("up", C.c_float * 3), ("dir", C.c_float * 3),
-                ("near_t", C.c_float), ("far_t", C.c_float), ("type", C.c_uint32), ("_pad", C.c_uint32)]
+                ("near_t", C.c_float), ("far_t", C.c_float), ("type", C.c_uint32), ("has_dof", C.c_uint32),
+                ("aperture_x", C.c_float * 3), ("aperture_y", C.c_float * 3)]
 
 
 class Sampler(C.Structure):

@@ -1397,9 +1397,16 @@ PRB_DEV void constructCameraRay(const DScene& S, uint32_t px, uint32_t py, uint3
 		o.origin = (ld3(S.camera.origin) + ld3(S.camera.right) * nx) + ld3(S.camera.up) * ny;
 		o.dir	 = ld3(S.camera.dir);
 	} else {
-		const V3 dir = (ld3(S.camera.right) * nx + ld3(S.camera.up) * ny) + ld3(S.camera.dir);
-		o.origin	 = ld3(S.camera.origin);
-		o.dir		 = normalized(dir);
+		V3 dir	 = (ld3(S.camera.right) * nx + ld3(S.camera.up) * ny) + ld3(S.camera.dir);
+		o.origin = ld3(S.camera.origin);
+		if (S.camera.has_dof) { // PerspectiveCamera<HasDOF = true>::constructRay, perspective.cpp:66-75
+			float s, c;
+			cr_sincos(2 * PR_PI * lx, &s, &c);
+			const V3 e = (ld3(S.camera.aperture_x) * ly) * s + (ld3(S.camera.aperture_y) * ly) * c;
+			o.origin   = o.origin + e;
+			dir		   = dir - e;
+		}
+		o.dir = normalized(dir);
 	}
 	o.tmin		   = S.camera.near_t;
 	o.tmax		   = S.camera.far_t;

@@ -224,13 +224,15 @@ public:
 };
 
 // ------------------------------------------------------------------ camera
-class PerspectiveCamera : public ICamera { // plugins/main/cameras/perspective.cpp:15-137 (no-DOF branch)
+class PerspectiveCamera : public ICamera { // plugins/main/cameras/perspective.cpp:15-137 (both the HasDOF and the pinhole form)
 public:
-	PerspectiveCamera(const std::string& name, const Transformf& t, float w, float h, float nearT, float farT, const Vector3f& ld, const Vector3f& lr,
-					  const Vector3f& lu)
+	PerspectiveCamera(const std::string& name, const Transformf& t, float w, float h, float fstop, float apert, float nearT, float farT, const Vector3f& ld,
+					  const Vector3f& lr, const Vector3f& lu)
 		: ICamera(name, t)
 		, mWidth(w)
 		, mHeight(h)
+		, mFStop(fstop)
+		, mApertureRadius(apert)
 		, mNearT(nearT)
 		, mFarT(farT)
 		, mLD(ld)
@@ -241,23 +243,38 @@ public:
 	std::string type() const override { return "perspective"; }
 	void describe(prb_camera& out) const override
 	{ // cache(), perspective.cpp:84-113
-		const Vector3f dir	 = transform().linear() * mLD;
-		const Vector3f right = (transform().linear() * mLR) * (0.5f * mWidth);
-		const Vector3f up	 = (transform().linear() * mLU) * (0.5f * mHeight);
-		const Vector3f o	 = transform().translation();
-		for (int i = 0; i < 3; ++i) {
-			out.origin[i] = o[i];
-			out.right[i]  = right[i];
-			out.up[i]	  = up[i];
-			out.dir[i]	  = dir[i];
+		const bool hasDOF = mApertureRadius > PR_EPSILON && mFStop > PR_EPSILON; // PerspectiveCameraPlugin::create, :156
+		Vector3f dir	  = transform().linear() * mLD;
+		Vector3f right	  = transform().linear() * mLR;
+		Vector3f up		  = transform().linear() * mLU;
+		Vector3f apx(0, 0, 0), apy(0, 0, 0);
+		if (!hasDOF) {
+			right = right * (0.5f * mWidth);
+			up	  = up * (0.5f * mHeight);
+		} else {
+			dir	  = dir * (mFStop + 1); // mFocalDistance_Cache
+			apx	  = right * mApertureRadius;
+			apy	  = up * mApertureRadius;
+			right = right * (0.5f * mWidth * (mFStop + 1));
+			up	  = up * (0.5f * mHeight * (mFStop + 1));
 		}
-		out.near_t = mNearT;
-		out.far_t  = mFarT;
-		out.type   = PRB_CAMERA_PERSPECTIVE;
+		const Vector3f o = transform().translation();
+		for (int i = 0; i < 3; ++i) {
+			out.origin[i]	  = o[i];
+			out.right[i]	  = right[i];
+			out.up[i]		  = up[i];
+			out.dir[i]		  = dir[i];
+			out.aperture_x[i] = apx[i];
+			out.aperture_y[i] = apy[i];
+		}
+		out.near_t	= mNearT;
+		out.far_t	= mFarT;
+		out.type	= PRB_CAMERA_PERSPECTIVE;
+		out.has_dof = hasDOF ? 1u : 0u;
 	}
 
 private:
-	float mWidth, mHeight, mNearT, mFarT;
+	float mWidth, mHeight, mFStop, mApertureRadius, mNearT, mFarT;
 	Vector3f mLD, mLR, mLU;
 };
 class OrthoCamera : public ICamera { // plugins/main/cameras/ortho.cpp:15-84
@@ -319,13 +336,9 @@ public:
 		const ParameterGroup& params = ctx.parameters();
 		const float apr				 = params.getNumber("aperture_radius", 0.05f);
 		const float fstop			 = params.getNumber("fstop", 0);
-		if (apr > PR_EPSILON && fstop > PR_EPSILON) {
-			PR_LOG(L_ERROR) << "perspective camera: depth of field is not supported on the device path" << std::endl;
-			return nullptr;
-		}
 		// ICamera::DefaultDirection (0,1,0) /Right (1,0,0) /Up (0,0,1) (src/core/camera/ICamera.cpp:5-7) and NEAR/FAR defaults (perspective.cpp:12-13)
 		return std::make_shared<PerspectiveCamera>(params.getString("name", "__unnamed__"), ctx.transform(), params.getNumber("width", 1),
-												   params.getNumber("height", 1), params.getNumber("near", 0.000001f), params.getNumber("far", PR_INF),
+												   params.getNumber("height", 1), fstop, apr, params.getNumber("near", 0.000001f), params.getNumber("far", PR_INF),
 												   params.getVector3f("local_direction", Vector3f(0, 1, 0)), params.getVector3f("local_right", Vector3f(1, 0, 0)),
 												   params.getVector3f("local_up", Vector3f(0, 0, 1)));
 	}
@@ -334,7 +347,10 @@ public:
 		static std::vector<std::string> names({ "standard_camera", "standard", "default", "perspective" });
 		return names;
 	}
-	std::string specification(const std::string&) const override { return "Perspective Camera: width, height, near, far, local_direction, local_right, local_up"; }
+	std::string specification(const std::string&) const override
+	{
+		return "Perspective Camera: width, height, fstop (0), aperture_radius (0.05), near, far, local_direction, local_right, local_up";
+	}
 };
 
 // ------------------------------------------------------------------ emission

@@ -281,3 +281,7 @@ NESTED_MATERIALS = """ (material :name 'n2' :type 'blend' :material1 'b_none' :m
 MATERIAL_ZOO4 = (MATERIAL_ZOO3.replace(" (entity :name 'floor'", NESTED_MATERIALS + " (entity :name 'floor'")
                  .replace(":material 'b_none' :position", ":material 'n2' :position").replace(":material 'b_first' :position", ":material 'n3' :position")
                  .replace(":material 'b_second' :position", ":material 'n_delta_first' :position").replace(":material 'b_all' :position", ":material 'n_all' :position"))
+
+
+# depth of field (PerspectiveCamera<HasDOF>, perspective.cpp:66-75): the material zoo through a lens; {dof} = camera options
+DOF_ZOO = MATERIAL_ZOO.replace(":near 0.1 :far 100", ":near 0.1 :far 100 {dof}")

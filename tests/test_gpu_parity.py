@@ -90,6 +90,25 @@ def test_film_vs_golden(name, shading):
     assert [int(getattr(st, k)) for k in STAT_NAMES] == [int(v) for v in g["stats"]]
 
 
+def test_depth_of_field_camera_rays_and_film_bit_exact():
+    """PerspectiveCamera<HasDOF = true> (perspective.cpp:66-75): the lens sample moves the ray origin inside the aperture"""
+    from scene_strings import DOF_ZOO
+    scene = prb.Scene.from_string(DOF_ZOO.format(dof=":fstop 3 :aperture_radius 0.08"))
+    assert scene.desc.contents.camera.has_dof == 1
+    ctx = make_ctx(scene)
+    ora = OracleScene(scene)
+    tiles = [(0, 0, scene.width, scene.height)]
+    for it in (0, 5):
+        org, dr, wvl, pix = ctx.generate_camera_rays(tiles, it)
+        oorg, odr, owvl, opix = ora.generate_camera_rays(tiles, it)
+        assert np.array_equal(org.view(np.uint32), oorg.view(np.uint32)) and np.array_equal(dr.view(np.uint32), odr.view(np.uint32))
+        assert np.ptp(org, axis=0).max() > 0.05  # the origins really spread over the aperture
+    ctx.render_tiles(tiles, 0, 4)
+    ref = ora.render(tiles, 0, 4)
+    assert np.array_equal(ctx.film()[0].view(np.uint32), ref["filtered"].view(np.uint32))
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
+
+
 def test_camera_rays_bit_exact():
     scene = load_scene("c2_cornellbox")
     ctx = make_ctx(scene)

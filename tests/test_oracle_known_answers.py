@@ -551,3 +551,28 @@ def test_nested_blend_and_add():
     sc4 = prb.Scene.from_string(deep)
     d4 = sc4.desc.contents
     assert d4.n_materials == d.n_materials  # n4 was not created (logged as an error)
+
+
+def test_depth_of_field_rays_focus_on_the_focal_plane():
+    """PerspectiveCamera<HasDOF> (perspective.cpp:45-113): with the same seeds a lens camera draws the same film and lens samples
+    as the pinhole camera; its ray starts inside the aperture disc and crosses the pinhole ray of the same sample on the focal
+    plane, (fstop + 1) x |direction| in front of the camera"""
+    from scene_strings import DOF_ZOO
+    fstop, apr = 3.0, 0.08
+    pin = prb.Scene.from_string(DOF_ZOO.format(dof=""))
+    dof = prb.Scene.from_string(DOF_ZOO.format(dof=":fstop %g :aperture_radius %g" % (fstop, apr)))
+    assert pin.desc.contents.camera.has_dof == 0 and dof.desc.contents.camera.has_dof == 1
+    tiles = [(0, 0, pin.width, pin.height)]
+    po, pd, pw, _ = ob.OracleScene(pin).generate_camera_rays(tiles, 2)
+    do, dd, dw, _ = ob.OracleScene(dof).generate_camera_rays(tiles, 2)
+    assert np.array_equal(pw, dw)  # same wavelengths: the random streams stay in step
+    cam = np.array([0, 0, 4.0])
+    fwd = np.array([0, 0, -1.0])
+    assert np.allclose(po, cam)
+    off = do.astype(np.float64) - cam
+    assert np.abs(off @ fwd).max() < 1e-6 and np.linalg.norm(off, axis=1).max() <= apr * 1.0001 and np.linalg.norm(off, axis=1).max() > 0.5 * apr
+    depth = fstop + 1  # |local_direction| = 1
+    on_plane_pin = cam + pd.astype(np.float64) * (depth / (pd.astype(np.float64) @ fwd))[:, None]
+    t = (depth - off @ fwd) / (dd.astype(np.float64) @ fwd)
+    on_plane_dof = do.astype(np.float64) + dd.astype(np.float64) * t[:, None]
+    assert np.abs(on_plane_dof - on_plane_pin).max() < 2e-5
