@@ -44,8 +44,8 @@ struct DScene { // device pointers + by-value small structs; passed to kernels b
 	uint32_t hasCombined; // any blend / add material in the scene (keeps the check off the path of scenes without them)
 	// tiny scenes (<= SMALL_MAX_TRIS triangles in <= SMALL_MAX_ENTS entities: the Cornell boxes and the sphere scene of the
 	// reference's examples): a flat list of entity headers + their local-space triangles for the BVH-free trace kernel
-	const uint4* small; // nSmallEnts x 4 uint4 headers, then the triangles (3 x float4 each)
-	uint32_t nSmallEnts, nSmallU4;
+	const uint4* small; // nSmallEnts x 4 uint4 headers; the padded world-space boxes of the nSmallFaces faces (lo, hi as float4; lo.w = first triangle, hi.w = triangle count; list padded to a multiple of 8); the triangles (3 x float4 each; c.w = index of the entity header)
+	uint32_t nSmallEnts, nSmallFaces, nSmallU4;
 	// light path expressions (prb_scene_desc::lpe): dense DFA tables, bytes
 	const uint8_t* lpeTables;
 	uint32_t nLPE;
@@ -538,43 +538,112 @@ PRB_DEV bool traverseScene(const DScene& S, bool live, bool anyHit, V3 wO, V3 wD
 	return tr.hit();
 }
 
-// BVH-free closest / any hit for tiny scenes: every lane tests its ray against EVERY entity and triangle of the scene, read
-// from shared memory at warp-uniform addresses (broadcast loads, no divergence, no stack, no node tests).  For the
-// 32-triangle Cornell box a BVH traversal spends ~4900 warp instructions per warp of rays at 20 of 32 lanes, almost all of it
-// TLAS -> BLAS entries and exits of eight tiny instances; the exhaustive loop needs ~3000 at full lanes.  Same triangle
-// test in the same (instance-local) space and the same (t, entity, prim) order as the traversal: bit-identical results.
-PRB_DEV bool traverseSmall(const uint4* __restrict__ sm, uint32_t nEnts, bool live, bool anyHit, V3 O, V3 D, float tmin, float tmax, HitRec& best)
+// BVH-free closest / any hit for tiny scenes (flat list in shared memory, DScene::small), in two phases:
+//   1. every lane tests its ray against the padded world-space box of EVERY face (a triangle, or the two triangles of a
+//      quad / plane: warp-uniform broadcast loads, ~25 instructions per box, no divergence) and keeps one candidate bit per
+//      face whose box meets [tmin, tmax];
+//   2. every lane runs the watertight test on the triangles of its own candidates only (1-3 of the 17 faces of a Cornell
+//      box), in the triangle's instance-local space like the BVH traversal: same test, same (t, entity, prim) order ->
+//      bit-identical results.
+// The first version tested every triangle exhaustively (~3400 warp instructions per warp of rays, the second half of each test
+// at the few lanes that passed the edge functions; this one ~1700); a BVH traversal of the 32-triangle Cornell box needs ~4900
+// at 20 of 32 lanes, almost all of it TLAS -> BLAS entries and exits of eight tiny instances.
+// The boxes are conservative in the way the oracle's and the BVH8's are: padded by 8e-6 of the face's largest coordinate
+// (covers the rounding of the instance transform and of the plane parameters near the origin), plane parameters widened by
+// 4e-6 relative (covers it far away), so that the box test never culls what the triangle test could accept.
+// Scenes with at most SMALL_BOX_MIN_FACES faces (the sphere scene: one plane) skip phase 1: every face is a candidate.
+constexpr float SMALL_T_SLACK		  = 4e-6f;
+constexpr uint32_t SMALL_BOX_MIN_FACES = 4;
+// one bit per box (up to 32) that the ray meets within [tmin, tmax]; warp-uniform loop over broadcast loads.  The host pads the
+// box list to a multiple of 8 so that the loop unrolls with constant bit positions; the caller masks the padding bits off
+PRB_DEV uint32_t smallBoxMask(const float4* __restrict__ boxes, uint32_t n8, V3 inv, V3 oi, float tmin, float tmax)
+{
+	uint32_t m = 0;
+	for (uint32_t g = 0; g < n8; ++g) {
+		uint32_t mg = 0;
+#pragma unroll
+		for (uint32_t k = 0; k < 8; ++k) {
+			const float4 lo = boxes[2 * (8 * g + k)], hi = boxes[2 * (8 * g + k) + 1];
+			const float ax = fmaf(lo.x, inv.x, oi.x), cx = fmaf(hi.x, inv.x, oi.x);
+			const float ay = fmaf(lo.y, inv.y, oi.y), cy = fmaf(hi.y, inv.y, oi.y);
+			const float az = fmaf(lo.z, inv.z, oi.z), cz = fmaf(hi.z, inv.z, oi.z);
+			float tn	   = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fminf(az, cz));
+			float tf	   = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fmaxf(az, cz));
+			tn			   = fmaf(-fabsf(tn), SMALL_T_SLACK, tn); // plane parameters widened (monotonic: once after the reduction is the same as per axis)
+			tf			   = fmaf(fabsf(tf), SMALL_T_SLACK, tf);
+			if (fmaxf(tn, tmin) <= fminf(tf, tmax))
+				mg |= 1u << k;
+		}
+		m |= mg << (8 * g);
+	}
+	return m;
+}
+PRB_DEV uint32_t lowBits(uint32_t n) { return n >= 32u ? 0xFFFFFFFFu : (1u << n) - 1u; }
+// warp-synchronous: every lane of the warp must call (lanes without a ray pass live = false); anyHit may differ between lanes
+PRB_DEV bool traverseSmall(const uint4* __restrict__ sm, uint32_t nEnts, uint32_t nFaces, bool live, bool anyHit, V3 O, V3 D, float tmin, float tmax, HitRec& best)
 {
 	best.entity = PRB_INVALID_ID;
 	best.prim	= 0;
 	best.u = best.v = 0;
 	best.t			= tmax;
-	bool done		= !live;
+	const float4* __restrict__ boxes = reinterpret_cast<const float4*>(sm + 4 * nEnts); // per face: lo (w: first triangle), hi (w: triangle count)
+	const uint32_t nBoxes			 = (nFaces + 7u) & ~7u;
+	const uint4* __restrict__ tris	 = sm + 4 * nEnts + 2 * nBoxes;
+	// ---- phase 1: candidate faces by box
+	uint32_t cand0 = lowBits(nFaces), cand1 = nFaces > 32u ? lowBits(nFaces - 32u) : 0u;
+	if (nFaces > SMALL_BOX_MIN_FACES) { // warp-uniform
+		const V3 inv = mk(safeInv(D.x), safeInv(D.y), safeInv(D.z));
+		const V3 oi	 = mk(-(O.x * inv.x), -(O.y * inv.y), -(O.z * inv.z));
+		cand0 &= smallBoxMask(boxes, (min(nFaces, 32u) + 7u) / 8u, inv, oi, tmin, tmax);
+		if (nFaces > 32u)
+			cand1 &= smallBoxMask(boxes + 64, (nFaces - 32u + 7u) / 8u, inv, oi, tmin, tmax);
+	}
+	if (!live)
+		cand0 = cand1 = 0u;
+	// ---- the analytic spheres (no triangles)
 	for (uint32_t e = 0; e < nEnts; ++e) { // warp-uniform
-		const uint4 h = sm[4 * e];		   // type, entity id, first triangle (uint4 index), triangle count
-		const float4 r0 = *reinterpret_cast<const float4*>(sm + 4 * e + 1), r1 = *reinterpret_cast<const float4*>(sm + 4 * e + 2),
-					 r2 = *reinterpret_cast<const float4*>(sm + 4 * e + 3);
-		if (h.x == PRB_ENTITY_SPHERE) {
-			float t;
-			if (!done && sphereTest(O, D, tmin, best.t, mk(r0.x, r0.y, r0.z), r0.w, t) && betterHit(t, h.y, 0, best)) {
-				best.entity = h.y;
-				best.prim	= 0;
-				best.t		= t;
-				best.u = best.v = 0;
-				done			= anyHit;
+		const uint4 h = sm[4 * e];		   // type, entity id
+		if (h.x != PRB_ENTITY_SPHERE)
+			continue;
+		const float4 r0 = *reinterpret_cast<const float4*>(sm + 4 * e + 1);
+		float t;
+		if (live && !(anyHit && best.entity != PRB_INVALID_ID) && sphereTest(O, D, tmin, best.t, mk(r0.x, r0.y, r0.z), r0.w, t) && betterHit(t, h.y, 0, best)) {
+			best.entity = h.y;
+			best.prim	= 0;
+			best.t		= t;
+			best.u = best.v = 0;
+		}
+	}
+	if (anyHit && best.entity != PRB_INVALID_ID)
+		cand0 = cand1 = 0u;
+	// ---- phase 2: the watertight test on the triangles of the lane's own candidate faces
+	while (__any_sync(0xFFFFFFFFu, (cand0 | cand1) != 0u)) {
+		if ((cand0 | cand1) != 0u) {
+			uint32_t f;
+			if (cand0) {
+				f = __ffs(cand0) - 1;
+				cand0 &= cand0 - 1;
+			} else {
+				f = 32 + __ffs(cand1) - 1;
+				cand1 &= cand1 - 1;
 			}
-		} else {
+			const uint32_t first = __float_as_uint(boxes[2 * f].w), count = __float_as_uint(boxes[2 * f + 1].w);
+			const float4* tp	 = reinterpret_cast<const float4*>(tris + 3 * first);
+			const uint32_t es	 = __float_as_uint(tp[2].w); // index of the face's entity header
+			const uint4 h		 = sm[4 * es];
 			V3 lo = O, ld = D;
 			if (h.x == PRB_ENTITY_MESH) { // planes are stored in world space
+				const float4 r0 = *reinterpret_cast<const float4*>(sm + 4 * es + 1), r1 = *reinterpret_cast<const float4*>(sm + 4 * es + 2),
+							 r2 = *reinterpret_cast<const float4*>(sm + 4 * es + 3);
 				const float m[12] = { r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w };
 				lo				  = xfPointE(m, O);
 				ld				  = xfVecE(m, D);
 			}
-			const float4* tp = reinterpret_cast<const float4*>(sm + h.z);
-			for (uint32_t k = 0; k < h.w; ++k, tp += 3) {
+#pragma unroll 1
+			for (uint32_t j = 0; j < count; ++j, tp += 3) {
 				const float4 a = tp[0], b = tp[1], c = tp[2];
 				float t, u, v;
-				if (!done && triTest(lo, ld, tmin, best.t, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v)) {
+				if (triTest(lo, ld, tmin, best.t, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), t, u, v)) {
 					const uint32_t prim = __float_as_uint(a.w);
 					if (betterHit(t, h.y, prim, best)) {
 						if (__float_as_uint(b.w) & 1u) {
@@ -586,13 +655,14 @@ PRB_DEV bool traverseSmall(const uint4* __restrict__ sm, uint32_t nEnts, bool li
 						best.t		= t;
 						best.u		= u;
 						best.v		= v;
-						done		= anyHit;
+						if (anyHit) {
+							cand0 = cand1 = 0u;
+							break;
+						}
 					}
 				}
 			}
 		}
-		if (anyHit && __all_sync(0xFFFFFFFFu, done))
-			break;
 	}
 	return best.entity != PRB_INVALID_ID;
 }

@@ -52,10 +52,24 @@ PRB_DEV V3 operator/(V3 a, float f) { return { a.x / f, a.y / f, a.z / f }; }
 PRB_DEV float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 PRB_DEV V3 cross(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
 PRB_DEV float norm2(V3 a) { return dot(a, a); }
+// x / s for s > 0 (not NaN), bit-identical to the IEEE division.  The division sequence (reciprocal + Newton steps + FCHK)
+// leaves through a ~40-instruction out-of-line slow path whenever its numerator is ZERO, and the normals and tangents of
+// axis-aligned faces (every wall of a Cornell box) have two zero components: ncu counted 14 such calls per warp in k_shade,
+// 11 % of its instructions (profiles/r02_kshade_experiments.txt, item 7).  +-0 / s = +-0 for s > 0, so a zero numerator
+// skips the division; `asm volatile` keeps the compiler from speculating the division above the branch.
+PRB_DEV float divPositive(float x, float s)
+{
+	if (x != 0.0f)
+		asm volatile("div.rn.ftz.f32 %0, %0, %1;" : "+f"(x) : "f"(s));
+	return x;
+}
 PRB_DEV_MED V3 normalized(V3 a)
 {
 	const float z = norm2(a);
-	return z > 0 ? a / sqrtf(z) : a;
+	if (!(z > 0))
+		return a;
+	const float s = sqrtf(z);
+	return { divPositive(a.x, s), divPositive(a.y, s), divPositive(a.z, s) };
 }
 PRB_DEV bool isZero(V3 a, float prec) { return fabsf(a.x) <= prec && fabsf(a.y) <= prec && fabsf(a.z) <= prec; }
 PRB_DEV V3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }

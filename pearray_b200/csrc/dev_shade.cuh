@@ -335,7 +335,8 @@ __device__ __noinline__ void provideGeometryPoint(const DScene& S, uint32_t enti
 				if (det <= PR_EPSILON) {
 					tangent_frame(pt.N, pt.Nx, pt.Ny);
 				} else {
-					V3 nx = (dp1 * dv2 - dp2 * dv1) / det;
+					const V3 nd = dp1 * dv2 - dp2 * dv1;
+				V3 nx		= mk(divPositive(nd.x, det), divPositive(nd.y, det), divPositive(nd.z, det)); // det > 0: see divPositive
 					nx	  = nx - pt.N * dot(pt.N, nx);
 					nx	  = normalized(nx);
 					pt.Nx = nx;

@@ -134,7 +134,7 @@ struct prb_ctx {
 	uint64_t graphKey[2] = { 0, 0 }, stateVersion = 1; // stateVersion: bumped whenever the scene or the slot buffers change
 	bool wantAOV = true;
 	bool persistentTrace = true; // k_trace (persistent threads) vs k_trace_static, chosen per scene in prb_upload_scene
-	bool smallScene = false;	 // k_trace_static<true>: exhaustive test of a tiny scene from shared memory, no BVH
+	bool smallScene = false;	 // k_trace_small: a tiny scene traced from shared memory, no BVH
 	DBuf<uint4> small;
 	// per-stage profiling (prb_set_profiling)
 	bool profiling = false;
@@ -486,9 +486,10 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 	// tiny scenes: flat entity / triangle list for the BVH-free trace kernel (traverseSmall)
 	c->smallScene	= false;
 	c->S.small		= nullptr;
-	c->S.nSmallEnts = c->S.nSmallU4 = 0;
+	c->S.nSmallEnts = c->S.nSmallFaces = c->S.nSmallU4 = 0;
 	if (!c->persistentTrace && d->n_bvh_tris <= SMALL_MAX_TRIS && d->n_entities <= SMALL_MAX_ENTS && d->n_entities > 0) {
-		std::vector<uint4> blob(4 * (size_t)d->n_entities);
+		std::vector<uint4> blob(4 * (size_t)d->n_entities), tris;
+		std::vector<float4> boxes; // per face: lo (w: first triangle), hi (w: triangle count)
 		bool ok = true;
 		for (uint32_t e = 0; e < d->n_entities && ok; ++e) {
 			const prb_entity& en = d->entities[e];
@@ -498,8 +499,8 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 				rows[0] = en.geo[0], rows[1] = en.geo[1], rows[2] = en.geo[2], rows[3] = en.geo[3];
 			} else {
 				std::memcpy(rows, en.world_to_local, sizeof(rows));
-				h.z = (uint32_t)blob.size();
-				// every triangle below the BLAS root, in leaf order
+				// every triangle below the BLAS root
+				std::vector<prb_bvh_tri> own;
 				std::vector<uint32_t> todo{ en.blas_root };
 				while (!todo.empty() && ok) {
 					const uint32_t ni = todo.back();
@@ -521,24 +522,119 @@ prb_status prb_upload_scene(prb_ctx* c, const prb_scene_desc* d)
 									ok = false;
 									break;
 								}
-								const uint4* t = reinterpret_cast<const uint4*>(d->bvh_tris + first + k);
-								blob.insert(blob.end(), t, t + 3);
-								++h.w;
+								own.push_back(d->bvh_tris[first + k]);
 							}
 						}
 					}
+				}
+				// faces: two triangles share one box when the union of their world-space boxes is hardly larger than the larger
+				// of the two -- the halves of a quad, or the two triangles a modeller split a planar rectangle into (the walls
+				// of the Cornell boxes); greedy, best partner first
+				auto worldBox = [&](const prb_bvh_tri& bt, double lo[3], double hi[3]) {
+					const float* vtx[3] = { bt.v0, bt.v1, bt.v2 };
+					for (int a = 0; a < 3; ++a)
+						lo[a] = 1e300, hi[a] = -1e300;
+					for (int j = 0; j < 3; ++j)
+						for (int a = 0; a < 3; ++a) {
+							double w = vtx[j][a];
+							if (en.type == PRB_ENTITY_MESH) {
+								const float* m = en.local_to_world + 4 * a;
+								w			   = (double)m[0] * vtx[j][0] + (double)m[1] * vtx[j][1] + (double)m[2] * vtx[j][2] + (double)m[3];
+							}
+							lo[a] = std::min(lo[a], w);
+							hi[a] = std::max(hi[a], w);
+						}
+				};
+				auto halfArea = [](const double lo[3], const double hi[3]) {
+					const double x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+					return x * y + y * z + z * x + 1e-3 * (x + y + z) * (x + y + z); // the second term orders flat (zero-area) boxes by extent
+				};
+				std::vector<prb_bvh_tri> paired;
+				std::vector<char> used(own.size(), 0);
+				std::vector<uint32_t> faceCount;
+				for (size_t i = 0; i < own.size(); ++i) {
+					if (used[i])
+						continue;
+					used[i] = 1;
+					double li[3], hi_[3];
+					worldBox(own[i], li, hi_);
+					size_t bestJ	 = own.size();
+					double bestRatio = 1.1;
+					for (size_t j = i + 1; j < own.size(); ++j) {
+						if (used[j])
+							continue;
+						double lj[3], hj[3], lu[3], hu[3];
+						worldBox(own[j], lj, hj);
+						for (int a = 0; a < 3; ++a)
+							lu[a] = std::min(li[a], lj[a]), hu[a] = std::max(hi_[a], hj[a]);
+						const double ratio = halfArea(lu, hu) / std::max(std::max(halfArea(li, hi_), halfArea(lj, hj)), 1e-300);
+						if (ratio < bestRatio)
+							bestRatio = ratio, bestJ = j;
+					}
+					paired.push_back(own[i]);
+					faceCount.push_back(1);
+					if (bestJ < own.size()) {
+						used[bestJ] = 1;
+						paired.push_back(own[bestJ]);
+						faceCount.back() = 2;
+					}
+				}
+				own.swap(paired);
+				size_t face = 0;
+				for (size_t i = 0; i < own.size(); ++face) {
+					const size_t n = faceCount[face];
+					// padded world-space box (traverseSmall, phase 1): mesh triangles are stored in the instance's local space, planes in world space
+					double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 }, mag = 0;
+					const uint32_t firstTri = (uint32_t)(tris.size() / 3);
+					for (size_t k = i; k < i + n; ++k) {
+						const prb_bvh_tri& bt = own[k];
+						const uint4* t		  = reinterpret_cast<const uint4*>(&bt);
+						tris.insert(tris.end(), t, t + 3);
+						tris.back().w = e; // index of the entity header (traverseSmall, phase 2)
+						const float* vtx[3] = { bt.v0, bt.v1, bt.v2 };
+						for (int j = 0; j < 3; ++j)
+							for (int a = 0; a < 3; ++a) {
+								double w = vtx[j][a];
+								if (en.type == PRB_ENTITY_MESH) {
+									const float* m = en.local_to_world + 4 * a;
+									w			   = (double)m[0] * vtx[j][0] + (double)m[1] * vtx[j][1] + (double)m[2] * vtx[j][2] + (double)m[3];
+								}
+								lo[a] = std::min(lo[a], w);
+								hi[a] = std::max(hi[a], w);
+								mag	  = std::max(mag, std::fabs(w));
+							}
+					}
+					const double pad = std::max(8e-6 * mag, 1e-30);
+					float4 blo, bhi;
+					blo.x = std::nextafterf((float)(lo[0] - pad), -INFINITY), blo.y = std::nextafterf((float)(lo[1] - pad), -INFINITY),
+					blo.z = std::nextafterf((float)(lo[2] - pad), -INFINITY);
+					bhi.x = std::nextafterf((float)(hi[0] + pad), INFINITY), bhi.y = std::nextafterf((float)(hi[1] + pad), INFINITY),
+					bhi.z = std::nextafterf((float)(hi[2] + pad), INFINITY);
+					uint32_t cnt = (uint32_t)n;
+					std::memcpy(&blo.w, &firstTri, 4);
+					std::memcpy(&bhi.w, &cnt, 4);
+					boxes.push_back(blo);
+					boxes.push_back(bhi);
+					i += n;
 				}
 			}
 			blob[4 * e] = h;
 			std::memcpy(&blob[4 * e + 1], rows, sizeof(rows));
 		}
-		if (ok && blob.size() <= SMALL_MAX_ENTS * 4 + SMALL_MAX_TRIS * 3) {
+		const size_t nSmallFaces = boxes.size() / 2;
+		if (ok && tris.size() / 3 <= SMALL_MAX_TRIS) {
+			while (boxes.size() % 16) // the box loop of traverseSmall runs in groups of 8 (bits past the last face are masked off)
+				boxes.push_back(make_float4(0, 0, 0, 0));
+			const uint4* bx = reinterpret_cast<const uint4*>(boxes.data());
+			blob.insert(blob.end(), bx, bx + boxes.size());
+			blob.insert(blob.end(), tris.begin(), tris.end());
 			CU(c->small.upload(blob.data(), blob.size(), s));
 			CU(cudaStreamSynchronize(s));
-			c->S.small		= c->small.p;
-			c->S.nSmallEnts = d->n_entities;
-			c->S.nSmallU4	= (uint32_t)blob.size();
-			c->smallScene	= true;
+			c->S.small		 = c->small.p;
+			c->S.nSmallEnts	 = d->n_entities;
+			c->S.nSmallFaces = (uint32_t)nSmallFaces;
+			c->S.nSmallU4	 = (uint32_t)blob.size();
+			c->smallScene	 = true;
 		}
 	}
 	if (const char* m = std::getenv("PRB_TRACE_MODE"))
@@ -752,9 +848,9 @@ static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s
 	if (c->persistentTrace)
 		k_trace<<<c->gridTrace, 128, 0, s>>>(c->S, W);
 	else if (c->smallScene)
-		k_trace_static<true><<<blocks, 128, 0, s>>>(c->S, W);
+		k_trace_small<<<blocks, 128, 0, s>>>(c->S, W);
 	else
-		k_trace_static<false><<<blocks, 128, 0, s>>>(c->S, W);
+		k_trace_static<<<blocks, 128, 0, s>>>(c->S, W);
 }
 
 static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)

@@ -1,0 +1,17 @@
+#!/bin/sh
+# round 2, call Y: greedy pairing of coplanar triangles into faces (one box per pair)
+mkdir -p gpurun_out /tmp/reps
+q() { python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,1), d['stage_ms'], d.get('shading'))"; }
+timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r02_gpu_tests_y.log 2>&1; tail -4 gpurun_out/r02_gpu_tests_v.log
+python bench.py --scene c2 --no-cpu --no-extras --steps 2 --warmup 1 2>/dev/null | q
+python bench.py --scene c0 --no-cpu --steps 2 --warmup 1 2>/dev/null | q
+python bench.py --scene c1 --no-cpu --steps 2 --warmup 1 2>/dev/null | q
+python bench.py --scene c3 --no-cpu --steps 2 --warmup 1 2>/dev/null | q
+python bench.py --scene c4 --no-cpu --steps 1 --warmup 1 --spp 64 2>/dev/null | q
+python bench.py --scene c4c --no-cpu --steps 1 --warmup 1 --spp 16 2>/dev/null | q
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_trace|k_shade" -s 30 -c 2 -o /tmp/reps/r02_c2_y -f python bench.py --scene c2 --no-cpu --no-extras --steps 1 --warmup 1 --spp 16 > gpurun_out/ncu_c2_y.log 2>&1
+python tools/ncu_summary.py /tmp/reps/r02_c2_y.ncu-rep --all > gpurun_out/r02_ncu_c2_y.txt 2>&1
+python tools/ncu_hotspots.py /tmp/reps/r02_c2_y.ncu-rep k_shade pearray_b200/libprb200.so 400 k_shadeILi128ELi1ELi2E > gpurun_out/r02_hotspots_c2_shade_y.txt 2>&1
+python tools/ncu_hotspots.py /tmp/reps/r02_c2_y.ncu-rep k_trace_small pearray_b200/libprb200.so 200 k_trace_small > gpurun_out/r02_hotspots_c2_trace_y.txt 2>&1
+cp /tmp/reps/r02_c2_y.ncu-rep gpurun_out/
+du -sh gpurun_out

@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """Attribute ncu per-instruction samples of one kernel to source lines / inlined functions.
-  python tools/ncu_hotspots.py <report.ncu-rep> <kernel-name> <lib.so> [topN]
+  python tools/ncu_hotspots.py <report.ncu-rep> <kernel-name> <lib.so> [topN [section-substring]]
+kernel-name selects the launches in the report (ncu --kernel-name: base name or regex:...); section-substring selects the ONE
+.text section of the cubin whose line table is used (mangled name, e.g. k_shadeILi128ELi1ELi2E; default: the kernel name).
 Joins `ncu --page source --csv` (SASS view: address, #samples, instructions executed) with
 `nvdisasm --print-line-info` of the cubin extracted from the library (needs -lineinfo)."""
 import collections
@@ -13,6 +15,7 @@ import tempfile
 
 rep, kernel, lib = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+section = sys.argv[5] if len(sys.argv) > 5 else kernel
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -27,7 +30,7 @@ insec = False
 prev_annot = False
 for line in dis.splitlines():
     if line.startswith("//--------------------- .text."):
-        insec = kernel in line
+        insec = section in line
         continue
     if not insec:
         continue
