@@ -19,7 +19,7 @@ constexpr int CIE_N		   = 441;
 constexpr float CIE_Y_NORM = 113.042314572337f * (CIE_RANGE / (CIE_N - 1));
 PRB_DEV float cieEval(const DScene& S, int c, float w)
 { // CIE::eval_x/y/z, src/core/spectral/CIE.h:41-58
-	return fdiv(tableLookup(S.pool + S.cieOffset + c * CIE_N, CIE_N, CIE_START, CIE_END, w), CIE_Y_NORM) * CIE_RANGE;
+	return divPositive(tableLookup(S.pool + S.cieOffset + c * CIE_N, CIE_N, CIE_START, CIE_END, w), CIE_Y_NORM) * CIE_RANGE; // z-bar is zero above 650 nm: see divPositive
 }
 
 // leaf node kinds; MUL / CHECKER reference other nodes.  The flattened graph is shallow (depth <= 3 in the
@@ -316,7 +316,7 @@ PRB_DEV float faceArea(const FaceData& f)
 	return 0.5f * sqrtf(norm2(cross(f.V[1] - f.V[0], f.V[2] - f.V[0])));
 }
 
-__device__ __noinline__ void provideGeometryPoint(const DScene& S, uint32_t entityID, uint32_t prim, float qu, float qv, V3 position, GeomPoint& pt)
+PRB_DEV void provideGeometryPointBody(const DScene& S, uint32_t entityID, uint32_t prim, float qu, float qv, V3 position, GeomPoint& pt)
 {
 	const prb_entity& en = S.entities[entityID];
 	pt.entity			 = entityID;
@@ -388,6 +388,13 @@ __device__ __noinline__ void provideGeometryPoint(const DScene& S, uint32_t enti
 		pt.prim		= 0;
 		pt.material = S.entityMaterials[en.material_offset];
 	}
+}
+// Out of line for the generic kernels; the kernels that inline the Lambert code inline this as well (PRB_GEOM_INLINE): out of line
+// it reads every DScene field it needs through a generic pointer to the kernel parameter (LD.E + a descriptor R2UR pair per
+// load: 6.5 % of k_shade's instructions on the Cornell box, and a dependent load in front of every data access)
+__device__ __noinline__ void provideGeometryPoint(const DScene& S, uint32_t entityID, uint32_t prim, float qu, float qv, V3 position, GeomPoint& pt)
+{
+	provideGeometryPointBody(S, entityID, prim, qu, qv, position, pt);
 }
 
 // ------------------------------------------------------------------ materials
@@ -1683,7 +1690,10 @@ PRB_DEV void sampleLightBody(const DScene& S, const prb_light& l, V3 P, const Bl
 		sv				  = dot(ld3(en.geo + 35), lp) * en.geo[39];
 	}
 	GeomPoint gp;
-	provideGeometryPoint(S, l.entity_id, prim, su, sv, pos, gp);
+	if (ENVMAP)
+		provideGeometryPoint(S, l.entity_id, prim, su, sv, pos, gp);
+	else
+		provideGeometryPointBody(S, l.entity_id, prim, su, sv, pos, gp);
 	o.outgoing = normalized(pos - P);
 	o.dirPDF_S = 1;
 	o.cosLight = fminf(1.0f, fmaxf(-1.0f, -dot(o.outgoing, gp.N)));
