@@ -273,6 +273,16 @@ PRB_DEV Blob evalNodeBody(const DScene& S, uint32_t id, const Blob& w, float u, 
 __device__ __noinline__ Blob evalNodeBase(const DScene& S, uint32_t id, const Blob& w, float u, float v) { return evalNodeBody<false>(S, id, w, u, v); }
 __device__ __noinline__ Blob evalNodeTex(const DScene& S, uint32_t id, const Blob& w, float u, float v) { return evalNodeBody<true>(S, id, w, u, v); }
 PRB_DEV Blob evalNode(const DScene& S, uint32_t id, const Blob& w, float u, float v) { return evalNodeTex(S, id, w, u, v); }
+// The kernels that inline the Lambert code (scenes without image nodes) evaluate a LEAF node -- nearly every albedo and radiance
+// is one -- in line: one node load and the leaf formula instead of the out-of-line graph walk with its stack in local memory and
+// its generic loads of the scene descriptor.  A product of one factor is that factor: same value.
+PRB_DEV Blob evalNodeFast(const DScene& S, uint32_t id, const Blob& w, float u, float v)
+{
+	const prb_node n = loadNode(S, id);
+	if (n.type != PRB_NODE_MUL && n.type != PRB_NODE_CHECKER)
+		return evalLeafNode(S, n, w);
+	return evalNodeBase(S, id, w, u, v);
+}
 
 // ------------------------------------------------------------------ geometry point (GeometryPoint.h:10-25)
 struct GeomPoint {
@@ -389,9 +399,9 @@ PRB_DEV void provideGeometryPointBody(const DScene& S, uint32_t entityID, uint32
 		pt.material = S.entityMaterials[en.material_offset];
 	}
 }
-// Out of line for the generic kernels; the kernels that inline the Lambert code inline this as well (PRB_GEOM_INLINE): out of line
-// it reads every DScene field it needs through a generic pointer to the kernel parameter (LD.E + a descriptor R2UR pair per
-// load: 6.5 % of k_shade's instructions on the Cornell box, and a dependent load in front of every data access)
+// Out-of-line form for the generic light sampling (sampleLight); the shading kernels call the body in line: out of line it reads
+// every DScene field it needs through a generic pointer to the kernel parameter (LD.E + a descriptor R2UR pair per load: 6.5 %
+// of k_shade's instructions on the Cornell box, and a dependent load in front of every data access; C2 328 -> 354 Msamples/s)
 __device__ __noinline__ void provideGeometryPoint(const DScene& S, uint32_t entityID, uint32_t prim, float qu, float qv, V3 position, GeomPoint& pt)
 {
 	provideGeometryPointBody(S, entityID, prim, qu, qv, position, pt);
@@ -425,6 +435,7 @@ struct MatCtx {
 	// evaluation goes straight to the leaf-only evalNodeBase; a compile-time constant there, so the test folds away
 	bool noImageNodes = false;
 };
+template <bool FAST = false>
 PRB_DEV Blob evalNodeCached(const DScene& S, const MatCtx& c, uint32_t node);
 PRB_DEV uint32_t contribFlags(const prb_material& m) { return (m.flags & PRB_MATF_SPECTRAL_VARYING) ? MSF_SpectralVarying : 0; }
 PRB_DEV void rejectSample(MatSample& s, uint32_t type, uint32_t flags)
@@ -766,23 +777,27 @@ struct RoughDielectric {
 #ifndef PRB_NODE_CACHE
 #define PRB_NODE_CACHE 1
 #endif
+// FAST: called from a kernel that inlines the Lambert code (evalNodeFast)
+template <bool FAST>
 PRB_DEV Blob evalNodeCached(const DScene& S, const MatCtx& c, uint32_t node)
 {
 	if (!PRB_NODE_CACHE)
-		return c.noImageNodes ? evalNodeBase(S, node, c.wvl, c.u, c.v) : evalNodeTex(S, node, c.wvl, c.u, c.v);
+		return FAST ? evalNodeFast(S, node, c.wvl, c.u, c.v) : c.noImageNodes ? evalNodeBase(S, node, c.wvl, c.u, c.v) : evalNodeTex(S, node, c.wvl, c.u, c.v);
 	if (c.cachedNode != node) {
-		c.cachedValue = c.noImageNodes ? evalNodeBase(S, node, c.wvl, c.u, c.v) : evalNodeTex(S, node, c.wvl, c.u, c.v);
+		c.cachedValue = FAST ? evalNodeFast(S, node, c.wvl, c.u, c.v) : c.noImageNodes ? evalNodeBase(S, node, c.wvl, c.u, c.v) : evalNodeTex(S, node, c.wvl, c.u, c.v);
 		c.cachedNode  = node;
 	}
 	return c.cachedValue;
 }
+template <bool FAST = false>
 PRB_DEV void lambertEval(const DScene& S, const prb_material& m, const MatCtx& c, MatEval& out)
 {
 	const bool two = m.flags & PRB_MATF_TWO_SIDED;
 	const float d  = sameHemisphere(c.V, c.L) ? (two ? fabsf(c.L.z) : fmaxf(0.0f, c.L.z)) : 0;
-	out.weight	   = evalNodeCached(S, c, m.node[0]) * d * PR_INV_PI;
+	out.weight	   = evalNodeCached<FAST>(S, c, m.node[0]) * d * PR_INV_PI;
 	out.pdf		   = blob(cos_hemi_pdf(d));
 }
+template <bool FAST = false>
 PRB_DEV void lambertSample(const DScene& S, const prb_material& m, const MatCtx& c, Rng& rnd, MatSample& out)
 {
 	if (!(m.flags & PRB_MATF_TWO_SIDED) && c.V.z < 0.0f) {
@@ -792,7 +807,7 @@ PRB_DEV void lambertSample(const DScene& S, const prb_material& m, const MatCtx&
 	const float u2 = rnd.getFloat(); // cos_hemi(RND.getFloat(), RND.getFloat()): second argument drawn first
 	const float u1 = rnd.getFloat();
 	out.L		   = cos_hemi(u1, u2);
-	out.weight	   = evalNodeCached(S, c, m.node[0]);
+	out.weight	   = evalNodeCached<FAST>(S, c, m.node[0]);
 	out.pdf		   = blob(cos_hemi_pdf(out.L.z));
 	out.L		   = makeSameHemisphere(c.V, out.L);
 }
@@ -1125,7 +1140,7 @@ PRB_DEV void materialEval(const DScene& S, uint32_t matID, const MatCtx& c, MatE
 	} else if (KIND == SHADE_MATERIALS_LAMBERT) { // every material of the scene is a Lambert material (Cornell box)
 		out.flags = 0;
 		out.type  = 0;
-		lambertEval(S, S.materials[matID], c, out);
+		lambertEval<true>(S, S.materials[matID], c, out);
 	} else if (KIND == SHADE_MATERIALS_COMBINED && isCombination(S.materials[matID].type)) {
 		materialEvalCombined(S, matID, c, out);
 	} else {
@@ -1165,7 +1180,7 @@ PRB_DEV void materialSample(const DScene& S, uint32_t matID, const MatCtx& c, Rn
 	} else if (KIND == SHADE_MATERIALS_LAMBERT) {
 		out.flags = 0;
 		out.type  = 0;
-		lambertSample(S, S.materials[matID], c, rnd, out);
+		lambertSample<true>(S, S.materials[matID], c, rnd, out);
 	} else if (KIND == SHADE_MATERIALS_COMBINED && isCombination(S.materials[matID].type)) {
 		materialSampleCombined(S, matID, c, rnd, out);
 	} else {
@@ -1617,7 +1632,7 @@ PRB_DEV void sampleLightBody(const DScene& S, const prb_light& l, V3 P, const Bl
 		const V3 local = cos_hemi(dx, dy);
 		o.dirPDF_S	   = cos_hemi_pdf(local.z);
 		o.outgoing	   = m3mul(l.normal_matrix, local);
-		o.radiance	   = ENVMAP ? evalNodeTex(S, l.radiance_node, wvl, dx, dy) : evalNodeBase(S, l.radiance_node, wvl, dx, dy);
+		o.radiance	   = ENVMAP ? evalNodeTex(S, l.radiance_node, wvl, dx, dy) : evalNodeFast(S, l.radiance_node, wvl, dx, dy);
 		o.lightPos	   = P + l.scene_radius * o.outgoing;
 		o.posPDF	   = 1;
 		o.cosLight	   = 1;
@@ -1697,7 +1712,7 @@ PRB_DEV void sampleLightBody(const DScene& S, const prb_light& l, V3 P, const Bl
 	o.outgoing = normalized(pos - P);
 	o.dirPDF_S = 1;
 	o.cosLight = fminf(1.0f, fmaxf(-1.0f, -dot(o.outgoing, gp.N)));
-	o.radiance = ENVMAP ? evalNodeTex(S, S.emissions[l.emission_id].radiance_node, wvl, gp.u, gp.v) : evalNodeBase(S, S.emissions[l.emission_id].radiance_node, wvl, gp.u, gp.v);
+	o.radiance = ENVMAP ? evalNodeTex(S, S.emissions[l.emission_id].radiance_node, wvl, gp.u, gp.v) : evalNodeFast(S, S.emissions[l.emission_id].radiance_node, wvl, gp.u, gp.v);
 	o.posPDF   = pdfA;
 	o.lightPos = pos;
 }
