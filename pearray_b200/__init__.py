@@ -503,6 +503,18 @@ class Context:
         self._chk(self._lib.prb_trace_any(self._h, C.byref(rays), n, _ptr(occ)), "prb_trace_any")
         return occ
 
+    def trace_closest_soa(self, cols, n, out):
+        """prb_trace_closest over caller-owned host COLUMNS (8 float32 arrays: origin xyz, direction xyz, tmin, tmax -- the
+        last two may be None) into caller-owned result columns (entity, prim: uint32; u, v, t: float32).  No conversion and no
+        allocation on the way: with page-locked arrays the copies run at PCIe speed (the way bench.py's e2e leg calls it)."""
+        rays = RaySoA(*[None if c is None else c.ctypes.data for c in cols])
+        hits = HitSoA(*[a.ctypes.data for a in out])
+        self._chk(self._lib.prb_trace_closest(self._h, C.byref(rays), n, C.byref(hits)), "prb_trace_closest")
+
+    def trace_any_soa(self, cols, n, occluded):
+        rays = RaySoA(*[None if c is None else c.ctypes.data for c in cols])
+        self._chk(self._lib.prb_trace_any(self._h, C.byref(rays), n, _ptr(occluded)), "prb_trace_any")
+
     def trace_closest_device(self, ray_ptrs, n, hit_ptrs):
         rays = RaySoA(*ray_ptrs)
         hits = HitSoA(*hit_ptrs)

@@ -108,7 +108,8 @@ struct prb_ctx {
 	uint8_t queueOfType[SHADE_QUEUES];	   // material type -> queue index, 0xFF when the scene has no material of the type
 	bool queueWantsNEE[SHADE_QUEUES] = {}; // some material of the queue's type has a non-delta lobe
 	uint32_t nQueues = 0, nNeeQueues = 0;
-	uint32_t launchesPerIteration(bool stagedMode) const { return stagedMode ? 3 + nQueues + nNeeQueues : 3; }
+	uint32_t launchesPerIteration(bool stagedMode) const { return (stagedMode ? 3 + nQueues + nNeeQueues : 3) - (regenInTrace() ? 1 : 0); }
+	bool regenInTrace() const { return smallScene && !persistentTrace; } // k_trace_small regenerates ended paths itself: no k_regen launch
 	DBuf<uint4> hit;
 	DBuf<float> hitT;
 	// light path expression channels (scenes with prb_scene_desc::n_lpe > 0)
@@ -784,7 +785,8 @@ static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s);
 static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s)
 {
 	launchShadeOnly(c, W, s);
-	k_regen<<<(int)((c->nSlots + 127) / 128), 128, 0, s>>>(c->S, W);
+	if (!W.regenInTrace) // small scenes: k_trace_small regenerates the flagged slots in its prologue
+		k_regen<<<(int)((c->nSlots + 127) / 128), 128, 0, s>>>(c->S, W);
 }
 // staged shading: k_shade_geom, then one k_shade_nee / k_shade_scatter launch per material TYPE present in the scene over that
 // type's queue (grids sized for the worst case; blocks past the end of a queue return at once)
@@ -902,6 +904,7 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.nSlots	  = c->nSlots;
 	W.firstIter	  = first;
 	W.endIter	  = first + count;
+	W.regenInTrace = c->regenInTrace() ? 1u : 0u;
 	return W;
 }
 

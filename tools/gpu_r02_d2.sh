@@ -1,0 +1,19 @@
+#!/bin/sh
+# round 2, call D2: camera-sample regeneration in the prologue of k_trace_small (no k_regen launch on small scenes), against call C2's build; C5 e2e with page-locked host columns
+mkdir -p gpurun_out /tmp/reps
+q() { python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,1), d['stage_ms'], d.get('shading'))"; }
+run() {
+  python bench.py --scene c2 --no-cpu --no-extras --steps 2 --warmup 1 2>/dev/null | q
+  python bench.py --scene c0 --no-cpu --steps 2 --warmup 1 2>/dev/null | q
+  python bench.py --scene c1 --no-cpu --steps 2 --warmup 1 2>/dev/null | q
+  python bench.py --scene c3 --no-cpu --steps 2 --warmup 1 2>/dev/null | q
+}
+timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r02_gpu_tests_d2.log 2>&1; tail -3 gpurun_out/r02_gpu_tests_d2.log
+echo "== new"; run
+cp pearray_b200/libprb200.so /tmp/lib_new.so
+cp gpurun_variants/lib_c2.so pearray_b200/libprb200.so
+echo "== call C2 build"; run
+cp /tmp/lib_new.so pearray_b200/libprb200.so
+python bench.py --scene c5 --no-cpu --steps 1 --warmup 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('c5', round(d['value']/1e6,1), d['e2e'])"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_trace" -s 30 -c 1 -o /tmp/reps/r02_c2_d2 -f python bench.py --scene c2 --no-cpu --no-extras --steps 1 --warmup 1 --spp 16 > gpurun_out/ncu_c2_d2.log 2>&1
+python tools/ncu_summary.py /tmp/reps/r02_c2_d2.ncu-rep --all > gpurun_out/r02_ncu_c2_d2.txt 2>&1
