@@ -99,7 +99,7 @@ struct prb_ctx {
 	DBuf<uint32_t> reduceU;	 // spread feedback bits
 	float lastReduceMs = 0;
 	// wavefront
-	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters, regenList, neeList, scatterList;
+	DBuf<uint32_t> pixel, iter, flagsDepth, slotState, counters, regenList, activeList, neeList, scatterList;
 	DBuf<float4> rayO, rayD, wvl, thr, pathPDF, prevPDF, wvlPDF, lastPos, shO, shD, shXYZ, iterXYZ, prevAcc, vxP, vxN, vxNx, vxNy, vxD;
 	bool staged = false;	   // k_shade_geom -> k_shade_nee / k_shade_scatter per material type instead of k_shade
 	bool stagedAuto = false;   // not pinned: decided by measurement (tuneStep / tuneMs) during the first render of the scene
@@ -108,7 +108,7 @@ struct prb_ctx {
 	uint8_t queueOfType[SHADE_QUEUES];	   // material type -> queue index, 0xFF when the scene has no material of the type
 	bool queueWantsNEE[SHADE_QUEUES] = {}; // some material of the queue's type has a non-delta lobe
 	uint32_t nQueues = 0, nNeeQueues = 0;
-	uint32_t launchesPerIteration(bool stagedMode) const { return (stagedMode ? 3 + nQueues + nNeeQueues : 3) - (regenInTrace() ? 1 : 0); }
+	uint32_t launchesPerIteration(bool stagedMode) const { return (stagedMode ? 3 + nQueues + nNeeQueues : 3) - (regenInTrace() ? 1 : 0) + (persistentTrace ? 1 : 0); }
 	bool regenInTrace() const { return smallScene && !persistentTrace; } // k_trace_small regenerates ended paths itself: no k_regen launch
 	DBuf<uint4> hit;
 	DBuf<float> hitT;
@@ -234,7 +234,7 @@ void prb_destroy(prb_ctx* c)
 	c->reduceF.release();
 	c->reduceU.release();
 	DBuf<uint32_t>* ub[] = { &c->entityMaterials, &c->faceIndices, &c->faceSlots, &c->tlasRefs, &c->sampleCount, &c->feedback, &c->pixel, &c->iter, &c->flagsDepth,
-							 &c->slotState, &c->counters, &c->regenList, &c->neeList, &c->scatterList, &c->scratchU };
+							 &c->slotState, &c->counters, &c->regenList, &c->activeList, &c->neeList, &c->scatterList, &c->scratchU };
 	for (auto* b : ub)
 		b->release();
 	DBuf<float>* fb[] = { &c->vertices, &c->normals, &c->uvs, &c->lightCDF, &c->pool, &c->rrProb, &c->filmMean, &c->filmTmp, &c->aov, &c->aovExt, &c->varMean, &c->varVar, &c->hitT, &c->scratchF };
@@ -750,6 +750,7 @@ static prb_status setupSlots(prb_ctx* c, const prb_tile* tiles, size_t n_tiles)
 	CU(c->flagsDepth.alloc(n));
 	CU(c->slotState.alloc(n));
 	CU(c->regenList.alloc(n));
+	CU(c->activeList.alloc(n));
 	if (c->staged || c->stagedAuto) { // one queue per material type of the scene
 		CU(c->neeList.alloc(n * std::max<size_t>(c->nQueues, 1)));
 		CU(c->scatterList.alloc(n * std::max<size_t>(c->nQueues, 1)));
@@ -847,9 +848,10 @@ static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s)
 }
 static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s)
 {
-	if (c->persistentTrace)
+	if (c->persistentTrace) {
+		k_compact_active<<<(int)((c->nSlots + 1023) / 1024), 1024, 0, s>>>(W);
 		k_trace<<<c->gridTrace, 128, 0, s>>>(c->S, W);
-	else if (c->smallScene)
+	} else if (c->smallScene)
 		k_trace_small<<<blocks, 128, 0, s>>>(c->S, W);
 	else
 		k_trace_static<<<blocks, 128, 0, s>>>(c->S, W);
@@ -879,6 +881,7 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.state		  = c->slotState.p;
 	W.counters	  = c->counters.p;
 	W.regenList	  = c->regenList.p;
+	W.activeList  = c->activeList.p;
 	W.neeList	  = c->neeList.p;
 	W.scatterList = c->scatterList.p;
 	W.vxP		  = c->vxP.p;
