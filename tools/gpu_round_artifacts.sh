@@ -27,7 +27,7 @@ timeout 500 ncu --set full --clock-control none --import-source on -k regex:k_tr
 ls -la /tmp/reps
 for w in c2 c4 c5; do python tools/ncu_summary.py /tmp/reps/${R}_$w.ncu-rep --all > gpurun_out/${R}_ncu_$w.txt 2>&1; done
 python tools/ncu_hotspots.py /tmp/reps/${R}_c2.ncu-rep k_shade $LIB 60 k_shadeILi128ELi1ELi2E > gpurun_out/${R}_hotspots_c2_shade.txt 2>&1
-python tools/ncu_hotspots.py /tmp/reps/${R}_c2.ncu-rep k_trace_static $LIB 40 k_trace_staticILb1E > gpurun_out/${R}_hotspots_c2_trace.txt 2>&1
+python tools/ncu_hotspots.py /tmp/reps/${R}_c2.ncu-rep k_trace_small $LIB 40 k_trace_small > gpurun_out/${R}_hotspots_c2_trace.txt 2>&1
 python tools/ncu_hotspots.py /tmp/reps/${R}_c5.ncu-rep k_trace_closest $LIB 40 > gpurun_out/${R}_hotspots_c5_closest.txt 2>&1
 python tools/ncu_hotspots.py /tmp/reps/${R}_c4.ncu-rep k_shade_geom $LIB 40 k_shade_geomILb0E > gpurun_out/${R}_hotspots_c4_geom.txt 2>&1
 sz=$(stat -c %s /tmp/reps/${R}_c2.ncu-rep 2>/dev/null || echo 999999999)
