@@ -908,6 +908,7 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.firstIter	  = first;
 	W.endIter	  = first + count;
 	W.regenInTrace = c->regenInTrace() ? 1u : 0u;
+	W.useActiveList = c->persistentTrace ? 1u : 0u;
 	return W;
 }
 

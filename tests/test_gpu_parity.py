@@ -445,6 +445,65 @@ def test_lpe_channels_bit_exact_vs_oracle(tmp_path):
     assert np.array_equal(ctx.film_lpe(1).view(np.uint32), ref["lpe_filtered"][1].view(np.uint32))
 
 
+def _many_faces_scene(seed, n_meshes=3, tris_per_mesh=14):
+    """a small scene (<= 64 triangles, <= 16 entities: k_trace_small) whose triangles do NOT pair into quads, so that it has more
+    than 32 faces (second candidate word of traverseSmall), in rotated / scaled instances (world-space face boxes)"""
+    rs = np.random.RandomState(seed)
+    fmt = lambda a: ",".join("[%.6f, %.6f, %.6f]" % tuple(v) for v in a)
+    parts = ["""(scene :render_width 48 :render_height 48 :camera 'Camera'
+(integrator :type 'direct' :max_ray_depth 5)
+(sampler :slot 'aa' :type 'mjitt' :sample_count 16)
+(camera :name 'Camera' :type 'standard' :width 0.72 :height 0.72 :local_direction [0,0,-1] :local_up [0,1,0] :local_right [1,0,0]
+ :near 0.1 :far 100.0 :transform [1.0,0.0,0.0,0.0,0.0,0.0,-1.0,-3.9,0.0,1.0,0.0,1.0,0.0,0.0,0.0,1.0])
+(emission :name 'light_em' :type 'standard' :radiance (smul (illuminant "D65") (illum 17 12 4)))
+(material :name 'light' :type 'diffuse' :albedo (refl 0.78 0.78 0.78))
+(material :name 'floor' :type 'diffuse' :albedo (refl 0.725 0.71 0.68))
+(material :name 'red' :type 'diffuse' :albedo (refl 0.63 0.065 0.05))
+(material :name 'green' :type 'diffuse' :albedo (refl 0.14 0.45 0.091))
+(mesh :name 'lightm' (attribute :type 'p' [-0.4,-0.3,1.98],[-0.4,0.3,1.98],[0.4,0.3,1.98],[0.4,-0.3,1.98])
+ (attribute :type 'n' [0,0,-1],[0,0,-1],[0,0,-1],[0,0,-1]) (faces [0,1,2],[0,2,3]))
+(entity :name 'lightm' :type 'mesh' :materials 'light' :emission 'light_em' :mesh 'lightm')
+(mesh :name 'floorm' (attribute :type 'p' [-1.5,-1.5,0],[1.5,-1.5,0],[1.5,1.5,0],[-1.5,1.5,0])
+ (attribute :type 'n' [0,0,1],[0,0,1],[0,0,1],[0,0,1]) (faces [0,1,2],[0,2,3]))
+(entity :name 'floorm' :type 'mesh' :materials 'floor' :mesh 'floorm')
+"""]
+    for m in range(n_meshes):
+        centres = rs.uniform([-0.8, -0.8, 0.1], [0.8, 0.8, 1.6], size=(tris_per_mesh, 3))
+        verts = (centres[:, None, :] + rs.normal(scale=0.22, size=(tris_per_mesh, 3, 3))).reshape(-1, 3)
+        nrm = np.repeat(np.cross(verts[1::3] - verts[0::3], verts[2::3] - verts[0::3]), 3, axis=0)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        faces = ",".join("[%d,%d,%d]" % (3 * i, 3 * i + 1, 3 * i + 2) for i in range(tris_per_mesh))
+        a = rs.uniform(0, 2 * np.pi)
+        sc = rs.uniform(0.7, 1.2)
+        c, s_ = np.cos(a) * sc, np.sin(a) * sc
+        xf = [c, -s_, 0.0, rs.uniform(-0.2, 0.2), s_, c, 0.0, rs.uniform(-0.2, 0.2), 0.0, 0.0, sc, rs.uniform(0.0, 0.2), 0.0, 0.0, 0.0, 1.0]
+        parts.append("(mesh :name 'soup%d' (attribute :type 'p' %s) (attribute :type 'n' %s) (faces %s))\n" % (m, fmt(verts), fmt(nrm), faces))
+        parts.append("(entity :name 'soup%d' :type 'mesh' :materials '%s' :mesh 'soup%d' :transform [%s])\n"
+                     % (m, ("red", "green", "floor")[m % 3], m, ",".join("%.6f" % v for v in xf)))
+    parts.append(")")
+    return "".join(parts)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_small_scene_with_more_than_32_faces_vs_oracle(seed):
+    """k_trace_small past its first candidate word: 44 faces (random triangles do not pair into quads) in rotated, scaled
+    instances; films, per-pixel RNG states and the statistics bit exact against the oracle (whose triangle loop for meshes of
+    <= 16 triangles is exhaustive: the box phase of the device must not cull anything the watertight test accepts)"""
+    scene = prb.Scene.from_string(_many_faces_scene(seed))
+    d = scene.desc.contents
+    assert 32 < d.n_bvh_tris <= 64 and d.n_entities <= 16
+    ctx = make_ctx(scene)
+    tiles = [(0, 0, scene.width, scene.height)]
+    ctx.render_tiles(tiles, 0, 8)
+    xyz, cnt = ctx.film()
+    ref = OracleScene(scene).render(tiles, 0, 8)
+    assert np.array_equal(ctx.download_rng(), ref["rng"])
+    assert np.array_equal(xyz.view(np.uint32), ref["filtered"].view(np.uint32)) and xyz.max() > 0
+    st = ctx.stats()
+    for k in STAT_NAMES:
+        assert int(getattr(st, k)) == int(ref["stats"][k]), k
+
+
 def test_uniform_non_lambert_scene_uses_the_generic_single_pass_kernel():
     """all materials of one non-Lambert type: k_shade<128, 1, leaf dispatch> (the Cornell box takes the all-Lambert
     instantiation, mixed scenes the 512-thread one)"""
