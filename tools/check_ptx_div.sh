@@ -8,7 +8,8 @@ F="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=
 nvcc $F -ftz=false -ptx csrc/prb_api.cu -o /tmp/prb_ftz0.ptx &
 nvcc $F -ftz=true -ptx csrc/prb_api.cu -o /tmp/prb_ftz1.ptx
 wait
-A=$(grep -c "div\.rn\.f32" /tmp/prb_ftz0.ptx)
-B=$(grep -c "div\.rn\.ftz\.f32" /tmp/prb_ftz1.ptx)
+# (divPositive writes its division as inline PTX, `div.rn.ftz.f32` in both builds: count both spellings in both files)
+A=$(grep -c "div\.rn\(\.ftz\)\?\.f32" /tmp/prb_ftz0.ptx)
+B=$(grep -c "div\.rn\(\.ftz\)\?\.f32" /tmp/prb_ftz1.ptx)
 echo "IEEE divisions: -ftz=false $A, -ftz=true $B"
 test "$A" = "$B"
