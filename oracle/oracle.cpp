@@ -2924,6 +2924,13 @@ void orc_tangent_frame(const float* N, float* Nx, float* Ny)
 	Nx[0] = x.x, Nx[1] = x.y, Nx[2] = x.z;
 	Ny[0] = y.x, Ny[1] = y.y, Ny[2] = y.z;
 }
+// Spherical::cartesian_from_uv / uv_from_normal (src/base/math/Spherical.h), for the known answers of src/tests/sphere.cpp
+void orc_cartesian_from_uv(float u, float v, float* out)
+{
+	const V3 n = cartesian_from_uv(u, v);
+	out[0] = n.x, out[1] = n.y, out[2] = n.z;
+}
+void orc_uv_from_normal(const float* N, float* uv) { uv_from_normal(mk(N[0], N[1], N[2]), uv[0], uv[1]); }
 void orc_random_stream(uint64_t seed, uint32_t n, uint32_t* out32, float* outf)
 {
 	Rng a{ seed | 3u }, b{ seed | 3u };

@@ -56,6 +56,8 @@ def lib():
         l.orc_halfway_reflection.argtypes = [C.c_void_p] * 3
         l.orc_cos_hemi.argtypes = [C.c_float, C.c_float, C.c_void_p]
         l.orc_tangent_frame.argtypes = [C.c_void_p] * 3
+        l.orc_cartesian_from_uv.argtypes = [C.c_float, C.c_float, C.c_void_p]
+        l.orc_uv_from_normal.argtypes = [C.c_void_p] * 2
         l.orc_random_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         l.orc_eval_node.restype = C.c_float
         l.orc_eval_node.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float]

@@ -445,6 +445,28 @@ def test_lpe_channels_bit_exact_vs_oracle(tmp_path):
     assert np.array_equal(ctx.film_lpe(1).view(np.uint32), ref["lpe_filtered"][1].view(np.uint32))
 
 
+def test_reference_plane_and_sphere_known_answers_on_device():
+    """the Plane / Sphere intersection cases of the reference's own tests (src/tests/plane.cpp:66-117, sphere.cpp:77-110) through
+    prb_trace_closest: the device returns what the oracle returns, and the oracle is checked against the reference's expected
+    values in test_oracle_known_answers.py"""
+    from test_oracle_known_answers import GEOMETRY_SCENE
+    cases = [("(entity :name 'ball' :type 'sphere' :radius 1 :material 'white')", [[-2, 0, 0], [-2, 0, 0], [0, 0, 0]], [[1, 0, 0], [-1, 0, 0], [1, 0, 0]]),
+             ("(entity :name 'quad' :type 'plane' :x_axis [1,0,0] :y_axis [0,1,0] :material 'white')", [[0.5, 0.5, -1], [0.5, 0.5, -1]], [[0, 0, 1], [0, 1, 0]]),
+             ("(entity :name 'quad' :type 'plane' :x_axis [10,0,0] :y_axis [0,20,0] :material 'white')", [[5, 10, -1]], [[0, 0, 1]])]
+    for ent_src, org, dr in cases:
+        scene = prb.Scene.from_string(GEOMETRY_SCENE % ent_src)
+        ctx = make_ctx(scene)
+        org, dr = np.array(org, np.float32), np.array(dr, np.float32)
+        tmin = np.zeros(len(org), np.float32)
+        got = ctx.trace_closest(org, dr, tmin)
+        ref = OracleScene(scene).trace_closest(org, dr, tmin=tmin)
+        hit = ref[0] != 0xFFFFFFFF
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+        for k in (2, 3, 4):
+            assert np.array_equal(got[k][hit].view(np.uint32), ref[k][hit].view(np.uint32))
+        assert hit[0] and abs(float(got[4][0]) - 1) <= 2 * np.finfo(np.float32).eps
+
+
 def _many_faces_scene(seed, n_meshes=3, tris_per_mesh=14):
     """a small scene (<= 64 triangles, <= 16 entities: k_trace_small) whose triangles do NOT pair into quads, so that it has more
     than 32 faces (second candidate word of traverseSmall), in rotated / scaled instances (world-space face boxes)"""

@@ -576,3 +576,65 @@ def test_depth_of_field_rays_focus_on_the_focal_plane():
     t = (depth - off @ fwd) / (dd.astype(np.float64) @ fwd)
     on_plane_dof = do.astype(np.float64) + dd.astype(np.float64) * t[:, None]
     assert np.abs(on_plane_dof - on_plane_pin).max() < 2e-5
+
+
+# ---------------------------------------------------------------- src/tests/sphere.cpp:11-68 (Spherical), :77-110 (Sphere); plane.cpp:66-122
+GEOMETRY_SCENE = """
+(scene :name 'geometry' :render_width 8 :render_height 8 :camera 'Camera'
+ (integrator :type 'direct' :max_ray_depth 2)
+ (sampler :slot 'aa' :type 'random' :sample_count 1)
+ (camera :name 'Camera' :type 'standard' :width 1 :height 1 :local_direction [0,0,-1] :local_up [0,1,0] :local_right [1,0,0]
+   :near 0.01 :far 100 :transform [1,0,0,0, 0,1,0,0, 0,0,1,30, 0,0,0,1])
+ (material :name 'white' :type 'diffuse' :albedo 1)
+ %s
+ (light :type 'env' :radiance 1)
+)
+"""
+# the reference computes these with libm's sin / cos / atan2 / acos; both sides here use the correctly rounded functions (DESIGN.md
+# section 3), a few ulp apart: 4 x PRT_EPSILON
+SPHERICAL_TOL = 4 * EPS
+
+
+@pytest.mark.parametrize("uv,expect", [((0.0, 0.0), (0.0, 0.0)), ((1.0, 0.0), (0.0, 0.0)), ((0.0, 1.0), (0.5, 1.0)), ((1.0, 1.0), (0.5, 1.0)),
+                                       ((0.5, 0.5), (0.5, 0.5)), ((0.75, 0.25), (0.75, 0.25)), ((0.25, 0.75), (0.25, 0.75))])
+def test_spherical_uv_round_trip(uv, expect):
+    """Spherical::uv_from_normal(cartesian_from_uv(u, v)), src/tests/sphere.cpp:12-67 incl. the ambiguous poles / seam"""
+    n = np.zeros(3, np.float32)
+    got = np.zeros(2, np.float32)
+    ob.lib().orc_cartesian_from_uv(uv[0], uv[1], p(n))
+    assert abs(float(np.linalg.norm(n)) - 1) < SPHERICAL_TOL
+    ob.lib().orc_uv_from_normal(p(n), p(got))
+    # the seam u = 0 == u = 1: compare modulo 1 there
+    du = abs(float(got[0]) - expect[0])
+    assert min(du, abs(du - 1)) < SPHERICAL_TOL and abs(float(got[1]) - expect[1]) < SPHERICAL_TOL
+
+
+def test_sphere_intersections():
+    """Sphere::intersects, src/tests/sphere.cpp:77-110: from outside (t = 1), pointing away (miss), from inside (t = 1)"""
+    scene = prb.Scene.from_string(GEOMETRY_SCENE % "(entity :name 'ball' :type 'sphere' :radius 1 :material 'white')")
+    ora = ob.OracleScene(scene)
+    org = np.array([[-2, 0, 0], [-2, 0, 0], [0, 0, 0]], np.float32)
+    dr = np.array([[1, 0, 0], [-1, 0, 0], [1, 0, 0]], np.float32)
+    ent, prim, u, v, t = ora.trace_closest(org, dr, tmin=np.zeros(3, np.float32))
+    assert ent[0] == 0 and abs(float(t[0]) - 1) <= EPS
+    assert ent[1] == 0xFFFFFFFF
+    assert ent[2] == 0 and abs(float(t[2]) - 1) <= EPS
+
+
+@pytest.mark.parametrize("axes,origin,direction,expect", [
+    (("[1,0,0]", "[0,1,0]"), (0.5, 0.5, -1), (0, 0, 1), (1.0, 0.5, 0.5)),      # plane.cpp:66-78  "Intersects 1"
+    (("[1,0,0]", "[0,1,0]"), (0.5, 0.5, -1), (0, 1, 0), None),                   # plane.cpp:80-89  "Intersects 2": parallel, no hit
+    (("[10,0,0]", "[0,10,0]"), (5, 5, -1), (0, 0, 1), (1.0, 0.5, 0.5)),         # plane.cpp:91-103 "Intersects 3"
+    (("[10,0,0]", "[0,20,0]"), (5, 10, -1), (0, 0, 1), (1.0, 0.5, 0.5)),        # plane.cpp:105-117 "Intersects 4"
+])
+def test_plane_intersections(axes, origin, direction, expect):
+    """Plane::intersects: hit distance and the plane parameters (u, v) of the hit, src/tests/plane.cpp:66-117 -- here through the
+    two triangles the plane entity is traced as (Embree's quad convention)"""
+    scene = prb.Scene.from_string(GEOMETRY_SCENE % ("(entity :name 'quad' :type 'plane' :x_axis %s :y_axis %s :material 'white')" % axes))
+    ora = ob.OracleScene(scene)
+    ent, prim, u, v, t = ora.trace_closest(np.array([origin], np.float32), np.array([direction], np.float32), tmin=np.zeros(1, np.float32))
+    if expect is None:
+        assert ent[0] == 0xFFFFFFFF
+    else:
+        assert ent[0] == 0
+        assert abs(float(t[0]) - expect[0]) <= EPS and abs(float(u[0]) - expect[1]) <= EPS and abs(float(v[0]) - expect[2]) <= EPS
