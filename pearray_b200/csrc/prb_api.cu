@@ -852,7 +852,7 @@ static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s
 		k_compact_active<<<(int)((c->nSlots + 1023) / 1024), 1024, 0, s>>>(W);
 		k_trace<<<c->gridTrace, 128, 0, s>>>(c->S, W);
 	} else if (c->smallScene)
-		k_trace_small<<<blocks, 128, 0, s>>>(c->S, W);
+		k_trace_small<<<(int)((c->nSlots + TRACE_SMALL_BLOCK - 1) / TRACE_SMALL_BLOCK), TRACE_SMALL_BLOCK, 0, s>>>(c->S, W);
 	else
 		k_trace_static<<<blocks, 128, 0, s>>>(c->S, W);
 }
