@@ -109,7 +109,19 @@ struct prb_ctx {
 	bool queueWantsNEE[SHADE_QUEUES] = {}; // some material of the queue's type has a non-delta lobe
 	uint32_t nQueues = 0, nNeeQueues = 0;
 	uint32_t launchesPerIteration(bool stagedMode) const { return (stagedMode ? 3 + nQueues + nNeeQueues : 3) - (regenInTrace() ? 1 : 0) + (persistentTrace ? 1 : 0); }
-	bool regenInTrace() const { return smallScene && !persistentTrace; } // k_trace_small regenerates ended paths itself: no k_regen launch
+	bool regenInTrace() const { return smallScene && !persistentTrace; }
+	// all-Lambert small scenes: k_trace_small lists the slots whose path goes on, k_shade walks the list (PRB_COMPACT_SMALL=0 / 1
+	// overrides).  Dense warps pay once k_shade is throughput bound, i.e. from about two waves of its blocks (4 x 128 slots per SM):
+	// cornellbox 500 x 500: 373.8 -> 384.0 Msamples/s; the 256 x 256 evaluation scene, one wave, loses the extra dependent load
+	// (249.6 -> 244.9)
+	bool compactSmall() const
+	{
+		if (!regenInTrace() || !allLambert)
+			return false;
+		if (const char* e = std::getenv("PRB_COMPACT_SMALL"))
+			return e[0] != '0';
+		return nSlots >= (size_t)smCount * 4 * 128 * 2;
+	} // k_trace_small regenerates ended paths itself: no k_regen launch
 	DBuf<uint4> hit;
 	DBuf<float> hitT;
 	// light path expression channels (scenes with prb_scene_desc::n_lpe > 0)
@@ -846,6 +858,16 @@ static void launchShadeOnly(prb_ctx* c, const WFState& W, cudaStream_t s)
 	else
 		k_shade<SHADE_BLOCK_MIXED, SHADE_ROUNDS_MIXED, SHADE_MATERIALS_LEAF><<<grid, SHADE_BLOCK_MIXED, 0, s>>>(c->S, W, rounds);
 }
+// one wavefront iteration; `iteration` alternates the counter of the compacted small-scene mode (WFState::parity)
+static void launchShade(prb_ctx* c, const WFState& W, cudaStream_t s);
+static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s);
+static void launchIteration(prb_ctx* c, WFState W, int blocks, cudaStream_t s, int iteration, bool shade = true)
+{
+	W.parity = (uint32_t)(iteration & 1);
+	launchTrace(c, W, blocks, s);
+	if (shade)
+		launchShade(c, W, s);
+}
 static void launchTrace(prb_ctx* c, const WFState& W, int blocks, cudaStream_t s)
 {
 	if (c->persistentTrace) {
@@ -909,6 +931,8 @@ static WFState makeWF(prb_ctx* c, uint32_t first, uint32_t count)
 	W.endIter	  = first + count;
 	W.regenInTrace = c->regenInTrace() ? 1u : 0u;
 	W.useActiveList = c->persistentTrace ? 1u : 0u;
+	W.compactSmall	= c->compactSmall() ? 1u : 0u;
+	W.parity		= 0;
 	return W;
 }
 
@@ -961,11 +985,13 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 		while (!finished && done < maxIters + ITERS_PER_GRAPH * GRAPHS_PER_POLL) {
 			size_t ne = 0;
 			for (int r = 0; r < ITERS_PER_GRAPH * GRAPHS_PER_POLL; ++r) {
+				WFState Wi = W;
+				Wi.parity  = (uint32_t)(r & 1);
 				CU(cudaEventRecord(c->profEvents[ne++], s));
-				launchTrace(c, W, blocks, s);
+				launchTrace(c, Wi, blocks, s);
 				CU(cudaEventRecord(c->profEvents[ne++], s));
 				CU(cudaEventRecord(c->profEvents[ne++], s));
-				launchShade(c, W, s);
+				launchShade(c, Wi, s);
 				CU(cudaEventRecord(c->profEvents[ne++], s));
 				CU(cudaGetLastError());
 			}
@@ -997,10 +1023,8 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 			cudaGraph_t graph = nullptr;
 			cudaError_t be	  = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
 			if (be == cudaSuccess)
-				for (int r = 0; r < ITERS_PER_GRAPH; ++r) {
-					launchTrace(c, W, blocks, s);
-					launchShade(c, W, s);
-				}
+				for (int r = 0; r < ITERS_PER_GRAPH; ++r)
+					launchIteration(c, W, blocks, s, r);
 			c->staged = keep;
 			const cudaError_t ce = be == cudaSuccess ? cudaGetLastError() : be;
 			const cudaError_t ee = be == cudaSuccess ? cudaStreamEndCapture(s, &graph) : be;
@@ -1053,7 +1077,7 @@ prb_status prb_render_tiles(prb_ctx* c, const prb_tile* tiles, size_t n_tiles, u
 		}
 	}
 	// flush: samples that ended with their last shadow ray in flight are folded into the film by k_trace
-	launchTrace(c, W, blocks, s);
+	launchIteration(c, W, blocks, s, 0, false); // (an even number of iterations has run: parity 0)
 	c->kernelLaunches += 1;
 	CU(cudaGetLastError());
 	c->wavefrontIterations += done;

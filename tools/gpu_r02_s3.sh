@@ -1,0 +1,12 @@
+#!/bin/sh
+# round 2, call S3: k_trace_small lists the slots whose path goes on (no extra launch), the all-Lambert k_shade walks that list; PRB_COMPACT_SMALL=0 is the previous behaviour
+mkdir -p gpurun_out
+q() { python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,1), d['stage_ms'])"; }
+run() {
+  python bench.py --scene c2 --no-cpu --no-extras --steps 2 --warmup 1 2>/dev/null | q
+  python bench.py --scene c0 --no-cpu --steps 2 --warmup 1 2>/dev/null | q
+}
+timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r02_gpu_tests_s3.log 2>&1; tail -3 gpurun_out/r02_gpu_tests_s2.log
+echo "== compacted"; run
+export PRB_COMPACT_SMALL=0
+echo "== PRB_COMPACT_SMALL=0"; run
